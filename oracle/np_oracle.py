@@ -1,0 +1,383 @@
+"""numpy oracle: CPU restatement of the reference's cluster / memory / loss /
+scoring arithmetic.  TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
+
+All paths cited are relative to ``/root/reference``.  ``dtype`` selects the
+arithmetic type: ``np.float32`` follows the reference's fp32 operation order
+(mm-form cdist etc.); ``np.float64`` is the high-precision adjudicator used to
+classify near-ties when argmin/argmax indices are compared.
+
+Parity pinning: checked against fixtures produced by the reference's own
+modules (``tests/golden/make_golden.py``); the reference has no tests or golden
+vectors of its own.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# primitives
+# ----------------------------------------------------------------------------
+
+
+def layer_norm(x, weight, bias, eps=1e-5, dtype=np.float32):
+    """``nn.LayerNorm(C)`` over the last axis (model/cluster.py:64,84 —
+    ``self.norm(x_temp)``): biased variance, eps inside the sqrt."""
+    x = np.asarray(x, dtype)
+    mu = x.mean(-1, keepdims=True, dtype=dtype)
+    xc = x - mu
+    var = (xc * xc).mean(-1, keepdims=True, dtype=dtype)
+    rstd = (1.0 / np.sqrt(var + dtype(eps))).astype(dtype)
+    xhat = xc * rstd
+    z = xhat * np.asarray(weight, dtype) + np.asarray(bias, dtype)
+    return z.astype(dtype), mu[..., 0].astype(dtype), rstd[..., 0].astype(dtype)
+
+
+def cdist_mm(a, b, dtype=np.float32):
+    """``torch.cdist(a, b)`` (p=2) in the matmul form ATen uses when either
+    side has more than 25 rows (model/cluster.py:61,87):
+    ``sqrt(clamp_min(||a||^2 + ||b||^2 - 2 a.b^T, 0))``.  ``a`` [..., R, C],
+    ``b`` [..., P, C] -> [..., R, P]."""
+    a = np.asarray(a, dtype)
+    b = np.asarray(b, dtype)
+    aa = (a * a).sum(-1, dtype=dtype)[..., :, None]
+    bb = (b * b).sum(-1, dtype=dtype)[..., None, :]
+    ab = np.matmul(a, np.swapaxes(b, -1, -2))
+    sq = aa + bb - dtype(2.0) * ab
+    return np.sqrt(np.maximum(sq, dtype(0.0))).astype(dtype)
+
+
+def neg_soft_assign(d, alpha, dtype=np.float32):
+    """``NegSoftAssign.forward`` over the last axis (model/cluster.py:48-55):
+    ``exp(-alpha (d - min d)) / sum``."""
+    d = np.asarray(d, dtype)
+    dmin = d.min(-1, keepdims=True)
+    e = np.exp(dtype(-alpha) * (d - dmin)).astype(dtype)
+    return (e / e.sum(-1, keepdims=True, dtype=dtype)).astype(dtype)
+
+
+def pos_soft_assign(x, alpha, dtype=np.float32):
+    """``PosSoftAssign.forward`` (model/cluster.py:33-39)."""
+    x = np.asarray(x, dtype)
+    xmax = x.max(-1, keepdims=True)
+    e = np.exp(dtype(alpha) * (x - xmax)).astype(dtype)
+    return (e / e.sum(-1, keepdims=True, dtype=dtype)).astype(dtype)
+
+
+# ----------------------------------------------------------------------------
+# C1 / C2: EuclidDistance_Assign_Module forward + backward
+# ----------------------------------------------------------------------------
+
+
+def cluster_forward(x, centers, ln_w, ln_b, alpha, eps=1e-5, dtype=np.float32):
+    """``EuclidDistance_Assign_Module.forward`` (model/cluster.py:81-99).
+
+    x [B,D,H,W,C], centers [K,C] -> dict with
+    D [B,D,H,W,K], A [B,D,H,W,K], S [K,K], x_rec [B,D,H,W,C],
+    feature [N,C], label [N] int64 (+ mu, rstd [N] saved for the backward)."""
+    x = np.asarray(x, dtype)
+    lead = x.shape[:-1]
+    C = x.shape[-1]
+    c = np.asarray(centers, dtype)
+    z, mu, rstd = layer_norm(x.reshape(-1, C), ln_w, ln_b, eps, dtype)
+    D = cdist_mm(z, c, dtype)                        # cluster.py:87
+    label = D.argmin(-1).astype(np.int64)            # cluster.py:88 (first min)
+    A = neg_soft_assign(D, alpha, dtype)             # cluster.py:92
+    S = cdist_mm(c, c, dtype)                        # cluster.py:93,77-79
+    R = (A @ c).astype(dtype)                        # cluster.py:94-95
+    K = c.shape[0]
+    return dict(D=D.reshape(*lead, K), A=A.reshape(*lead, K), S=S,
+                x_rec=R.reshape(*lead, C), feature=z, label=label,
+                mu=mu, rstd=rstd)
+
+
+def frobenius_loss(D, A, dtype=np.float32):
+    """``torch.norm(x_distance * x_assign)`` (model/backbone.py:94,98)."""
+    p = np.asarray(D, dtype) * np.asarray(A, dtype)
+    return np.sqrt((p.astype(np.float64) ** 2).sum()).astype(dtype)
+
+
+def layer_norm_backward(gz, x, mu, rstd, ln_w, dtype=np.float32):
+    """autograd of ``nn.LayerNorm`` (implicit; main_predict.py:296)."""
+    gz = np.asarray(gz, dtype)
+    x = np.asarray(x, dtype)
+    xhat = (x - mu[:, None]) * rstd[:, None]
+    gw = (gz * xhat).sum(0, dtype=dtype)
+    gb = gz.sum(0, dtype=dtype)
+    gxh = gz * np.asarray(ln_w, dtype)
+    m1 = gxh.mean(-1, keepdims=True, dtype=dtype)
+    m2 = (gxh * xhat).mean(-1, keepdims=True, dtype=dtype)
+    gx = (gxh - m1 - xhat * m2) * rstd[:, None]
+    return gx.astype(dtype), gw, gb
+
+
+def cluster_backward(x, centers, ln_w, ln_b, alpha, gD=None, gA=None, gR=None,
+                     gF=None, gS=None, eps=1e-5, dtype=np.float32):
+    """autograd of ``EuclidDistance_Assign_Module.forward`` — the reference's
+    "centroid update" (``loss.backward()``
+    main_predict.py:296; ATen ``_euclidean_dist_backward``: ratio = grad/dist,
+    0 where dist == 0).  Returns gx [N,C], gcenters [K,C], g_ln_w, g_ln_b."""
+    x = np.asarray(x, dtype).reshape(-1, np.asarray(x).shape[-1])
+    c = np.asarray(centers, dtype)
+    N, C = x.shape
+    K = c.shape[0]
+    f = cluster_forward(x.reshape(1, 1, 1, N, C), c, ln_w, ln_b, alpha, eps, dtype)
+    z, D, A = f["feature"], f["D"].reshape(N, K), f["A"].reshape(N, K)
+    zero_nk = np.zeros((N, K), dtype)
+    gD = zero_nk if gD is None else np.asarray(gD, dtype).reshape(N, K)
+    gA = zero_nk if gA is None else np.asarray(gA, dtype).reshape(N, K)
+    gR = np.zeros((N, C), dtype) if gR is None else np.asarray(gR, dtype).reshape(N, C)
+    gF = np.zeros((N, C), dtype) if gF is None else np.asarray(gF, dtype).reshape(N, C)
+    gA_tot = gA + gR @ c.T                                   # x_rec = A @ centers
+    gc = A.T @ gR
+    dot = (gA_tot * A).sum(-1, keepdims=True, dtype=dtype)
+    gD_tot = gD - dtype(alpha) * A * (gA_tot - dot)          # softmin backward
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(D == 0, dtype(0), gD_tot / D).astype(dtype)
+    gz = z * r.sum(-1, keepdims=True, dtype=dtype) - r @ c + gF
+    gc = gc + c * r.sum(0, dtype=dtype)[:, None] - r.T @ z
+    if gS is not None:                                       # self_similarity()
+        S = f["S"]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rs = np.where(S == 0, dtype(0), np.asarray(gS, dtype) / S).astype(dtype)
+        rs = rs + rs.T
+        gc = gc + c * rs.sum(-1, dtype=dtype)[:, None] - rs @ c
+    gx, gw, gb = layer_norm_backward(gz, x, f["mu"], f["rstd"], ln_w, dtype)
+    return gx, gc.astype(dtype), gw, gb
+
+
+def frobenius_loss_grads(D, A, gL=1.0, dtype=np.float32):
+    """d ``torch.norm(D*A)`` / d(D, A) (model/backbone.py:94,98)."""
+    D = np.asarray(D, dtype)
+    A = np.asarray(A, dtype)
+    L = frobenius_loss(D, A, dtype)
+    s = dtype(gL) / L
+    return (D * A * A * s).astype(dtype), (D * D * A * s).astype(dtype)
+
+
+# ----------------------------------------------------------------------------
+# C3: Space_EuclidDistance_Assign_Module forward + backward
+# ----------------------------------------------------------------------------
+
+
+def space_cluster_forward(x, centers, ln_w, ln_b, alpha, eps=1e-5, dtype=np.float32):
+    """``Space_EuclidDistance_Assign_Module.forward`` (model/cluster.py:127-149).
+
+    x [B,D,H,W,C], centers [C,K,P] with P = H*W ->
+    Ds [B,D,C,K], As [B,D,C,K], S [C,K,K]; x_rec is ``[]`` in the reference."""
+    x = np.asarray(x, dtype)
+    B, Dd, H, W, C = x.shape
+    cen = np.asarray(centers, dtype)
+    z, mu, rstd = layer_norm(x.reshape(-1, C), ln_w, ln_b, eps, dtype)
+    zt = z.reshape(B * Dd, H * W, C).transpose(2, 0, 1)      # 'B D H W C -> C (B D) (H W)'
+    Dc = cdist_mm(zt, cen, dtype)                            # [C, M, K]   cluster.py:133
+    Ds = Dc.reshape(C, B, Dd, -1).transpose(1, 2, 0, 3)      # 'C (B D) CN -> B D C CN'
+    As = neg_soft_assign(Ds, alpha, dtype)
+    S = cdist_mm(cen, cen, dtype)                            # [C, K, K]   cluster.py:148
+    return dict(D=np.ascontiguousarray(Ds), A=As, S=S, mu=mu, rstd=rstd,
+                feature=z)
+
+
+def space_cluster_backward(x, centers, ln_w, ln_b, alpha, gD=None, gA=None,
+                           eps=1e-5, dtype=np.float32):
+    """autograd of the space head (implicit; main_predict.py:296).
+    Returns gx [B,D,H,W,C], gcenters [C,K,P], g_ln_w, g_ln_b."""
+    x = np.asarray(x, dtype)
+    B, Dd, H, W, C = x.shape
+    cen = np.asarray(centers, dtype)
+    K = cen.shape[1]
+    f = space_cluster_forward(x, cen, ln_w, ln_b, alpha, eps, dtype)
+    Ds, As = f["D"], f["A"]
+    gD = np.zeros_like(Ds) if gD is None else np.asarray(gD, dtype)
+    gA = np.zeros_like(Ds) if gA is None else np.asarray(gA, dtype)
+    dot = (gA * As).sum(-1, keepdims=True, dtype=dtype)
+    gDt = gD - dtype(alpha) * As * (gA - dot)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(Ds == 0, dtype(0), gDt / Ds).astype(dtype)   # [B,D,C,K]
+    rc = r.transpose(2, 0, 1, 3).reshape(C, B * Dd, K)            # [C,M,K]
+    zt = f["feature"].reshape(B * Dd, H * W, C).transpose(2, 0, 1)  # [C,M,P]
+    gzt = zt * rc.sum(-1, keepdims=True, dtype=dtype) - np.matmul(rc, cen)
+    gcen = cen * rc.sum(1, dtype=dtype)[:, :, None] - np.matmul(rc.transpose(0, 2, 1), zt)
+    gz = gzt.transpose(1, 2, 0).reshape(-1, C)
+    gx, gw, gb = layer_norm_backward(gz, x.reshape(-1, C), f["mu"], f["rstd"], ln_w, dtype)
+    return gx.reshape(x.shape), gcen.astype(dtype), gw, gb
+
+
+# ----------------------------------------------------------------------------
+# L2 / L3: reconstruction losses
+# ----------------------------------------------------------------------------
+
+
+def recon_l1(x, target, patch_d=1, dtype=np.float32):
+    """``Recon_Loss.forward`` (loss_tool/Recon_Loss.py:23-32): zero-pad target
+    on D up to a multiple of patch_size[0], same-shape assert, mean |x - t|."""
+    x = np.asarray(x, dtype)
+    t = np.asarray(target, dtype)
+    Dd = t.shape[2]
+    if Dd % patch_d != 0:
+        pad = patch_d - Dd % patch_d
+        t = np.pad(t, ((0, 0), (0, 0), (0, pad), (0, 0), (0, 0)))
+    assert x.shape == t.shape
+    return dtype(np.abs(x.astype(np.float64) - t).mean())
+
+
+def mse_mean(x, target, dtype=np.float32):
+    """``torch.mean(nn.MSELoss(reduction='none')(r, t))`` (main.py:191)."""
+    e = np.asarray(x, np.float64) - np.asarray(target, np.float64)
+    return dtype((e * e).mean())
+
+
+def e4_norm(x, target, dtype=np.float32):
+    """``torch.norm(nn.MSELoss(reduction='none')(r, t))`` = sqrt(sum e^4)
+    (main_predict.py:273-275)."""
+    e = np.asarray(x, dtype).astype(np.float64) - np.asarray(target, dtype)
+    return dtype(np.sqrt((e ** 4).sum()))
+
+
+# ----------------------------------------------------------------------------
+# E1-E4: per-frame error, PSNR, regularity score, per-scene AUC
+# ----------------------------------------------------------------------------
+
+
+def frame_mse(recon, clip, dtype=np.float32):
+    """per-frame reconstruction error (tool/evaluate.py:175-179,
+    tool/contrast_evaluae.py:232-236): ``(recon-clip)^2`` [B,C,D,H,W] ->
+    'B D C H W' -> mean over W, H, C -> [B, D]."""
+    e = np.asarray(recon, dtype) - np.asarray(clip, dtype)
+    sq = (e * e).astype(dtype).transpose(0, 2, 1, 3, 4)
+    return sq.mean(4, dtype=dtype).mean(3, dtype=dtype).mean(2, dtype=dtype)
+
+
+def clip_mse(recon, clip, dtype=np.float32):
+    """per-clip error of tool/predict_evaluae.py:228-234 (one score per clip)."""
+    e = np.asarray(recon, dtype) - np.asarray(clip, dtype)
+    return (e * e).reshape(e.shape[0], -1).mean(1, dtype=np.float64).astype(dtype)
+
+
+def psnr(mse):
+    """``utils.psnr`` (misc/utils.py:124-128), Python float64."""
+    return [10 * math.log10(1.0 / float(m)) for m in mse]
+
+
+def anomly_score(p):
+    """``utils.anomly_score`` (misc/utils.py:131-135): 1 - minmax(psnr) per
+    video; ZeroDivisionError for a constant list, like the reference."""
+    hi, lo = max(p), min(p)
+    return [1.0 - (v - lo) / (hi - lo) for v in p]
+
+
+def roc_auc(labels, scores):
+    """Area under the ROC curve with tie handling identical to
+    ``sklearn.metrics.roc_auc_score`` (tool/evaluate.py:214,
+    tool/contrast_evaluae.py:278): Mann-Whitney U with mid-ranks."""
+    y = np.asarray(labels).astype(bool)
+    s = np.asarray(scores, np.float64)
+    n_pos, n_neg = int(y.sum()), int((~y).sum())
+    if n_pos == 0 or n_neg == 0:
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+    order = np.argsort(s, kind="mergesort")
+    ss = s[order]
+    ranks = np.empty(len(s), np.float64)
+    i = 0
+    while i < len(ss):
+        j = i
+        while j + 1 < len(ss) and ss[j + 1] == ss[i]:
+            j += 1
+        ranks[order[i:j + 1]] = 0.5 * (i + j) + 1.0
+        i = j + 1
+    u = ranks[y].sum() - n_pos * (n_pos + 1) / 2.0
+    return float(u / (n_pos * n_neg))
+
+
+def scene_auc(video_mse, video_labels, video_scene):
+    """evaluation aggregate (tool/evaluate.py:198-224 =
+    tool/contrast_evaluae.py:262-299): per video psnr -> anomly_score; concat
+    per scene (insertion order); roc_auc per scene; arithmetic mean."""
+    scores, labels = {}, {}
+    for mse, lab, sc in zip(video_mse, video_labels, video_scene):
+        s = np.array(anomly_score(psnr(mse)))
+        lab = np.asarray(lab)
+        if sc in scores:
+            scores[sc] = np.append(scores[sc], s)
+            labels[sc] = np.append(labels[sc], lab)
+        else:
+            scores[sc], labels[sc] = s, lab
+    per = {k: roc_auc(labels[k], scores[k]) for k in scores}
+    return sum(per.values()) / len(per), per
+
+
+# ----------------------------------------------------------------------------
+# M1-M5: Memory module
+# ----------------------------------------------------------------------------
+
+
+def _softmax(s, axis, dtype):
+    m = s.max(axis, keepdims=True)
+    e = np.exp(s - m).astype(dtype)
+    return (e / e.sum(axis, keepdims=True, dtype=dtype)).astype(dtype)
+
+
+def l2_normalize(x, axis, eps=1e-12, dtype=np.float32):
+    """``F.normalize(x, dim)`` (model/Memory.py:148,193)."""
+    x = np.asarray(x, dtype)
+    n = np.sqrt((x * x).sum(axis, keepdims=True, dtype=dtype))
+    return (x / np.maximum(n, dtype(eps))).astype(dtype)
+
+
+def memory_get_score(keys, q, dtype=np.float32):
+    """``Memory.get_score`` (model/Memory.py:133-143): q [N,d] (already
+    normalised + flattened), keys [m,d] -> (softmax over tokens, softmax over
+    slots), both [N,m]."""
+    s = (np.asarray(q, dtype) @ np.asarray(keys, dtype).T).astype(dtype)
+    return _softmax(s, 0, dtype), _softmax(s, 1, dtype)
+
+
+def memory_prepare_query(query, dtype=np.float32):
+    """``F.normalize(query, dim=1)`` + permute to [B,h,w,d] (Memory.py:148-149),
+    returned flattened [N,d]."""
+    qn = l2_normalize(np.asarray(query, dtype), 1, dtype=dtype)
+    B, d, h, w = qn.shape
+    return np.ascontiguousarray(qn.transpose(0, 2, 3, 1)).reshape(B * h * w, d)
+
+
+def memory_forward(query, keys, train=True, dtype=np.float32):
+    """``Memory.forward`` (model/Memory.py:145-175) with gather_loss (:233-247),
+    spread_loss (:214-231), read (:249-261), update/get_update_query (:177-204,
+    :94-131).  query [B,d,h,w], keys [m,d]."""
+    query = np.asarray(query, dtype)
+    keys = np.asarray(keys, dtype)
+    B, d, h, w = query.shape
+    q = memory_prepare_query(query, dtype)
+    N = q.shape[0]
+    sq, sm = memory_get_score(keys, q, dtype)
+    top = np.argsort(-sm, axis=1, kind="stable")[:, :2]
+    g1 = top[:, 0]
+    gather = dtype(((q - keys[g1]).astype(np.float64) ** 2).mean())
+    concat = (sm @ keys).astype(dtype)
+    uq = np.concatenate([q, concat], 1).reshape(B, h, w, 2 * d).transpose(0, 3, 1, 2)
+    out = dict(updated_query=uq, score_query=sq, score_memory=sm,
+               gathering_loss=gather, top1=g1, top2=top[:, 1], q=q)
+    if not train:
+        out["updated_memory"] = keys
+        return out
+    # TripletMarginLoss(margin=1, p=2, eps=1e-6): pairwise_distance adds eps to the difference
+    pos, neg = keys[g1], keys[top[:, 1]]
+    dap = np.sqrt((((q - pos).astype(np.float64) + 1e-6) ** 2).sum(1))
+    dan = np.sqrt((((q - neg).astype(np.float64) + 1e-6) ** 2).sum(1))
+    out["spreading_loss"] = dtype(np.maximum(dap - dan + 1.0, 0.0).mean())
+    # update: slot i <- sum_{n: argmax_m sm[n]=i} (sq[n,i] / max_n sq[:,i]) q_n
+    colmax = sq.max(0)
+    wgt = (sq[np.arange(N), g1] / colmax[g1]).astype(dtype)
+    upd = np.zeros_like(keys)
+    np.add.at(upd, g1, wgt[:, None] * q)
+    out["query_update"] = upd
+    out["updated_memory"] = l2_normalize(upd + keys, 1, dtype=dtype)
+    return out
+
+
+def memory_separateness(keys, dtype=np.float32):
+    """``MemoryLoss`` (model/Memory.py:52-59)."""
+    k = np.asarray(keys, np.float64)
+    m = k.shape[0]
+    sim = np.abs(k @ k.T / 2 + 0.5 - np.eye(m))
+    return dtype(sim.sum() / (m * (m - 1)))

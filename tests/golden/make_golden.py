@@ -1,0 +1,192 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/*.npz by running the
+REFERENCE'S OWN modules (imported from /root/reference, unmodified) on seeded
+synthetic inputs.  Runs only in the build container (the reference does not
+travel to the GPU box); the fixtures it writes are committed.
+
+    python tests/golden/make_golden.py
+
+Stubs: misc/utils.py imports matplotlib / skimage / cv2 at module import;
+they are not installed here and are not used by psnr()/anomly_score(), so
+empty stub modules are injected (recipe from SURVEY.md §8(c)).  Memory.py
+hard-codes ``.cuda()``; on this CPU-only box ``Tensor.cuda`` is shimmed to the
+identity.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    for n in ("matplotlib", "matplotlib.pyplot", "skimage", "skimage.io",
+              "skimage.transform", "skimage.color"):
+        if n not in sys.modules:
+            try:
+                __import__(n)
+            except Exception:
+                _stub(n)
+    sk = sys.modules["skimage"]
+    for sub in ("io", "transform", "color"):
+        if not hasattr(sk, sub):
+            setattr(sk, sub, sys.modules.get("skimage." + sub, _stub("skimage." + sub)))
+    from model import cluster as ref_cluster
+    from model import Memory as ref_memory
+    from loss_tool import Recon_Loss as ref_recon
+    from misc import utils as ref_utils
+    return ref_cluster, ref_memory, ref_recon, ref_utils
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+def gen_cluster(ref_cluster, name, B, D, H, W, C, K, alpha, clustered, seed):
+    g = torch.Generator().manual_seed(seed)
+    mod = ref_cluster.EuclidDistance_Assign_Module(C, K, soft_assign_alpha=alpha)
+    with torch.no_grad():
+        mod.cluster_center.copy_(torch.rand(K, C, generator=g))
+        mod.norm.weight.copy_(1.0 + 0.2 * torch.randn(C, generator=g))
+        mod.norm.bias.copy_(0.1 * torch.randn(C, generator=g))
+    if clustered:
+        idx = torch.randint(0, K, (B, D, H, W), generator=g)
+        x = mod.cluster_center.detach()[idx] * 3.0 + 0.3 * torch.randn(B, D, H, W, C, generator=g)
+    else:
+        x = torch.randn(B, D, H, W, C, generator=g) * 1.7 + 0.4
+    x.requires_grad_(True)
+    Dm, A, S, R, F, lab = mod(x)
+    GR = torch.randn(R.shape, generator=g)
+    GF = 0.05 * torch.randn(F.shape, generator=g)
+    # the reference's training objective for this head (backbone.py:98) plus
+    # linear probes of x_rec / feature so every backward input is exercised
+    closs = torch.norm(Dm * A)
+    obj = closs + (R * GR).sum() + (F * GF).sum()
+    obj.backward()
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        x=t2n(x), centers=t2n(mod.cluster_center), ln_w=t2n(mod.norm.weight),
+        ln_b=t2n(mod.norm.bias), alpha=np.float32(alpha),
+        D=t2n(Dm), A=t2n(A), S=t2n(S), x_rec=t2n(R), feature=t2n(F), label=t2n(lab),
+        cluster_loss=t2n(closs), gR=t2n(GR), gF=t2n(GF),
+        gx=t2n(x.grad), gcenters=t2n(mod.cluster_center.grad),
+        g_ln_w=t2n(mod.norm.weight.grad), g_ln_b=t2n(mod.norm.bias.grad))
+
+
+def gen_space(ref_cluster, name, B, D, H, C, K, alpha, seed):
+    g = torch.Generator().manual_seed(seed)
+    mod = ref_cluster.Space_EuclidDistance_Assign_Module(C, K, space_size=H, soft_assign_alpha=alpha)
+    with torch.no_grad():
+        mod.cluster_center.copy_(torch.rand(C, K, H * H, generator=g))
+        mod.norm.weight.copy_(1.0 + 0.2 * torch.randn(C, generator=g))
+        mod.norm.bias.copy_(0.1 * torch.randn(C, generator=g))
+    x = (torch.randn(B, D, H, H, C, generator=g) * 1.3 - 0.2).requires_grad_(True)
+    Ds, As, S, rec = mod(x)
+    assert rec == []
+    loss = torch.norm(Ds * As)                      # backbone.py:94
+    loss.backward()
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        x=t2n(x), centers=t2n(mod.cluster_center), ln_w=t2n(mod.norm.weight),
+        ln_b=t2n(mod.norm.bias), alpha=np.float32(alpha),
+        D=t2n(Ds), A=t2n(As), S=t2n(S), space_loss=t2n(loss),
+        gx=t2n(x.grad), gcenters=t2n(mod.cluster_center.grad),
+        g_ln_w=t2n(mod.norm.weight.grad), g_ln_b=t2n(mod.norm.bias.grad))
+
+
+def gen_memory(ref_memory, name, B, d, h, w, m, seed):
+    g = torch.Generator().manual_seed(seed)
+    torch.Tensor.cuda = lambda self, *a, **k: self          # SURVEY.md D5 shim
+    mem = ref_memory.Memory(m, d, d, 0.1, 0.1)
+    keys = torch.nn.functional.normalize(torch.rand(m, d, generator=g), dim=1)  # main.py:131
+    query = torch.randn(B, d, h, w, generator=g)
+    uq, um, sq, sm, gl, sl = mem(query, keys, train=True)
+    uq_t, um_t, sq_t, sm_t, gl_t = mem(query, keys, train=False)
+    sep = ref_memory.MemoryLoss(keys)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        query=t2n(query), keys=t2n(keys),
+        updated_query=t2n(uq.contiguous()), updated_memory=t2n(um), score_query=t2n(sq),
+        score_memory=t2n(sm), gathering_loss=t2n(gl), spreading_loss=t2n(sl),
+        test_updated_query=t2n(uq_t.contiguous()), test_updated_memory=t2n(um_t),
+        test_gathering_loss=t2n(gl_t), separateness=t2n(sep))
+
+
+def gen_losses_scoring(ref_recon, ref_utils, name, seed):
+    from sklearn.metrics import roc_auc_score
+    g = torch.Generator().manual_seed(seed)
+    # L2: Recon_Loss with D padding (patch 2, D = 3 -> 4)
+    rl = ref_recon.Recon_Loss((2, 4, 4))
+    xr = torch.rand(2, 3, 4, 8, 8, generator=g)
+    tg = torch.rand(2, 3, 3, 8, 8, generator=g)
+    l1_pad = rl(xr, tg)
+    tg4 = torch.rand(2, 3, 4, 8, 8, generator=g)
+    l1 = rl(xr, tg4)
+    mse_none = torch.nn.MSELoss(reduction="none")
+    l_mse = torch.mean(mse_none(xr, tg4))                       # main.py:191
+    l_e4 = torch.norm(mse_none(xr, tg4))                        # main_predict.py:273-275
+    # E1-E4 on a tiny labelled set: 5 videos, 3 scenes
+    from einops import rearrange
+    vids, mses, labs, scenes = [], [], [], []
+    scene_dict, scene_label = {}, {}
+    for v, (T, sc) in enumerate([(12, "01"), (8, "01"), (16, "02"), (8, "03"), (12, "02")]):
+        clip = torch.rand(1, 3, T, 16, 16, generator=g)
+        lab = (torch.rand(T, generator=g) < 0.4).long()
+        lab[0], lab[1] = 0, 1
+        noise = 0.05 * torch.randn(clip.shape, generator=g)
+        noise = noise * (1.0 + 2.0 * lab.float().view(1, 1, T, 1, 1))
+        recon = clip + noise
+        loss = mse_none(recon, clip)
+        loss = rearrange(loss, "B C D H W -> B D C H W")          # contrast_evaluae.py:234
+        lf = torch.mean(loss, dim=4).mean(dim=3).mean(dim=2)      # :235
+        lf = sum(lf.tolist(), [])                                 # :236-237
+        ps = ref_utils.psnr(lf)                                   # :238
+        score = np.array([ref_utils.anomly_score(ps)])[0]         # :265
+        vids.append((t2n(clip), t2n(recon)))
+        mses.append(np.array(lf, np.float64)); labs.append(t2n(lab)); scenes.append(sc)
+        if sc in scene_dict:
+            scene_dict[sc] = np.append(scene_dict[sc], score)
+            scene_label[sc] = np.append(scene_label[sc], t2n(lab))
+        else:
+            scene_dict[sc], scene_label[sc] = score, t2n(lab)
+    aucs = [roc_auc_score(scene_label[k], scene_dict[k]) for k in scene_dict]   # :278
+    auc = sum(aucs) / len(aucs)                                                  # :298
+    d = dict(l1_x=t2n(xr), l1_t_pad=t2n(tg), l1_t=t2n(tg4), l1_pad=t2n(l1_pad), l1=t2n(l1),
+             mse=t2n(l_mse), e4=t2n(l_e4), auc=np.float64(auc), scene_aucs=np.array(aucs),
+             scenes=np.array(scenes), n_videos=np.int64(len(vids)))
+    for i, ((c, r), ms, lb) in enumerate(zip(vids, mses, labs)):
+        d[f"clip{i}"], d[f"recon{i}"], d[f"mse{i}"], d[f"label{i}"] = c, r, ms, lb
+        d[f"psnr{i}"] = np.array(ref_utils.psnr(ms.tolist()))
+        d[f"score{i}"] = np.array(ref_utils.anomly_score(ref_utils.psnr(ms.tolist())))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    ref_cluster, ref_memory, ref_recon, ref_utils = import_reference()
+    gen_cluster(ref_cluster, "cluster_c64_k32", 1, 2, 4, 4, 64, 32, 16.0, False, 1)
+    gen_cluster(ref_cluster, "cluster_c32_k16", 2, 2, 4, 4, 32, 16, 32.0, False, 2)
+    gen_cluster(ref_cluster, "cluster_c192_k48_peaked", 1, 1, 6, 6, 192, 48, 16.0, True, 3)
+    gen_space(ref_cluster, "space_c8_k6_p16", 2, 3, 4, 8, 6, 32.0, 4)
+    gen_space(ref_cluster, "space_c16_k40_p36", 3, 10, 6, 16, 40, 32.0, 5)
+    gen_memory(ref_memory, "memory_d32_m10", 2, 32, 4, 4, 10, 6)
+    gen_memory(ref_memory, "memory_d64_m50", 1, 64, 6, 6, 50, 7)
+    gen_losses_scoring(ref_recon, ref_utils, "losses_scoring", 8)
+    print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
+
+
+if __name__ == "__main__":
+    main()
