@@ -1,0 +1,55 @@
+"""helpers for the -m gpu parity tests"""
+import numpy as np
+import torch
+
+from oracle import np_oracle as O
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def T(a, dtype=torch.float32, grad=False):
+    t = torch.as_tensor(np.asarray(a), dtype=dtype).to(dev())
+    if grad:
+        t.requires_grad_(True)
+    return t
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def assert_labels_match(label, D64, what="label"):
+    """argmin indices must be bit-exact except where the fp64 oracle itself
+    sees a (near-)tie: a mismatching pick is accepted only if its fp64 distance
+    is within 1e-6 relative of the fp64 minimum (fp32 rounding noise of the
+    reference's own SGEMM is ~1e-7..1e-6 relative; BASELINE.json: 'bit-exact
+    (excluding exact ties)')."""
+    label = np.asarray(label).reshape(-1)
+    D64 = np.asarray(D64, np.float64).reshape(label.shape[0], -1)
+    ref = D64.argmin(-1)
+    bad = np.flatnonzero(label != ref)
+    if bad.size:
+        gap = (D64[bad, label[bad]] - D64[bad, ref[bad]]) / D64[bad, ref[bad]]
+        assert gap.max() < 1e-6, f"{what}: {bad.size} mismatches, worst fp64 gap {gap.max():.3e}"
+    return bad.size
+
+
+def assert_selfdist_close(S, Sref, tol=2e-6):
+    S2, R2 = np.asarray(S, np.float64) ** 2, np.asarray(Sref, np.float64) ** 2
+    assert np.abs(S2 - R2).max() < tol * R2.max()
+
+
+def make_cluster_module(V, C, K, alpha, centers, ln_w, ln_b, impl=None):
+    m = V.EuclidDistance_Assign_Module(C, K, soft_assign_alpha=alpha).to(dev())
+    with torch.no_grad():
+        m.cluster_center.copy_(T(centers)); m.norm.weight.copy_(T(ln_w)); m.norm.bias.copy_(T(ln_b))
+    if impl is not None:
+        m.impl = impl
+    return m

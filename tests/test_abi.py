@@ -1,0 +1,114 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every
+symbol include/vadc.h declares, and the host mirror fails loudly without CUDA
+(no fallback).  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import videoad_b200 as V
+from videoad_b200 import _lib
+
+
+def test_header_declares_and_library_exports_every_symbol():
+    protos = _lib.parse_header()
+    with open(_lib.HEADER) as fh:
+        declared = set(re.findall(r"\b(vadc_\w+)\s*\(", fh.read()))
+    assert declared == set(protos), declared ^ set(protos)
+    assert len(protos) >= 30
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(raw, name), f"libvadc.so does not export {name}"
+
+
+def test_version_and_error_strings():
+    l = _lib.lib()
+    assert l.vadc_version().decode().startswith("vadc")
+    for code in range(0, -8, -1):
+        assert len(l.vadc_error_string(code).decode()) > 1
+    assert "unknown" in l.vadc_error_string(-99).decode()
+
+
+def test_workspace_queries_are_pure_host_functions():
+    l = _lib.lib()
+    assert l.vadc_cluster_fwd_workspace_bytes(1024, 192, 32, 0) > 0
+    assert l.vadc_cluster_bwd_workspace_bytes(1024, 192, 32) > 1024 * 192 * 4
+    assert l.vadc_space_cluster_fwd_workspace_bytes(8, 784, 192, 128) > 0
+    assert l.vadc_memory_score_workspace_bytes(2048, 2000, 768) >= 2048 * 2000 * 4
+    assert l.vadc_pixel_loss_workspace_bytes(1 << 20) > 0
+
+
+def test_argument_validation_happens_before_any_cuda_call():
+    l = _lib.lib()
+    # bad shape (K % 4 != 0) and NULL pointers are rejected on the host
+    assert l.vadc_cluster_fwd(None, None, None, None, 8, 192, 30, 16.0, 1e-5, None, None, None, None,
+                              None, None, None, None, None, 0, 0, None) == -1
+    assert l.vadc_cluster_fwd(None, None, None, None, 8, 192, 32, 16.0, 1e-5, None, None, None, None,
+                              None, None, None, None, None, 0, 0, None) == -2
+    assert l.vadc_pixel_loss(None, None, 0, None, 0, 0, None, None, 0, None) == -1
+    assert l.vadc_pixel_loss(None, None, 16, None, 0, 7, None, None, 0, None) == -1
+
+
+def test_no_cpu_fallback():
+    mod = V.EuclidDistance_Assign_Module(32, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mod(torch.randn(1, 1, 2, 2, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        V.e4_norm(torch.rand(4, 4), torch.rand(4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        V.frame_mse(torch.rand(1, 3, 2, 4, 4), torch.rand(1, 3, 2, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        V.Memory(10, 8, 8, 0.1, 0.1)(torch.randn(1, 8, 2, 2), torch.rand(10, 8))
+
+
+def test_missing_library_is_a_loud_error(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libvadc.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_state_dict_keys_match_reference_contract():
+    """SURVEY.md §5 checkpoint contract: parameter names and shapes"""
+    m = V.EuclidDistance_Assign_Module(192, 1024, soft_assign_alpha=16.0)
+    sd = m.state_dict()
+    assert set(sd) == {"cluster_center", "identity_matrix", "norm.weight", "norm.bias"}
+    assert sd["cluster_center"].shape == (1024, 192) and sd["identity_matrix"].shape == (1024, 1024)
+    assert m.cluster_center.requires_grad and not m.identity_matrix.requires_grad
+    assert float(m.cluster_center.min()) >= 0 and float(m.cluster_center.max()) <= 1   # torch.rand init
+    s = V.Space_EuclidDistance_Assign_Module(8, 6, space_size=4)
+    sd = s.state_dict()
+    assert sd["cluster_center"].shape == (8, 6, 16) and sd["identity_matrix"].shape == (8, 6, 6)
+    assert torch.equal(sd["identity_matrix"][3], torch.eye(6))
+    assert m.assign_func.alpha == 16.0 and m.assign_func.dims == -1
+
+
+def test_host_scoring_functions_match_reference_fixture():
+    from conftest import load_golden
+    import numpy as np
+    g = load_golden("losses_scoring")
+    mses, labs = [], []
+    for i in range(int(g["n_videos"])):
+        ms = g[f"mse{i}"].tolist()
+        assert V.psnr(ms) == g[f"psnr{i}"].tolist()
+        assert V.anomly_score(V.psnr(ms)) == g[f"score{i}"].tolist()
+        mses.append(ms); labs.append(g[f"label{i}"])
+    auc, per = V.regularity_auc(mses, labs, [str(s) for s in g["scenes"]])
+    assert abs(auc - float(g["auc"])) < 1e-12
+    np.testing.assert_allclose(list(per.values()), g["scene_aucs"], atol=1e-12)
+    with pytest.raises(ZeroDivisionError):
+        V.anomly_score([1.0, 1.0])
+    with pytest.raises(ValueError):
+        V.roc_auc_score([1, 1, 1], [0.1, 0.2, 0.3])
+
+
+def test_roc_auc_matches_sklearn():
+    import numpy as np
+    from sklearn.metrics import roc_auc_score
+    rng = np.random.default_rng(1)
+    for n in (2, 17, 400):
+        y = rng.integers(0, 2, n); y[0], y[-1] = 0, 1
+        s = np.round(rng.random(n), 2)
+        assert abs(V.roc_auc_score(y, s) - roc_auc_score(y, s)) < 1e-12

@@ -1,0 +1,187 @@
+"""C1 / C2 / L1 parity on the GPU, through the C ABI (ctypes -> libvadc.so).
+Tolerances: distances / losses 1e-4 relative (BASELINE.json north_star) — the
+kernels are in fact held to ~1e-5; argmin bit-exact excluding fp64-adjudicated
+ties."""
+import numpy as np
+import pytest
+import torch
+
+import videoad_b200 as V
+from oracle import np_oracle as O
+from conftest import load_golden
+from gpu_util import T, N, rel, dev, assert_labels_match, assert_selfdist_close, make_cluster_module
+
+pytestmark = pytest.mark.gpu
+IMPLS = [V.IMPL_SIMT, V.IMPL_AUTO]
+GOLDEN = ["cluster_c64_k32", "cluster_c32_k16", "cluster_c192_k48_peaked"]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_forward_backward(name, impl):
+    """the reference module's own outputs and autograd gradients (fixtures)"""
+    g = load_golden(name)
+    C, K = g["centers"].shape[1], g["centers"].shape[0]
+    m = make_cluster_module(V, C, K, float(g["alpha"]), g["centers"], g["ln_w"], g["ln_b"], impl)
+    m.cluster_center.requires_grad_(True)
+    x = T(g["x"], grad=True)
+    D, A, S, R, F, lab = m(x)
+    assert D.shape == g["D"].shape and R.shape == g["x_rec"].shape and F.shape == g["feature"].shape
+    assert lab.dtype == torch.int64 and lab.shape == g["label"].shape
+    assert rel(N(F), g["feature"]) < 1e-5
+    assert rel(N(D), g["D"]) < 1e-5
+    np.testing.assert_allclose(N(A), g["A"], rtol=1e-3, atol=2e-6)
+    assert rel(N(R), g["x_rec"]) < 1e-4
+    assert_selfdist_close(N(S), g["S"])
+    D64 = O.cluster_forward(g["x"], g["centers"], g["ln_w"], g["ln_b"], float(g["alpha"]), dtype=np.float64)["D"]
+    assert_labels_match(N(lab), D64)
+    # the reference's objective: torch.norm(D*A) + probes (make_golden.py)
+    closs = torch.norm(D * A)
+    assert abs(float(closs) - float(g["cluster_loss"])) < 1e-4 * float(g["cluster_loss"])
+    assert abs(float(m.fused_cluster_loss()) - float(g["cluster_loss"])) < 1e-4 * float(g["cluster_loss"])
+    obj = closs + (R * T(g["gR"])).sum() + (F * T(g["gF"])).sum()
+    obj.backward()
+    assert rel(N(x.grad), g["gx"]) < 2e-4
+    assert rel(N(m.cluster_center.grad), g["gcenters"]) < 2e-4
+    assert rel(N(m.norm.weight.grad), g["g_ln_w"]) < 2e-4
+    assert rel(N(m.norm.bias.grad), g["g_ln_b"]) < 2e-4
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_fused_loss_backward_equals_explicit(impl):
+    """fused d sum(D*A)^2 path == autograd through torch.norm(D*A)"""
+    g = load_golden("cluster_c64_k32")
+    grads = []
+    for fused in (False, True):
+        m = make_cluster_module(V, 64, 32, 16.0, g["centers"], g["ln_w"], g["ln_b"], impl)
+        x = T(g["x"], grad=True)
+        D, A, S, R, F, lab = m(x)
+        loss = m.fused_cluster_loss() if fused else torch.norm(D * A)
+        (loss * 1.7 + (R * T(g["gR"])).sum()).backward()
+        grads.append((N(x.grad), N(m.cluster_center.grad), N(m.norm.weight.grad), N(m.norm.bias.grad)))
+    for a, b in zip(*grads):
+        assert rel(a, b) < 2e-5
+
+
+SHAPES = [  # (N tokens, C, K, alpha): BASELINE configs at oracle-sized N + ragged / edge shapes
+    (6272, 192, 1024, 16.0),   # reference-native (cfg1)
+    (4096, 192, 32, 16.0),     # cfg2 head
+    (2048, 768, 16, 32.0), (2048, 768, 64, 32.0), (2048, 768, 256, 32.0),   # cfg3 sweep
+    (77, 192, 32, 16.0),       # ragged: not a multiple of any tile
+    (1, 64, 16, 32.0),         # single token
+    (300, 20, 12, 8.0),        # C, K only multiples of 4
+]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("Ntok,C,K,alpha", SHAPES)
+def test_forward_vs_oracle(Ntok, C, K, alpha, impl):
+    rng = np.random.default_rng(Ntok + C + K)
+    x = (rng.standard_normal((1, 1, 1, Ntok, C)) * 1.5 + 0.3).astype(np.float32)
+    cen = rng.random((K, C)).astype(np.float32)
+    w = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    m = make_cluster_module(V, C, K, alpha, cen, w, b, impl)
+    with torch.no_grad():
+        D, A, S, R, F, lab = m(T(x))
+    o32 = O.cluster_forward(x, cen, w, b, alpha)
+    o64 = O.cluster_forward(x, cen, w, b, alpha, dtype=np.float64)
+    assert rel(N(F), o64["feature"]) < 1e-5
+    assert rel(N(D), o64["D"]) < 1e-5            # spec: 1e-4
+    assert_labels_match(N(lab), o64["D"])
+    # A = exp(-alpha (D - Dmin)): an fp32 ulp of D (~1e-6) moves A by alpha*1e-6 relative
+    np.testing.assert_allclose(N(A), o64["A"], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(N(A).sum(-1), 1.0, rtol=1e-5)
+    assert rel(N(R), o64["x_rec"]) < 1e-4
+    assert_selfdist_close(N(S), o32["S"])
+    lo = float(O.frobenius_loss(o64["D"], o64["A"], np.float64))
+    assert abs(float(m.fused_cluster_loss()) - lo) < 1e-4 * lo
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("Ntok,C,K,alpha", [(1500, 192, 32, 16.0), (700, 768, 64, 32.0), (515, 192, 1024, 16.0)])
+def test_backward_vs_oracle(Ntok, C, K, alpha, impl):
+    rng = np.random.default_rng(7 * Ntok + K)
+    x = (rng.standard_normal((1, 1, 1, Ntok, C)) * 1.2).astype(np.float32)
+    cen = rng.random((K, C)).astype(np.float32)
+    w = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    gR = rng.standard_normal((Ntok, C)).astype(np.float32)
+    gF = (0.05 * rng.standard_normal((Ntok, C))).astype(np.float32)
+    gDx = (0.1 * rng.standard_normal((Ntok, K))).astype(np.float32)
+    gAx = rng.standard_normal((Ntok, K)).astype(np.float32)
+    m = make_cluster_module(V, C, K, alpha, cen, w, b, impl)
+    xt = T(x, grad=True)
+    D, A, S, R, F, lab = m(xt)
+    obj = (D * T(gDx).view_as(D)).sum() + (A * T(gAx).view_as(A)).sum() + (R * T(gR).view_as(R)).sum() \
+        + (F * T(gF)).sum() + 0.5 * m.fused_cluster_loss()
+    obj.backward()
+    f64 = O.cluster_forward(x, cen, w, b, alpha, dtype=np.float64)
+    lD, lA = O.frobenius_loss_grads(f64["D"], f64["A"], 0.5, np.float64)
+    gx, gc, gw, gb = O.cluster_backward(x, cen, w, b, alpha, gD=gDx + lD.reshape(Ntok, K),
+                                        gA=gAx + lA.reshape(Ntok, K), gR=gR, gF=gF, dtype=np.float64)
+    assert rel(N(xt.grad).reshape(Ntok, C), gx) < 2e-4
+    assert rel(N(m.cluster_center.grad), gc) < 2e-4
+    assert rel(N(m.norm.weight.grad), gw) < 2e-4
+    assert rel(N(m.norm.bias.grad), gb) < 2e-4
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_empty_batch(impl):
+    m = make_cluster_module(V, 64, 16, 16.0, np.random.rand(16, 64), np.ones(64), np.zeros(64), impl)
+    x = torch.zeros((0, 2, 4, 4, 64), device=dev(), requires_grad=True)
+    D, A, S, R, F, lab = m(x)
+    assert D.shape == (0, 2, 4, 4, 16) and R.shape == (0, 2, 4, 4, 64) and F.shape == (0, 64) and lab.numel() == 0
+    assert float(m.loss_sq) == 0.0 and S.shape == (16, 16)
+    (R.sum() + m.loss_sq.sum()).backward()
+    assert float(m.cluster_center.grad.abs().sum()) == 0.0
+
+
+def test_alpha_kwarg_persists_like_reference():
+    """cluster.py:49-50: a forward-time alpha overwrites assign_func.alpha for good"""
+    g = load_golden("cluster_c64_k32")
+    m = make_cluster_module(V, 64, 32, 16.0, g["centers"], g["ln_w"], g["ln_b"])
+    with torch.no_grad():
+        A8 = m(T(g["x"]), alpha=8.0)[1]
+        assert m.assign_func.alpha == 8.0
+        A8b = m(T(g["x"]))[1]
+    assert torch.equal(A8, A8b)
+    ref = O.cluster_forward(g["x"], g["centers"], g["ln_w"], g["ln_b"], 8.0, dtype=np.float64)["A"]
+    np.testing.assert_allclose(N(A8), ref, rtol=1e-3, atol=1e-6)
+
+
+def test_shape_errors_surface_as_exceptions():
+    m = make_cluster_module(V, 64, 16, 16.0, np.random.rand(16, 64), np.ones(64), np.zeros(64))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros((1, 1, 2, 2, 32), device=dev()))       # wrong C: LayerNorm / cdist column mismatch
+    with pytest.raises(ValueError):
+        m(torch.zeros((4, 64), device=dev()))                # B, D, H, W, C = x.shape
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_full_size_properties(impl):
+    """BASELINE cfg2 size (B=64,T=16,256x256 -> N=524288 tokens, C=192, K=32):
+    size-independent invariants instead of the (minutes-long) CPU oracle."""
+    torch.manual_seed(0)
+    Ntok, C, K = 524288, 192, 32
+    m = V.EuclidDistance_Assign_Module(C, K, soft_assign_alpha=16.0).to(dev())
+    m.impl = impl
+    x = torch.randn(64, 8, 32, 32, C, device=dev())
+    with torch.no_grad():
+        D, A, S, R, F, lab = m(x)
+        D2, A2 = D.view(Ntok, K), A.view(Ntok, K)
+        assert torch.isfinite(D2).all() and torch.isfinite(A2).all()
+        # rows of A are a distribution; the label is the argmin of the returned D and the argmax of A
+        assert float((A2.sum(-1) - 1).abs().max()) < 1e-5
+        assert torch.equal(lab, D2.argmin(-1)) or float((D2.gather(1, lab[:, None])[:, 0] - D2.min(-1).values).abs().max()) == 0.0
+        # LayerNorm invariants: per-token mean 0 / var 1 (affine is identity at init)
+        assert float(F.mean(-1).abs().max()) < 1e-5 and float((F.var(-1, unbiased=False) - 1).abs().max()) < 1e-3
+        # x_rec is the A-weighted centroid mix; D matches a direct (non-mm) evaluation on a sample
+        idx = torch.randint(0, Ntok, (4096,), device=dev())
+        Rs = (A2[idx].double() @ m.cluster_center.double()).float()
+        assert float((R.view(Ntok, C)[idx] - Rs).abs().max()) < 1e-4
+        Dd = (F[idx].double()[:, None, :] - m.cluster_center.double()[None]).norm(dim=-1)
+        assert float(((D2[idx].double() - Dd).abs() / Dd).max()) < 1e-5
+        # fused loss == checksum of the returned tensors
+        ref = (D2.double() * A2.double()).pow(2).sum().sqrt()
+        assert abs(float(m.fused_cluster_loss()) - float(ref)) < 1e-5 * float(ref)

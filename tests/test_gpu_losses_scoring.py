@@ -1,0 +1,101 @@
+"""L2 / L3 pixel losses and E1-E4 scoring parity on the GPU through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import videoad_b200 as V
+from oracle import np_oracle as O
+from conftest import load_golden
+from gpu_util import T, N, rel, dev
+
+pytestmark = pytest.mark.gpu
+
+
+def test_losses_golden():
+    g = load_golden("losses_scoring")
+    rl = V.Recon_Loss((2, 4, 4))
+    assert abs(float(rl(T(g["l1_x"]), T(g["l1_t_pad"]))) - float(g["l1_pad"])) < 1e-6
+    assert abs(float(rl(T(g["l1_x"]), T(g["l1_t"]))) - float(g["l1"])) < 1e-6
+    assert abs(float(V.mse_mean(T(g["l1_x"]), T(g["l1_t"]))) - float(g["mse"])) < 1e-6
+    assert abs(float(V.e4_norm(T(g["l1_x"]), T(g["l1_t"]))) - float(g["e4"])) < 1e-5 * float(g["e4"])
+    with pytest.raises(AssertionError):
+        rl(T(g["l1_x"])[:, :, :3], T(g["l1_t"]))            # Recon_Loss.py:27 shape assert
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 64, 64), (1, 3, 5, 37, 41), (1, 1, 1, 1, 3), (2, 3, 16, 256, 256)])
+def test_losses_vs_oracle_and_autograd(shape):
+    rng = np.random.default_rng(sum(shape))
+    x = rng.random(shape).astype(np.float32)
+    t = rng.random(shape).astype(np.float32)
+    for fn, ofn, tfn in (
+        (V.l1_mean, lambda a, b: O.recon_l1(a, b), lambda a, b: torch.nn.functional.l1_loss(a, b)),
+        (V.mse_mean, O.mse_mean, lambda a, b: torch.mean(torch.nn.MSELoss(reduction="none")(a, b))),
+        (V.e4_norm, O.e4_norm, lambda a, b: torch.norm(torch.nn.MSELoss(reduction="none")(a, b))),
+    ):
+        xt = T(x, grad=True)
+        out = fn(xt, T(t))
+        ref = float(ofn(x, t))
+        assert abs(float(out) - ref) < 1e-5 * max(abs(ref), 1e-12)
+        (out * 3.0).backward()
+        xr = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        (tfn(xr, torch.tensor(t, dtype=torch.float64)) * 3.0).backward()
+        assert rel(N(xt.grad), xr.grad.numpy()) < 1e-4
+    xt = T(x, grad=True)
+    s = V.e4_sum(xt, T(t))
+    assert abs(float(s) - float(O.e4_norm(x, t)) ** 2) < 1e-5 * float(s)
+    torch.sqrt(s).backward()
+    xr = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    torch.norm((xr - torch.tensor(t, dtype=torch.float64)) ** 2).backward()
+    assert rel(N(xt.grad), xr.grad.numpy()) < 1e-4
+
+
+def test_scoring_golden_end_to_end_auc():
+    """per-frame MSE on the GPU -> psnr -> anomly_score -> per-scene AUC == the
+    reference evaluation loop's value (AUC within 1e-4: BASELINE.json)"""
+    g = load_golden("losses_scoring")
+    mses, labs = [], []
+    for i in range(int(g["n_videos"])):
+        m = V.frame_mse(T(g[f"recon{i}"]), T(g[f"clip{i}"]))
+        assert m.shape == (1, g[f"mse{i}"].shape[0])
+        assert rel(N(m)[0], g[f"mse{i}"]) < 2e-6
+        mses.append(N(m)[0]); labs.append(g[f"label{i}"])
+    auc, per = V.regularity_auc(mses, labs, [str(s) for s in g["scenes"]])
+    assert abs(auc - float(g["auc"])) < 1e-4
+    np.testing.assert_allclose(list(per.values()), g["scene_aucs"], atol=1e-4)
+
+
+@pytest.mark.parametrize("B,C,Tt,H,W", [(2, 3, 8, 224, 224), (1, 3, 5, 30, 22), (3, 1, 4, 64, 64), (1, 3, 1, 7, 9)])
+def test_frame_mse_vs_oracle(B, C, Tt, H, W):
+    rng = np.random.default_rng(B + H)
+    clip = rng.random((B, C, Tt, H, W)).astype(np.float32)
+    recon = (clip + 0.05 * rng.standard_normal(clip.shape)).astype(np.float32)
+    m, ps = V.frame_mse(T(recon), T(clip), want_psnr=True)
+    ref = O.frame_mse(recon, clip)
+    assert rel(N(m), ref) < 2e-6
+    np.testing.assert_allclose(N(ps).reshape(-1), O.psnr(N(m).reshape(-1).tolist()), rtol=1e-12)
+    cm = V.clip_mse(T(recon), T(clip))
+    assert rel(N(cm), O.clip_mse(recon, clip)) < 2e-6
+    assert V.frame_mse(T(recon)[:0], T(clip)[:0]).shape == (0, Tt)
+
+
+def test_minmax_score_device_and_synthetic_auc():
+    """synthetic ShanghaiTech-shaped labelled set at reduced resolution: the
+    device pipeline (frame_mse+psnr+minmax) equals the host float64 functions and
+    the AUC equals the oracle's"""
+    rng = np.random.default_rng(0)
+    lens = [24, 40, 16, 32, 48, 24]
+    scenes = ["01", "01", "02", "03", "02", "03"]
+    mses, labs, ps_all = [], [], []
+    for Tn in lens:
+        clip = rng.random((1, 3, Tn, 32, 32)).astype(np.float32)
+        lab = (rng.random(Tn) < 0.4).astype(np.int64); lab[0], lab[1] = 0, 1
+        recon = clip + (0.05 * rng.standard_normal(clip.shape) * (1 + 2 * lab)[None, None, :, None, None]).astype(np.float32)
+        m, ps = V.frame_mse(T(recon), T(clip), want_psnr=True)
+        mses.append(N(m)[0]); labs.append(lab); ps_all.append(ps[0])
+    off = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=dev())
+    score = V.minmax_score_device(torch.cat(ps_all), off)
+    host = np.concatenate([V.anomly_score(V.psnr(m.tolist())) for m in mses])
+    np.testing.assert_allclose(N(score), host, rtol=0, atol=1e-12)
+    auc, _ = V.regularity_auc(mses, labs, scenes)
+    oauc, _ = O.scene_auc([m.tolist() for m in mses], labs, scenes)
+    assert abs(auc - oauc) < 1e-12 and 0.5 < auc <= 1.0

@@ -1,0 +1,59 @@
+// abi.cu — library-level entry points of the C ABI (include/vadc.h).
+#include "common.cuh"
+#include <stdio.h>
+#include <string.h>
+
+namespace vadc {
+thread_local char g_last_cuda_error[256] = "";
+unsigned long long g_launch_count = 0;
+
+int record_cuda_error(cudaError_t e, const char* what) {
+  snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
+  return VADC_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+    cached = n;
+    return n;
+  }
+  (void)cudaGetLastError();
+  return 148;   // B200; only reached on a host without a device (workspace sizing in CPU tests)
+}
+}  // namespace vadc
+
+extern "C" const char* vadc_version(void) { return "vadc 0.1.0 (sm_100a)"; }
+
+extern "C" const char* vadc_error_string(int code) {
+  switch (code) {
+    case VADC_OK: return "ok";
+    case VADC_ERR_BAD_SHAPE: return "bad shape: a size is non-positive or violates the documented divisibility constraint";
+    case VADC_ERR_NULL_POINTER: return "a required pointer is NULL";
+    case VADC_ERR_MISALIGNED: return "a tensor pointer is not 16-byte aligned";
+    case VADC_ERR_WORKSPACE: return "workspace smaller than *_workspace_bytes()";
+    case VADC_ERR_CUDA: return "CUDA error (see vadc_last_cuda_error)";
+    case VADC_ERR_UNSUPPORTED: return "shape not supported by the selected kernel variant";
+    case VADC_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    default: return "unknown vadc error";
+  }
+}
+
+extern "C" const char* vadc_last_cuda_error(void) { return vadc::g_last_cuda_error; }
+
+extern "C" int vadc_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" unsigned long long vadc_launch_count(void) {
+  return __atomic_load_n(&vadc::g_launch_count, __ATOMIC_RELAXED);
+}

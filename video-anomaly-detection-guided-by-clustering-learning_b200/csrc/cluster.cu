@@ -1,0 +1,431 @@
+// cluster.cu — EuclidDistance_Assign_Module forward / backward (C1, C2, L1),
+// SIMT fp32 path (VADC_IMPL_SIMT): valid for every shape; the tcgen05 kernel in
+// cluster_tc.cu takes over when the shape fits (VADC_IMPL_AUTO).
+#include "common.cuh"
+#include "sgemm.cuh"
+#include "rows.cuh"
+#include "cluster.h"
+
+namespace vadc {
+
+// D = sqrt(max(0, |a|^2 + |b|^2 - 2 a.b))   torch.cdist mm form
+struct DistEpilogue {
+  float* out; const float* aa; const float* bb;
+  long long ldo;            // row stride of out
+  long long batch_out, batch_aa, batch_bb, col_stride;
+  __device__ __forceinline__ void operator()(int batch, int, int m, int n, float v) const {
+    float sq = aa[batch * batch_aa + m] + bb[batch * batch_bb + n] - 2.0f * v;
+    out[batch * batch_out + (long long)m * ldo + (long long)n * col_stride] = sqrtf(fmaxf(sq, 0.f));
+  }
+};
+
+struct StoreEpilogue {
+  float* out; long long ldo;
+  __device__ __forceinline__ void operator()(int, int, int m, int n, float v) const {
+    out[(long long)m * ldo + n] = v;
+  }
+};
+
+// gz = feature * rsum - acc + gF
+struct GzEpilogue {
+  float* out; const float* feature; const float* rsum; const float* gF; long long ld;
+  __device__ __forceinline__ void operator()(int, int, int m, int n, float v) const {
+    long long i = (long long)m * ld + n;
+    float o = feature[i] * rsum[m] - v;
+    if (gF) o += gF[i];
+    out[i] = o;
+  }
+};
+
+// split-K partial store: out[split][m][n]
+struct PartialEpilogue {
+  float* out; long long ld, split_stride;
+  __device__ __forceinline__ void operator()(int, int split, int m, int n, float v) const {
+    out[split * split_stride + (long long)m * ld + n] = v;
+  }
+};
+
+// gcenters[k,c] = sum_s (P1 - P2)[s,k,c] + centers[k,c] * rcol[k]
+__global__ void __launch_bounds__(256)
+gcenters_finalize_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int splits,
+                         const float* __restrict__ centers, const float* __restrict__ rcol,
+                         int K, int C, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)K * C;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) {
+    float a = p1 ? p1[sp * n + i] : 0.f;
+    s += a - p2[sp * n + i];
+  }
+  out[i] = s + centers[i] * rcol[i / C];
+}
+
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
+                       float* __restrict__ gw, float* __restrict__ gb) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 2 * C + c];
+  if (c < C) gw[c] = s; else gb[c - C] = s;
+}
+
+__global__ void zero_kernel(float* p, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers shared with space_cluster.cu / memory.cu
+// ---------------------------------------------------------------------------
+int launch_ln_rows(const float* x, const float* w, const float* b, long long N, int C, float eps,
+                   float* z, float* mu, float* rstd, float* zz, cudaStream_t st) {
+  if (N == 0) return VADC_OK;
+  const int wpb = 8;
+  dim3 grid((unsigned)((N + wpb - 1) / wpb));
+#define LN_CASE(V) ln_rows_kernel<V><<<grid, wpb * 32, 0, st>>>(x, w, b, N, C, eps, z, mu, rstd, zz)
+  if (C <= 128) LN_CASE(1);
+  else if (C <= 256) LN_CASE(2);
+  else if (C <= 512) LN_CASE(4);
+  else if (C <= 768) LN_CASE(6);
+  else if (C <= 1024) LN_CASE(8);
+  else return VADC_ERR_UNSUPPORTED;
+#undef LN_CASE
+  VADC_CHECK_LAUNCH("ln_rows_kernel");
+  return VADC_OK;
+}
+
+int launch_row_sqnorm(const float* a, long long R, int C, float* out, cudaStream_t st) {
+  if (R == 0) return VADC_OK;
+  row_sqnorm_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(a, R, C, out);
+  VADC_CHECK_LAUNCH("row_sqnorm_kernel");
+  return VADC_OK;
+}
+
+static inline int group_for(int K) {
+  int nv = K / 4;
+  if (nv <= 4) return 4;
+  if (nv <= 8) return 8;
+  if (nv <= 16) return 16;
+  return 32;
+}
+
+int softmin_blocks(long long R, int K) {
+  int G = group_for(K);
+  return (int)((R + (256 / G) - 1) / (256 / G));
+}
+
+// A, label, loss_sq from D.  partial: softmin_blocks(R,K) doubles.
+int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* A, long long* label,
+                        double* partial, float* loss_sq, cudaStream_t st) {
+  if (R == 0) {
+    zero_kernel<<<1, 32, 0, st>>>(loss_sq, 1);
+    VADC_CHECK_LAUNCH("zero_kernel");
+    return VADC_OK;
+  }
+  int G = group_for(K);
+  int nb = softmin_blocks(R, K);
+  switch (G) {
+    case 4: softmin_rows_kernel<4><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
+    case 8: softmin_rows_kernel<8><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
+    case 16: softmin_rows_kernel<16><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
+    default: softmin_rows_kernel<32><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
+  }
+  VADC_CHECK_LAUNCH("softmin_rows_kernel");
+  finalize_sum_kernel<<<1, 256, 0, st>>>(partial, nb, loss_sq);
+  VADC_CHECK_LAUNCH("finalize_sum_kernel");
+  return VADC_OK;
+}
+
+int launch_bwd_rows(const float* D, const float* A, const float* gemm, const float* gD,
+                    const float* gA, const float* g_loss_sq, long long R, int K,
+                    float alpha, float* r, float* rsum, cudaStream_t st) {
+  if (R == 0) return VADC_OK;
+  int G = group_for(K);
+  int nb = (int)((R + (256 / G) - 1) / (256 / G));
+#define BR_CASE(GG) bwd_rows_kernel<GG><<<nb, 256, 0, st>>>(D, A, gemm, gD, gA, g_loss_sq, R, K, alpha, r, rsum)
+  switch (G) {
+    case 4: BR_CASE(4); break;
+    case 8: BR_CASE(8); break;
+    case 16: BR_CASE(16); break;
+    default: BR_CASE(32); break;
+  }
+#undef BR_CASE
+  VADC_CHECK_LAUNCH("bwd_rows_kernel");
+  return VADC_OK;
+}
+
+int ln_bwd_blocks(long long N) {
+  long long b = (N + 63) / 64;          // >= 8 rows per warp before another block is worth it
+  long long cap = (long long)sm_count() * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// gx, g_ln_w, g_ln_b from gz (row-major).  partial: ln_bwd_blocks(N)*2C floats.
+int launch_ln_bwd(const float* gz, const float* x, const float* mu, const float* rstd,
+                  const float* w, long long N, int C, float* gx, float* partial, float* gw,
+                  float* gb, cudaStream_t st) {
+  int nb = ln_bwd_blocks(N);
+  size_t smem = (size_t)8 * 2 * C * sizeof(float);
+#define LB_CASE(V)                                                                              \
+  do {                                                                                          \
+    if (smem > 48 * 1024)                                                                       \
+      VADC_CUDA(cudaFuncSetAttribute(ln_bwd_rows_kernel<V>,                                     \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    ln_bwd_rows_kernel<V><<<nb, 256, smem, st>>>(gz, x, mu, rstd, w, N, C, gx, partial);        \
+  } while (0)
+  if (C <= 128) LB_CASE(1);
+  else if (C <= 256) LB_CASE(2);
+  else if (C <= 512) LB_CASE(4);
+  else if (C <= 768) LB_CASE(6);
+  else if (C <= 1024) LB_CASE(8);
+  else return VADC_ERR_UNSUPPORTED;
+#undef LB_CASE
+  VADC_CHECK_LAUNCH("ln_bwd_rows_kernel");
+  ln_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, nb, C, gw, gb);
+  VADC_CHECK_LAUNCH("ln_bwd_finalize_kernel");
+  return VADC_OK;
+}
+
+// batched cdist on precomputed norms
+int launch_dist(const float* a, const float* b, const float* aa, const float* bb, int nb,
+                long long R, long long P, int C, float* out, cudaStream_t st) {
+  if (R == 0 || P == 0 || nb == 0) return VADC_OK;
+  Operand A{a, C, 1};
+  Operand B{b, 1, C};          // opB[k=c, n=p] = b[p*C + c]
+  DistEpilogue epi{out, aa, bb, P, R * P, R, P, 1};
+  cudaError_t e = sgemm_auto((int)R, (int)P, C, A, B, R * C, P * C, nb, 1, epi, st);
+  if (e != cudaSuccess) return record_cuda_error(e, "dist sgemm");
+  return VADC_OK;
+}
+
+int split_count(long long Ntok, int tiles) {
+  long long want = ((long long)sm_count() * 2 + tiles - 1) / tiles;
+  long long maxs = (Ntok + 511) / 512;
+  if (want > maxs) want = maxs;
+  if (want > 256) want = 256;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace vadc
+
+using namespace vadc;
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" size_t vadc_cluster_fwd_workspace_bytes(int64_t N, int C, int K, int impl) {
+  (void)impl;
+  size_t b = 0;
+  b += align_up((size_t)(N > 0 ? N : 1) * sizeof(float), 256);           // |z|^2
+  b += align_up((size_t)K * sizeof(float), 256);                         // |c|^2
+  b += align_up((size_t)(softmin_blocks(N, K) + 1) * sizeof(double), 256);
+  b += vadc_cluster_tc_extra_workspace_bytes(N, C, K);
+  return b + 256;
+}
+
+extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
+                                const float* centers, int64_t N, int C, int K, float alpha,
+                                float eps, float* D, float* A, float* x_rec, float* feature,
+                                int64_t* label, float* mu, float* rstd, float* loss_sq,
+                                void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  VADC_REQUIRE(N >= 0 && C > 0 && K > 0 && (C % 4) == 0 && (K % 4) == 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(N < (1ll << 31) && C <= 1024, VADC_ERR_UNSUPPORTED);
+  VADC_REQUIRE(ln_w && ln_b && centers && loss_sq && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(N == 0 || (x && D && A && x_rec && feature && label && mu && rstd), VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(aligned16(x) && aligned16(ln_w) && aligned16(ln_b) && aligned16(centers) &&
+               aligned16(D) && aligned16(A) && aligned16(x_rec) && aligned16(feature) &&
+               aligned16(workspace), VADC_ERR_MISALIGNED);
+  VADC_REQUIRE(workspace_bytes >= vadc_cluster_fwd_workspace_bytes(N, C, K, impl), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  if (impl != VADC_IMPL_SIMT) {
+    int rc = vadc_cluster_fwd_tc(x, ln_w, ln_b, centers, N, C, K, alpha, eps, D, A, x_rec, feature,
+                                 label, mu, rstd, loss_sq, workspace, workspace_bytes, st);
+    if (rc != VADC_ERR_UNSUPPORTED || impl == VADC_IMPL_TCGEN05) return rc;
+  }
+  Carver ws(workspace, workspace_bytes);
+  float* zz = ws.take<float>(N > 0 ? N : 1);
+  float* cc = ws.take<float>(K);
+  double* partial = ws.take<double>(softmin_blocks(N, K) + 1);
+  int rc;
+  if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, feature, mu, rstd, zz, st))) return rc;
+  if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
+  if ((rc = launch_dist(feature, centers, zz, cc, 1, N, K, C, D, st))) return rc;
+  if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
+  if (N > 0) {
+    Operand Aop{A, K, 1}, Bop{centers, C, 1};
+    StoreEpilogue epi{x_rec, C};
+    cudaError_t e = sgemm_auto((int)N, C, K, Aop, Bop, 0, 0, 1, 1, epi, st);
+    if (e != cudaSuccess) return record_cuda_error(e, "x_rec sgemm");
+  }
+  return VADC_OK;
+}
+
+extern "C" size_t vadc_cdist_workspace_bytes(int nb, int64_t R, int64_t P, int C) {
+  (void)C;
+  return align_up((size_t)nb * R * sizeof(float), 256) + align_up((size_t)nb * P * sizeof(float), 256) + 256;
+}
+
+extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int64_t P, int C,
+                          float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(nb >= 0 && R >= 0 && P >= 0 && C > 0, VADC_ERR_BAD_SHAPE);
+  if (nb == 0 || R == 0 || P == 0) return VADC_OK;
+  VADC_REQUIRE(a && b && out && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(R < (1ll << 31) && P < (1ll << 31), VADC_ERR_UNSUPPORTED);
+  VADC_REQUIRE(workspace_bytes >= vadc_cdist_workspace_bytes(nb, R, P, C), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver ws(workspace, workspace_bytes);
+  float* aa = ws.take<float>((size_t)nb * R);
+  float* bb = ws.take<float>((size_t)nb * P);
+  int rc;
+  if ((rc = launch_row_sqnorm(a, (long long)nb * R, C, aa, st))) return rc;
+  if ((rc = launch_row_sqnorm(b, (long long)nb * P, C, bb, st))) return rc;
+  return launch_dist(a, b, aa, bb, nb, R, P, C, out, st);
+}
+
+extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
+  size_t n = (size_t)(N > 0 ? N : 1);
+  int tiles = ((K + 63) / 64) * ((C + 63) / 64);
+  int splits = split_count(N, tiles);
+  size_t b = 0;
+  b += align_up(n * K * sizeof(float), 256);                 // gR.c^T
+  b += align_up(n * K * sizeof(float), 256);                 // r
+  b += align_up(n * sizeof(float), 256);                     // rsum
+  b += align_up(n * C * sizeof(float), 256);                 // gz
+  b += 2 * align_up((size_t)splits * K * C * sizeof(float), 256);   // split-K partials
+  b += align_up((size_t)colsum_chunks(N) * K * sizeof(float), 256); // colsum partial
+  b += align_up((size_t)K * sizeof(float), 256);             // rcol
+  b += align_up((size_t)ln_bwd_blocks(N) * 2 * C * sizeof(float), 256);
+  return b + 256;
+}
+
+extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd,
+                                const float* feature, const float* ln_w, const float* centers,
+                                const float* D, const float* A, const float* gD, const float* gA,
+                                const float* gR, const float* gF, const float* g_loss_sq,
+                                int64_t N, int C, int K, float alpha,
+                                float* gx, float* gcenters, float* g_ln_w, float* g_ln_b,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(N >= 0 && C > 0 && K > 0 && (C % 4) == 0 && (K % 4) == 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(N < (1ll << 31) && C <= 1024, VADC_ERR_UNSUPPORTED);
+  VADC_REQUIRE(ln_w && centers && gcenters && g_ln_w && g_ln_b && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(N == 0 || (x && mu && rstd && feature && D && A && gx), VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(workspace_bytes >= vadc_cluster_bwd_workspace_bytes(N, C, K), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long KC = (long long)K * C;
+  if (N == 0) {
+    zero_kernel<<<(unsigned)((KC + 255) / 256), 256, 0, st>>>(gcenters, KC);
+    zero_kernel<<<(C + 255) / 256, 256, 0, st>>>(g_ln_w, C);
+    zero_kernel<<<(C + 255) / 256, 256, 0, st>>>(g_ln_b, C);
+    VADC_CHECK_LAUNCH("zero_kernel");
+    return VADC_OK;
+  }
+  int tiles = ((K + 63) / 64) * ((C + 63) / 64);
+  int splits = split_count(N, tiles);
+  Carver ws(workspace, workspace_bytes);
+  float* gemm = ws.take<float>((size_t)N * K);
+  float* r = ws.take<float>((size_t)N * K);
+  float* rsum = ws.take<float>(N);
+  float* gz = ws.take<float>((size_t)N * C);
+  float* p1 = ws.take<float>((size_t)splits * KC);
+  float* p2 = ws.take<float>((size_t)splits * KC);
+  float* cpart = ws.take<float>((size_t)colsum_chunks(N) * K);
+  float* rcol = ws.take<float>(K);
+  float* lnpart = ws.take<float>((size_t)ln_bwd_blocks(N) * 2 * C);
+  cudaError_t e;
+  int rc;
+  // (1) gR . centers^T  -> gemm [N,K]
+  if (gR) {
+    Operand Aop{gR, C, 1}, Bop{centers, 1, C};
+    StoreEpilogue epi{gemm, K};
+    e = sgemm_auto((int)N, K, C, Aop, Bop, 0, 0, 1, 1, epi, st);
+    if (e != cudaSuccess) return record_cuda_error(e, "bwd sgemm gR.cT");
+  }
+  // (2) softmin backward + cdist ratio
+  if ((rc = launch_bwd_rows(D, A, gR ? gemm : nullptr, gD, gA, g_loss_sq, N, K, alpha, r, rsum, st))) return rc;
+  // (3) gz = feature * rsum - r @ centers + gF
+  {
+    Operand Aop{r, K, 1}, Bop{centers, C, 1};
+    GzEpilogue epi{gz, feature, rsum, gF, C};
+    e = sgemm_auto((int)N, C, K, Aop, Bop, 0, 0, 1, 1, epi, st);
+    if (e != cudaSuccess) return record_cuda_error(e, "bwd sgemm r.c");
+  }
+  // (4) gcenters = A^T gR - r^T feature + centers * colsum(r)   (split over tokens)
+  {
+    PartialEpilogue e1{p1, C, KC}, e2{p2, C, KC};
+    if (gR) {
+      Operand Aop{A, 1, K}, Bop{gR, C, 1};
+      e = launch_sgemm<64, 64>(K, C, (int)N, Aop, Bop, 0, 0, 1, splits, e1, st);
+      if (e != cudaSuccess) return record_cuda_error(e, "bwd sgemm AT.gR");
+    }
+    Operand Aop{r, 1, K}, Bop{feature, C, 1};
+    e = launch_sgemm<64, 64>(K, C, (int)N, Aop, Bop, 0, 0, 1, splits, e2, st);
+    if (e != cudaSuccess) return record_cuda_error(e, "bwd sgemm rT.z");
+    e = launch_colsum(r, N, K, cpart, rcol, st);
+    if (e != cudaSuccess) return record_cuda_error(e, "colsum r");
+    gcenters_finalize_kernel<<<(unsigned)((KC + 255) / 256), 256, 0, st>>>(gR ? p1 : nullptr, p2, splits, centers, rcol, K, C, gcenters);
+    VADC_CHECK_LAUNCH("gcenters_finalize_kernel");
+  }
+  // (5) LayerNorm backward
+  return launch_ln_bwd(gz, x, mu, rstd, ln_w, N, C, gx, lnpart, g_ln_w, g_ln_b, st);
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone PosSoftAssign / NegSoftAssign (model/cluster.py:27-55) over the
+// last axis of a [rows, K] matrix, any K; one warp per row.
+// y = exp(a (x - ext)) / sum, ext = max x for a > 0 and min x for a < 0.
+// ---------------------------------------------------------------------------
+namespace vadc {
+__global__ void __launch_bounds__(256)
+soft_assign_kernel(const float* __restrict__ x, long long rows, int K, float a, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * K;
+  float ext = (a >= 0.f) ? -INFINITY : INFINITY;
+  for (int i = lane; i < K; i += 32) ext = (a >= 0.f) ? fmaxf(ext, xr[i]) : fminf(ext, xr[i]);
+  ext = (a >= 0.f) ? warp_max(ext) : warp_min(ext);
+  float s = 0.f;
+  for (int i = lane; i < K; i += 32) s += expf(a * (xr[i] - ext));
+  s = warp_sum(s);
+  for (int i = lane; i < K; i += 32) y[row * K + i] = expf(a * (xr[i] - ext)) / s;
+}
+
+// gx = a * y * (g - sum_k g*y)
+__global__ void __launch_bounds__(256)
+soft_assign_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g, long long rows,
+                       int K, float a, float* __restrict__ gx) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int i = lane; i < K; i += 32) dot += y[row * K + i] * g[row * K + i];
+  dot = warp_sum(dot);
+  for (int i = lane; i < K; i += 32) gx[row * K + i] = a * y[row * K + i] * (g[row * K + i] - dot);
+}
+}  // namespace vadc
+
+extern "C" int vadc_soft_assign(const float* x, int64_t rows, int K, float signed_alpha, float* y,
+                                void* stream) {
+  VADC_REQUIRE(rows >= 0 && K > 0, VADC_ERR_BAD_SHAPE);
+  if (rows == 0) return VADC_OK;
+  VADC_REQUIRE(x && y, VADC_ERR_NULL_POINTER);
+  soft_assign_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, K, signed_alpha, y);
+  VADC_CHECK_LAUNCH("soft_assign_kernel");
+  return VADC_OK;
+}
+
+extern "C" int vadc_soft_assign_bwd(const float* y, const float* g, int64_t rows, int K,
+                                    float signed_alpha, float* gx, void* stream) {
+  VADC_REQUIRE(rows >= 0 && K > 0, VADC_ERR_BAD_SHAPE);
+  if (rows == 0) return VADC_OK;
+  VADC_REQUIRE(y && g && gx, VADC_ERR_NULL_POINTER);
+  soft_assign_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, g, rows, K, signed_alpha, gx);
+  VADC_CHECK_LAUNCH("soft_assign_bwd_kernel");
+  return VADC_OK;
+}

@@ -1,0 +1,527 @@
+// memory.cu — Memory module (M1-M5), model/Memory.py:62-261 (MNAD memory):
+// addressing scores with the two softmaxes, top-1/top-2 slots, read,
+// gather / spread losses, weighted segmented update, separateness.
+#include "common.cuh"
+#include "sgemm.cuh"
+#include "rows.cuh"
+#include "cluster.h"
+
+namespace vadc {
+
+// ---- F.normalize(query, dim=1) + permute (Memory.py:148-149) --------------
+// query [B, d, HW]: norms over d for every (b, hw); threads run along hw.
+__global__ void __launch_bounds__(256)
+query_norm_kernel(const float* __restrict__ query, int d, long long HW, float* __restrict__ inv) {
+  const long long hw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (hw >= HW) return;
+  const float* p = query + (long long)b * d * HW + hw;
+  float s = 0.f;
+  for (int c = 0; c < d; ++c) { float v = __ldg(p + (long long)c * HW); s += v * v; }
+  inv[(long long)b * HW + hw] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+}
+
+// 32x32 tiled transpose with the per-position scale: q[(b*HW+hw), c] = query[b,c,hw]*inv
+__global__ void __launch_bounds__(256)
+query_transpose_kernel(const float* __restrict__ query, const float* __restrict__ inv, int d,
+                       long long HW, float* __restrict__ q) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long hw0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j;
+    long long hw = hw0 + tx;
+    tile[j][tx] = (c < d && hw < HW) ? __ldg(query + ((long long)b * d + c) * HW + hw) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    long long hw = hw0 + j;
+    int c = c0 + tx;
+    if (hw < HW && c < d) q[((long long)b * HW + hw) * d + c] = tile[tx][j] * __ldg(inv + (long long)b * HW + hw);
+  }
+}
+
+// ---- row softmax over m + top-1 / top-2 (Memory.py:141,185,223,241) -------
+// one warp per token row of logits [N, m]
+__global__ void __launch_bounds__(256)
+row_softmax_top2_kernel(const float* __restrict__ logits, long long N, int m,
+                        float* __restrict__ out, long long* __restrict__ top1,
+                        long long* __restrict__ top2) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float* lr = logits + row * m;
+  float b1 = -INFINITY, b2 = -INFINITY;
+  int i1 = 0x7fffffff, i2 = 0x7fffffff;
+  for (int i = lane; i < m; i += 32) {
+    float v = lr[i];
+    if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = i; }
+    else if (v > b2) { b2 = v; i2 = i; }
+  }
+  // merge (value desc, index asc) pairs across the warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o);
+    int oi1 = __shfl_xor_sync(0xffffffffu, i1, o), oi2 = __shfl_xor_sync(0xffffffffu, i2, o);
+    bool other_first = (ob1 > b1) || (ob1 == b1 && oi1 < i1);
+    float n1, n2; int j1, j2;
+    if (other_first) {
+      n1 = ob1; j1 = oi1;
+      bool s = (b1 > ob2) || (b1 == ob2 && i1 < oi2);
+      n2 = s ? b1 : ob2; j2 = s ? i1 : oi2;
+    } else {
+      n1 = b1; j1 = i1;
+      bool s = (ob1 > b2) || (ob1 == b2 && oi1 < i2);
+      n2 = s ? ob1 : b2; j2 = s ? oi1 : i2;
+    }
+    b1 = n1; i1 = j1; b2 = n2; i2 = j2;
+  }
+  float s = 0.f;
+  for (int i = lane; i < m; i += 32) s += expf(lr[i] - b1);
+  s = warp_sum(s);
+  float* orow = out + row * m;
+  for (int i = lane; i < m; i += 32) orow[i] = expf(lr[i] - b1) / s;
+  if (lane == 0) {
+    if (top1) top1[row] = i1;
+    if (top2) top2[row] = (m > 1) ? i2 : 0;
+  }
+}
+
+// ---- column softmax over tokens (Memory.py:140): online max/sum per chunk --
+__global__ void __launch_bounds__(256)
+col_stats_stage1_kernel(const float* __restrict__ logits, long long N, int m, long long rpb,
+                        float* __restrict__ pmax, float* __restrict__ psum) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= m) return;
+  long long r0 = (long long)blockIdx.y * rpb, r1 = min(N, r0 + rpb);
+  float mx = -INFINITY, s = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    float v = __ldg(logits + r * m + col);
+    if (v > mx) { s = s * expf(mx - v) + 1.0f; mx = v; } else { s += expf(v - mx); }
+  }
+  pmax[(long long)blockIdx.y * m + col] = mx;
+  psum[(long long)blockIdx.y * m + col] = s;
+}
+
+__global__ void __launch_bounds__(256)
+col_stats_stage2_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int chunks,
+                        int m, float* __restrict__ colmax, float* __restrict__ colsum) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= m) return;
+  float mx = -INFINITY;
+  for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, pmax[(long long)c * m + col]);
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    float pm = pmax[(long long)c * m + col];
+    if (pm > -INFINITY) s += psum[(long long)c * m + col] * expf(pm - mx);
+  }
+  colmax[col] = mx;
+  colsum[col] = s;
+}
+
+__global__ void __launch_bounds__(256)
+col_softmax_apply_kernel(const float* __restrict__ logits, const float* __restrict__ colmax,
+                         const float* __restrict__ colsum, long long total, int m,
+                         float* __restrict__ out) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int col = (int)(i % m);
+    out[i] = expf(logits[i] - __ldg(colmax + col)) / __ldg(colsum + col);
+  }
+}
+
+struct StoreLogits {
+  float* out; long long ld;
+  __device__ __forceinline__ void operator()(int, int, int m, int n, float v) const {
+    out[(long long)m * ld + n] = v;
+  }
+};
+
+// ---- read (Memory.py:249-261): uq[n, 0:d] = q, uq[n, d:2d] = score_memory @ keys
+struct ReadEpilogue {
+  float* uq; const float* q; int d;
+  __device__ __forceinline__ void operator()(int, int, int m, int n, float v) const {
+    long long o = (long long)m * 2 * d;
+    uq[o + n] = q[(long long)m * d + n];
+    uq[o + d + n] = v;
+  }
+};
+
+// ---- gather / spread losses (Memory.py:214-247), one warp per token --------
+__global__ void __launch_bounds__(256)
+memory_losses_kernel(const float* __restrict__ q, const float* __restrict__ keys,
+                     const long long* __restrict__ top1, const long long* __restrict__ top2,
+                     long long N, int d, double* __restrict__ partial /*[grid][2]*/) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  double g = 0.0, sp = 0.0;
+  if (row < N) {
+    const float* qr = q + row * d;
+    const float* pos = keys + top1[row] * d;
+    const float* neg = top2 ? keys + top2[row] * d : nullptr;
+    float s1 = 0.f, sap = 0.f, san = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      float qv = qr[c], pv = __ldg(pos + c);
+      float e = qv - pv;
+      s1 += e * e;
+      float ep = e + 1e-6f;                       // pairwise_distance eps (TripletMarginLoss)
+      sap += ep * ep;
+      if (neg) { float en = qv - __ldg(neg + c) + 1e-6f; san += en * en; }
+    }
+    s1 = warp_sum(s1); sap = warp_sum(sap); san = warp_sum(san);
+    if (lane == 0) {
+      g = (double)s1;
+      if (neg) sp = (double)fmaxf(sqrtf(sap) - sqrtf(san) + 1.0f, 0.f);
+    }
+  }
+  double gt = block_sum<double>(g, red);
+  double st = block_sum<double>(sp, red);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = gt; partial[2 * blockIdx.x + 1] = st; }
+}
+
+__global__ void __launch_bounds__(256)
+memory_losses_finalize_kernel(const double* __restrict__ partial, int nb, double nd, double n,
+                              float* __restrict__ out) {
+  __shared__ double red[32];
+  double g = 0.0, s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) { g += partial[2 * i]; s += partial[2 * i + 1]; }
+  g = block_sum<double>(g, red);
+  s = block_sum<double>(s, red);
+  if (threadIdx.x == 0) { out[0] = (float)(g / nd); out[1] = (float)(s / n); }
+}
+
+// ---- update (Memory.py:177-204, :94-131) ----------------------------------
+// column max of score_query (the reference divides by torch.max(score[:, i]))
+__global__ void __launch_bounds__(256)
+colmax_stage1_kernel(const float* __restrict__ a, long long N, int m, long long rpb,
+                     float* __restrict__ pmax) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= m) return;
+  long long r0 = (long long)blockIdx.y * rpb, r1 = min(N, r0 + rpb);
+  float mx = -INFINITY;
+  for (long long r = r0; r < r1; ++r) mx = fmaxf(mx, __ldg(a + r * m + col));
+  pmax[(long long)blockIdx.y * m + col] = mx;
+}
+__global__ void __launch_bounds__(256)
+colmax_stage2_kernel(const float* __restrict__ pmax, int chunks, int m, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= m) return;
+  float mx = -INFINITY;
+  for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, pmax[(long long)c * m + col]);
+  out[col] = mx;
+}
+
+// stable counting sort of tokens by their top-1 slot: histogram per block of
+// 1024 consecutive tokens, scan, then an in-order placement, so every slot's
+// token list is in ascending token order and the weighted sum below is
+// deterministic (the reference's python loop over slots with nonzero() visits
+// tokens in the same ascending order).
+constexpr int kSortChunk = 1024;
+
+__global__ void __launch_bounds__(256)
+slot_hist_kernel(const long long* __restrict__ top1, long long N, int m, int* __restrict__ hist /*[chunks][m]*/) {
+  long long r0 = (long long)blockIdx.x * kSortChunk, r1 = min(N, r0 + kSortChunk);
+  int* h = hist + (long long)blockIdx.x * m;
+  for (long long r = r0 + threadIdx.x; r < r1; r += blockDim.x) atomicAdd(h + (int)top1[r], 1);
+}
+
+// offsets[chunk][slot] = start of that chunk's run inside slot's list; seg[slot] = list start
+__global__ void __launch_bounds__(256)
+slot_scan_kernel(int* __restrict__ hist, int chunks, int m, int* __restrict__ seg /*[m+1]*/) {
+  // per-slot exclusive scan over chunks (threads over slots), then a serial scan over slots
+  __shared__ int total_s[1];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < m; s += gridDim.x * blockDim.x) {
+    int run = 0;
+    for (int c = 0; c < chunks; ++c) { int v = hist[(long long)c * m + s]; hist[(long long)c * m + s] = run; run += v; }
+    seg[s + 1] = run;     // count, turned into offsets by slot_scan2
+  }
+  (void)total_s;
+}
+__global__ void slot_scan2_kernel(int* __restrict__ seg, int m) {
+  // single thread block, serial over m (m is a few thousand at most)
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int run = 0;
+    seg[0] = 0;
+    for (int s = 0; s < m; ++s) { int c = seg[s + 1]; run += c; seg[s + 1] = run; }
+  }
+}
+
+// one warp walks a chunk's tokens in order (32 at a time) and ranks equal slots
+// with match_any so placement is stable
+__global__ void __launch_bounds__(32)
+slot_place_kernel(const long long* __restrict__ top1, long long N, int m,
+                  const int* __restrict__ hist, const int* __restrict__ seg,
+                  int* __restrict__ cursor /*[chunks][m] zeroed*/, int* __restrict__ order) {
+  const int lane = threadIdx.x;
+  long long r0 = (long long)blockIdx.x * kSortChunk, r1 = min(N, r0 + kSortChunk);
+  const int* off = hist + (long long)blockIdx.x * m;
+  int* cur = cursor + (long long)blockIdx.x * m;
+  for (long long base = r0; base < r1; base += 32) {
+    long long r = base + lane;
+    bool valid = r < r1;
+    int slot = valid ? (int)top1[r] : -1 - lane;
+    unsigned peers = __match_any_sync(0xffffffffu, slot);
+    int rank = __popc(peers & ((1u << lane) - 1u));
+    int cnt = __popc(peers);
+    int start = 0;
+    if (valid) start = cur[slot];
+    __syncwarp();
+    if (valid) {
+      order[seg[slot] + off[slot] + start + rank] = (int)r;
+      if (rank == cnt - 1) cur[slot] = start + cnt;
+    }
+    __syncwarp();
+  }
+}
+
+// one block per slot: u_i = sum_n (score_query[n,i]/colmax_sq[i]) q_n in token
+// order (warps interleave tokens, partials combined in fixed warp order), then
+// updated_memory[i] = normalize(u_i + keys[i])  (Memory.py:193)
+__global__ void __launch_bounds__(256)
+slot_update_kernel(const float* __restrict__ q, const float* __restrict__ keys,
+                   const float* __restrict__ score_query, const float* __restrict__ colmax_sq,
+                   const int* __restrict__ seg, const int* __restrict__ order, int m, int d,
+                   float* __restrict__ query_update, float* __restrict__ updated) {
+  extern __shared__ float sm[];        // [8][d] partials + [32] reduction
+  const int slot = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int a = seg[slot], b = seg[slot + 1];
+  const float inv = 1.0f / colmax_sq[slot];
+  float* part = sm + (size_t)wid * d;
+  for (int c = lane; c < d; c += 32) part[c] = 0.f;
+  for (int j = a + wid; j < b; j += 8) {
+    const long long n = order[j];
+    const float wgt = score_query[n * m + slot] * inv;
+    const float* qr = q + n * d;
+    for (int c = lane; c < d; c += 32) part[c] += wgt * qr[c];
+  }
+  __syncthreads();
+  float nrm = 0.f;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    float u = 0.f;
+    for (int w = 0; w < 8; ++w) u += sm[(size_t)w * d + c];
+    query_update[(long long)slot * d + c] = u;
+    float v = u + keys[(long long)slot * d + c];
+    sm[c] = v;                        // safe: column c is only touched by this thread from here on
+    nrm += v * v;
+  }
+  __shared__ float red[32];
+  nrm = block_sum<float>(nrm, red);
+  const float s = 1.0f / fmaxf(sqrtf(nrm), 1e-12f);
+  for (int c = threadIdx.x; c < d; c += 256) updated[(long long)slot * d + c] = sm[c] * s;
+}
+
+__global__ void zero_int_kernel(int* p, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+
+// MemoryLoss (Memory.py:52-59)
+struct SeparatenessEpilogue {
+  float* out; int m;
+  __device__ __forceinline__ void operator()(int, int, int r, int c, float v) const {
+    out[(long long)r * m + c] = fabsf(v * 0.5f + 0.5f - (r == c ? 1.0f : 0.0f));
+  }
+};
+__global__ void __launch_bounds__(256)
+sum_all_kernel(const float* __restrict__ a, long long n, double scale, float* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)a[i];
+  s = block_sum<double>(s, red);
+  if (threadIdx.x == 0) out[0] = (float)(s * scale);
+}
+
+static int col_chunks(long long N) {
+  long long c = (N + 255) / 256;
+  if (c > 2048) c = 2048;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+}  // namespace vadc
+
+using namespace vadc;
+
+extern "C" size_t vadc_memory_prepare_query_workspace_bytes(int B, int64_t HW) {
+  return align_up((size_t)(B > 0 ? B : 1) * HW * sizeof(float), 256) + 256;
+}
+
+extern "C" int vadc_memory_prepare_query(const float* query, int B, int d, int64_t HW, float* q,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(B >= 0 && d > 0 && HW > 0, VADC_ERR_BAD_SHAPE);
+  if (B == 0) return VADC_OK;
+  VADC_REQUIRE(query && q && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(B <= 65535 && (d + 31) / 32 <= 65535, VADC_ERR_UNSUPPORTED);
+  VADC_REQUIRE(workspace_bytes >= vadc_memory_prepare_query_workspace_bytes(B, HW), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* inv = static_cast<float*>(workspace);
+  dim3 g1((unsigned)((HW + 255) / 256), B);
+  query_norm_kernel<<<g1, 256, 0, st>>>(query, d, HW, inv);
+  VADC_CHECK_LAUNCH("query_norm_kernel");
+  dim3 g2((unsigned)((HW + 31) / 32), (d + 31) / 32, B);
+  query_transpose_kernel<<<g2, 256, 0, st>>>(query, inv, d, HW, q);
+  VADC_CHECK_LAUNCH("query_transpose_kernel");
+  return VADC_OK;
+}
+
+extern "C" size_t vadc_memory_score_workspace_bytes(int64_t N, int m, int d) {
+  (void)d;
+  size_t n = (size_t)(N > 0 ? N : 1);
+  return align_up(n * m * sizeof(float), 256) + 2 * align_up((size_t)col_chunks(N) * m * sizeof(float), 256) + 256;
+}
+
+extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, int m, int d,
+                                 float* score_query, float* score_memory, float* colmax,
+                                 float* colsum, int64_t* top1, int64_t* top2, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(N >= 0 && m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
+  if (N == 0) return VADC_OK;
+  VADC_REQUIRE(q && keys && score_memory && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(!score_query || (colmax && colsum), VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(N < (1ll << 31), VADC_ERR_UNSUPPORTED);
+  VADC_REQUIRE(workspace_bytes >= vadc_memory_score_workspace_bytes(N, m, d), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver ws(workspace, workspace_bytes);
+  float* logits = ws.take<float>((size_t)N * m);
+  int chunks = col_chunks(N);
+  float* pmax = ws.take<float>((size_t)chunks * m);
+  float* psum = ws.take<float>((size_t)chunks * m);
+  {
+    Operand Aop{q, d, 1}, Bop{keys, 1, d};
+    StoreLogits epi{logits, m};
+    cudaError_t e = sgemm_auto((int)N, m, d, Aop, Bop, 0, 0, 1, 1, epi, st);
+    if (e != cudaSuccess) return record_cuda_error(e, "memory score sgemm");
+  }
+  row_softmax_top2_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(logits, N, m, score_memory, (long long*)top1, (long long*)top2);
+  VADC_CHECK_LAUNCH("row_softmax_top2_kernel");
+  if (score_query) {
+    long long rpb = (N + chunks - 1) / chunks;
+    dim3 g1((m + 255) / 256, chunks);
+    col_stats_stage1_kernel<<<g1, 256, 0, st>>>(logits, N, m, rpb, pmax, psum);
+    VADC_CHECK_LAUNCH("col_stats_stage1_kernel");
+    col_stats_stage2_kernel<<<(m + 255) / 256, 256, 0, st>>>(pmax, psum, chunks, m, colmax, colsum);
+    VADC_CHECK_LAUNCH("col_stats_stage2_kernel");
+    long long total = (long long)N * m;
+    long long nb = (total + 1023) / 1024;
+    long long cap = (long long)sm_count() * 16;
+    if (nb > cap) nb = cap;
+    col_softmax_apply_kernel<<<(unsigned)nb, 256, 0, st>>>(logits, colmax, colsum, total, m, score_query);
+    VADC_CHECK_LAUNCH("col_softmax_apply_kernel");
+  }
+  return VADC_OK;
+}
+
+extern "C" int vadc_memory_read(const float* q, const float* score_memory, const float* keys,
+                                int64_t N, int m, int d, float* updated_query, void* stream) {
+  VADC_REQUIRE(N >= 0 && m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
+  if (N == 0) return VADC_OK;
+  VADC_REQUIRE(q && score_memory && keys && updated_query, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(N < (1ll << 31), VADC_ERR_UNSUPPORTED);
+  Operand Aop{score_memory, m, 1}, Bop{keys, d, 1};
+  ReadEpilogue epi{updated_query, q, d};
+  cudaError_t e = sgemm_auto((int)N, d, m, Aop, Bop, 0, 0, 1, 1, epi, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return record_cuda_error(e, "memory read sgemm");
+  return VADC_OK;
+}
+
+extern "C" size_t vadc_memory_losses_workspace_bytes(int64_t N, int d) {
+  (void)d;
+  return align_up((size_t)((N + 7) / 8 + 1) * 2 * sizeof(double), 256) + 256;
+}
+
+extern "C" int vadc_memory_losses(const float* q, const float* keys, const int64_t* top1,
+                                  const int64_t* top2, int64_t N, int m, int d, float* out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(N > 0 && m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(q && keys && top1 && out && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(workspace_bytes >= vadc_memory_losses_workspace_bytes(N, d), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(workspace);
+  int nb = (int)((N + 7) / 8);
+  memory_losses_kernel<<<nb, 256, 0, st>>>(q, keys, (const long long*)top1, (const long long*)top2, N, d, partial);
+  VADC_CHECK_LAUNCH("memory_losses_kernel");
+  memory_losses_finalize_kernel<<<1, 256, 0, st>>>(partial, nb, (double)N * d, (double)N, out);
+  VADC_CHECK_LAUNCH("memory_losses_finalize_kernel");
+  return VADC_OK;
+}
+
+static int sort_chunks(int64_t N) { return (int)((N + kSortChunk - 1) / kSortChunk); }
+
+extern "C" size_t vadc_memory_update_workspace_bytes(int64_t N, int m, int d) {
+  (void)d;
+  size_t n = (size_t)(N > 0 ? N : 1);
+  size_t b = 0;
+  b += align_up((size_t)col_chunks(N) * m * sizeof(float), 256);     // column-max partials
+  b += align_up((size_t)m * sizeof(float), 256);                     // column max of score_query
+  b += 2 * align_up((size_t)sort_chunks(n) * m * sizeof(int), 256);  // hist/offsets + cursors
+  b += align_up((size_t)(m + 1) * sizeof(int), 256);                 // segment starts
+  b += align_up(n * sizeof(int), 256);                               // token order
+  return b + 256;
+}
+
+extern "C" int vadc_memory_update(const float* q, const float* keys, const float* score_query,
+                                  const int64_t* top1, int64_t N, int m, int d,
+                                  float* query_update, float* updated_memory, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(N > 0 && m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(q && keys && score_query && top1 && query_update && updated_memory && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(N < (1ll << 31), VADC_ERR_UNSUPPORTED);
+  VADC_REQUIRE(workspace_bytes >= vadc_memory_update_workspace_bytes(N, m, d), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver ws(workspace, workspace_bytes);
+  int cch = col_chunks(N), sch = sort_chunks(N);
+  float* pmax = ws.take<float>((size_t)cch * m);
+  float* cmax = ws.take<float>(m);
+  int* hist = ws.take<int>((size_t)sch * m);
+  int* cursor = ws.take<int>((size_t)sch * m);
+  int* seg = ws.take<int>(m + 1);
+  int* order = ws.take<int>(N);
+  long long rpb = (N + cch - 1) / cch;
+  dim3 g1((m + 255) / 256, cch);
+  colmax_stage1_kernel<<<g1, 256, 0, st>>>(score_query, N, m, rpb, pmax);
+  VADC_CHECK_LAUNCH("colmax_stage1_kernel");
+  colmax_stage2_kernel<<<(m + 255) / 256, 256, 0, st>>>(pmax, cch, m, cmax);
+  VADC_CHECK_LAUNCH("colmax_stage2_kernel");
+  long long hz = (cursor + (long long)sch * m) - hist;   // hist and cursor are adjacent in the workspace
+  zero_int_kernel<<<(unsigned)((hz + 255) / 256), 256, 0, st>>>(hist, hz);
+  VADC_CHECK_LAUNCH("zero_int_kernel");
+  slot_hist_kernel<<<sch, 256, 0, st>>>((const long long*)top1, N, m, hist);
+  VADC_CHECK_LAUNCH("slot_hist_kernel");
+  slot_scan_kernel<<<(m + 255) / 256, 256, 0, st>>>(hist, sch, m, seg);
+  VADC_CHECK_LAUNCH("slot_scan_kernel");
+  slot_scan2_kernel<<<1, 32, 0, st>>>(seg, m);
+  VADC_CHECK_LAUNCH("slot_scan2_kernel");
+  slot_place_kernel<<<sch, 32, 0, st>>>((const long long*)top1, N, m, hist, seg, cursor, order);
+  VADC_CHECK_LAUNCH("slot_place_kernel");
+  size_t smem = (size_t)8 * d * sizeof(float);
+  if (smem > 48 * 1024)
+    VADC_CUDA(cudaFuncSetAttribute(slot_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  slot_update_kernel<<<m, 256, smem, st>>>(q, keys, score_query, cmax, seg, order, m, d, query_update, updated_memory);
+  VADC_CHECK_LAUNCH("slot_update_kernel");
+  return VADC_OK;
+}
+
+extern "C" size_t vadc_memory_separateness_workspace_bytes(int m, int d) {
+  (void)d;
+  return align_up((size_t)m * m * sizeof(float), 256) + 256;
+}
+
+extern "C" int vadc_memory_separateness(const float* keys, int m, int d, float* out, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(m > 1 && d > 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(keys && out && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(workspace_bytes >= vadc_memory_separateness_workspace_bytes(m, d), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* sim = static_cast<float*>(workspace);
+  Operand Aop{keys, d, 1}, Bop{keys, 1, d};
+  SeparatenessEpilogue epi{sim, m};
+  cudaError_t e = sgemm_auto(m, m, d, Aop, Bop, 0, 0, 1, 1, epi, st);
+  if (e != cudaSuccess) return record_cuda_error(e, "separateness sgemm");
+  sum_all_kernel<<<1, 256, 0, st>>>(sim, (long long)m * m, 1.0 / ((double)m * (m - 1)), out);
+  VADC_CHECK_LAUNCH("sum_all_kernel");
+  return VADC_OK;
+}

@@ -1,0 +1,355 @@
+// rows.cuh — row-wise kernels shared by the cluster head, the space head and
+// the memory module: LayerNorm rows, squared row norms, the softmin / argmin /
+// loss row pass, the backward row pass, and deterministic column reductions.
+#pragma once
+#include "common.cuh"
+
+namespace vadc {
+
+// ---------------------------------------------------------------------------
+// LayerNorm over the last axis, one warp per row (model/cluster.py:84,129).
+// Two-pass statistics (mean, then variance about the mean) held in registers.
+// Writes z (row-major), mu, rstd and optionally |z|^2 per row.
+// VPL = float4 per lane (C <= 128*VPL).  C % 4 == 0.
+// ---------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+               long long N, int C, float eps, float* __restrict__ z, float* __restrict__ mu,
+               float* __restrict__ rstd, float* __restrict__ zz) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int nv = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    int c4 = lane + 32 * i;
+    v[i] = (c4 < nv) ? ld_stream(xr + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    int c4 = lane + 32 * i;
+    if (c4 < nv) {
+      float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b2 * b2) + (c2 * c2 + d * d);
+    }
+  }
+  const float var = warp_sum(q) / (float)C;
+  const float rs = 1.0f / sqrtf(var + eps);
+  float nz = 0.f;
+  float4* zr = reinterpret_cast<float4*>(z + row * C);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    int c4 = lane + 32 * i;
+    if (c4 < nv) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(w) + c4);
+      float4 be = __ldg(reinterpret_cast<const float4*>(b) + c4);
+      float4 o;
+      o.x = (v[i].x - mean) * rs * g.x + be.x;
+      o.y = (v[i].y - mean) * rs * g.y + be.y;
+      o.z = (v[i].z - mean) * rs * g.z + be.z;
+      o.w = (v[i].w - mean) * rs * g.w + be.w;
+      zr[c4] = o;
+      nz += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+    }
+  }
+  nz = warp_sum(nz);
+  if (lane == 0) {
+    mu[row] = mean;
+    rstd[row] = rs;
+    if (zz) zz[row] = nz;
+  }
+}
+
+// |row|^2 for a [R, C] matrix, one warp per row (any C).
+static __global__ void __launch_bounds__(256)
+row_sqnorm_kernel(const float* __restrict__ a, long long R, int C, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float* p = a + row * C;
+  float s = 0.f;
+  if ((C & 3) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    for (int i = lane; i < (C >> 2); i += 32) {
+      float4 v = __ldg(p4 + i);
+      s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  } else {
+    for (int i = lane; i < C; i += 32) { float v = __ldg(p + i); s += v * v; }
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+
+// ---------------------------------------------------------------------------
+// softmin / argmin / loss row pass (model/cluster.py:88,92 + backbone.py:94,98).
+// G lanes cooperate on one row of K distances (G in {4,8,16,32}; K % 4 == 0).
+//   label = first argmin, A = exp(-alpha (d - dmin)) / sum, part += (d*A)^2.
+// Block partial sums of (d*A)^2 go to `partial[blockIdx.x]` (double).
+// ---------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+softmin_rows_kernel(const float* __restrict__ D, long long R, int K, float alpha,
+                    float* __restrict__ A, long long* __restrict__ label,
+                    double* __restrict__ partial) {
+  __shared__ double red[32];
+  const int tid = threadIdx.x;
+  const int g = tid / G, gl = tid % G;
+  const long long row = (long long)blockIdx.x * (blockDim.x / G) + g;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) / G * G));
+  double lsum = 0.0;
+  if (row < R) {
+    const float4* dr = reinterpret_cast<const float4*>(D + row * K);
+    const int nv = K >> 2;
+    float best = INFINITY;
+    int bidx = 0x7fffffff;
+    for (int i = gl; i < nv; i += G) {
+      float4 v = dr[i];
+      int k = i * 4;
+      if (v.x < best) { best = v.x; bidx = k; }
+      if (v.y < best) { best = v.y; bidx = k + 1; }
+      if (v.z < best) { best = v.z; bidx = k + 2; }
+      if (v.w < best) { best = v.w; bidx = k + 3; }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(gmask, best, o, G);
+      int oi = __shfl_xor_sync(gmask, bidx, o, G);
+      if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    float s = 0.f;
+    for (int i = gl; i < nv; i += G) {
+      float4 v = dr[i];
+      s += (expf(-alpha * (v.x - best)) + expf(-alpha * (v.y - best))) +
+           (expf(-alpha * (v.z - best)) + expf(-alpha * (v.w - best)));
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o, G);
+    float4* ar = reinterpret_cast<float4*>(A + row * K);
+    float l = 0.f;
+    for (int i = gl; i < nv; i += G) {
+      float4 v = dr[i], a;
+      a.x = expf(-alpha * (v.x - best)) / s;
+      a.y = expf(-alpha * (v.y - best)) / s;
+      a.z = expf(-alpha * (v.z - best)) / s;
+      a.w = expf(-alpha * (v.w - best)) / s;
+      ar[i] = a;
+      float p0 = v.x * a.x, p1 = v.y * a.y, p2 = v.z * a.z, p3 = v.w * a.w;
+      l += (p0 * p0 + p1 * p1) + (p2 * p2 + p3 * p3);
+    }
+    lsum = (double)l;
+    if (gl == 0 && label) label[row] = bidx;
+  }
+  double tot = block_sum<double>(lsum, red);
+  if (tid == 0) partial[blockIdx.x] = tot;
+}
+
+// sum `n` doubles (one block), write float out[0] (and out[1] = sqrt if wanted)
+static __global__ void __launch_bounds__(256)
+finalize_sum_kernel(const double* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  s = block_sum<double>(s, red);
+  if (threadIdx.x == 0) out[0] = (float)s;
+}
+
+// ---------------------------------------------------------------------------
+// backward row pass (softmin backward + cdist ratio), G lanes per row:
+//   gA_tot = gemm + gA + 2 g D^2 A                (x_rec path, explicit grad, fused loss grad;
+//                                                  g = d objective / d sum (D*A)^2)
+//   gD_tot = gD + 2 g D A^2 - alpha*A*(gA_tot - sum_k gA_tot*A)
+//   r      = gD_tot / D   (0 where D == 0; ATen _euclidean_dist_backward)
+//   rsum   = sum_k r
+// ---------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+bwd_rows_kernel(const float* __restrict__ D, const float* __restrict__ A,
+                const float* __restrict__ gemm, const float* __restrict__ gD,
+                const float* __restrict__ gA, const float* __restrict__ g_loss_sq,
+                long long R, int K, float alpha,
+                float* __restrict__ r, float* __restrict__ rsum) {
+  const int tid = threadIdx.x;
+  const int g = tid / G, gl = tid % G;
+  const long long row = (long long)blockIdx.x * (blockDim.x / G) + g;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) / G * G));
+  if (row >= R) return;
+  const float sc = g_loss_sq ? 2.0f * __ldg(g_loss_sq) : 0.f;
+  const int nv = K >> 2;
+  const long long base = row * K;
+  float dot = 0.f;
+  for (int i = gl; i < nv; i += G) {
+    float4 d = reinterpret_cast<const float4*>(D + base)[i];
+    float4 a = reinterpret_cast<const float4*>(A + base)[i];
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gemm) t = reinterpret_cast<const float4*>(gemm + base)[i];
+    if (gA) { float4 u = reinterpret_cast<const float4*>(gA + base)[i]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    t.x += sc * d.x * d.x * a.x; t.y += sc * d.y * d.y * a.y;
+    t.z += sc * d.z * d.z * a.z; t.w += sc * d.w * d.w * a.w;
+    dot += (t.x * a.x + t.y * a.y) + (t.z * a.z + t.w * a.w);
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o, G);
+  float rs = 0.f;
+  for (int i = gl; i < nv; i += G) {
+    float4 d = reinterpret_cast<const float4*>(D + base)[i];
+    float4 a = reinterpret_cast<const float4*>(A + base)[i];
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gemm) t = reinterpret_cast<const float4*>(gemm + base)[i];
+    if (gA) { float4 u = reinterpret_cast<const float4*>(gA + base)[i]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    t.x += sc * d.x * d.x * a.x; t.y += sc * d.y * d.y * a.y;
+    t.z += sc * d.z * d.z * a.z; t.w += sc * d.w * d.w * a.w;
+    float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gD) gd = reinterpret_cast<const float4*>(gD + base)[i];
+    gd.x += sc * d.x * a.x * a.x - alpha * a.x * (t.x - dot);
+    gd.y += sc * d.y * a.y * a.y - alpha * a.y * (t.y - dot);
+    gd.z += sc * d.z * a.z * a.z - alpha * a.z * (t.z - dot);
+    gd.w += sc * d.w * a.w * a.w - alpha * a.w * (t.w - dot);
+    float4 o;
+    o.x = (d.x == 0.f) ? 0.f : gd.x / d.x;
+    o.y = (d.y == 0.f) ? 0.f : gd.y / d.y;
+    o.z = (d.z == 0.f) ? 0.f : gd.z / d.z;
+    o.w = (d.w == 0.f) ? 0.f : gd.w / d.w;
+    reinterpret_cast<float4*>(r + base)[i] = o;
+    rs += (o.x + o.y) + (o.z + o.w);
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) rs += __shfl_xor_sync(gmask, rs, o, G);
+  if (gl == 0) rsum[row] = rs;
+}
+
+// ---------------------------------------------------------------------------
+// deterministic column sums of a [R, W] matrix: stage 1 writes
+// partial[blockIdx.y][col] over a row chunk, stage 2 adds the chunks in order.
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+colsum_stage1_kernel(const float* __restrict__ a, long long R, int W, long long rows_per_block,
+                     float* __restrict__ partial) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= W) return;
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = min(R, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += __ldg(a + r * W + col);
+    s1 += __ldg(a + (r + 1) * W + col);
+    s2 += __ldg(a + (r + 2) * W + col);
+    s3 += __ldg(a + (r + 3) * W + col);
+  }
+  for (; r < r1; ++r) s0 += __ldg(a + r * W + col);
+  partial[(long long)blockIdx.y * W + col] = (s0 + s1) + (s2 + s3);
+}
+
+static __global__ void __launch_bounds__(256)
+colsum_stage2_kernel(const float* __restrict__ partial, int nchunks, int W, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= W) return;
+  float s = 0.f;
+  for (int c = 0; c < nchunks; ++c) s += partial[(long long)c * W + col];
+  out[col] = s;
+}
+
+inline int colsum_chunks(long long R) {
+  long long c = (R + 1023) / 1024;
+  if (c > 1024) c = 1024;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+// out[col] = sum_r a[r, col]; `partial` holds colsum_chunks(R) * W floats.
+inline cudaError_t launch_colsum(const float* a, long long R, int W, float* partial, float* out,
+                                 cudaStream_t st) {
+  int chunks = colsum_chunks(R);
+  long long rpb = (R + chunks - 1) / chunks;
+  if (rpb < 1) rpb = 1;
+  dim3 g1((W + 255) / 256, chunks);
+  colsum_stage1_kernel<<<g1, 256, 0, st>>>(a, R, W, rpb, partial);
+  colsum_stage2_kernel<<<(W + 255) / 256, 256, 0, st>>>(partial, chunks, W, out);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm backward, one warp per row, warps loop over rows so gamma/beta
+// partials stay in registers; block partials -> [gridDim.x, 2C] -> stage 2.
+// gz row-major [N,C].  gx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = gz*w.
+// ---------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+ln_bwd_rows_kernel(const float* __restrict__ gz, const float* __restrict__ x,
+                   const float* __restrict__ mu, const float* __restrict__ rstd,
+                   const float* __restrict__ w, long long N, int C,
+                   float* __restrict__ gx, float* __restrict__ partial /*[grid,2C]*/) {
+  extern __shared__ float sm[];   // [nwarps][2C]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nv = C >> 2;
+  float4 gw[VPL], gb[VPL], wv[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    gw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gb[i] = gw[i];
+    int c4 = lane + 32 * i;
+    wv[i] = (c4 < nv) ? __ldg(reinterpret_cast<const float4*>(w) + c4) : gw[i];
+  }
+  for (long long row = (long long)blockIdx.x * nw + wid; row < N; row += (long long)gridDim.x * nw) {
+    const float m = __ldg(mu + row), rs = __ldg(rstd + row);
+    float4 g[VPL], xh[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      int c4 = lane + 32 * i;
+      if (c4 < nv) {
+        float4 gv = ld_stream(reinterpret_cast<const float4*>(gz + row * C) + c4);
+        float4 xv = ld_stream(reinterpret_cast<const float4*>(x + row * C) + c4);
+        xh[i].x = (xv.x - m) * rs; xh[i].y = (xv.y - m) * rs;
+        xh[i].z = (xv.z - m) * rs; xh[i].w = (xv.w - m) * rs;
+        gw[i].x += gv.x * xh[i].x; gw[i].y += gv.y * xh[i].y;
+        gw[i].z += gv.z * xh[i].z; gw[i].w += gv.w * xh[i].w;
+        gb[i].x += gv.x; gb[i].y += gv.y; gb[i].z += gv.z; gb[i].w += gv.w;
+        g[i].x = gv.x * wv[i].x; g[i].y = gv.y * wv[i].y;
+        g[i].z = gv.z * wv[i].z; g[i].w = gv.w * wv[i].w;
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      int c4 = lane + 32 * i;
+      if (c4 < nv) {
+        float4 o;
+        o.x = (g[i].x - s1 - xh[i].x * s2) * rs;
+        o.y = (g[i].y - s1 - xh[i].y * s2) * rs;
+        o.z = (g[i].z - s1 - xh[i].z * s2) * rs;
+        o.w = (g[i].w - s1 - xh[i].w * s2) * rs;
+        reinterpret_cast<float4*>(gx + row * C)[c4] = o;
+      }
+    }
+  }
+  // block reduce of the gamma / beta partials in fixed warp order
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    int c4 = lane + 32 * i;
+    if (c4 < nv) {
+      reinterpret_cast<float4*>(sm + (size_t)wid * 2 * C)[c4] = gw[i];
+      reinterpret_cast<float4*>(sm + (size_t)wid * 2 * C + C)[c4] = gb[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float s = 0.f;
+    for (int ww = 0; ww < nw; ++ww) s += sm[(size_t)ww * 2 * C + c];
+    partial[(size_t)blockIdx.x * 2 * C + c] = s;
+  }
+}
+
+}  // namespace vadc

@@ -1,0 +1,172 @@
+"""NCCL replacement for utils/distritributed_model.py (gloo + DDP in the
+reference): same function names / side effects
+(``init_distributed_mode`` sets args.rank / world_size / gpu, mutes print on
+non-master ranks), plus the packed all-reduce helpers the hot path needs.
+One process per GPU; NCCL over NVLink 5 / NVSwitch when CUDA is present, gloo
+for the CPU tests of the host logic."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def setup_for_distributed(is_master):
+    """disable printing when not in master process (utils/distritributed_model.py:23-35)"""
+    import builtins as __builtin__
+    builtin_print = __builtin__.print
+    if getattr(builtin_print, "_vadc_wrapped", False):
+        builtin_print = builtin_print._vadc_orig
+
+    def print(*args, **kwargs):
+        force = kwargs.pop('force', False)
+        if is_master or force:
+            builtin_print(*args, **kwargs)
+
+    print._vadc_wrapped = True
+    print._vadc_orig = builtin_print
+    __builtin__.print = print
+
+
+def init_distributed_mode(args):
+    """utils/distritributed_model.py:38-70 with backend nccl (gloo when no GPU)."""
+    if 'RANK' in os.environ and 'WORLD_SIZE' in os.environ:
+        args.rank = int(os.environ["RANK"])
+        args.world_size = int(os.environ['WORLD_SIZE'])
+        args.gpu = int(os.environ.get('LOCAL_RANK', 0))
+    elif 'SLURM_PROCID' in os.environ:
+        args.rank = int(os.environ['SLURM_PROCID'])
+        args.gpu = args.rank % max(torch.cuda.device_count(), 1)
+        args.world_size = int(os.environ.get('SLURM_NTASKS', getattr(args, 'world_size', 1)))
+    elif torch.cuda.is_available():
+        print('Will run the code on one GPU.')
+        args.rank, args.gpu, args.world_size = 0, 0, 1
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+    else:
+        print('Does not support training without GPU.')
+        sys.exit(1)
+
+    use_cuda = torch.cuda.is_available()
+    backend = "nccl" if use_cuda else "gloo"
+    kwargs = {}
+    if use_cuda:
+        torch.cuda.set_device(args.gpu)
+        kwargs["device_id"] = torch.device("cuda", args.gpu)
+    dist.init_process_group(backend=backend, init_method=getattr(args, "dist_url", "env://"),
+                            world_size=args.world_size, rank=args.rank, **kwargs)
+    print('| distributed init (rank {}): {}'.format(args.rank, getattr(args, "dist_url", "env://")), flush=True)
+    dist.barrier()
+    setup_for_distributed(args.rank == 0)
+
+
+def fix_random_seeds(seed=31):
+    """utils/distritributed_model.py:73-79"""
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    np.random.seed(seed)
+
+
+def get_sha():
+    """utils/distritributed_model.py:82-100"""
+    cwd = os.path.dirname(os.path.abspath(__file__))
+
+    def _run(command):
+        return subprocess.check_output(command, cwd=cwd, stderr=subprocess.DEVNULL).decode('ascii').strip()
+
+    sha, diff, branch = 'N/A', "clean", 'N/A'
+    try:
+        sha = _run(['git', 'rev-parse', 'HEAD'])
+        diff = _run(['git', 'diff-index', 'HEAD'])
+        diff = "has uncommited changes" if diff else "clean"
+        branch = _run(['git', 'rev-parse', '--abbrev-ref', 'HEAD'])
+    except Exception:
+        pass
+    return f"sha: {sha}, status: {diff}, branch: {branch}"
+
+
+# ---------------------------------------------------------------------------
+# hot-path collectives
+# ---------------------------------------------------------------------------
+def is_dist():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def shard_range(n_items, rank=None, world_size=None):
+    """contiguous split of ``n_items`` clips over ranks (first ranks get the remainder)"""
+    if rank is None:
+        rank = dist.get_rank() if is_dist() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if is_dist() else 1
+    base, rem = divmod(n_items, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_packed(tensors, average=False, async_op=False):
+    """ONE all-reduce(sum) for a list of tensors: they are packed into a flat
+    buffer, reduced, and copied back in place (centroid grads [K,C] + LN grads
+    [2C] + loss scalars are latency-bound messages: one collective, not four).
+    ``average=True`` divides by world size (DDP-compatible mean).  Returns the
+    work handle when ``async_op`` (call ``finish()`` on it)."""
+    if not is_dist():
+        return _Done()
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op)
+
+    def unpack():
+        if average:
+            flat.div_(dist.get_world_size())
+        off = 0
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t))
+            off += n
+
+    if async_op:
+        return _Pending(work, unpack)
+    unpack()
+    return _Done()
+
+
+class _Done:
+    def finish(self):
+        return None
+
+
+class _Pending:
+    def __init__(self, work, fn):
+        self.work, self.fn = work, fn
+
+    def finish(self):
+        self.work.wait()
+        self.fn()
+
+
+class _AllReduceSum(torch.autograd.Function):
+    """y = sum over ranks of x; backward: identity (every rank's objective sees
+    the global sum, SURVEY.md §8e 'global-batch semantics')."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = x.clone()
+        if is_dist():
+            dist.all_reduce(y, op=dist.ReduceOp.SUM)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def global_frobenius(loss_sq, ddp_compat=False):
+    """sqrt of the cross-rank sum of a local sum-of-squares (cluster loss
+    backbone.py:94,98; pixel loss main_predict.py:273-275) so that N ranks
+    reproduce the single-process full-batch value.  ``ddp_compat`` keeps the
+    reference's DDP behaviour instead (per-rank norm)."""
+    if ddp_compat or not is_dist():
+        return torch.sqrt(loss_sq)
+    return torch.sqrt(_AllReduceSum.apply(loss_sq))

@@ -1,0 +1,184 @@
+"""Host-side mirror of the MNAD memory module (model/Memory.py:62-261) on top
+of libvadc.so.  Same class / method names and return tuples; ``keys`` in,
+``updated_memory`` out (stateless, detached) like the reference.
+
+What changes underneath: ``get_score`` is computed ONCE per
+forward instead of four times, and the python loop over memory slots with a
+``nonzero()`` host sync per slot (Memory.py:100-113) is a stable counting sort
+plus a segmented weighted sum on the device.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, f32c, ptr, stream, workspace
+
+
+def MemoryLoss(memory):
+    """model/Memory.py:52-59: separateness sum |K K^T/2 + 1/2 - I| / (m (m-1))"""
+    _lib.require_cuda(memory)
+    k = f32c(memory)
+    m, d = k.shape
+    out = torch.empty((1,), device=k.device, dtype=torch.float32)
+    l = _lib.lib()
+    ws = workspace(l.vadc_memory_separateness_workspace_bytes(m, d), k.device)
+    check(l.vadc_memory_separateness(ptr(k), m, d, ptr(out), ptr(ws), ws.numel(), stream()),
+          "vadc_memory_separateness")
+    return out[0]
+
+
+class _Scores:
+    """everything ``get_score`` + the topk calls derive from one (query, keys) pair"""
+    __slots__ = ("q", "score_query", "score_memory", "colmax", "colsum", "top1", "top2")
+
+
+def _compute_scores(q, keys, need_query_softmax=True):
+    N, d = q.shape
+    m = keys.shape[0]
+    dev = q.device
+    s = _Scores()
+    s.q = q
+    s.score_memory = torch.empty((N, m), device=dev, dtype=torch.float32)
+    s.score_query = torch.empty((N, m), device=dev, dtype=torch.float32) if need_query_softmax else None
+    s.colmax = torch.empty((m,), device=dev, dtype=torch.float32)
+    s.colsum = torch.empty((m,), device=dev, dtype=torch.float32)
+    s.top1 = torch.empty((N,), device=dev, dtype=torch.int64)
+    s.top2 = torch.empty((N,), device=dev, dtype=torch.int64)
+    l = _lib.lib()
+    ws = workspace(l.vadc_memory_score_workspace_bytes(N, m, d), dev)
+    check(l.vadc_memory_score(ptr(q), ptr(keys), N, m, d, ptr(s.score_query), ptr(s.score_memory),
+                              ptr(s.colmax), ptr(s.colsum), ptr(s.top1), ptr(s.top2),
+                              ptr(ws), ws.numel(), stream()), "vadc_memory_score")
+    return s
+
+
+class Memory(nn.Module):
+    """Drop-in for model/Memory.py:62-261.  Forward-only: outputs are detached
+    (the reference module is not wired into ``Mymodel``)."""
+
+    def __init__(self, memory_size, feature_dim, key_dim, temp_update, temp_gather):
+        super().__init__()
+        self.memory_size = memory_size
+        self.feature_dim = feature_dim
+        self.key_dim = key_dim
+        self.temp_update = temp_update
+        self.temp_gather = temp_gather
+
+    # -- helpers ------------------------------------------------------------
+    @staticmethod
+    def _flat(query):
+        """[B,h,w,d] (the layout every public method of the reference takes) -> [N,d]"""
+        _lib.require_cuda(query)
+        B, h, w, d = query.shape
+        return f32c(query).reshape(B * h * w, d), (B, h, w, d)
+
+    @staticmethod
+    def prepare_query(query):
+        """F.normalize(query, dim=1) + permute(0,2,3,1)  (Memory.py:148-149):
+        [B,d,h,w] -> [B,h,w,d] contiguous"""
+        _lib.require_cuda(query)
+        qc = f32c(query)
+        B, d, h, w = qc.shape
+        out = torch.empty((B, h, w, d), device=qc.device, dtype=torch.float32)
+        l = _lib.lib()
+        ws = workspace(l.vadc_memory_prepare_query_workspace_bytes(B, h * w), qc.device)
+        check(l.vadc_memory_prepare_query(ptr(qc), B, d, h * w, ptr(out), ptr(ws), ws.numel(), stream()),
+              "vadc_memory_prepare_query")
+        return out
+
+    # -- reference API --------------------------------------------------------
+    def get_score(self, mem, query):
+        """Memory.py:133-143 -> (softmax over tokens, softmax over slots), [N,m] each"""
+        q, _ = self._flat(query)
+        s = _compute_scores(q, f32c(mem))
+        return s.score_query, s.score_memory
+
+    def forward(self, query, keys, train=True):
+        """Memory.py:145-175.  query [B,d,h,w], keys [m,d]."""
+        with torch.no_grad():
+            keys_c = f32c(keys)
+            q4 = self.prepare_query(query)
+            q, shp = self._flat(q4)
+            s = _compute_scores(q, keys_c)
+            gathering_loss, spreading_loss = self._losses(s, keys_c, train)
+            updated_query = self._read(s, keys_c, shp)
+            if train:
+                updated_memory = self._update(s, keys_c)
+                return (updated_query, updated_memory, s.score_query, s.score_memory,
+                        gathering_loss, spreading_loss)
+            return updated_query, keys, s.score_query, s.score_memory, gathering_loss
+
+    def update(self, query, keys, train):
+        """Memory.py:177-204"""
+        with torch.no_grad():
+            q, _ = self._flat(query)
+            keys_c = f32c(keys)
+            return self._update(_compute_scores(q, keys_c), keys_c)
+
+    def get_update_query(self, mem, max_indices, update_indices, score, query, train):
+        """Memory.py:94-131: weighted sum of the queries assigned to each slot"""
+        with torch.no_grad():
+            q = f32c(query)
+            return self._segmented_update(q, f32c(mem), f32c(score),
+                                          max_indices.reshape(-1).to(torch.int64).contiguous())[0]
+
+    def pointwise_gather_loss(self, query_reshape, keys, gathering_indices, train):
+        """Memory.py:206-212 (elementwise, not a hot path: plain indexing)"""
+        return (query_reshape - keys[gathering_indices].squeeze(1).detach()) ** 2
+
+    def spread_loss(self, query, keys, train):
+        """Memory.py:214-231"""
+        with torch.no_grad():
+            q, _ = self._flat(query)
+            keys_c = f32c(keys)
+            return self._losses(_compute_scores(q, keys_c, False), keys_c, True)[1]
+
+    def gather_loss(self, query, keys, train):
+        """Memory.py:233-247"""
+        with torch.no_grad():
+            q, _ = self._flat(query)
+            keys_c = f32c(keys)
+            return self._losses(_compute_scores(q, keys_c, False), keys_c, False)[0]
+
+    def read(self, query, updated_memory):
+        """Memory.py:249-261"""
+        with torch.no_grad():
+            q, shp = self._flat(query)
+            keys_c = f32c(updated_memory)
+            s = _compute_scores(q, keys_c)
+            return self._read(s, keys_c, shp), s.score_query, s.score_memory
+
+    # -- kernels --------------------------------------------------------------
+    def _losses(self, s, keys, with_spread):
+        N, d = s.q.shape
+        m = keys.shape[0]
+        if with_spread and m < 2:
+            raise RuntimeError("selected index k out of range")      # torch.topk(…, 2) on m < 2
+        out = torch.empty((2,), device=s.q.device, dtype=torch.float32)
+        l = _lib.lib()
+        ws = workspace(l.vadc_memory_losses_workspace_bytes(N, d), s.q.device)
+        check(l.vadc_memory_losses(ptr(s.q), ptr(keys), ptr(s.top1), ptr(s.top2) if with_spread else None,
+                                   N, m, d, ptr(out), ptr(ws), ws.numel(), stream()), "vadc_memory_losses")
+        return out[0], (out[1] if with_spread else None)
+
+    def _read(self, s, keys, shp):
+        B, h, w, d = shp
+        N, m = s.q.shape[0], keys.shape[0]
+        uq = torch.empty((N, 2 * d), device=s.q.device, dtype=torch.float32)
+        check(_lib.lib().vadc_memory_read(ptr(s.q), ptr(s.score_memory), ptr(keys), N, m, d, ptr(uq), stream()),
+              "vadc_memory_read")
+        return uq.view(B, h, w, 2 * d).permute(0, 3, 1, 2)          # Memory.py:258-259
+
+    def _segmented_update(self, q, keys, score_query, top1):
+        N, d = q.shape
+        m = keys.shape[0]
+        qu = torch.empty((m, d), device=q.device, dtype=torch.float32)
+        um = torch.empty((m, d), device=q.device, dtype=torch.float32)
+        l = _lib.lib()
+        ws = workspace(l.vadc_memory_update_workspace_bytes(N, m, d), q.device)
+        check(l.vadc_memory_update(ptr(q), ptr(keys), ptr(score_query), ptr(top1), N, m, d, ptr(qu), ptr(um),
+                                   ptr(ws), ws.numel(), stream()), "vadc_memory_update")
+        return qu, um
+
+    def _update(self, s, keys):
+        return self._segmented_update(s.q, keys, s.score_query, s.top1)[1].detach()
