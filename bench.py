@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the cluster-head training step (BASELINE.json
+configs[1]) on N B200s, plus the roofline of its dominant op, the reference CPU
+path timed beside it, an end-to-end number through the public API with host
+buffers, and short sub-benchmarks of the other hot-path rows (memory, pixel
+loss, frame scoring).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic tokens:
+  C1+L1  EuclidDistance_Assign_Module.forward with the fused cluster loss
+  (all-reduce of the loss' sum of squares when N > 1: full-batch semantics)
+  C2     its backward from the cluster loss and an upstream gradient on x_rec
+         (centroid / LayerNorm / token gradients — the "centroid update")
+  one packed NCCL all-reduce(sum) of the centroid + LayerNorm gradients (N > 1)
+Workload per GPU (weak scaling): B=64 clips, T=16, 256x256 -> tokens
+[64, 8, 32, 32, 192] = 524288 x 192 fp32, K=32 centroids, alpha=16.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "cluster+memory+score tokens/sec"
+UNIT = "tokens/s"
+CFG = dict(B=64, T=16, side=256, C=192, K=32, alpha=16.0)
+CPU_SAMPLE_CLIPS = 8          # bounded CPU sample: 8 of the 64 clips (65536 tokens)
+
+
+def tokens_shape(B):
+    return (B, CFG["T"] // 2, CFG["side"] // 8, CFG["side"] // 8, CFG["C"])
+
+
+def config_dict(n_gpus):
+    return {
+        "workload": "BASELINE configs[1]: cluster-head training step (C1 fwd + fused cluster loss + C2 bwd"
+                    " + centroid/LN grad all-reduce), synthetic ShanghaiTech-shaped clips B=64 T=16 256x256"
+                    " per GPU -> 524288 tokens x C=192, K=32 centroids, alpha=16",
+        "tokens_per_gpu": 64 * 8 * 32 * 32, "C": 192, "K": 32,
+        "global_clips": 64 * n_gpus, "parallelism": f"dp{n_gpus}",
+        "l2": "inputs (402 MB tokens + 402 MB upstream grad per step) exceed the 126 MB L2; no flush needed",
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(kernel):
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture, or None"""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh).get(kernel)
+    return None
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", f"--id={self.index}"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------
+# reference arm / CPU baseline (oracle port, torch CPU ops = what the reference runs)
+# ----------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, budget_s=25.0):
+    """time oracle/ref_port.cluster_train_step on a bounded sample of the workload
+    (CPU_SAMPLE_CLIPS of the 64 clips) with every host core; returns tokens/s etc."""
+    from oracle import ref_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    shp = tokens_shape(CPU_SAMPLE_CLIPS)
+    x = torch.randn(shp, generator=g)
+    gR = torch.randn(shp, generator=g) * 1e-3
+    cen = torch.rand(CFG["K"], CFG["C"], generator=g)
+    w, b = torch.ones(CFG["C"]), torch.zeros(CFG["C"])
+    ntok = x.numel() // CFG["C"]
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        ref_port.cluster_train_step(x, cen, w, b, CFG["alpha"], gR)
+        if time.perf_counter() - t_start > budget_s / 2:
+            break
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ref_port.cluster_train_step(x, cen, w, b, CFG["alpha"], gR)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 3:
+            break
+    ms = statistics.median(times) * 1e3
+    return dict(value=ntok / (ms * 1e-3), ms_per_step=ms, cores=cores, steps=len(times), tokens=ntok,
+                sample=f"{CPU_SAMPLE_CLIPS} of 64 clips = {ntok} tokens x C=192, K=32, same step "
+                       f"(fwd + torch.norm(D*A) + backward), median of {len(times)} steps, torch "
+                       f"{torch.__version__} CPU, {cores} threads")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import videoad_b200 as V
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: videoad_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    V.fix_random_seeds(1234 + rank)
+    C, K = CFG["C"], CFG["K"]
+    mod = V.EuclidDistance_Assign_Module(C, K, soft_assign_alpha=CFG["alpha"]).to(dev)
+    if args.kernel == "simt":
+        mod.impl = V.IMPL_SIMT
+    elif args.kernel == "tcgen05":
+        mod.impl = V.IMPL_TCGEN05
+    if world > 1:                       # identical parameters on every rank (DDP broadcast)
+        for p in mod.parameters():
+            dist.broadcast(p.data, 0)
+    shp = tokens_shape(CFG["B"])
+    x_buf = torch.randn(shp, device=dev)
+    gR = torch.randn(shp, device=dev) * 1e-3
+    ntok = x_buf.numel() // C
+    params = [mod.cluster_center, mod.norm.weight, mod.norm.bias]
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    marks = []
+
+    def step(x_src, record=False):
+        for p in params:
+            p.grad = None
+        x = x_src.detach().requires_grad_(True)
+        if record:
+            e0 = ev(); e0.record()
+        D, A, S, R, F, lab = mod(x)
+        if record:
+            e1 = ev(); e1.record()
+        loss = V.global_frobenius(mod.loss_sq)           # all-reduce(sum) of the scalar when world > 1
+        torch.autograd.backward([loss, R], [None, gR])
+        if record:
+            e2 = ev(); e2.record()
+            marks.append((e0, e1, e2))
+        V.allreduce_sum_packed([p.grad for p in params])
+        return loss, x.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_buf)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = V.launch_count()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        step(x_buf, record=True)
+    t1.record()
+    barrier()
+    launches = V.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_total = t0.elapsed_time(t1)
+    tm = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_step = float(tm) / args.steps
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in marks)
+    bwd_ms = statistics.mean(b.elapsed_time(c) for _, b, c in marks)
+
+    # ---- end to end through the public API with host buffers ----
+    e2e_steps = max(3, args.steps // 4)
+    x_host = torch.randn(shp).pin_memory()
+    g_host = (torch.randn(shp) * 1e-3).pin_memory()
+    out_host = torch.empty(1 + K * C + 2 * C).pin_memory()
+    x_dev = torch.empty(shp, device=dev)
+
+    def e2e_step():
+        x_dev.copy_(x_host, non_blocking=True)
+        gR.copy_(g_host, non_blocking=True)
+        loss, _ = step(x_dev)
+        flat = torch.cat([loss.reshape(1)] + [p.grad.reshape(-1) for p in params])
+        out_host.copy_(flat, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    barrier()
+    te = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te) / e2e_steps
+    h2d = 2 * x_host.numel() * 4
+    d2h = out_host.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    alg_fwd = ntok * (12 * C + 8 * K + 8) + 4 * K * C + 4 * K * K       # SURVEY.md §8(d) C1+L1
+    alg_bwd = ntok * (12 * C + 8 * K) + 4 * K * C                        # SURVEY.md §8(d) C2, fused-loss variant
+    ach = alg_fwd / (fwd_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": world * ntok / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(world),
+        "roofline": {"kernel": "vadc_cluster_fwd (C1+L1)", "bound": "hbm", "achieved": ach, "peak": peak,
+                     "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("cluster_fwd"),
+                     "algorithmic_bytes": alg_fwd, "ms": fwd_ms, "peak_source": peak_src,
+                     "bwd": {"kernel": "vadc_cluster_bwd (C2)", "algorithmic_bytes": alg_bwd, "ms": bwd_ms,
+                             "achieved": alg_bwd / (bwd_ms * 1e-3) / 1e9,
+                             "frac": alg_bwd / (bwd_ms * 1e-3) / 1e9 / peak}},
+        "e2e": {"value": world * ntok / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "kernel_family": {0: "auto", 1: "simt", 2: "tcgen05"}[mod.impl],
+    }
+    if world == 1:
+        r = cpu_reference_run(10, 1, budget_s=20.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"], "ms_per_step": r["ms_per_step"]}
+        if not args.no_extra:
+            line["extra"] = extra_benchmarks(V, dev, peak)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_op(fn, iters, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()                  # > L2-sized write between timed iterations
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return statistics.median(ms)
+
+
+def extra_benchmarks(V, dev, peak):
+    """short sub-benchmarks of the other §8 rows (not the headline): each reports its own
+    algorithmic bytes / flops and time; L2 is flushed (512 MB write) between iterations for
+    the small ones."""
+    out = {}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    with torch.no_grad():
+        # L3 pixel loss and E1 frame scoring on one clip batch (B=16 of the 64: 201 MB per tensor)
+        r = torch.rand(16, 3, 16, 256, 256, device=dev)
+        c = torch.rand(16, 3, 16, 256, 256, device=dev)
+        nbytes = 2 * r.numel() * 4
+        ms = time_op(lambda: V.e4_norm(r, c), 10, flush)
+        out["pixel_loss_e4"] = {"ms": ms, "GB/s": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / peak}
+        ms = time_op(lambda: V.frame_mse(r, c, want_psnr=True), 10, flush)
+        out["frame_mse_psnr"] = {"ms": ms, "frames/s": 256 / (ms * 1e-3), "GB/s": nbytes / ms / 1e6,
+                                 "frac_hbm": nbytes / ms / 1e6 / peak}
+        del r, c
+        # M1-M5 memory forward (cfg3: m=2000, d=768, N=2048)
+        mem = V.Memory(2000, 768, 768, 0.1, 0.1)
+        q = torch.randn(2, 768, 32, 32, device=dev)
+        keys = torch.nn.functional.normalize(torch.rand(2000, 768, device=dev), dim=1)
+        ms = time_op(lambda: mem(q, keys, train=True), 10, flush)
+        out["memory_train_m2000_d768_n2048"] = {"ms": ms, "tokens/s": 2048 / (ms * 1e-3)}
+        ms = time_op(lambda: mem(q, keys, train=False), 10, flush)
+        out["memory_eval_m2000_d768_n2048"] = {"ms": ms, "tokens/s": 2048 / (ms * 1e-3),
+                                               "TFLOP/s": 4 * 2000 * 768 * 2048 / ms / 1e9}
+        # C1 at the reference-native head (C=192, K=1024) and the cfg3 sweep, forward only
+        for (C, K, n) in ((192, 1024, 65536), (768, 16, 65536), (768, 64, 65536), (768, 256, 65536)):
+            m = V.EuclidDistance_Assign_Module(C, K, soft_assign_alpha=16.0).to(dev)
+            x = torch.randn(1, 1, 1, n, C, device=dev)
+            ms = time_op(lambda: m(x), 5, flush)
+            byt = n * (12 * C + 8 * K + 8)
+            out[f"cluster_fwd_C{C}_K{K}_N{n}"] = {"ms": ms, "tokens/s": n / (ms * 1e-3),
+                                                   "alg_GB/s": byt / ms / 1e6, "frac_hbm": byt / ms / 1e6 / peak,
+                                                   "TFLOP/s": (4 * K * C + 4 * K) * n / ms / 1e9}
+        # C3 space head forward (cfg2 shape scaled to B=8: M=64, P=1024, C=192, K=128)
+        sp = V.Space_EuclidDistance_Assign_Module(192, 128, space_size=32).to(dev)
+        xs = torch.randn(8, 8, 32, 32, 192, device=dev)
+        ms = time_op(lambda: sp(xs), 5, flush)
+        out["space_fwd_M64_P1024_C192_K128"] = {"ms": ms, "tokens/s": 65536 / (ms * 1e-3)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -230,6 +230,15 @@ size_t vadc_memory_separateness_workspace_bytes(int m, int d);
 int vadc_memory_separateness(const float* keys, int m, int d, float* out,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * Debug / self-test: one CTA runs out[128,N] = A * B on tcgen05 (TMEM
+ * accumulator, SWIZZLE_128B shared-memory operands).  mode bit0: B is [Kd,N]
+ * (MN-major) instead of [N,Kd]; bit1: bf16 inputs (kind::f16) instead of tf32;
+ * bit2: A is [Kd,128] (MN-major) instead of [128,Kd].  Used by the tests to
+ * pin the descriptor encodings the fused kernels rely on.
+ * ------------------------------------------------------------------------ */
+int vadc_debug_umma(const float* A, const float* B, float* out, int N, int Kd, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,121 @@
+// umma_test.cu — single-CTA tcgen05 unit test behind vadc_debug_umma (used by
+// tests/test_gpu_umma.py): validates the shared-memory descriptor encoding
+// (K-major and MN-major SWIZZLE_128B), the instruction descriptor, TMEM
+// allocation and the tcgen05.ld accumulator layout against numpy, for
+// kind::tf32 and kind::f16 (bf16), before the fused kernels rely on them.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace vadc {
+using namespace tc;
+
+// mode bit0: B is MN-major ([Kd, N] row-major) instead of K-major ([N, Kd] row-major)
+// mode bit1: bf16 (kind::f16) instead of tf32
+// mode bit2: A is MN-major ([Kd, 128] row-major) instead of K-major ([128, Kd])
+// mode bit3: A (K-major) uses the un-swizzled core-matrix layout
+//            [k-chunk of 16 B][16 row groups][8 rows x 16 B]  (LBO 2048, SBO 128)
+__global__ void __launch_bounds__(128)
+umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out,
+                 int N, int Kd, int mode) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const bool b_mn = mode & 1, bf = mode & 2, a_mn = mode & 4, a_ns = mode & 8;
+  const int es = bf ? 2 : 4;                 // element size
+  const int epr = 128 / es;                  // elements per 128-byte row
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // ---- operand A ----
+  uint8_t* sA = smem;
+  uint32_t a_bytes;
+  if (a_ns) {    // K-major, no swizzle: core matrices of 8 rows x 16 bytes
+    const int epc = 16 / es;                 // elements per 16-byte chunk
+    a_bytes = 128 * Kd * es;
+    for (int i = tid; i < 128 * Kd; i += 128) {
+      int r = i / Kd, k = i % Kd;
+      uint32_t off = (k / epc) * 2048 + (r / 8) * 128 + (r % 8) * 16 + (k % epc) * es;
+      if (bf) *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16(A[i]);
+      else *reinterpret_cast<float*>(sA + off) = A[i];
+    }
+  } else if (!a_mn) {   // K-major: Kd/epr blocks of [128 rows x 128 B]
+    a_bytes = (Kd / epr) * 128 * 128;
+    for (int i = tid; i < 128 * Kd; i += 128) {
+      int r = i / Kd, k = i % Kd;
+      uint32_t off = (k / epr) * (128 * 128) + sw128(r, (k % epr) * es);
+      if (bf) *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16(A[i]);
+      else *reinterpret_cast<float*>(sA + off) = A[i];
+    }
+  } else {       // MN-major: 128/epr blocks of [Kd rows(k) x 128 B]; A given as [Kd, 128]
+    a_bytes = (128 / epr) * Kd * 128;
+    for (int i = tid; i < 128 * Kd; i += 128) {
+      int k = i / 128, m = i % 128;
+      uint32_t off = (m / epr) * (Kd * 128) + sw128(k, (m % epr) * es);
+      if (bf) *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16(A[i]);
+      else *reinterpret_cast<float*>(sA + off) = A[i];
+    }
+  }
+  uint8_t* sB = smem + ((a_bytes + 1023) & ~1023u);
+  if (!b_mn) {   // K-major: Kd/epr blocks of [N rows x 128 B]; B given as [N, Kd]
+    for (int i = tid; i < N * Kd; i += 128) {
+      int r = i / Kd, k = i % Kd;
+      uint32_t off = (k / epr) * (N * 128) + sw128(r, (k % epr) * es);
+      if (bf) *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(B[i]);
+      else *reinterpret_cast<float*>(sB + off) = B[i];
+    }
+  } else {       // MN-major: N/epr blocks of [Kd rows(k) x 128 B]; B given as [Kd, N]
+    for (int i = tid; i < N * Kd; i += 128) {
+      int k = i / N, n = i % N;
+      uint32_t off = (n / epr) * (Kd * 128) + sw128(k, (n % epr) * es);
+      if (bf) *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(B[i]);
+      else *reinterpret_cast<float*>(sB + off) = B[i];
+    }
+  }
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)N) ncols <<= 1;
+  if (warp == 0) tmem_alloc(&tmem_base, ncols);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = instr_desc(bf ? kFmtBF16 : kFmtTF32, 128, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    const int kstep = bf ? 16 : 8;           // elements per MMA along the contraction
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    for (int k = 0; k < Kd; k += kstep) {
+      uint64_t ad, bd;
+      if (a_ns) ad = smem_desc_noswz(a0 + (k / (16 / es)) * 2048, 2048, 128);
+      else if (!a_mn) ad = smem_desc_sw128(a0 + (k / epr) * (128 * 128) + (k % epr) * es, 0, 1024);
+      else ad = smem_desc_sw128(a0 + (k / 8) * 1024, Kd * 128, 1024);
+      if (!b_mn) bd = smem_desc_sw128(b0 + (k / epr) * (N * 128) + (k % epr) * es, 0, 1024);
+      else bd = smem_desc_sw128(b0 + (k / 8) * 1024, Kd * 128, 1024);
+      if (bf) mma_f16(tmem, ad, bd, idesc, k > 0); else mma_tf32(tmem, ad, bd, idesc, k > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    for (int j = 0; j < 32 && c0 + j < N; ++j) out[(size_t)tid * N + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+}  // namespace vadc
+
+extern "C" int vadc_debug_umma(const float* A, const float* B, float* out, int N, int Kd, int mode,
+                               void* stream) {
+  using namespace vadc;
+  VADC_REQUIRE(N >= 8 && N <= 256 && (N % 8) == 0 && Kd >= 32 && (Kd % 64) == 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(!(mode & 1) || (N % 64) == 0 || (!(mode & 2) && (N % 32) == 0), VADC_ERR_BAD_SHAPE);
+  size_t smem = (size_t)(128 + N) * Kd * 4 + 4096;
+  VADC_REQUIRE(smem <= 200 * 1024, VADC_ERR_UNSUPPORTED);
+  VADC_CUDA(cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_test_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, B, out, N, Kd, mode);
+  VADC_CHECK_LAUNCH("umma_test_kernel");
+  return VADC_OK;
+}
