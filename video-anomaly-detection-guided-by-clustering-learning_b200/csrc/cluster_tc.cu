@@ -51,7 +51,7 @@ __host__ __device__ inline TcSmemPlan tc_plan(int C, int K) {
   p.z_bytes = 3u * kTileM * C * 2u;                 // three bf16 terms of the 128 x C token tile
   p.c_bytes = 3u * K * C * 2u;                      // three bf16 terms of the K x C centroids
   p.a_off = 0;                                      // aliases the token operand after GEMM1
-  p.dst_off = p.a_off + 3u * kTileM * K * 2u;       // D staging  [K/32 blocks][128 x 128 B]
+  p.dst_off = p.a_off + 2u * kTileM * K * 2u;       // (2 bf16 terms of A) then D staging [K/32][128 x 128 B]
   p.ast_off = p.dst_off + kTileM * K * 4u;          // A staging
   p.xst_off = p.ast_off + kTileM * K * 4u;          // x_rec staging, 2 slots of [128 x 128 B]
   p.alias_end = p.xst_off + 2u * kTileM * 128u;
@@ -99,6 +99,35 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& t1, __nv_bfloat16
   t3 = __float2bfloat16_rn(r2);
 }
 
+// packed 3-term split of two floats: one F2FP per term converts and packs both values
+__device__ __forceinline__ uint32_t pack_rn(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);       // a -> low half, b -> high half
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  p1 = pack_rn(a, b);
+  float ra = a - bf_lo(p1), rb = b - bf_hi(p1);
+  p2 = pack_rn(ra, rb);
+  ra -= bf_lo(p2); rb -= bf_hi(p2);
+  p3 = pack_rn(ra, rb);
+}
+__device__ __forceinline__ void split2_pair(float a, float b, uint32_t& p1, uint32_t& p2) {
+  p1 = pack_rn(a, b);
+  p2 = pack_rn(a - bf_lo(p1), b - bf_hi(p1));
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -120,12 +149,13 @@ struct TcParams {
   long long N; int C, K; float alpha, eps;
 };
 
+template <int F4, int KCH>
 __global__ void __launch_bounds__(kTcThreads, 1)
 cluster_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapA,
                       const __grid_constant__ CUtensorMap mapR, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int C = p.C, K = p.K;
+  constexpr int C = F4 * 32, K = KCH * 32;
   const TcSmemPlan pl = tc_plan(C, K);
   uint8_t* sZ = smem;                                   // [3][C/64][128 x 128 B]
   uint8_t* sC = smem + pl.z_bytes;                      // [3][C/64][K x 128 B]
@@ -169,14 +199,16 @@ cluster_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmemD = tmem, tmemR = tmem + (uint32_t)K;
 
-  // LayerNorm affine parameters of this lane's channels (2 float4 per lane: C <= 256)
-  const int nv = C >> 2;
-  float4 gam[2], bet[2];
+  // P1 mapping: 8 lanes per token row (lane j owns float4 chunks j, j+8, ...), 4 rows per warp
+  // instruction; the two rows sharing a 16-lane store phase differ by 4 so that their swizzled
+  // 64-byte pieces fall in disjoint banks.
+  const int lj = lane & 7, lg = lane >> 3;
+  const int rsel = (lg & 1) * 4 + (lg >> 1);            // rows +0, +4, +1, +5 within an 8-row block
+  float4 gam[F4], bet[F4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    int c4 = lane + 32 * i;
-    gam[i] = (c4 < nv) ? __ldg(reinterpret_cast<const float4*>(p.ln_w) + c4) : make_float4(0, 0, 0, 0);
-    bet[i] = (c4 < nv) ? __ldg(reinterpret_cast<const float4*>(p.ln_b) + c4) : make_float4(0, 0, 0, 0);
+  for (int i = 0; i < F4; ++i) {
+    gam[i] = __ldg(reinterpret_cast<const float4*>(p.ln_w) + lj + 8 * i);
+    bet[i] = __ldg(reinterpret_cast<const float4*>(p.ln_b) + lj + 8 * i);
   }
   const uint32_t idesc1 = instr_desc(kFmtBF16, 128, K, 0, 0);
   const uint32_t idesc2 = instr_desc(kFmtBF16, 128, C, 0, 1);
@@ -194,58 +226,67 @@ cluster_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
       }
     }
     // ------------------------------------------------------------------ P1
-    for (int rr = warp; rr < kTileM; rr += 4 * (kTcThreads / 32)) {
-      float4 v[4][2];
+    for (int blk = warp; blk < kTileM / 8; blk += kTcThreads / 32) {
+      float4 v[2][F4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long row = row0 + rr + u * (kTcThreads / 32);
+      for (int u = 0; u < 2; ++u) {
+        const long long row = row0 + blk * 8 + rsel + 2 * u;
+        const float4* xr = reinterpret_cast<const float4*>(p.x + row * C) + lj;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          int c4 = lane + 32 * i;
-          v[u][i] = (row < p.N && c4 < nv) ? ld_stream(reinterpret_cast<const float4*>(p.x + row * C) + c4)
-                                           : make_float4(0, 0, 0, 0);
-        }
+        for (int i = 0; i < F4; ++i)
+          v[u][i] = (row < p.N) ? ld_stream(xr + 8 * i) : make_float4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = rr + u * (kTcThreads / 32);
+      for (int u = 0; u < 2; ++u) {
+        const int r = blk * 8 + rsel + 2 * u;
         const long long row = row0 + r;
-        float s = (v[u][0].x + v[u][0].y) + (v[u][0].z + v[u][0].w) + (v[u][1].x + v[u][1].y) + (v[u][1].z + v[u][1].w);
-        const float mean = warp_sum(s) * invC;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < F4; ++i) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const float mean = s * invC;
         float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (lane + 32 * i < nv) {
-            float a = v[u][i].x - mean, b = v[u][i].y - mean, c = v[u][i].z - mean, d = v[u][i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
-          }
+        for (int i = 0; i < F4; ++i) {
+          v[u][i].x -= mean; v[u][i].y -= mean; v[u][i].z -= mean; v[u][i].w -= mean;
+          q += (v[u][i].x * v[u][i].x + v[u][i].y * v[u][i].y) + (v[u][i].z * v[u][i].z + v[u][i].w * v[u][i].w);
         }
-        const float rs = 1.0f / sqrtf(warp_sum(q) * invC + p.eps);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 4);
+        const float rs = 1.0f / sqrtf(q * invC + p.eps);
+        const bool live = row < p.N;
         float nz = 0.f;
+        const uint32_t rowoff = (uint32_t)r * 128u;
+        const uint32_t rx = (uint32_t)(r & 7);
+        float4* frow = reinterpret_cast<float4*>(p.feature + row * C) + lj;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c4 = lane + 32 * i;
-          if (c4 < nv) {
-            float4 o;
-            o.x = (v[u][i].x - mean) * rs * gam[i].x + bet[i].x;
-            o.y = (v[u][i].y - mean) * rs * gam[i].y + bet[i].y;
-            o.z = (v[u][i].z - mean) * rs * gam[i].z + bet[i].z;
-            o.w = (v[u][i].w - mean) * rs * gam[i].w + bet[i].w;
-            if (row >= p.N) o = make_float4(0, 0, 0, 0);
-            else reinterpret_cast<float4*>(p.feature + row * C)[c4] = o;
-            nz += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-            __nv_bfloat16 a1, a2, a3, b1, b2, b3, c1, c2, c3, d1, d2, d3;
-            split3(o.x, a1, a2, a3); split3(o.y, b1, b2, b3); split3(o.z, c1, c2, c3); split3(o.w, d1, d2, d3);
-            const uint32_t off = (uint32_t)(c4 >> 4) * (kTileM * 128u) + sw128(r, (c4 & 15) * 8);
-            *reinterpret_cast<uint2*>(sZ + off) = make_uint2(pack2(a1, b1), pack2(c1, d1));
-            *reinterpret_cast<uint2*>(sZ + zterm + off) = make_uint2(pack2(a2, b2), pack2(c2, d2));
-            *reinterpret_cast<uint2*>(sZ + 2 * zterm + off) = make_uint2(pack2(a3, b3), pack2(c3, d3));
-          }
+        for (int i = 0; i < F4; ++i) {
+          float4 o;
+          o.x = v[u][i].x * rs * gam[i].x + bet[i].x;
+          o.y = v[u][i].y * rs * gam[i].y + bet[i].y;
+          o.z = v[u][i].z * rs * gam[i].z + bet[i].z;
+          o.w = v[u][i].w * rs * gam[i].w + bet[i].w;
+          if (live) frow[8 * i] = o; else o = make_float4(0, 0, 0, 0);
+          nz += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+          uint32_t a1, a2, a3, b1, b2, b3;
+          split3_pair(o.x, o.y, a1, a2, a3);
+          split3_pair(o.z, o.w, b1, b2, b3);
+          const int f = lj + 8 * i;                          // float4 index in the row: channels 4f..4f+3
+          const uint32_t byte = (uint32_t)(f & 15) * 8u;     // 8 bytes of bf16 in the 128-byte row of block f/16
+          const uint32_t off = (uint32_t)(f >> 4) * (kTileM * 128u) + rowoff + ((((byte >> 4) ^ rx) << 4) | (byte & 15u));
+          *reinterpret_cast<uint2*>(sZ + off) = make_uint2(a1, b1);
+          *reinterpret_cast<uint2*>(sZ + zterm + off) = make_uint2(a2, b2);
+          *reinterpret_cast<uint2*>(sZ + 2 * zterm + off) = make_uint2(a3, b3);
         }
-        nz = warp_sum(nz);
-        if (lane == 0) {
+        nz += __shfl_xor_sync(0xffffffffu, nz, 1);
+        nz += __shfl_xor_sync(0xffffffffu, nz, 2);
+        nz += __shfl_xor_sync(0xffffffffu, nz, 4);
+        if (lj == 0) {
           sZZ[r] = nz;
-          if (row < p.N) { p.mu[row] = mean; p.rstd[row] = rs; }
+          if (live) { p.mu[row] = mean; p.rstd[row] = rs; }
         }
       }
     }
@@ -278,59 +319,77 @@ cluster_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
       const long long row = row0 + r;
       const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
       const float zz = sZZ[r];
+      const bool live = row < p.N;
+      const float nalpha = -p.alpha * 1.4426950408889634f;     // exp(-a t) = 2^(-a log2(e) t)
       float best = INFINITY; int bidx = 0;
       float dv[32];
-      for (int c0 = 0; c0 < K; c0 += 32) {
-        tmem_ld32(tmemD + lane_addr + c0, dv);
+      if (KCH == 1) {
+        tmem_ld32(tmemD + lane_addr, dv);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float d = sqrtf(fmaxf(zz + sCC[c0 + j] - 2.0f * dv[j], 0.f));
-          if (d < best) { best = d; bidx = c0 + j; }
+          dv[j] = fast_sqrt(fmaxf(zz + sCC[j] - 2.0f * dv[j], 0.f));
+          if (dv[j] < best) { best = dv[j]; bidx = j; }
+        }
+      } else {
+        for (int c0 = 0; c0 < K; c0 += 32) {
+          tmem_ld32(tmemD + lane_addr + c0, dv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float d = fast_sqrt(fmaxf(zz + sCC[c0 + j] - 2.0f * dv[j], 0.f));
+            if (d < best) { best = d; bidx = c0 + j; }
+          }
         }
       }
       float sum = 0.f;
-      for (int c0 = 0; c0 < K; c0 += 32) {
-        if (K > 32) tmem_ld32(tmemD + lane_addr + c0, dv);
+      if (KCH > 1) {
+        for (int c0 = 0; c0 < K; c0 += 32) {
+          tmem_ld32(tmemD + lane_addr + c0, dv);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float d = sqrtf(fmaxf(zz + sCC[c0 + j] - 2.0f * dv[j], 0.f));
-          sum += expf(-p.alpha * (d - best));
+          for (int j = 0; j < 32; ++j) {
+            float d = fast_sqrt(fmaxf(zz + sCC[c0 + j] - 2.0f * dv[j], 0.f));
+            sum += exp2f(nalpha * (d - best));
+          }
         }
       }
       for (int c0 = 0; c0 < K; c0 += 32) {
-        if (K > 32) tmem_ld32(tmemD + lane_addr + c0, dv);
+        float ev[32];
+        if (KCH > 1) {
+          tmem_ld32(tmemD + lane_addr + c0, dv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            dv[j] = fast_sqrt(fmaxf(zz + sCC[c0 + j] - 2.0f * dv[j], 0.f));
+            ev[j] = exp2f(nalpha * (dv[j] - best));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { ev[j] = exp2f(nalpha * (dv[j] - best)); sum += ev[j]; }
+        }
+        const float inv = fast_rcp(sum);
         uint8_t* dblk = smem + pl.dst_off + (c0 >> 5) * (kTileM * 128u);
         uint8_t* ablk = smem + pl.ast_off + (c0 >> 5) * (kTileM * 128u);
+        float lrow = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float d[4], a[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            d[e] = sqrtf(fmaxf(zz + sCC[c0 + 4 * q + e] - 2.0f * dv[4 * q + e], 0.f));
-            a[e] = expf(-p.alpha * (d[e] - best)) / sum;
-            float pr = d[e] * a[e];
-            if (row < p.N) loss_thread += pr * pr;
+            ev[4 * q + e] *= inv;
+            float pr = dv[4 * q + e] * ev[4 * q + e];
+            lrow = fmaf(pr, pr, lrow);
           }
-          *reinterpret_cast<float4*>(dblk + sw128(r, q * 16)) = make_float4(d[0], d[1], d[2], d[3]);
-          *reinterpret_cast<float4*>(ablk + sw128(r, q * 16)) = make_float4(a[0], a[1], a[2], a[3]);
-          dv[4 * q + 0] = a[0]; dv[4 * q + 1] = a[1]; dv[4 * q + 2] = a[2]; dv[4 * q + 3] = a[3];
+          *reinterpret_cast<float4*>(dblk + sw128(r, q * 16)) = make_float4(dv[4 * q], dv[4 * q + 1], dv[4 * q + 2], dv[4 * q + 3]);
+          *reinterpret_cast<float4*>(ablk + sw128(r, q * 16)) = make_float4(ev[4 * q], ev[4 * q + 1], ev[4 * q + 2], ev[4 * q + 3]);
         }
-        // A operand of GEMM2: 3 bf16 terms, un-swizzled K-major core matrices (8 rows x 16 B)
+        if (live) loss_thread += lrow;
+        // A operand of GEMM2: 2 bf16 terms, un-swizzled K-major core matrices (8 rows x 16 B)
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
-          uint32_t w1[4], w2[4], w3[4];
+          uint32_t w1[4], w2[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 x1, x2, x3, y1, y2, y3;
-            split3(dv[8 * kc + 2 * e], x1, x2, x3);
-            split3(dv[8 * kc + 2 * e + 1], y1, y2, y3);
-            w1[e] = pack2(x1, y1); w2[e] = pack2(x2, y2); w3[e] = pack2(x3, y3);
-          }
+          for (int e = 0; e < 4; ++e) split2_pair(ev[8 * kc + 2 * e], ev[8 * kc + 2 * e + 1], w1[e], w2[e]);
           const uint32_t off = (uint32_t)((c0 >> 3) + kc) * 2048u + (r >> 3) * 128u + (r & 7) * 16u;
           const uint32_t aterm = (uint32_t)kTileM * K * 2u;
           *reinterpret_cast<uint4*>(smem + pl.a_off + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
           *reinterpret_cast<uint4*>(smem + pl.a_off + aterm + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-          *reinterpret_cast<uint4*>(smem + pl.a_off + 2 * aterm + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
         }
       }
       if (row < p.N) p.label[row] = bidx;
@@ -348,9 +407,9 @@ cluster_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
         const uint32_t ab = smem_u32(smem + pl.a_off), cb = smem_u32(sC);
         const uint32_t aterm = (uint32_t)kTileM * K * 2u;
         uint32_t acc = 0;
-        const int pi[6] = {0, 0, 1, 0, 1, 2}, pj[6] = {0, 1, 0, 2, 1, 0};
+        const int pi[5] = {0, 0, 1, 0, 1}, pj[5] = {0, 1, 0, 2, 1};
 #pragma unroll 1
-        for (int t = 0; t < 6; ++t) {
+        for (int t = 0; t < 5; ++t) {
           for (int ks = 0; ks < K / 16; ++ks) {
             uint64_t ad = smem_desc_noswz(ab + pi[t] * aterm + (uint32_t)(2 * ks) * 2048u, 2048, 128);
             uint64_t bd = smem_desc_sw128(cb + pj[t] * cterm + (uint32_t)(2 * ks) * 1024u, (uint32_t)K * 128u, 1024);
@@ -440,8 +499,8 @@ static int make_map(CUtensorMap* m, float* base, long long rows, int cols) {
 
 static bool tc_shape_ok(long long N, int C, int K) {
   if (N < 1 || N >= (1ll << 31)) return false;
-  if (C % 64 || C < 64 || C > 256) return false;
-  if (K % 32 || K < 32 || K > 256 || K + C > 512) return false;
+  if (C != 64 && C != 128 && C != 192) return false;   // instantiated (C/32, K/32) combinations
+  if (K != 32 && K != 64) return false;
   TcSmemPlan pl = tc_plan(C, K);
   if (pl.alias_end > pl.z_bytes) return false;          // staging must fit in the dead operand tiles
   if (pl.total + 1024 > 227 * 1024) return false;
@@ -482,14 +541,19 @@ int vadc_cluster_fwd_tc(const float* x, const float* ln_w, const float* ln_b, co
 
   const TcSmemPlan pl = tc_plan(C, K);
   const size_t smem = pl.total + 1024;
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    VADC_CUDA(cudaFuncSetAttribute(cluster_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
   TcParams p{x, ln_w, ln_b, image, cc, feature, reinterpret_cast<long long*>(label), mu, rstd, partial,
              (long long)N, C, K, alpha, eps};
-  cluster_fwd_tc_kernel<<<grid, kTcThreads, smem, st>>>(mD, mA, mR, p);
+#define TC_CASE(F4_, KCH_)                                                                              \
+  if (C == 32 * F4_ && K == 32 * KCH_) {                                                                \
+    VADC_CUDA(cudaFuncSetAttribute(cluster_fwd_tc_kernel<F4_, KCH_>,                                     \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    cluster_fwd_tc_kernel<F4_, KCH_><<<grid, kTcThreads, smem, st>>>(mD, mA, mR, p);                     \
+    launched = true;                                                                                    \
+  }
+  bool launched = false;
+  TC_CASE(2, 1) TC_CASE(4, 1) TC_CASE(6, 1) TC_CASE(4, 2) TC_CASE(6, 2)
+#undef TC_CASE
+  if (!launched) return VADC_ERR_UNSUPPORTED;
   VADC_CHECK_LAUNCH("cluster_fwd_tc_kernel");
   finalize_sum_kernel<<<1, 256, 0, st>>>(partial, grid, loss_sq);
   VADC_CHECK_LAUNCH("finalize_sum_kernel");

@@ -32,7 +32,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  while (!mbar_try_wait(bar, parity)) __nanosleep(20);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads, TMA stores)
