@@ -5,6 +5,8 @@
 #include "sgemm.cuh"
 #include "rows.cuh"
 #include "cluster.h"
+#include <algorithm>
+#include <stdlib.h>
 
 namespace vadc {
 
@@ -301,7 +303,7 @@ extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
   b += align_up((size_t)colsum_chunks(N) * K * sizeof(float), 256); // colsum partial
   b += align_up((size_t)K * sizeof(float), 256);             // rcol
   b += align_up((size_t)ln_bwd_blocks(N) * 2 * C * sizeof(float), 256);
-  return b + 256;
+  return std::max(b + 256, bwd_fused_workspace_bytes(N, C, K));
 }
 
 extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd,
@@ -325,6 +327,10 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
     VADC_CHECK_LAUNCH("zero_kernel");
     return VADC_OK;
   }
+  if (bwd_fused_shape_ok(N, C, K) && !getenv("VADC_BWD_GENERIC"))
+    return launch_cluster_bwd_fused(x, mu, rstd, feature, ln_w, centers, D, A, gD, gA, gR, gF, g_loss_sq,
+                                    N, C, K, alpha, gx, gcenters, g_ln_w, g_ln_b, workspace,
+                                    workspace_bytes, st);
   int tiles = ((K + 63) / 64) * ((C + 63) / 64);
   int splits = split_count(N, tiles);
   Carver ws(workspace, workspace_bytes);

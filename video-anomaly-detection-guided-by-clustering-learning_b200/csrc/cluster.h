@@ -19,6 +19,15 @@ int launch_ln_bwd(const float* gz, const float* x, const float* mu, const float*
 int launch_dist(const float* a, const float* b, const float* aa, const float* bb, int nb,
                 long long R, long long P, int C, float* out, cudaStream_t st);
 int split_count(long long Ntok, int tiles);
+// fused small-K backward (cluster_bwd_fused.cu)
+bool bwd_fused_shape_ok(long long N, int C, int K);
+size_t bwd_fused_workspace_bytes(long long N, int C, int K);
+int launch_cluster_bwd_fused(const float* x, const float* mu, const float* rstd, const float* feature,
+                             const float* ln_w, const float* centers, const float* D, const float* A,
+                             const float* gD, const float* gA, const float* gR, const float* gF,
+                             const float* g_loss_sq, long long N, int C, int K, float alpha, float* gx,
+                             float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st);
 }  // namespace vadc
 
 // tcgen05 path (cluster_tc.cu)
