@@ -57,6 +57,7 @@ class _ClusterAssign(torch.autograd.Function):
         ctx.save_for_backward(x2, cen, w, D, A, F, mu, rstd)
         ctx.alpha, ctx.lead = float(alpha), lead
         ctx.mark_non_differentiable(label)
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero tensors
         return (D.view(*lead, K), A.view(*lead, K), R.view(*lead, C), F, label, loss_sq)
 
     @staticmethod
@@ -69,7 +70,8 @@ class _ClusterAssign(torch.autograd.Function):
         def prep(g, cols):
             return None if g is None else f32c(g).reshape(-1, cols)
 
-        gD, gA, gR, gF, gLsq = prep(gD, K), prep(gA, K), prep(gR, C), prep(gF, C), f32c(gLsq)
+        gD, gA, gR, gF = prep(gD, K), prep(gA, K), prep(gR, C), prep(gF, C)
+        gLsq = None if gLsq is None else f32c(gLsq)
         gx = torch.empty((N, C), device=dev, dtype=torch.float32)
         gc = torch.empty((K, C), device=dev, dtype=torch.float32)
         gw = torch.empty((C,), device=dev, dtype=torch.float32)
@@ -266,6 +268,7 @@ class _SpaceClusterAssign(torch.autograd.Function):
               "vadc_space_cluster_fwd")
         ctx.save_for_backward(x2, cen, w, Ds, As, zt, mu, rstd)
         ctx.alpha, ctx.shape = float(alpha), (B, Dd, H, W, C)
+        ctx.set_materialize_grads(False)
         return Ds.view(B, Dd, C, K), As.view(B, Dd, C, K), loss_sq
 
     @staticmethod
@@ -276,7 +279,7 @@ class _SpaceClusterAssign(torch.autograd.Function):
         dev = x2.device
         gD = None if gD is None else f32c(gD).reshape(M, C, K)
         gA = None if gA is None else f32c(gA).reshape(M, C, K)
-        gLsq = f32c(gLsq)
+        gLsq = None if gLsq is None else f32c(gLsq)
         gx = torch.empty((M * P, C), device=dev, dtype=torch.float32)
         gc = torch.empty_like(cen)
         gw = torch.empty((C,), device=dev, dtype=torch.float32)
