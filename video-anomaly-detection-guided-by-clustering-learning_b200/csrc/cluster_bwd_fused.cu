@@ -14,6 +14,8 @@
 // hi*hi + hi*lo + lo*hi, fp32 accumulate: ~2^-19 relative), because the fp32
 // CUDA-core version of this kernel was shared-memory-bandwidth bound (ncu:
 // l1tex 90 %, FMA pipe 22 %): MMA fragments are re-used from registers.
+// (Pre-splitting the operand tiles into {hi,lo} pairs in shared memory was tried: it doubles the
+// shared wavefronts per fragment and was 1.6x slower, so the split stays in registers.)
 // Per-CTA partials (gcenters, colsum r, gamma, beta) go to the workspace and a
 // small second kernel adds them in fixed order (deterministic).
 #include "common.cuh"
