@@ -226,7 +226,7 @@ extern "C" size_t vadc_cluster_fwd_workspace_bytes(int64_t N, int C, int K, int 
   b += align_up((size_t)(N > 0 ? N : 1) * sizeof(float), 256);           // |z|^2
   b += align_up((size_t)K * sizeof(float), 256);                         // |c|^2
   b += align_up((size_t)(softmin_blocks(N, K) + 1) * sizeof(double), 256);
-  b += vadc_cluster_tc_extra_workspace_bytes(N, C, K);
+  b += std::max(vadc_cluster_tc_extra_workspace_bytes(N, C, K), vadc_cluster_ws_extra_workspace_bytes(N, C, K));
   return b + 256;
 }
 
@@ -245,6 +245,11 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
   VADC_REQUIRE(workspace_bytes >= vadc_cluster_fwd_workspace_bytes(N, C, K, impl), VADC_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+  if (impl != VADC_IMPL_SIMT && !getenv("VADC_FWD_NO_WS")) {
+    int rc = vadc_cluster_fwd_ws(x, ln_w, ln_b, centers, N, C, K, alpha, eps, D, A, x_rec, feature,
+                                 label, mu, rstd, loss_sq, workspace, workspace_bytes, st);
+    if (rc != VADC_ERR_UNSUPPORTED) return rc;
+  }
   if (impl != VADC_IMPL_SIMT) {
     int rc = vadc_cluster_fwd_tc(x, ln_w, ln_b, centers, N, C, K, alpha, eps, D, A, x_rec, feature,
                                  label, mu, rstd, loss_sq, workspace, workspace_bytes, st);

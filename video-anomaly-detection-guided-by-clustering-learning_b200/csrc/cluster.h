@@ -36,3 +36,9 @@ int vadc_cluster_fwd_tc(const float* x, const float* ln_w, const float* ln_b, co
                         int64_t N, int C, int K, float alpha, float eps, float* D, float* A,
                         float* x_rec, float* feature, int64_t* label, float* mu, float* rstd,
                         float* loss_sq, void* workspace, size_t workspace_bytes, cudaStream_t st);
+// warp-specialised tcgen05 path, K == 32 (cluster_fwd_ws.cu)
+size_t vadc_cluster_ws_extra_workspace_bytes(int64_t N, int C, int K);
+int vadc_cluster_fwd_ws(const float* x, const float* ln_w, const float* ln_b, const float* centers,
+                        int64_t N, int C, int K, float alpha, float eps, float* D, float* A,
+                        float* x_rec, float* feature, int64_t* label, float* mu, float* rstd,
+                        float* loss_sq, void* workspace, size_t workspace_bytes, cudaStream_t st);
