@@ -109,7 +109,8 @@ int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int64_t P, int
  * ------------------------------------------------------------------------ */
 size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K);
 int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd,
-                     const float* feature, const float* ln_w, const float* centers,
+                     const float* feature, const float* ln_w, const float* ln_b,
+                     const float* centers,
                      const float* D, const float* A,
                      const float* gD, const float* gA, const float* gR, const float* gF,
                      const float* g_loss_sq,

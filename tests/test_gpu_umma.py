@@ -63,6 +63,57 @@ def test_umma_modes(mode, Nn, Kd):
         assert et < er, "kind::tf32 truncates (does not round) fp32 operands to tf32"
 
 
+def f16_rne(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", [2 | 16, 2 | 32, 3 | 16, 7 | 32, 6 | 16])
+def test_umma_mixed_f16_bf16_operands(mode):
+    """one kind::f16 MMA may take an fp16 A with a bf16 B and vice versa (a_format / b_format are
+    independent fields of the instruction descriptor): the fused backward multiplies fp16-split
+    LayerNorm outputs with bf16-split gradients."""
+    Nn, Kd = 64, 128
+    rng = np.random.default_rng(mode)
+    A = rng.standard_normal((128, Kd)).astype(np.float32)
+    B = rng.standard_normal((Nn, Kd)).astype(np.float32)
+    Ain = np.ascontiguousarray(A.T) if mode & 4 else A
+    Bin = np.ascontiguousarray(B.T) if mode & 1 else B
+    got = run(Ain, Bin, Nn, Kd, mode)
+    Ar = f16_rne(A) if mode & 16 else bf16_rne(A)
+    Br = f16_rne(B) if mode & 32 else bf16_rne(B)
+    ref = Ar.astype(np.float64) @ Br.astype(np.float64).T
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("mode", [3, 7])
+@pytest.mark.parametrize("Kd", [64, 128])
+def test_umma_bf16_mn_major_b_half_swizzle_row(mode, Kd):
+    """N = 32 bf16 columns of an MN-major B fill only half of the 128-byte swizzle row"""
+    rng = np.random.default_rng(mode + Kd)
+    A = rng.standard_normal((128, Kd)).astype(np.float32)
+    B = rng.standard_normal((32, Kd)).astype(np.float32)
+    Ain = np.ascontiguousarray(A.T) if mode & 4 else A
+    got = run(Ain, np.ascontiguousarray(B.T), 32, Kd, mode)
+    ref = bf16_rne(A).astype(np.float64) @ bf16_rne(B).astype(np.float64).T
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("mode", [3 | 64, 7 | 64])
+def test_umma_bf16_mn_major_b_second_half_of_the_row(mode):
+    """B = columns [32, 64) of a [Kd, 64] MN-major tile, addressed by a +64-byte start offset"""
+    Kd = 64
+    rng = np.random.default_rng(mode)
+    A = rng.standard_normal((128, Kd)).astype(np.float32)
+    B = rng.standard_normal((64, Kd)).astype(np.float32)
+    Ain = np.ascontiguousarray(A.T) if mode & 4 else A
+    got = run(Ain, np.ascontiguousarray(B.T), 32, Kd, mode)
+    ref = bf16_rne(A).astype(np.float64) @ bf16_rne(B[32:]).astype(np.float64).T
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err
+
+
 def test_tf32_mn_major_needs_the_32B_base_swizzle():
     """tf32 MN-major operands only exist in the SWIZZLE_128B_BASE32B layout, which differs from the
     K-major SWIZZLE_128B tile: this is why the fused kernels use a 3-term bf16 split (kind::f16), whose

@@ -1,6 +1,7 @@
 // cluster.cu — EuclidDistance_Assign_Module forward / backward (C1, C2, L1),
 // SIMT fp32 path (VADC_IMPL_SIMT): valid for every shape; the tcgen05 kernel in
 // cluster_tc.cu takes over when the shape fits (VADC_IMPL_AUTO).
+#include <string.h>
 #include "common.cuh"
 #include "sgemm.cuh"
 #include "rows.cuh"
@@ -308,11 +309,12 @@ extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
   b += align_up((size_t)colsum_chunks(N) * K * sizeof(float), 256); // colsum partial
   b += align_up((size_t)K * sizeof(float), 256);             // rcol
   b += align_up((size_t)ln_bwd_blocks(N) * 2 * C * sizeof(float), 256);
-  return std::max(b + 256, bwd_fused_workspace_bytes(N, C, K));
+  return std::max(std::max(b + 256, bwd_fused_workspace_bytes(N, C, K)), bwd_tc_workspace_bytes(N, C, K));
 }
 
 extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd,
-                                const float* feature, const float* ln_w, const float* centers,
+                                const float* feature, const float* ln_w, const float* ln_b,
+                                const float* centers,
                                 const float* D, const float* A, const float* gD, const float* gA,
                                 const float* gR, const float* gF, const float* g_loss_sq,
                                 int64_t N, int C, int K, float alpha,
@@ -332,7 +334,12 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
     VADC_CHECK_LAUNCH("zero_kernel");
     return VADC_OK;
   }
-  if (bwd_fused_shape_ok(N, C, K) && !getenv("VADC_BWD_GENERIC"))
+  const char* bimpl = getenv("VADC_BWD_IMPL");            // debugging / A-B runs: tc | fused | generic
+  const bool want_tc = !bimpl || !strcmp(bimpl, "tc");
+  if (want_tc && ln_b && gR && !gD && !gA && !gF && bwd_tc_shape_ok(N, C, K))
+    return launch_cluster_bwd_tc(x, mu, rstd, ln_w, ln_b, centers, D, A, gR, g_loss_sq, N, C, K, alpha, gx,
+                                 gcenters, g_ln_w, g_ln_b, workspace, workspace_bytes, st);
+  if (bwd_fused_shape_ok(N, C, K) && !getenv("VADC_BWD_GENERIC") && !(bimpl && !strcmp(bimpl, "generic")))
     return launch_cluster_bwd_fused(x, mu, rstd, feature, ln_w, centers, D, A, gD, gA, gR, gF, g_loss_sq,
                                     N, C, K, alpha, gx, gcenters, g_ln_w, g_ln_b, workspace,
                                     workspace_bytes, st);

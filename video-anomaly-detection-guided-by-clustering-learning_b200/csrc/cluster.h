@@ -28,6 +28,14 @@ int launch_cluster_bwd_fused(const float* x, const float* mu, const float* rstd,
                              const float* g_loss_sq, long long N, int C, int K, float alpha, float* gx,
                              float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
                              size_t workspace_bytes, cudaStream_t st);
+// tcgen05 warp-specialised backward, K == 32, training-graph case (cluster_bwd_tc.cu)
+bool bwd_tc_shape_ok(long long N, int C, int K);
+size_t bwd_tc_workspace_bytes(long long N, int C, int K);
+int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, const float* ln_w,
+                          const float* ln_b, const float* centers, const float* D, const float* A,
+                          const float* gR, const float* g_loss_sq, long long N, int C, int K, float alpha,
+                          float* gx, float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
+                          size_t workspace_bytes, cudaStream_t st);
 }  // namespace vadc
 
 // tcgen05 path (cluster_tc.cu)

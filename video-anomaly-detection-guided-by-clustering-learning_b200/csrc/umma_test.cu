@@ -5,15 +5,25 @@
 // kind::tf32 and kind::f16 (bf16), before the fused kernels rely on them.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace vadc {
 using namespace tc;
+
+__device__ __forceinline__ void st16(uint8_t* p, float v, bool half) {
+  if (half) *reinterpret_cast<__half*>(p) = __float2half_rn(v);
+  else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16(v);
+}
 
 // mode bit0: B is MN-major ([Kd, N] row-major) instead of K-major ([N, Kd] row-major)
 // mode bit1: bf16 (kind::f16) instead of tf32
 // mode bit2: A is MN-major ([Kd, 128] row-major) instead of K-major ([128, Kd])
 // mode bit3: A (K-major) uses the un-swizzled core-matrix layout
 //            [k-chunk of 16 B][16 row groups][8 rows x 16 B]  (LBO 2048, SBO 128)
+// mode bit4: (with bit1) A is fp16 while B stays bf16  -- mixed a_format / b_format in one kind::f16 MMA
+// mode bit5: (with bit1) B is fp16 while A stays bf16
+// mode bit6: (with bit0|bit1) B is given as [Kd, 2N]; the MMA uses only columns [N, 2N) through a
+//            +N*2-byte start-address offset inside the 128-byte swizzle row (N == 32)
 __global__ void __launch_bounds__(128)
 umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out,
                  int N, int Kd, int mode) {
@@ -22,6 +32,8 @@ umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
   const bool b_mn = mode & 1, bf = mode & 2, a_mn = mode & 4, a_ns = mode & 8;
+  const bool a_h = mode & 16, b_h = mode & 32, b_sub = mode & 64;
+  const int NB = b_sub ? 2 * N : N;          // columns of B present in shared memory
   const int es = bf ? 2 : 4;                 // element size
   const int epr = 128 / es;                  // elements per 128-byte row
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -34,7 +46,7 @@ umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float
     for (int i = tid; i < 128 * Kd; i += 128) {
       int r = i / Kd, k = i % Kd;
       uint32_t off = (k / epc) * 2048 + (r / 8) * 128 + (r % 8) * 16 + (k % epc) * es;
-      if (bf) *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16(A[i]);
+      if (bf) st16(sA + off, A[i], a_h);
       else *reinterpret_cast<float*>(sA + off) = A[i];
     }
   } else if (!a_mn) {   // K-major: Kd/epr blocks of [128 rows x 128 B]
@@ -42,7 +54,7 @@ umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float
     for (int i = tid; i < 128 * Kd; i += 128) {
       int r = i / Kd, k = i % Kd;
       uint32_t off = (k / epr) * (128 * 128) + sw128(r, (k % epr) * es);
-      if (bf) *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16(A[i]);
+      if (bf) st16(sA + off, A[i], a_h);
       else *reinterpret_cast<float*>(sA + off) = A[i];
     }
   } else {       // MN-major: 128/epr blocks of [Kd rows(k) x 128 B]; A given as [Kd, 128]
@@ -50,7 +62,7 @@ umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float
     for (int i = tid; i < 128 * Kd; i += 128) {
       int k = i / 128, m = i % 128;
       uint32_t off = (m / epr) * (Kd * 128) + sw128(k, (m % epr) * es);
-      if (bf) *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16(A[i]);
+      if (bf) st16(sA + off, A[i], a_h);
       else *reinterpret_cast<float*>(sA + off) = A[i];
     }
   }
@@ -59,14 +71,14 @@ umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float
     for (int i = tid; i < N * Kd; i += 128) {
       int r = i / Kd, k = i % Kd;
       uint32_t off = (k / epr) * (N * 128) + sw128(r, (k % epr) * es);
-      if (bf) *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(B[i]);
+      if (bf) st16(sB + off, B[i], b_h);
       else *reinterpret_cast<float*>(sB + off) = B[i];
     }
-  } else {       // MN-major: N/epr blocks of [Kd rows(k) x 128 B]; B given as [Kd, N]
-    for (int i = tid; i < N * Kd; i += 128) {
-      int k = i / N, n = i % N;
+  } else {       // MN-major: N/epr blocks of [Kd rows(k) x 128 B]; B given as [Kd, NB]
+    for (int i = tid; i < NB * Kd; i += 128) {
+      int k = i / NB, n = i % NB;
       uint32_t off = (n / epr) * (Kd * 128) + sw128(k, (n % epr) * es);
-      if (bf) *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(B[i]);
+      if (bf) st16(sB + off, B[i], b_h);
       else *reinterpret_cast<float*>(sB + off) = B[i];
     }
   }
@@ -80,7 +92,9 @@ umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float
   tc_fence_after();
   const uint32_t tmem = tmem_base;
   if (tid == 0) {
-    const uint32_t idesc = instr_desc(bf ? kFmtBF16 : kFmtTF32, 128, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    uint32_t idesc = instr_desc(bf ? kFmtBF16 : kFmtTF32, 128, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    if (a_h) idesc &= ~(7u << 7);            // a_format = F16
+    if (b_h) idesc &= ~(7u << 10);           // b_format = F16
     const int kstep = bf ? 16 : 8;           // elements per MMA along the contraction
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
     for (int k = 0; k < Kd; k += kstep) {
@@ -89,7 +103,7 @@ umma_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float
       else if (!a_mn) ad = smem_desc_sw128(a0 + (k / epr) * (128 * 128) + (k % epr) * es, 0, 1024);
       else ad = smem_desc_sw128(a0 + (k / 8) * 1024, Kd * 128, 1024);
       if (!b_mn) bd = smem_desc_sw128(b0 + (k / epr) * (N * 128) + (k % epr) * es, 0, 1024);
-      else bd = smem_desc_sw128(b0 + (k / 8) * 1024, Kd * 128, 1024);
+      else bd = smem_desc_sw128(b0 + (k / 8) * 1024 + (b_sub ? N * es : 0), Kd * 128, 1024);
       if (bf) mma_f16(tmem, ad, bd, idesc, k > 0); else mma_tf32(tmem, ad, bd, idesc, k > 0);
     }
     mma_commit(&bar);
@@ -111,8 +125,9 @@ extern "C" int vadc_debug_umma(const float* A, const float* B, float* out, int N
                                void* stream) {
   using namespace vadc;
   VADC_REQUIRE(N >= 8 && N <= 256 && (N % 8) == 0 && Kd >= 32 && (Kd % 64) == 0, VADC_ERR_BAD_SHAPE);
-  VADC_REQUIRE(!(mode & 1) || (N % 64) == 0 || (!(mode & 2) && (N % 32) == 0), VADC_ERR_BAD_SHAPE);
-  size_t smem = (size_t)(128 + N) * Kd * 4 + 4096;
+  VADC_REQUIRE(!(mode & 1) || (N % 64) == 0 || N == 32, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(!(mode & 64) || ((mode & 3) == 3 && N == 32), VADC_ERR_BAD_SHAPE);
+  size_t smem = (size_t)(128 + ((mode & 64) ? 2 * N : N)) * Kd * 4 + 4096;
   VADC_REQUIRE(smem <= 200 * 1024, VADC_ERR_UNSUPPORTED);
   VADC_CUDA(cudaFuncSetAttribute(umma_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_test_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, B, out, N, Kd, mode);
