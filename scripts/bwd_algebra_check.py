@@ -60,3 +60,10 @@ gc = P1.T - gam[None] * P2.T - bet[None] * rcol[:, None] + cen * rcol[:, None]
 gb = gz.sum(0); gw = (gz * xr).sum(0)
 for name, got, want in (("gx", gx, ref[0]), ("gcen", gc, ref[1]), ("g_ln_w", gw, ref[2]), ("g_ln_b", gb, ref[3])):
     print(f"{name:7s} max err / max |ref| = {np.abs(got - want).max() / np.abs(want).max():.2e}")
+# ---- algebraic g_ln_w / g_ln_b from P2, rcol and Q (no per-token column sums of gz needed)
+Q = (xr * xr * rsum[:, None]).sum(0)
+P2s = P2.sum(1)
+gb_alg = gam * P2s + bet * rcol.sum() - rcol @ cen
+gw_alg = gam * Q + bet * P2s - (cen.T * P2).sum(1)
+for name, got, want in (("g_ln_w (algebraic)", gw_alg, ref[2]), ("g_ln_b (algebraic)", gb_alg, ref[3])):
+    print(f"{name:20s} max err / max |ref| = {np.abs(got - want).max() / np.abs(want).max():.2e}")

@@ -16,7 +16,7 @@
 //                                      of A and r into the shared [A | r] operand tile
 //   warps 4,5,8,9,12,13     E3         thread = token x 64 channels: gz = z rsum - acc, LayerNorm
 //                                      backward, gx through swizzled staging + TMA tensor stores,
-//                                      column sums for g_gamma / g_beta (register butterflies)
+//                                      Q[c] = sum_n xhat^2 rsum (register butterfly) for g_gamma
 //
 // The token tile is the MMA's M (S1, S3: M = 128 with rows 64..127 reading past the tile — their
 // TMEM lanes are never read) and its K (S5: the same shared-memory bytes viewed MN-major, M =
@@ -30,7 +30,9 @@
 //   sum_c gg        = rsum * sum_c z gamma      - sum_k r_k (cen_k . gamma)
 //   sum_c gg xhat   = rsum * sum_c z gamma xhat - sum_k r_k T_k,  T_k = xhat . (gamma * cen_k)
 //   T_k = z.cen_k - beta.cen_k = (|z|^2 + |cen_k|^2 - D_k^2) / 2 - beta.cen_k      (D is an input)
-// so E3 is a single pass over the accumulator.  gcenters = P1^T - gamma * P2^T + (cen - beta) colsum(r).
+// so E3 is a single pass over the accumulator.  gcenters = P1^T - gamma * P2^T + (cen - beta) colsum(r),
+//   g_beta  = gamma * rowsum_k(P2) + beta * sum(rcol) - rcol . cen
+//   g_gamma = gamma * Q + beta * rowsum_k(P2) - sum_k cen[k,:] * P2[:,k]       (no column sums of gz).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -49,7 +51,7 @@ constexpr int kTok = 64;                     // tokens per tile
 constexpr int kK = 32;                       // centroids
 constexpr int kThreads = 512;
 constexpr int kProd = 7;                     // producer warps
-constexpr int kUnits = kTok / 8;             // 8-row producer units per tile
+constexpr int kUnits = kTok / 4;             // 4-row producer units per tile
 constexpr int kMmaWarp = 15;
 constexpr uint32_t kBlk = kTok * 128u;       // one [64 rows x 128 B] operand block
 
@@ -107,6 +109,31 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 r;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
   return r;
+}
+// read-only tables (gamma, beta, ...): not volatile, so the compiler may hoist / schedule the loads
+__device__ __forceinline__ float4 lds128f_const(uint32_t addr) {
+  float4 r;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float lds32f_const(uint32_t addr) {
+  float r;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+  return r;
+}
+// descriptor = {hi, lo}; lo carries the 14-bit (address >> 4) field, so a byte offset is one add
+__device__ __forceinline__ uint64_t desc_at(uint32_t lo, uint32_t hi, uint32_t byte_off) {
+  return ((uint64_t)hi << 32) | (uint64_t)(lo + (byte_off >> 4));
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  if (accumulate)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
   uint4 r;
@@ -208,11 +235,12 @@ centroid_prep_bwd_kernel(const float* __restrict__ centers, const float* __restr
 struct Params {
   const float* x; const float* gR; const float* D; const float* A; const float* mu; const float* rstd;
   const float* ln_w; const float* ln_b; const uint8_t* cimage; const float* cvec; const float* g_loss_sq;
-  float* part_p; float* part_rcol; float* part_ln;       // [grid][2][C][32], [grid][2][32], [grid][2][2][C]
+  float* part_p; float* part_rcol; float* part_ln;       // [grid][2][C][32], [grid][2][32], Q: [grid][2][C]
   long long N; float alpha; int pf;
+  unsigned long long* trace;                             // debugging: per-warp event log of CTA 0 (VADC_BWD_TRACE)
 };
 
-template <int F4>
+template <int F4, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -232,6 +260,17 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.misc_off + 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // event trace (debug): entry = {code << 32 | tile, clock64}
+  constexpr int kTraceCap = 1024;
+  int trace_n = 0;
+  auto TR = [&](int code, int it) {
+    if constexpr (!TRACE) return;
+    if (p.trace && blockIdx.x == 0 && lane == 0 && trace_n < kTraceCap) {
+      unsigned long long* e = p.trace + ((size_t)warp * kTraceCap + trace_n) * 2;
+      e[0] = ((unsigned long long)code << 32) | (unsigned)it; e[1] = (unsigned long long)clock64();
+      ++trace_n;
+    }
+  };
   const long long ntiles = (p.N + kTok - 1) / kTok;
   const int nmine = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA (>= 1)
   constexpr uint32_t kColG1 = 0, kColAcc = 64, kColP1 = 64 + C, kColP2 = kColP1 + 32 * MB;
@@ -276,8 +315,9 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   const bool is_e = (warp & 3) < 2;
   if (!is_e && warp != kMmaWarp) {
     // ======================================================================= PRODUCERS
-    // 8 lanes per token row (lane j owns float4 chunks j, j+8, ...), 4 rows per warp instruction; the
-    // two rows sharing a 16-lane store phase differ by 4 (disjoint banks after the 128B swizzle).
+    // 8 lanes per token row (lane j owns float4 chunks j, j+8, ...), 4 rows per warp instruction = one
+    // unit; the two rows sharing a 16-lane store phase differ by 4 (disjoint banks after the 128B
+    // swizzle): unit u of a tile covers rows 8 (u/2) + 2 (u%2) + {0, 4, 1, 5}.
     const int pw = (warp >> 2) * 2 + (warp & 1);         // 0..6
     const int lj = lane & 7, lg = lane >> 3;
     const int rsel = (lg & 1) * 4 + (lg >> 1);
@@ -285,67 +325,56 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     const float cB1 = sConst[0], cB2 = sConst[1];
     const uint32_t sG2a = smem_u32(sG2) + lj * 16, sBGa = smem_u32(sBG) + lj * 16;
     for (int g = pw; g < nunits; g += kProd) {
-      const int it = g / kUnits, blk = g % kUnits;
+      const int it = g / kUnits, u = g % kUnits;
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
       const long long row0 = tile * kTok;
-      if (p.pf > 0 && lane == 0) {                       // L2 prefetch of this warp's own unit, pf rounds ahead
-        const int gn = g + p.pf * kProd;
-        if (gn < nunits) {
-          const long long rn = ((long long)blockIdx.x + (long long)(gn / kUnits) * gridDim.x) * kTok + (gn % kUnits) * 8;
-          const long long rows = min(8ll, p.N - rn);
-          if (rows > 0) {
-            prefetch_l2_bulk(p.x + rn * C, (uint32_t)(rows * C * 4));
-            prefetch_l2_bulk(p.gR + rn * C, (uint32_t)(rows * C * 4));
-          }
+      if (p.pf > 0 && lane == 0 && (u & 1) == 0 && it + p.pf < nmine) {   // L2 prefetch: same 8-row group, pf tiles ahead
+        const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (u >> 1) * 8;
+        const long long rows = min(8ll, p.N - rn);
+        if (rows > 0) {
+          prefetch_l2_bulk(p.x + rn * C, (uint32_t)(rows * C * 4));
+          prefetch_l2_bulk(p.gR + rn * C, (uint32_t)(rows * C * 4));
         }
       }
-      float4 gv[2][F4], xv[2][F4];
-      float nmr[2], rs[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const long long row = row0 + blk * 8 + rsel + 2 * u;
-        const bool live = row < p.N;
-        const float4* gr = reinterpret_cast<const float4*>(p.gR + row * C) + lj;
+      const int r = (u >> 1) * 8 + (u & 1) * 2 + rsel;
+      const long long row = row0 + r;
+      const bool live = row < p.N;
+      float4 xv[F4], gv[F4];
+      {
         const float4* xr = reinterpret_cast<const float4*>(p.x + row * C) + lj;
+        const float4* gr = reinterpret_cast<const float4*>(p.gR + row * C) + lj;
 #pragma unroll
-        for (int i = 0; i < F4; ++i) gv[u][i] = live ? ld_stream(gr + 8 * i) : make_float4(0, 0, 0, 0);
+        for (int i = 0; i < F4; ++i) xv[i] = live ? ld_stream(xr + 8 * i) : make_float4(0, 0, 0, 0);
 #pragma unroll
-        for (int i = 0; i < F4; ++i) xv[u][i] = live ? ld_stream(xr + 8 * i) : make_float4(0, 0, 0, 0);
-        rs[u] = live ? __ldg(p.rstd + row) : 0.f;
-        nmr[u] = live ? -__ldg(p.mu + row) * rs[u] : 0.f;
+        for (int i = 0; i < F4; ++i) gv[i] = live ? ld_stream(gr + 8 * i) : make_float4(0, 0, 0, 0);
       }
+      const float rs = live ? __ldg(p.rstd + row) : 0.f;
+      const float nmr = live ? -__ldg(p.mu + row) * rs : 0.f;
+      TR(0, it);
       const int buf = it & 1;
-      // G: S1 / S5a of the previous tile have completed;  X[buf]: S5b and E3 of tile it-2 have finished
-      mbar_wait_spin(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));
+      const uint32_t rx = (uint32_t)(r & 7);
+      const uint32_t rowoff = (uint32_t)r * 128u;
+      // ---- xhat: X[buf] is free once S5b and E3 of tile it-2 have finished
       mbar_wait_spin(&bars[B_XEMPTY0 + buf], (uint32_t)(((it >> 1) & 1) ^ 1));
-      const uint32_t xb = sX32 + buf * pl.xbuf;
-      float* prow = sProw + buf * 3 * kTok;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int r = blk * 8 + rsel + 2 * u;
-        const uint32_t rx = (uint32_t)(r & 7);
-        const uint32_t rowoff = (uint32_t)r * 128u;
+      {
+        const uint32_t xb = sX32 + buf * pl.xbuf;
         float q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
         for (int i = 0; i < F4; ++i) {
           const int f = lj + 8 * i;                          // float4 index in the row: channels 4f..4f+3
           const uint32_t byte = (uint32_t)(f & 15) * 8u;     // 8 bytes of bf16 in the 128-byte row of block f/16
           const uint32_t off = (uint32_t)(f >> 4) * kBlk + rowoff + ((((byte >> 4) ^ rx) << 4) | (byte & 15u));
-          uint32_t a1, a2, b1, b2;
-          split2_bf(gv[u][i].x, gv[u][i].y, a1, a2);
-          split2_bf(gv[u][i].z, gv[u][i].w, b1, b2);
-          sts64(sG32 + off, a1, b1);
-          sts64(sG32 + pl.gterm + off, a2, b2);
           float4 h;
-          h.x = fmaf(xv[u][i].x, rs[u], nmr[u]); h.y = fmaf(xv[u][i].y, rs[u], nmr[u]);
-          h.z = fmaf(xv[u][i].z, rs[u], nmr[u]); h.w = fmaf(xv[u][i].w, rs[u], nmr[u]);
-          const float4 g2 = lds128f(sG2a + i * 128);
-          const float4 bg = lds128f(sBGa + i * 128);
+          h.x = fmaf(xv[i].x, rs, nmr); h.y = fmaf(xv[i].y, rs, nmr);
+          h.z = fmaf(xv[i].z, rs, nmr); h.w = fmaf(xv[i].w, rs, nmr);
+          const float4 g2 = lds128f_const(sG2a + i * 128);
+          const float4 bg = lds128f_const(sBGa + i * 128);
           float w;
           w = g2.x * h.x; q1 += w; q2 = fmaf(w, h.x, q2); q3 = fmaf(bg.x, h.x, q3);
           w = g2.y * h.y; q1 += w; q2 = fmaf(w, h.y, q2); q3 = fmaf(bg.y, h.y, q3);
           w = g2.z * h.z; q1 += w; q2 = fmaf(w, h.z, q2); q3 = fmaf(bg.z, h.z, q3);
           w = g2.w * h.w; q1 += w; q2 = fmaf(w, h.w, q2); q3 = fmaf(bg.w, h.w, q3);
+          uint32_t a1, a2, b1, b2;
           split2_bf(h.x, h.y, a1, a2);
           split2_bf(h.z, h.w, b1, b2);
           sts64(xb + off, a1, b1);
@@ -358,15 +387,30 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
           q3 += __shfl_xor_sync(0xffffffffu, q3, o);
         }
         if (lj == 0) {
-          const bool live = (row0 + r) < p.N;
+          float* prow = sProw + buf * 3 * kTok;
           prow[r] = live ? q2 + 2.f * q3 + cB2 : 0.f;        // |z|^2
           prow[kTok + r] = live ? q1 + cB1 : 0.f;            // sum z gamma
           prow[2 * kTok + r] = live ? q2 + q3 : 0.f;         // sum z gamma xhat
         }
       }
+      // ---- gR: G is free once S1 / S5a of the previous tile have completed
+      mbar_wait_spin(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));
+      TR(1, it);
+#pragma unroll
+      for (int i = 0; i < F4; ++i) {
+        const int f = lj + 8 * i;
+        const uint32_t byte = (uint32_t)(f & 15) * 8u;
+        const uint32_t off = (uint32_t)(f >> 4) * kBlk + rowoff + ((((byte >> 4) ^ rx) << 4) | (byte & 15u));
+        uint32_t a1, a2, b1, b2;
+        split2_bf(gv[i].x, gv[i].y, a1, a2);
+        split2_bf(gv[i].z, gv[i].w, b1, b2);
+        sts64(sG32 + off, a1, b1);
+        sts64(sG32 + pl.gterm + off, a2, b2);
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_PFULL]);
+      TR(2, it);
     }
   } else if (warp < 2) {
     // ======================================================================= E1
@@ -374,26 +418,46 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const float sc = p.g_loss_sq ? 2.0f * __ldg(p.g_loss_sq) : 0.f;
     const float invC = 1.0f / (float)C;
+    const uint32_t sHc32 = smem_u32(sHc), sCg32 = smem_u32(sCg);
     float rcol_acc = 0.f;
+    float dv[32], av[32];
+    float rs_next = 0.f;
+    auto load_da = [&](int it) {                         // D / A rows of tile `it` (software-pipelined one tile ahead)
+      const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + et;
+      const bool live = it < nmine && row < p.N;
+      const float4* dp = reinterpret_cast<const float4*>(p.D + row * K);
+      const float4* ap = reinterpret_cast<const float4*>(p.A + row * K);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 d4 = live ? ldg_nc(dp + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 a4 = live ? ldg_nc(ap + q) : make_float4(0, 0, 0, 0);
+        dv[4 * q] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
+        av[4 * q] = a4.x; av[4 * q + 1] = a4.y; av[4 * q + 2] = a4.z; av[4 * q + 3] = a4.w;
+      }
+      rs_next = live ? __ldg(p.rstd + row) : 0.f;
+    };
+    auto prefetch_da = [&](int it) {                     // L2 prefetch of a later tile's D / A rows (8 KB each)
+      if (et == 0 && it < nmine) {
+        const long long rn = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok;
+        const long long rows = min((long long)kTok, p.N - rn);
+        if (rows > 0) {
+          prefetch_l2_bulk(p.D + rn * K, (uint32_t)(rows * K * 4));
+          prefetch_l2_bulk(p.A + rn * K, (uint32_t)(rows * K * 4));
+        }
+      }
+    };
+    prefetch_da(1);
+    load_da(0);
     for (int it = 0; it < nmine; ++it) {
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
       const long long row = tile * kTok + et;
       const bool live = row < p.N;
-      float dv[32], av[32];
-      {
-        const float4* dp = reinterpret_cast<const float4*>(p.D + row * K);
-        const float4* ap = reinterpret_cast<const float4*>(p.A + row * K);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 d4 = live ? ldg_nc(dp + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-          const float4 a4 = live ? ldg_nc(ap + q) : make_float4(0, 0, 0, 0);
-          dv[4 * q] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
-          av[4 * q] = a4.x; av[4 * q + 1] = a4.y; av[4 * q + 2] = a4.z; av[4 * q + 3] = a4.w;
-        }
-      }
-      const float rs = live ? __ldg(p.rstd + row) : 0.f;
+      const float rs = rs_next;
+      TR(10, it);
+      prefetch_da(it + 2);
       // [A | r] tile free: S3 / S5 of the previous tile have completed
       mbar_wait(&bars[B_AREMPTY], (uint32_t)((it & 1) ^ 1));
+      TR(11, it);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t w1[4], w2[4];
@@ -406,13 +470,16 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       fence_async_smem();
       named_bar(1, 64);
       if (et == 0) mbar_arrive(&bars[B_AFULL]);
+      TR(12, it);
       // producer row sums of this tile
       mbar_wait(&bars[B_PFULL], (uint32_t)(it & 1));
+      TR(13, it);
       const int buf = it & 1;
       const float zz = sProw[buf * 3 * kTok + et];
       const float p1 = sProw[buf * 3 * kTok + kTok + et];
       const float p2 = sProw[buf * 3 * kTok + 2 * kTok + et];
       mbar_wait(&bars[B_G1FULL0 + buf], (uint32_t)((it >> 1) & 1));
+      TR(14, it);
       tc_fence_after();
       float gv[32];
       tmem_ld32(tmem + lane_addr + kColG1 + (uint32_t)(buf * 32), gv);
@@ -420,26 +487,27 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_G1EMPTY0 + buf]);
       // softmin backward + cdist ratio
-      float dot = 0.f;
+      float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const float u = sc * dv[k];
-        gv[k] = fmaf(u, dv[k] * av[k], gv[k]);           // gA_tot = G1 + sc D^2 A
-        dot = fmaf(gv[k], av[k], dot);
+      for (int k = 0; k < 32; k += 2) {
+        gv[k] = fmaf(sc * dv[k], dv[k] * av[k], gv[k]);              // gA_tot = G1 + sc D^2 A
+        gv[k + 1] = fmaf(sc * dv[k + 1], dv[k + 1] * av[k + 1], gv[k + 1]);
+        dot0 = fmaf(gv[k], av[k], dot0);
+        dot1 = fmaf(gv[k + 1], av[k + 1], dot1);
       }
-      float rsum = 0.f, sT = 0.f, sG = 0.f;
+      const float dot = dot0 + dot1;
+      float rsum0 = 0.f, rsum1 = 0.f, sT0 = 0.f, sT1 = 0.f, sG0 = 0.f, sG1 = 0.f;
       const float hz = 0.5f * zz;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        const float u = sc * dv[k];
-        const float gd = av[k] * fmaf(u, av[k], -p.alpha * (gv[k] - dot));
+        const float gd = av[k] * fmaf(sc * dv[k], av[k], -p.alpha * (gv[k] - dot));
         const float r = (dv[k] == 0.f || !live) ? 0.f : gd * fast_rcp(dv[k]);
         gv[k] = r;
-        rsum += r;
-        const float T = fmaf(-0.5f * dv[k], dv[k], hz + sHc[k]);
-        sT = fmaf(r, T, sT);
-        sG = fmaf(r, sCg[k], sG);
+        const float T = fmaf(-0.5f * dv[k], dv[k], hz + lds32f_const(sHc32 + 4 * k));
+        if (k & 1) { rsum1 += r; sT1 = fmaf(r, T, sT1); sG1 = fmaf(r, lds32f_const(sCg32 + 4 * k), sG1); }
+        else { rsum0 += r; sT0 = fmaf(r, T, sT0); sG0 = fmaf(r, lds32f_const(sCg32 + 4 * k), sG0); }
       }
+      const float rsum = rsum0 + rsum1, sT = sT0 + sT1, sG = sG0 + sG1;
       const float s1 = (rsum * p1 - sG) * invC, s2 = (rsum * p2 - sT) * invC;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -455,33 +523,42 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       fence_async_smem();
       named_bar(1, 64);
       if (et == 0) mbar_arrive(&bars[B_RFULL]);
+      TR(15, it);
+      // next tile's D / A rows: issued after the fence / barrier above (which would wait for them),
+      // their latency is covered by the butterfly and the wait for the [A | r] tile
+      load_da(it + 1);
       butterfly<1>(gv, lane);                            // lane l: sum over this warp's 32 rows of r[:, l]
       rcol_acc += gv[0];
+      TR(16, it);
     }
     p.part_rcol[((size_t)blockIdx.x * 2 + warp) * K + lane] = rcol_acc;
   } else if (is_e) {
     // ======================================================================= E3
     const int e3 = (warp >> 2) - 1;                      // 64-channel group
     const int q = warp & 1;                              // token half
-    float accw[2][8], accb[2][8];
+    float accq[2][8];
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { accw[c][j] = 0.f; accb[c][j] = 0.f; }
+      for (int j = 0; j < 8; ++j) accq[c][j] = 0.f;
     if (e3 < NCB) {
       const int rl = q * 32 + lane;                      // token row in the tile = TMEM lane
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       const uint64_t pol = policy_evict_first();
       const uint32_t stg32 = smem_u32(smem + pl.stg_off) + (uint32_t)(e3 * 2 + q) * 4096u;
       const uint32_t rx = (uint32_t)(rl & 7);
+      const uint32_t sGam32 = smem_u32(sGam), sBet32 = smem_u32(sBet);
       for (int it = 0; it < nmine; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
         const long long row0 = tile * kTok;
         const int buf = it & 1;
+        TR(19, it);
         mbar_wait(&bars[B_RFULL], (uint32_t)(it & 1));
+        TR(20, it);
         const float* scal = sScal + (it & 1) * 4 * kTok;
         const float rsum = scal[rl], s1r = scal[kTok + rl], s2r = scal[2 * kTok + rl], rs = scal[3 * kTok + rl];
         mbar_wait(&bars[B_ACCFULL], (uint32_t)(it & 1));
+        TR(21, it);
         tc_fence_after();
         const uint32_t xrow = sX32 + buf * pl.xbuf + (uint32_t)e3 * kBlk + (uint32_t)rl * 128u;
 #pragma unroll
@@ -504,8 +581,8 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 gm = *reinterpret_cast<const float4*>(sGam + c0 + 4 * j);
-            const float4 be = *reinterpret_cast<const float4*>(sBet + c0 + 4 * j);
+            const float4 gm = lds128f_const(sGam32 + (uint32_t)(c0 + 4 * j) * 4u);
+            const float4 be = lds128f_const(sBet32 + (uint32_t)(c0 + 4 * j) * 4u);
             float o[4];
             const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, bev[4] = {be.x, be.y, be.z, be.w};
 #pragma unroll
@@ -514,8 +591,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
               const float z = fmaf(xhv, gmv[e], bev[e]);
               const float gz = fmaf(z, rsum, -acc[4 * j + e]);
               o[e] = fmaf(-xhv, s2r, fmaf(gz * gmv[e], rs, -s1r));
-              acc[4 * j + e] = gz;                       // g_beta contribution
-              xh[4 * j + e] = gz * xhv;                  // g_gamma contribution
+              xh[4 * j + e] = xhv * xhv * rsum;          // Q contribution
             }
             sts128f(stg32 + (uint32_t)lane * 128u + ((((uint32_t)j) ^ (uint32_t)(lane & 7)) << 4), o[0], o[1], o[2], o[3]);
           }
@@ -525,24 +601,23 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
             tma_store_2d_hint(&mapGx, stg32, c0, (int)(row0 + q * 32), pol);
             bulk_commit();
           }
-          butterfly<8>(acc, lane);
+          if (ch == 1) {                                 // accumulator and xhat fully consumed: release them early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bars[B_ACCEMPTY]); mbar_arrive(&bars[B_XEMPTY0 + buf]); }
+          }
           butterfly<8>(xh, lane);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { accb[ch][j] += acc[j]; accw[ch][j] += xh[j]; }
+          for (int j = 0; j < 8; ++j) accq[ch][j] += xh[j];
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&bars[B_ACCEMPTY]); mbar_arrive(&bars[B_XEMPTY0 + buf]); }
+        TR(22, it);
       }
       if (lane == 0) bulk_wait0();
-      // finish the butterflies: lane l ends with the column sum of channel c0 + l over this warp's rows
+      // finish the butterflies: lane l ends with Q of channel c0 + l over this warp's rows
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        butterfly_tail<4, 8>(accb[ch], lane);
-        butterfly_tail<4, 8>(accw[ch], lane);
-        float* o = p.part_ln + ((size_t)blockIdx.x * 2 + q) * 2 * C;
-        o[e3 * 64 + ch * 32 + lane] = accw[ch][0];
-        o[C + e3 * 64 + ch * 32 + lane] = accb[ch][0];
+        butterfly_tail<4, 8>(accq[ch], lane);
+        p.part_ln[((size_t)blockIdx.x * 2 + q) * C + e3 * 64 + ch * 32 + lane] = accq[ch][0];
       }
     }
   } else if (lane == 0) {
@@ -554,6 +629,12 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     const uint32_t idesc3 = instr_desc(kFmtBF16, 128, C, 0, 1);      // S3: tokens x C, cen MN-major
     const uint32_t idesc5 = instr_desc(kFmtBF16, 128, K, 1, 1);      // S5: channels x K, both MN-major
     constexpr int pi[3] = {0, 1, 0}, pj[3] = {1, 0, 0};              // small terms first
+    // descriptor bases: hi word is constant per layout, lo word = (address >> 4) | LBO field
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
+    const uint32_t loG_k = (sG32 >> 4) & 0x3FFFu, loG_mn = loG_k | ((kBlk >> 4) << 16);
+    const uint32_t loAR_k = (sAR32 >> 4) & 0x3FFFu, loAR_mn = loAR_k | ((kBlk >> 4) << 16);
+    const uint32_t loC_k = (sCen32 >> 4) & 0x3FFFu, loC_mn = loC_k | (((uint32_t)K * 128u >> 4) << 16);
+    const uint32_t loX_mn0 = ((sX32 >> 4) & 0x3FFFu) | ((kBlk >> 4) << 16);
     mbar_wait(&bars[B_CEN], 0);
     int n1 = 0, n5 = 0, n3 = 0;
     while (n3 < nmine) {
@@ -561,40 +642,36 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
           mbar_try_wait(&bars[B_G1EMPTY0 + (n1 & 1)], (uint32_t)(((n1 >> 1) & 1) ^ 1))) {
         tc_fence_after();
         const uint32_t d = tmem + kColG1 + (uint32_t)((n1 & 1) * 32);
-        uint32_t acc = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint32_t ga = sG32 + pi[t] * pl.gterm, ca = sCen32 + pj[t] * pl.cterm;
 #pragma unroll
           for (int kk = 0; kk < C / 16; ++kk) {
-            const uint64_t ad = smem_desc_sw128(ga + (kk >> 2) * kBlk + (kk & 3) * 32u, 0, 1024);
-            const uint64_t bd = smem_desc_sw128(ca + (kk >> 2) * (K * 128u) + (kk & 3) * 32u, 0, 1024);
-            mma_f16(d, ad, bd, idesc1, acc);
-            acc = 1;
+            const uint64_t ad = desc_at(loG_k, kHi, pi[t] * pl.gterm + (kk >> 2) * kBlk + (kk & 3) * 32u);
+            const uint64_t bd = desc_at(loC_k, kHi, pj[t] * pl.cterm + (kk >> 2) * (K * 128u) + (kk & 3) * 32u);
+            mma_bf16(d, ad, bd, idesc1, t > 0 || kk > 0);
           }
         }
         mma_commit(&bars[B_G1FULL0 + (n1 & 1)]);
+        TR(30, n1);
         ++n1;
       }
       if (n5 < n1 && mbar_try_wait(&bars[B_AFULL], (uint32_t)(n5 & 1))) {
         tc_fence_after();
-        const uint32_t acc0 = n5 > 0 ? 1u : 0u;
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
           const uint32_t d = tmem + kColP1 + (uint32_t)(mb * 32);
-          uint32_t acc = acc0;
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
 #pragma unroll
             for (int ks = 0; ks < kTok / 16; ++ks) {
-              const uint64_t ad = smem_desc_sw128(sG32 + pi[t] * pl.gterm + (uint32_t)mb * 2u * kBlk + (uint32_t)ks * 2048u, kBlk, 1024);
-              const uint64_t bd = smem_desc_sw128(sAR32 + pj[t] * kBlk + (uint32_t)ks * 2048u, kBlk, 1024);
-              mma_f16(d, ad, bd, idesc5, acc);
-              acc = 1;
+              const uint64_t ad = desc_at(loG_mn, kHi, pi[t] * pl.gterm + (uint32_t)mb * 2u * kBlk + (uint32_t)ks * 2048u);
+              const uint64_t bd = desc_at(loAR_mn, kHi, pj[t] * kBlk + (uint32_t)ks * 2048u);
+              mma_f16(d, ad, bd, idesc5, (t > 0 || ks > 0 || n5 > 0) ? 1u : 0u);
             }
           }
         }
         mma_commit(&bars[B_GEMPTY]);
+        TR(31, n5);
         ++n5;
       }
       if (n3 < n5 && mbar_try_wait(&bars[B_RFULL], (uint32_t)(n3 & 1)) &&
@@ -602,38 +679,34 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         tc_fence_after();
         {
           const uint32_t d = tmem + kColAcc;
-          uint32_t acc = 0;
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
 #pragma unroll
             for (int ks = 0; ks < K / 16; ++ks) {
-              const uint64_t ad = smem_desc_sw128(sAR32 + pi[t] * kBlk + 64u + (uint32_t)ks * 32u, 0, 1024);
-              const uint64_t bd = smem_desc_sw128(sCen32 + pj[t] * pl.cterm + (uint32_t)(2 * ks) * 1024u, (uint32_t)K * 128u, 1024);
-              mma_f16(d, ad, bd, idesc3, acc);
-              acc = 1;
+              const uint64_t ad = desc_at(loAR_k, kHi, pi[t] * kBlk + 64u + (uint32_t)ks * 32u);
+              const uint64_t bd = desc_at(loC_mn, kHi, pj[t] * pl.cterm + (uint32_t)(2 * ks) * 1024u);
+              mma_bf16(d, ad, bd, idesc3, t > 0 || ks > 0);
             }
           }
           mma_commit(&bars[B_ACCFULL]);
         }
-        const uint32_t xb = sX32 + (uint32_t)(n3 & 1) * pl.xbuf;
-        const uint32_t acc0 = n3 > 0 ? 1u : 0u;
+        const uint32_t loX_mn = loX_mn0 + (uint32_t)(n3 & 1) * (pl.xbuf >> 4);
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
           const uint32_t d = tmem + kColP2 + (uint32_t)(mb * 32);
-          uint32_t acc = acc0;
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
 #pragma unroll
             for (int ks = 0; ks < kTok / 16; ++ks) {
-              const uint64_t ad = smem_desc_sw128(xb + pi[t] * pl.xterm + (uint32_t)mb * 2u * kBlk + (uint32_t)ks * 2048u, kBlk, 1024);
-              const uint64_t bd = smem_desc_sw128(sAR32 + pj[t] * kBlk + 64u + (uint32_t)ks * 2048u, kBlk, 1024);
-              mma_f16(d, ad, bd, idesc5, acc);
-              acc = 1;
+              const uint64_t ad = desc_at(loX_mn, kHi, pi[t] * pl.xterm + (uint32_t)mb * 2u * kBlk + (uint32_t)ks * 2048u);
+              const uint64_t bd = desc_at(loAR_mn, kHi, pj[t] * kBlk + 64u + (uint32_t)ks * 2048u);
+              mma_f16(d, ad, bd, idesc5, (t > 0 || ks > 0 || n3 > 0) ? 1u : 0u);
             }
           }
         }
         mma_commit(&bars[B_XEMPTY0 + (n3 & 1)]);
         mma_commit(&bars[B_AREMPTY]);
+        TR(32, n3);
         ++n3;
       }
     }
@@ -666,30 +739,33 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, ncols); }
 }
 
-// gcenters[k,c] = sum_b P1[b][c][k] - gamma_c sum_b P2[b][c][k] + (cen[k,c] - beta_c) rcol_k
-// g_ln_w / g_ln_b = sum over the per-warp partials (fixed order: deterministic)
+// One warp per channel c, lane = centroid k (K == 32), partials added in fixed order (deterministic):
+//   gcenters[k,c] = sum_b P1[b][c][k] - gamma_c sum_b P2[b][c][k] + (cen[k,c] - beta_c) rcol_k
+//   g_beta[c]  = gamma_c sum_k P2[c,k] + beta_c sum_k rcol_k - sum_k rcol_k cen[k,c]
+//   g_gamma[c] = gamma_c Q[c] + beta_c sum_k P2[c,k] - sum_k cen[k,c] P2[c,k]
 __global__ void __launch_bounds__(256)
 cluster_bwd_tc_finalize_kernel(const float* __restrict__ part_p, const float* __restrict__ part_rcol,
-                               const float* __restrict__ part_ln, const float* __restrict__ centers,
+                               const float* __restrict__ part_q, const float* __restrict__ centers,
                                const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                int nb, int K, int C, float* __restrict__ gcenters,
                                float* __restrict__ gw, float* __restrict__ gb) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), k = threadIdx.x & 31;
+  if (c >= C) return;
   const int KC = K * C;
-  if (i < KC) {
-    const int c = i / K, k = i % K;
-    float s1 = 0.f, s2 = 0.f, rc = 0.f;
-    for (int b = 0; b < nb; ++b) {
-      s1 += part_p[((size_t)b * 2) * KC + i];
-      s2 += part_p[((size_t)b * 2 + 1) * KC + i];
-      rc += part_rcol[((size_t)b * 2) * K + k] + part_rcol[((size_t)b * 2 + 1) * K + k];
-    }
-    gcenters[(size_t)k * C + c] = s1 - ln_w[c] * s2 + (centers[(size_t)k * C + c] - ln_b[c]) * rc;
-  } else if (i < KC + 2 * C) {
-    const int c = i - KC;                                // [0, C): gamma, [C, 2C): beta
-    float s = 0.f;
-    for (int b = 0; b < 2 * nb; ++b) s += part_ln[(size_t)b * 2 * C + c];
-    if (c < C) gw[c] = s; else gb[c - C] = s;
+  float s1 = 0.f, s2 = 0.f, rc = 0.f, qv = 0.f;
+  for (int b = 0; b < nb; ++b) {
+    s1 += part_p[((size_t)b * 2) * KC + c * K + k];
+    s2 += part_p[((size_t)b * 2 + 1) * KC + c * K + k];
+    rc += part_rcol[((size_t)b * 2) * K + k] + part_rcol[((size_t)b * 2 + 1) * K + k];
+  }
+  for (int b = k; b < 2 * nb; b += 32) qv += part_q[(size_t)b * C + c];
+  const float g = ln_w[c], be = ln_b[c], cen = centers[(size_t)k * C + c];
+  gcenters[(size_t)k * C + c] = s1 - g * s2 + (cen - be) * rc;
+  const float sp2 = warp_sum(s2), scp = warp_sum(cen * s2), src = warp_sum(rc), scr = warp_sum(rc * cen);
+  qv = warp_sum(qv);
+  if (k == 0) {
+    gb[c] = g * sp2 + be * src - scr;
+    gw[c] = g * qv + be * sp2 - scp;
   }
 }
 
@@ -773,22 +849,40 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
   VADC_CHECK_LAUNCH("centroid_prep_bwd_kernel");
 
   const size_t smem = bt::plan(C).total + 1024;
+  unsigned long long* trace = nullptr;
+  const char* trace_path = getenv("VADC_BWD_TRACE");       // debugging only: synchronises and writes a text file
+  const size_t trace_bytes = (size_t)16 * 1024 * 2 * sizeof(unsigned long long);
+  if (trace_path) { VADC_CUDA(cudaMalloc(&trace, trace_bytes)); VADC_CUDA(cudaMemsetAsync(trace, 0, trace_bytes, st)); }
   bt::Params p{x, gR, D, A, mu, rstd, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_ln,
-               N, alpha, getenv("VADC_BWD_PF") ? atoi(getenv("VADC_BWD_PF")) : 1};
+               N, alpha, getenv("VADC_BWD_PF") ? atoi(getenv("VADC_BWD_PF")) : 1, trace};
   bool launched = false;
 #define BT_CASE(F4_)                                                                                   \
   if (C == 32 * F4_) {                                                                                 \
-    VADC_CUDA(cudaFuncSetAttribute(bt::cluster_bwd_tc_kernel<F4_>,                                      \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    bt::cluster_bwd_tc_kernel<F4_><<<grid, bt::kThreads, smem, st>>>(mGx, p);                           \
+    auto kern = trace ? bt::cluster_bwd_tc_kernel<F4_, true> : bt::cluster_bwd_tc_kernel<F4_, false>;    \
+    VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<grid, bt::kThreads, smem, st>>>(mGx, p);                                                    \
     launched = true;                                                                                   \
   }
   BT_CASE(2) BT_CASE(4) BT_CASE(6)
 #undef BT_CASE
   if (!launched) return VADC_ERR_UNSUPPORTED;
   VADC_CHECK_LAUNCH("cluster_bwd_tc_kernel");
-  const int tot = K * C + 2 * C;
-  bt::cluster_bwd_tc_finalize_kernel<<<(tot + 255) / 256, 256, 0, st>>>(part_p, part_rcol, part_ln, centers, ln_w,
+  if (trace) {
+    VADC_CUDA(cudaStreamSynchronize(st));
+    unsigned long long* h = (unsigned long long*)malloc(trace_bytes);
+    VADC_CUDA(cudaMemcpy(h, trace, trace_bytes, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int w = 0; w < 16; ++w)
+        for (int i = 0; i < 1024; ++i) {
+          const unsigned long long a = h[((size_t)w * 1024 + i) * 2], c = h[((size_t)w * 1024 + i) * 2 + 1];
+          if (c) fprintf(f, "%d %d %d %llu\n", w, (int)(a >> 32), (int)(a & 0xffffffffu), c);
+        }
+      fclose(f);
+    }
+    free(h);
+    cudaFree(trace);
+  }
+  bt::cluster_bwd_tc_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part_p, part_rcol, part_ln, centers, ln_w,
                                                                         ln_b, grid, K, C, gcenters, g_ln_w, g_ln_b);
   VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize_kernel");
   return VADC_OK;
