@@ -239,6 +239,9 @@ int vadc_memory_separateness(const float* keys, int m, int d, float* out,
  * pin the descriptor encodings the fused kernels rely on.
  * ------------------------------------------------------------------------ */
 int vadc_debug_umma(const float* A, const float* B, float* out, int N, int Kd, int mode, void* stream);
+/* issue-rate micro-benchmark of one tcgen05.mma shape (bf16, shared-memory operands): `reps` x 8
+ * instructions back to back; out[0] = cycles until the commit arrives, out[1] = cycles to issue. */
+int vadc_debug_umma_bench(int M, int N, int a_mn, int b_mn, int reps, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,34 +5,48 @@
 //   in ONE persistent warp-specialised kernel; per token it reads x, gR, D, A (+ mu, rstd) once and
 //   writes gx once: 12 C + 8 K bytes (fused-loss variant).  64-token tiles:
 //
-//   warps 2,3,6,7,10,11,14  PRODUCERS  x, gR rows -> xhat = (x - mu) rstd -> two-term bf16 splits of
-//                           xhat and gR into SWIZZLE_128B operand tiles + three row sums of xhat
-//   warp 15 (one thread)    MMA        S1  G1 = gR cen^T            [tokens x K]   (TMEM, double buffer)
-//                                      S5a P1 += gR^T A             [channels x K] (TMEM, whole kernel)
-//                                      S3  acc = r cen              [tokens x C]
-//                                      S5b P2 += xhat^T r           [channels x K] (TMEM, whole kernel)
-//   warps 0,1               E1         thread = token: softmin backward + cdist ratio -> r; the
-//                                      LayerNorm-backward row statistics in closed form; bf16 splits
-//                                      of A and r into the shared [A | r] operand tile
+//   warps 0,1,6,7,10,11,14  PRODUCERS  x, gR rows -> xhat = (x - mu) rstd -> two-term bf16 splits of
+//                           xhat and gR into SWIZZLE_128B operand tiles + three row sums of xhat;
+//                           4-row single-tensor units, loads software-pipelined one unit ahead;
+//                           also the bf16 split of the A rows into the [A_hi | A_lo] operand tile
+//   warp 15 (one thread)    MMA        S1  G1 = gR [cen_hi; cen_lo]^T        [tokens x 2K]  (TMEM, double buffer)
+//                                      S3  acc = r cen                       [tokens x C]
+//                                      S5a PT[0:64]   += [A_hi | A_lo]^T gR  [2K x C]  (TMEM, whole kernel)
+//                                      S5b PT[64:128] += [r_hi | r_lo]^T xhat
+//   warps 2,3               E1         thread = token: softmin backward + cdist ratio -> r; the
+//                                      LayerNorm-backward row statistics in closed form; bf16 split
+//                                      of r into the [r_hi | r_lo] operand tile.  S1's A descriptor
+//                                      starts 64 rows BEFORE the gR tile, so G1 lands in TMEM lanes
+//                                      64..127: E1 runs on the schedulers of warps 2,3 (mod 4) and
+//                                      leaves those of warps 0,1 to E3 (a warp reads lanes 32 (w%4)..)
 //   warps 4,5,8,9,12,13     E3         thread = token x 64 channels: gz = z rsum - acc, LayerNorm
 //                                      backward, gx through swizzled staging + TMA tensor stores,
 //                                      Q[c] = sum_n xhat^2 rsum (register butterfly) for g_gamma
 //
-// The token tile is the MMA's M (S1, S3: M = 128 with rows 64..127 reading past the tile — their
-// TMEM lanes are never read) and its K (S5: the same shared-memory bytes viewed MN-major, M =
-// channels).  All operands are exact two-term bf16 splits v = h + l (16 significant bits, full fp32
-// exponent range — gradients have no a-priori scale, which rules out fp16); a product keeps
-// h*h + h*l + l*h in the fp32 accumulator (~2^-16 relative per element; the fp32 reference's own
-// error against fp64 is larger, scripts/bwd_algebra_check.py).
+// A small-N tcgen05.mma costs ~80 cycles whatever N is (the 128 x 32 B A-operand fetch from shared
+// memory bounds it; measured with the event trace, VADC_BWD_TRACE), so the contractions are shaped
+// to need few, fat instructions: the two centroid terms are stacked along N for S1 (N = 64), and the
+// centroid-gradient GEMMs take the small [A | r] tiles as the M side (slots, MN-major) and the token
+// tiles as the N side (N = C) with the tokens as the contraction — 62 -> 46 instructions per tile
+// and 7.8k -> ~4k tensor cycles.  S5a / S5b share one accumulator: their A operands are
+// [tileA, ZERO] and [ZERO, tileR] (a constant zero block), so rows 0..63 collect A^T gR and rows
+// 64..127 collect r^T xhat.
+// The token tile is the MMA's M for S1 / S3 (M = 128 with rows 64..127 reading past the tile —
+// their TMEM lanes are never read).  All operands are exact two-term bf16 splits v = h + l (16
+// significant bits, full fp32 exponent range — gradients have no a-priori scale, which rules out
+// fp16; one kind::f16 instruction cannot mix an fp16 with a bf16 operand: it faults); products keep
+// h*h + h*l + l*h (+ l*l where it is free) in the fp32 accumulator (~2^-16 relative per element;
+// the fp32 reference's own error against fp64 is larger, scripts/bwd_algebra_check.py).
 //
 // LayerNorm backward needs the row means of gg = gz*gamma and gg*xhat BEFORE gz exists per thread.
 // They follow in closed form from quantities E1 already has (z = gamma xhat + beta):
 //   sum_c gg        = rsum * sum_c z gamma      - sum_k r_k (cen_k . gamma)
 //   sum_c gg xhat   = rsum * sum_c z gamma xhat - sum_k r_k T_k,  T_k = xhat . (gamma * cen_k)
 //   T_k = z.cen_k - beta.cen_k = (|z|^2 + |cen_k|^2 - D_k^2) / 2 - beta.cen_k      (D is an input)
-// so E3 is a single pass over the accumulator.  gcenters = P1^T - gamma * P2^T + (cen - beta) colsum(r),
-//   g_beta  = gamma * rowsum_k(P2) + beta * sum(rcol) - rcol . cen
-//   g_gamma = gamma * Q + beta * rowsum_k(P2) - sum_k cen[k,:] * P2[:,k]       (no column sums of gz).
+// so E3 is a single pass over the accumulator.  With P1 = A^T gR, P2 = r^T xhat, rcol = colsum(r):
+//   gcenters = P1 - gamma * P2 + (cen - beta) rcol
+//   g_beta  = gamma * sum_k P2[k,:] + beta * sum(rcol) - rcol . cen
+//   g_gamma = gamma * Q + beta * sum_k P2[k,:] - sum_k cen[k,:] * P2[k,:]       (no column sums of gz).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -51,25 +65,27 @@ constexpr int kTok = 64;                     // tokens per tile
 constexpr int kK = 32;                       // centroids
 constexpr int kThreads = 512;
 constexpr int kProd = 7;                     // producer warps
-constexpr int kUnits = kTok / 4;             // 4-row producer units per tile
+constexpr int kUnits = 2 * (kTok / 4) + 2;   // producer units per tile: 16 x 4 rows of x, 16 x 4 rows of gR, 2 x 32 rows of A
 constexpr int kMmaWarp = 15;
 constexpr uint32_t kBlk = kTok * 128u;       // one [64 rows x 128 B] operand block
 
 struct Plan {
-  uint32_t x_off, g_off, ar_off, cen_off, stg_off, prow_off, scal_off, gam_off, bet_off, g2_off, bg_off,
-      cvec_off, misc_off, total;
-  uint32_t xbuf, xterm, gterm, cterm;
+  uint32_t x_off, g_off, ta_off, zero_off, tr_off, cen_off, stg_off, prow_off, scal_off, gam_off, bet_off,
+      g2_off, bg_off, cvec_off, misc_off, total;
+  uint32_t xbuf, xterm, gterm;
 };
 
 __host__ __device__ inline Plan plan(int C) {
   Plan p;
   const uint32_t ncb = (uint32_t)C / 64u;
   uint32_t off = 0;
-  p.xterm = ncb * kBlk; p.xbuf = 2u * p.xterm; p.gterm = p.xterm; p.cterm = ncb * (kK * 128u);
+  p.xterm = ncb * kBlk; p.xbuf = 2u * p.xterm; p.gterm = p.xterm;
   p.x_off = off; off += 2u * p.xbuf;                       // [2 bufs][2 terms][C/64][64 x 128 B]
   p.g_off = off; off += 2u * p.gterm;                      // [2 terms][C/64][64 x 128 B]
-  p.ar_off = off; off += 2u * kBlk;                        // [2 terms][64 x 128 B]: bytes 0..63 A, 64..127 r
-  p.cen_off = off; off += 2u * p.cterm;                    // [2 terms][C/64][32 x 128 B]
+  p.ta_off = off; off += kBlk;                             // [64 tokens x 128 B]: A_hi (32 slots) | A_lo
+  p.zero_off = off; off += kBlk;                           // constant zeros (the other half of S5's M)
+  p.tr_off = off; off += kBlk;                             // [64 tokens x 128 B]: r_hi | r_lo
+  p.cen_off = off; off += ncb * kBlk;                      // [C/64][64 rows x 128 B]: rows 0..31 cen_hi, 32..63 cen_lo
   p.stg_off = off; off += 6u * 4096u;                      // per E3 warp: [32 rows x 128 B]
   p.prow_off = off; off += 2u * 3u * kTok * 4u;            // producer row sums [buf][zz, p1, p2][64]
   p.scal_off = off; off += 2u * 4u * kTok * 4u;            // E1 row scalars [parity][rsum, s1r, s2r, rs][64]
@@ -77,14 +93,14 @@ __host__ __device__ inline Plan plan(int C) {
   p.bet_off = off; off += (uint32_t)C * 4u;
   p.g2_off = off; off += (uint32_t)C * 4u;                 // gamma^2
   p.bg_off = off; off += (uint32_t)C * 4u;                 // beta gamma
-  p.cvec_off = off; off += 3u * kK * 4u;                   // hc = |c|^2/2 - beta.c ; cg = gamma.c
+  p.cvec_off = off; off += 3u * kK * 4u;                   // hc = |c|^2/2 - beta.c ; cg = gamma.c ; consts
   p.misc_off = off; off += 256u;
   p.total = off;
   return p;
 }
 
-enum { B_CEN = 0, B_PFULL, B_GEMPTY, B_XEMPTY0, B_XEMPTY1, B_G1FULL0, B_G1FULL1, B_G1EMPTY0, B_G1EMPTY1,
-       B_AFULL, B_RFULL, B_AREMPTY, B_ACCFULL, B_ACCEMPTY, B_DONE, B_COUNT };
+enum { B_CEN = 0, B_XFULL0, B_XFULL1, B_GFULL, B_GEMPTY, B_XEMPTY0, B_XEMPTY1, B_G1FULL0, B_G1FULL1, B_G1EMPTY0, B_G1EMPTY1,
+       B_AFULL, B_AEMPTY, B_RFULL, B_REMPTY, B_ACCFULL, B_ACCEMPTY, B_DONE, B_COUNT };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -125,16 +141,6 @@ __device__ __forceinline__ float lds32f_const(uint32_t addr) {
 __device__ __forceinline__ uint64_t desc_at(uint32_t lo, uint32_t hi, uint32_t byte_off) {
   return ((uint64_t)hi << 32) | (uint64_t)(lo + (byte_off >> 4));
 }
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
-  if (accumulate)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
-  else
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
-}
 __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -159,7 +165,7 @@ __device__ __forceinline__ float4 ldg_nc(const float4* p) {
 }
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
-  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU (the non-ftz form expands into a subnormal-safe branch)
   return r;
 }
 
@@ -206,8 +212,9 @@ __device__ __forceinline__ void butterfly_tail(float (&v)[N], int lane) {
 }
 
 // ---------------------------------------------------------------------------
-// prologue: two-term bf16 centroid image ([term][C/64][32 rows x 128 B], SWIZZLE_128B) and the
-// per-centroid constants  hc_k = |c_k|^2 / 2 - beta.c_k,  cg_k = gamma.c_k
+// prologue: two-term bf16 centroid image ([C/64][64 rows x 128 B], SWIZZLE_128B: rows 0..31 the
+// high terms, rows 32..63 the low terms) and the per-centroid constants
+// hc_k = |c_k|^2 / 2 - beta.c_k,  cg_k = gamma.c_k
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 centroid_prep_bwd_kernel(const float* __restrict__ centers, const float* __restrict__ ln_w,
@@ -216,15 +223,14 @@ centroid_prep_bwd_kernel(const float* __restrict__ centers, const float* __restr
   const int k = blockIdx.x;
   __shared__ float red[32];
   float s = 0.f, sb = 0.f, sg = 0.f;
-  const uint32_t term = (uint32_t)K * C * 2u;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float v = centers[(size_t)k * C + c];
     s += v * v; sb += v * ln_b[c]; sg += v * ln_w[c];
     const __nv_bfloat16 h1 = __float2bfloat16_rn(v);
     const __nv_bfloat16 h2 = __float2bfloat16_rn(v - __bfloat162float(h1));
-    const uint32_t off = (uint32_t)(c / 64) * (K * 128u) + sw128(k, (c % 64) * 2);
-    *reinterpret_cast<__nv_bfloat16*>(image + off) = h1;
-    *reinterpret_cast<__nv_bfloat16*>(image + term + off) = h2;
+    const uint32_t blk = (uint32_t)(c / 64) * kBlk;
+    *reinterpret_cast<__nv_bfloat16*>(image + blk + sw128(k, (c % 64) * 2)) = h1;
+    *reinterpret_cast<__nv_bfloat16*>(image + blk + sw128(K + k, (c % 64) * 2)) = h2;
   }
   s = block_sum<float>(s, red);
   sb = block_sum<float>(sb, red);
@@ -235,7 +241,7 @@ centroid_prep_bwd_kernel(const float* __restrict__ centers, const float* __restr
 struct Params {
   const float* x; const float* gR; const float* D; const float* A; const float* mu; const float* rstd;
   const float* ln_w; const float* ln_b; const uint8_t* cimage; const float* cvec; const float* g_loss_sq;
-  float* part_p; float* part_rcol; float* part_ln;       // [grid][2][C][32], [grid][2][32], Q: [grid][2][C]
+  float* part_p; float* part_rcol; float* part_q;        // [grid][128 slots][C], [grid][2][32], [grid][2][C]
   long long N; float alpha; int pf;
   unsigned long long* trace;                             // debugging: per-warp event log of CTA 0 (VADC_BWD_TRACE)
 };
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int C = F4 * 32, K = kK, NCB = C / 64, MB = (C + 127) / 128;
+  constexpr int C = F4 * 32, K = kK, NCB = C / 64;
   const Plan pl = plan(C);
   float* sProw = reinterpret_cast<float*>(smem + pl.prow_off);
   float* sScal = reinterpret_cast<float*>(smem + pl.scal_off);
@@ -273,20 +279,20 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   };
   const long long ntiles = (p.N + kTok - 1) / kTok;
   const int nmine = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA (>= 1)
-  constexpr uint32_t kColG1 = 0, kColAcc = 64, kColP1 = 64 + C, kColP2 = kColP1 + 32 * MB;
-  constexpr uint32_t ncols = (kColP2 + 32 * MB <= 256) ? 256u : 512u;
+  constexpr uint32_t kColG1 = 0, kColAcc = 128, kColPT = 128 + C;   // G1: two buffers of 64 columns
+  constexpr uint32_t ncols = (kColPT + C <= 256) ? 256u : 512u;
   constexpr int kE3Warps = 2 * NCB;
 
   if (tid == 0) {
     mbar_init(&bars[B_CEN], 1);
-    mbar_init(&bars[B_PFULL], kUnits);
+    mbar_init(&bars[B_XFULL0], 16); mbar_init(&bars[B_XFULL1], 16);
+    mbar_init(&bars[B_GFULL], 16);
     mbar_init(&bars[B_GEMPTY], 1);
     mbar_init(&bars[B_XEMPTY0], kE3Warps + 1); mbar_init(&bars[B_XEMPTY1], kE3Warps + 1);
     mbar_init(&bars[B_G1FULL0], 1); mbar_init(&bars[B_G1FULL1], 1);
     mbar_init(&bars[B_G1EMPTY0], 2); mbar_init(&bars[B_G1EMPTY1], 2);
-    mbar_init(&bars[B_AFULL], 1);
-    mbar_init(&bars[B_RFULL], 1);
-    mbar_init(&bars[B_AREMPTY], 1);
+    mbar_init(&bars[B_AFULL], 2); mbar_init(&bars[B_AEMPTY], 1);
+    mbar_init(&bars[B_RFULL], 1); mbar_init(&bars[B_REMPTY], 1);
     mbar_init(&bars[B_ACCFULL], 1);
     mbar_init(&bars[B_ACCEMPTY], kE3Warps);
     mbar_init(&bars[B_DONE], 1);
@@ -299,64 +305,99 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     sGam[c] = g; sBet[c] = b; sG2[c] = g * g; sBG[c] = b * g;
   }
   for (int k = tid; k < 2 * K; k += kThreads) sHc[k] = p.cvec[k];
+  for (uint32_t i = tid; i < kBlk / 16u; i += kThreads)
+    *reinterpret_cast<uint4*>(smem + pl.zero_off + i * 16u) = make_uint4(0, 0, 0, 0);
   if (warp == 0) {
     float a = 0.f, b = 0.f;
     for (int c = lane; c < C; c += 32) { const float g = p.ln_w[c], be = p.ln_b[c]; a += be * g; b += be * be; }
     a = warp_sum(a); b = warp_sum(b);
     if (lane == 0) { sConst[0] = a; sConst[1] = b; }
   }
+  fence_async_smem();                                    // the zero block is an MMA operand
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t sX32 = smem_u32(smem + pl.x_off), sG32 = smem_u32(smem + pl.g_off);
-  const uint32_t sAR32 = smem_u32(smem + pl.ar_off), sCen32 = smem_u32(smem + pl.cen_off);
+  const uint32_t sTA32 = smem_u32(smem + pl.ta_off), sTR32 = smem_u32(smem + pl.tr_off);
+  const uint32_t sCen32 = smem_u32(smem + pl.cen_off);
 
-  const bool is_e = (warp & 3) < 2;
-  if (!is_e && warp != kMmaWarp) {
+  const bool is_e1 = warp == 2 || warp == 3;
+  const bool is_e3 = (warp & 3) < 2 && warp >= 4;
+  if (!is_e1 && !is_e3 && warp != kMmaWarp) {
     // ======================================================================= PRODUCERS
     // 8 lanes per token row (lane j owns float4 chunks j, j+8, ...), 4 rows per warp instruction = one
-    // unit; the two rows sharing a 16-lane store phase differ by 4 (disjoint banks after the 128B
-    // swizzle): unit u of a tile covers rows 8 (u/2) + 2 (u%2) + {0, 4, 1, 5}.
-    const int pw = (warp >> 2) * 2 + (warp & 1);         // 0..6
+    // unit of ONE tensor; the two rows sharing a 16-lane store phase differ by 4 (disjoint banks after
+    // the 128B swizzle): unit v (0..15) of a tile covers rows 8 (v/2) + 2 (v%2) + {0, 4, 1, 5}.
+    // Units 0..15 of a tile are xhat, 16..31 are gR; the loads of a warp's next unit are in flight
+    // while it converts the current one.
+    const int pw = warp < 2 ? warp : (warp >> 2) * 2 + (warp & 1);   // warps 0,1,6,7,10,11,14 -> 0..6
     const int lj = lane & 7, lg = lane >> 3;
     const int rsel = (lg & 1) * 4 + (lg >> 1);
     const int nunits = kUnits * nmine;
     const float cB1 = sConst[0], cB2 = sConst[1];
     const uint32_t sG2a = smem_u32(sG2) + lj * 16, sBGa = smem_u32(sBG) + lj * 16;
-    for (int g = pw; g < nunits; g += kProd) {
-      const int it = g / kUnits, u = g % kUnits;
+    struct Unit { union { float4 v[F4]; float4 a[8]; }; float rs, nmr; };   // a[]: the 8 float4 of an A unit
+    auto issue = [&](Unit& U, int g) {
+      if (g >= nunits) return;
+      const int it = g / kUnits, u = g % kUnits, v = u & 15;
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
-      const long long row0 = tile * kTok;
-      if (p.pf > 0 && lane == 0 && (u & 1) == 0 && it + p.pf < nmine) {   // L2 prefetch: same 8-row group, pf tiles ahead
-        const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (u >> 1) * 8;
-        const long long rows = min(8ll, p.N - rn);
-        if (rows > 0) {
-          prefetch_l2_bulk(p.x + rn * C, (uint32_t)(rows * C * 4));
-          prefetch_l2_bulk(p.gR + rn * C, (uint32_t)(rows * C * 4));
+      if (u >= 32) {                                     // A rows: 32 rows x 32 centroids, lane = (row, float4)
+        const long long rb = tile * kTok + (u - 32) * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const long long row = rb + (j >> 1) * 8 + (j & 1) * 2 + rsel;
+          U.a[j] = row < p.N ? ldg_nc(reinterpret_cast<const float4*>(p.A + row * K) + lj) : make_float4(0, 0, 0, 0);
         }
+        return;
       }
-      const int r = (u >> 1) * 8 + (u & 1) * 2 + rsel;
-      const long long row = row0 + r;
+      const bool isx = u < 16;
+      const float* src = isx ? p.x : p.gR;
+      if (p.pf > 0 && lane == 0 && (v & 1) == 0 && it + p.pf < nmine) {   // L2 prefetch: same 8-row group, pf tiles ahead
+        const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
+        const long long rows = min(8ll, p.N - rn);
+        if (rows > 0) prefetch_l2_bulk(src + rn * C, (uint32_t)(rows * C * 4));
+      }
+      const int r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
+      const long long row = tile * kTok + r;
       const bool live = row < p.N;
-      float4 xv[F4], gv[F4];
-      {
-        const float4* xr = reinterpret_cast<const float4*>(p.x + row * C) + lj;
-        const float4* gr = reinterpret_cast<const float4*>(p.gR + row * C) + lj;
+      const float4* sr = reinterpret_cast<const float4*>(src + row * C) + lj;
 #pragma unroll
-        for (int i = 0; i < F4; ++i) xv[i] = live ? ld_stream(xr + 8 * i) : make_float4(0, 0, 0, 0);
+      for (int i = 0; i < F4; ++i) U.v[i] = live ? ld_stream(sr + 8 * i) : make_float4(0, 0, 0, 0);
+      U.rs = (isx && live) ? __ldg(p.rstd + row) : 0.f;
+      U.nmr = (isx && live) ? -__ldg(p.mu + row) * U.rs : 0.f;
+    };
+    auto process = [&](Unit& U, int g) {
+      if (g >= nunits) return;
+      const int it = g / kUnits, u = g % kUnits, v = u & 15;
+      if (u >= 32) {
+        // tile A is free once S5a of the previous tile has completed
+        mbar_wait_spin(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));
 #pragma unroll
-        for (int i = 0; i < F4; ++i) gv[i] = live ? ld_stream(gr + 8 * i) : make_float4(0, 0, 0, 0);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t r = (uint32_t)((u - 32) * 32 + (j >> 1) * 8 + (j & 1) * 2 + rsel);
+          uint32_t a1, a2, b1, b2;
+          split2_bf(U.a[j].x, U.a[j].y, a1, a2);
+          split2_bf(U.a[j].z, U.a[j].w, b1, b2);
+          sts64(sTA32 + sw128(r, (uint32_t)lj * 8u), a1, b1);            // A_hi: slots 4 lj .. 4 lj + 3
+          sts64(sTA32 + sw128(r, 64u + (uint32_t)lj * 8u), a2, b2);      // A_lo
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_AFULL]);
+        return;
       }
-      const float rs = live ? __ldg(p.rstd + row) : 0.f;
-      const float nmr = live ? -__ldg(p.mu + row) * rs : 0.f;
-      TR(0, it);
+      const bool isx = u < 16;
       const int buf = it & 1;
+      const int r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
       const uint32_t rx = (uint32_t)(r & 7);
       const uint32_t rowoff = (uint32_t)r * 128u;
-      // ---- xhat: X[buf] is free once S5b and E3 of tile it-2 have finished
-      mbar_wait_spin(&bars[B_XEMPTY0 + buf], (uint32_t)(((it >> 1) & 1) ^ 1));
-      {
+      TR(0, it);
+      if (isx) {
+        // X[buf] is free once S5b and E3 of tile it-2 have finished
+        mbar_wait_spin(&bars[B_XEMPTY0 + buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + r;
+        const bool live = row < p.N;
         const uint32_t xb = sX32 + buf * pl.xbuf;
         float q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
@@ -365,8 +406,8 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
           const uint32_t byte = (uint32_t)(f & 15) * 8u;     // 8 bytes of bf16 in the 128-byte row of block f/16
           const uint32_t off = (uint32_t)(f >> 4) * kBlk + rowoff + ((((byte >> 4) ^ rx) << 4) | (byte & 15u));
           float4 h;
-          h.x = fmaf(xv[i].x, rs, nmr); h.y = fmaf(xv[i].y, rs, nmr);
-          h.z = fmaf(xv[i].z, rs, nmr); h.w = fmaf(xv[i].w, rs, nmr);
+          h.x = fmaf(U.v[i].x, U.rs, U.nmr); h.y = fmaf(U.v[i].y, U.rs, U.nmr);
+          h.z = fmaf(U.v[i].z, U.rs, U.nmr); h.w = fmaf(U.v[i].w, U.rs, U.nmr);
           const float4 g2 = lds128f_const(sG2a + i * 128);
           const float4 bg = lds128f_const(sBGa + i * 128);
           float w;
@@ -392,29 +433,39 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
           prow[kTok + r] = live ? q1 + cB1 : 0.f;            // sum z gamma
           prow[2 * kTok + r] = live ? q2 + q3 : 0.f;         // sum z gamma xhat
         }
-      }
-      // ---- gR: G is free once S1 / S5a of the previous tile have completed
-      mbar_wait_spin(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));
-      TR(1, it);
+      } else {
+        // G is free once S1 / S5a of the previous tile have completed
+        mbar_wait_spin(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));
 #pragma unroll
-      for (int i = 0; i < F4; ++i) {
-        const int f = lj + 8 * i;
-        const uint32_t byte = (uint32_t)(f & 15) * 8u;
-        const uint32_t off = (uint32_t)(f >> 4) * kBlk + rowoff + ((((byte >> 4) ^ rx) << 4) | (byte & 15u));
-        uint32_t a1, a2, b1, b2;
-        split2_bf(gv[i].x, gv[i].y, a1, a2);
-        split2_bf(gv[i].z, gv[i].w, b1, b2);
-        sts64(sG32 + off, a1, b1);
-        sts64(sG32 + pl.gterm + off, a2, b2);
+        for (int i = 0; i < F4; ++i) {
+          const int f = lj + 8 * i;
+          const uint32_t byte = (uint32_t)(f & 15) * 8u;
+          const uint32_t off = (uint32_t)(f >> 4) * kBlk + rowoff + ((((byte >> 4) ^ rx) << 4) | (byte & 15u));
+          uint32_t a1, a2, b1, b2;
+          split2_bf(U.v[i].x, U.v[i].y, a1, a2);
+          split2_bf(U.v[i].z, U.v[i].w, b1, b2);
+          sts64(sG32 + off, a1, b1);
+          sts64(sG32 + pl.gterm + off, a2, b2);
+        }
       }
+      TR(1, it);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_PFULL]);
+      // (one full-barrier per X buffer: an xhat unit of tile it+2 can never arrive into tile it's phase)
+      if (lane == 0) mbar_arrive(isx ? &bars[B_XFULL0 + buf] : &bars[B_GFULL]);
       TR(2, it);
+    };
+    Unit UA, UB;
+    issue(UA, pw);
+    for (int g = pw; g < nunits; g += 2 * kProd) {
+      issue(UB, g + kProd);
+      process(UA, g);
+      issue(UA, g + 2 * kProd);
+      process(UB, g + kProd);
     }
-  } else if (warp < 2) {
+  } else if (is_e1) {
     // ======================================================================= E1
-    const int et = tid;                                  // 0..63 = token row = TMEM lane
+    const int et = tid - 64;                             // 0..63 = token row; its G1 row sits in TMEM lane 64 + et
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const float sc = p.g_loss_sq ? 2.0f * __ldg(p.g_loss_sq) : 0.f;
     const float invC = 1.0f / (float)C;
@@ -455,26 +506,10 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       const float rs = rs_next;
       TR(10, it);
       prefetch_da(it + 2);
-      // [A | r] tile free: S3 / S5 of the previous tile have completed
-      mbar_wait(&bars[B_AREMPTY], (uint32_t)((it & 1) ^ 1));
-      TR(11, it);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t w1[4], w2[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split2_bf(av[8 * j + 2 * e], av[8 * j + 2 * e + 1], w1[e], w2[e]);
-        const uint32_t off = sw128((uint32_t)et, (uint32_t)j * 16u);
-        sts128(sAR32 + off, w1[0], w1[1], w1[2], w1[3]);
-        sts128(sAR32 + kBlk + off, w2[0], w2[1], w2[2], w2[3]);
-      }
-      fence_async_smem();
-      named_bar(1, 64);
-      if (et == 0) mbar_arrive(&bars[B_AFULL]);
-      TR(12, it);
       // producer row sums of this tile
-      mbar_wait(&bars[B_PFULL], (uint32_t)(it & 1));
-      TR(13, it);
       const int buf = it & 1;
+      mbar_wait(&bars[B_XFULL0 + buf], (uint32_t)((it >> 1) & 1));
+      TR(13, it);
       const float zz = sProw[buf * 3 * kTok + et];
       const float p1 = sProw[buf * 3 * kTok + kTok + et];
       const float p2 = sProw[buf * 3 * kTok + 2 * kTok + et];
@@ -482,10 +517,18 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       TR(14, it);
       tc_fence_after();
       float gv[32];
-      tmem_ld32(tmem + lane_addr + kColG1 + (uint32_t)(buf * 32), gv);
+      tmem_ld32(tmem + lane_addr + kColG1 + (uint32_t)(buf * 64), gv);           // gR . cen_hi (+ gR_lo . cen_hi)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                                               // + gR_hi . cen_lo
+        float g2[16];
+        tmem_ld16(tmem + lane_addr + kColG1 + (uint32_t)(buf * 64 + 32 + 16 * h), g2);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) gv[16 * h + k] += g2[k];
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_G1EMPTY0 + buf]);
+      TR(40, it);
       // softmin backward + cdist ratio
       float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll
@@ -501,7 +544,8 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         const float gd = av[k] * fmaf(sc * dv[k], av[k], -p.alpha * (gv[k] - dot));
-        const float r = (dv[k] == 0.f || !live) ? 0.f : gd * fast_rcp(dv[k]);
+        float r = gd * fast_rcp(dv[k]);                  // ATen cdist backward: grad / dist, 0 where dist == 0
+        r = (dv[k] == 0.f || !live) ? 0.f : r;
         gv[k] = r;
         const float T = fmaf(-0.5f * dv[k], dv[k], hz + lds32f_const(sHc32 + 4 * k));
         if (k & 1) { rsum1 += r; sT1 = fmaf(r, T, sT1); sG1 = fmaf(r, lds32f_const(sCg32 + 4 * k), sG1); }
@@ -509,30 +553,35 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       }
       const float rsum = rsum0 + rsum1, sT = sT0 + sT1, sG = sG0 + sG1;
       const float s1 = (rsum * p1 - sG) * invC, s2 = (rsum * p2 - sT) * invC;
+      TR(41, it);
+      // tile R free: S3 / S5b of the previous tile have completed
+      mbar_wait(&bars[B_REMPTY], (uint32_t)((it & 1) ^ 1));
+      TR(42, it);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t w1[4], w2[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) split2_bf(gv[8 * j + 2 * e], gv[8 * j + 2 * e + 1], w1[e], w2[e]);
-        const uint32_t off = sw128((uint32_t)et, 64u + (uint32_t)j * 16u);
-        sts128(sAR32 + off, w1[0], w1[1], w1[2], w1[3]);
-        sts128(sAR32 + kBlk + off, w2[0], w2[1], w2[2], w2[3]);
+        sts128(sTR32 + sw128((uint32_t)et, (uint32_t)j * 16u), w1[0], w1[1], w1[2], w1[3]);
+        sts128(sTR32 + sw128((uint32_t)et, 64u + (uint32_t)j * 16u), w2[0], w2[1], w2[2], w2[3]);
       }
       float* scal = sScal + (it & 1) * 4 * kTok;
       scal[et] = rsum; scal[kTok + et] = s1 * rs; scal[2 * kTok + et] = s2 * rs; scal[3 * kTok + et] = rs;
+      TR(43, it);
       fence_async_smem();
+      TR(44, it);
       named_bar(1, 64);
       if (et == 0) mbar_arrive(&bars[B_RFULL]);
       TR(15, it);
       // next tile's D / A rows: issued after the fence / barrier above (which would wait for them),
-      // their latency is covered by the butterfly and the wait for the [A | r] tile
+      // their latency is covered by the butterfly and the wait for tile A
       load_da(it + 1);
       butterfly<1>(gv, lane);                            // lane l: sum over this warp's 32 rows of r[:, l]
       rcol_acc += gv[0];
       TR(16, it);
     }
-    p.part_rcol[((size_t)blockIdx.x * 2 + warp) * K + lane] = rcol_acc;
-  } else if (is_e) {
+    p.part_rcol[((size_t)blockIdx.x * 2 + (warp - 2)) * K + lane] = rcol_acc;
+  } else if (is_e3) {
     // ======================================================================= E3
     const int e3 = (warp >> 2) - 1;                      // 64-channel group
     const int q = warp & 1;                              // token half
@@ -617,121 +666,123 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         butterfly_tail<4, 8>(accq[ch], lane);
-        p.part_ln[((size_t)blockIdx.x * 2 + q) * C + e3 * 64 + ch * 32 + lane] = accq[ch][0];
+        p.part_q[((size_t)blockIdx.x * 2 + q) * C + e3 * 64 + ch * 32 + lane] = accq[ch][0];
       }
     }
   } else if (lane == 0) {
     // ======================================================================= MMA (warp 15, one thread)
-    mbar_expect_tx(&bars[B_CEN], 2u * pl.cterm);
-    for (uint32_t off = 0; off < 2u * pl.cterm; off += 16384u)
-      bulk_g2s(smem + pl.cen_off + off, p.cimage + off, min(16384u, 2u * pl.cterm - off), &bars[B_CEN]);
-    const uint32_t idesc1 = instr_desc(kFmtBF16, 128, K, 0, 0);      // S1: tokens x K, both K-major
-    const uint32_t idesc3 = instr_desc(kFmtBF16, 128, C, 0, 1);      // S3: tokens x C, cen MN-major
-    const uint32_t idesc5 = instr_desc(kFmtBF16, 128, K, 1, 1);      // S5: channels x K, both MN-major
-    constexpr int pi[3] = {0, 1, 0}, pj[3] = {1, 0, 0};              // small terms first
-    // descriptor bases: hi word is constant per layout, lo word = (address >> 4) | LBO field
-    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
-    const uint32_t loG_k = (sG32 >> 4) & 0x3FFFu, loG_mn = loG_k | ((kBlk >> 4) << 16);
-    const uint32_t loAR_k = (sAR32 >> 4) & 0x3FFFu, loAR_mn = loAR_k | ((kBlk >> 4) << 16);
-    const uint32_t loC_k = (sCen32 >> 4) & 0x3FFFu, loC_mn = loC_k | (((uint32_t)K * 128u >> 4) << 16);
-    const uint32_t loX_mn0 = ((sX32 >> 4) & 0x3FFFu) | ((kBlk >> 4) << 16);
+    mbar_expect_tx(&bars[B_CEN], NCB * kBlk);
+    for (uint32_t off = 0; off < NCB * kBlk; off += 8192u)
+      bulk_g2s(smem + pl.cen_off + off, p.cimage + off, 8192u, &bars[B_CEN]);
+    const uint32_t idesc1a = instr_desc(kFmtBF16, 128, 2 * K, 0, 0);  // S1: tokens x [cen_hi; cen_lo], both K-major
+    const uint32_t idesc1b = instr_desc(kFmtBF16, 128, K, 0, 0);      //     gR_lo x cen_hi
+    const uint32_t idesc3 = instr_desc(kFmtBF16, 128, C, 0, 1);       // S3: tokens x C, cen MN-major
+    const uint32_t idesc5 = instr_desc(kFmtBF16, 128, C, 1, 1);       // S5: slots x C, both MN-major, K = tokens
+    // descriptor bases: hi word is constant (SBO 1024, version 1, SWIZZLE_128B); lo = (address >> 4) | LBO field
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t kLbo = (kBlk >> 4) << 16;                      // 8 KB between the 64-wide blocks of an MN-major operand
+    const uint32_t loG_k = (sG32 >> 4) & 0x3FFFu, loG_mn = loG_k | kLbo;
+    const uint32_t loG_k64 = loG_k - (kBlk >> 4);                    // S1: MMA rows 64..127 = the tile's rows 0..63
+    const uint32_t loX_mn0 = ((sX32 >> 4) & 0x3FFFu) | kLbo;
+    const uint32_t loTA_mn = ((sTA32 >> 4) & 0x3FFFu) | kLbo;         // blocks: tile A, ZERO
+    const uint32_t loZR_mn = loTA_mn + (kBlk >> 4);                   // blocks: ZERO, tile R
+    const uint32_t loTR_k = (sTR32 >> 4) & 0x3FFFu;
+    const uint32_t loC_k = (sCen32 >> 4) & 0x3FFFu, loC_mn = loC_k | kLbo;
     mbar_wait(&bars[B_CEN], 0);
-    int n1 = 0, n5 = 0, n3 = 0;
-    while (n3 < nmine) {
-      if (n1 < nmine && mbar_try_wait(&bars[B_PFULL], (uint32_t)(n1 & 1)) &&
-          mbar_try_wait(&bars[B_G1EMPTY0 + (n1 & 1)], (uint32_t)(((n1 >> 1) & 1) ^ 1))) {
+    int n1 = 0, n5a = 0, n3 = 0, n5b = 0;
+    while (n5b < nmine) {
+      // ---- S3 (feeds E3): acc = r_lo cen_hi + r_hi cen_lo + r_hi cen_hi
+      if (n3 < n1 && mbar_try_wait(&bars[B_RFULL], (uint32_t)(n3 & 1)) &&
+          mbar_try_wait(&bars[B_ACCEMPTY], (uint32_t)((n3 & 1) ^ 1))) {
         tc_fence_after();
-        const uint32_t d = tmem + kColG1 + (uint32_t)((n1 & 1) * 32);
+        const uint32_t d = tmem + kColAcc;
+        constexpr uint32_t ro[3] = {64u, 0u, 0u}, co[3] = {0u, 4096u, 0u};
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
 #pragma unroll
-          for (int kk = 0; kk < C / 16; ++kk) {
-            const uint64_t ad = desc_at(loG_k, kHi, pi[t] * pl.gterm + (kk >> 2) * kBlk + (kk & 3) * 32u);
-            const uint64_t bd = desc_at(loC_k, kHi, pj[t] * pl.cterm + (kk >> 2) * (K * 128u) + (kk & 3) * 32u);
-            mma_bf16(d, ad, bd, idesc1, t > 0 || kk > 0);
+          for (int ks = 0; ks < K / 16; ++ks) {
+            const uint64_t ad = desc_at(loTR_k, kHi, ro[t] + (uint32_t)ks * 32u);
+            const uint64_t bd = desc_at(loC_mn, kHi, co[t] + (uint32_t)(2 * ks) * 1024u);
+            mma_f16(d, ad, bd, idesc3, (t > 0 || ks > 0) ? 1u : 0u);
           }
+        }
+        mma_commit(&bars[B_ACCFULL]);
+        TR(32, n3);
+        ++n3;
+      }
+      // ---- S1 (feeds E1): G1[:, 0:32] = gR_hi cen_hi + gR_lo cen_hi, G1[:, 32:64] = gR_hi cen_lo
+      if (n1 < nmine && mbar_try_wait(&bars[B_GFULL], (uint32_t)(n1 & 1)) &&
+          mbar_try_wait(&bars[B_G1EMPTY0 + (n1 & 1)], (uint32_t)(((n1 >> 1) & 1) ^ 1))) {
+        tc_fence_after();
+        const uint32_t d = tmem + kColG1 + (uint32_t)((n1 & 1) * 64);
+#pragma unroll
+        for (int kk = 0; kk < C / 16; ++kk) {
+          const uint64_t ad = desc_at(loG_k64, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
+          const uint64_t bd = desc_at(loC_k, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
+          mma_f16(d, ad, bd, idesc1a, kk > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < C / 16; ++kk) {
+          const uint64_t ad = desc_at(loG_k64, kHi, pl.gterm + (kk >> 2) * kBlk + (kk & 3) * 32u);
+          const uint64_t bd = desc_at(loC_k, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
+          mma_f16(d, ad, bd, idesc1b, 1u);
         }
         mma_commit(&bars[B_G1FULL0 + (n1 & 1)]);
         TR(30, n1);
         ++n1;
       }
-      if (n5 < n1 && mbar_try_wait(&bars[B_AFULL], (uint32_t)(n5 & 1))) {
+      // ---- S5b (background): PT[64:128] += [r_hi | r_lo]^T (xhat_hi + xhat_lo)
+      if (n5b < n3 && n5b < n5a && mbar_try_wait(&bars[B_XFULL0 + (n5b & 1)], (uint32_t)((n5b >> 1) & 1))) {
+        tc_fence_after();
+        const uint32_t loX_mn = loX_mn0 + (uint32_t)(n5b & 1) * (pl.xbuf >> 4);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int ks = 0; ks < kTok / 16; ++ks) {
+            const uint64_t ad = desc_at(loZR_mn, kHi, (uint32_t)ks * 2048u);
+            const uint64_t bd = desc_at(loX_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
+            mma_f16(tmem + kColPT, ad, bd, idesc5, 1u);
+          }
+        }
+        mma_commit(&bars[B_XEMPTY0 + (n5b & 1)]);
+        mma_commit(&bars[B_REMPTY]);
+        TR(33, n5b);
+        ++n5b;
+      }
+      // ---- S5a (background): PT[0:64] += [A_hi | A_lo]^T (gR_hi + gR_lo)
+      if (n5a < n1 && mbar_try_wait(&bars[B_AFULL], (uint32_t)(n5a & 1))) {
         tc_fence_after();
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-          const uint32_t d = tmem + kColP1 + (uint32_t)(mb * 32);
+        for (int t = 0; t < 2; ++t) {
 #pragma unroll
-          for (int t = 0; t < 3; ++t) {
-#pragma unroll
-            for (int ks = 0; ks < kTok / 16; ++ks) {
-              const uint64_t ad = desc_at(loG_mn, kHi, pi[t] * pl.gterm + (uint32_t)mb * 2u * kBlk + (uint32_t)ks * 2048u);
-              const uint64_t bd = desc_at(loAR_mn, kHi, pj[t] * kBlk + (uint32_t)ks * 2048u);
-              mma_f16(d, ad, bd, idesc5, (t > 0 || ks > 0 || n5 > 0) ? 1u : 0u);
-            }
+          for (int ks = 0; ks < kTok / 16; ++ks) {
+            const uint64_t ad = desc_at(loTA_mn, kHi, (uint32_t)ks * 2048u);
+            const uint64_t bd = desc_at(loG_mn, kHi, (uint32_t)t * pl.gterm + (uint32_t)ks * 2048u);
+            mma_f16(tmem + kColPT, ad, bd, idesc5, (n5a > 0 || t > 0 || ks > 0) ? 1u : 0u);
           }
         }
         mma_commit(&bars[B_GEMPTY]);
-        TR(31, n5);
-        ++n5;
-      }
-      if (n3 < n5 && mbar_try_wait(&bars[B_RFULL], (uint32_t)(n3 & 1)) &&
-          mbar_try_wait(&bars[B_ACCEMPTY], (uint32_t)((n3 & 1) ^ 1))) {
-        tc_fence_after();
-        {
-          const uint32_t d = tmem + kColAcc;
-#pragma unroll
-          for (int t = 0; t < 3; ++t) {
-#pragma unroll
-            for (int ks = 0; ks < K / 16; ++ks) {
-              const uint64_t ad = desc_at(loAR_k, kHi, pi[t] * kBlk + 64u + (uint32_t)ks * 32u);
-              const uint64_t bd = desc_at(loC_mn, kHi, pj[t] * pl.cterm + (uint32_t)(2 * ks) * 1024u);
-              mma_bf16(d, ad, bd, idesc3, t > 0 || ks > 0);
-            }
-          }
-          mma_commit(&bars[B_ACCFULL]);
-        }
-        const uint32_t loX_mn = loX_mn0 + (uint32_t)(n3 & 1) * (pl.xbuf >> 4);
-#pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-          const uint32_t d = tmem + kColP2 + (uint32_t)(mb * 32);
-#pragma unroll
-          for (int t = 0; t < 3; ++t) {
-#pragma unroll
-            for (int ks = 0; ks < kTok / 16; ++ks) {
-              const uint64_t ad = desc_at(loX_mn, kHi, pi[t] * pl.xterm + (uint32_t)mb * 2u * kBlk + (uint32_t)ks * 2048u);
-              const uint64_t bd = desc_at(loAR_mn, kHi, pj[t] * kBlk + 64u + (uint32_t)ks * 2048u);
-              mma_f16(d, ad, bd, idesc5, (t > 0 || ks > 0 || n3 > 0) ? 1u : 0u);
-            }
-          }
-        }
-        mma_commit(&bars[B_XEMPTY0 + (n3 & 1)]);
-        mma_commit(&bars[B_AREMPTY]);
-        TR(32, n3);
-        ++n3;
+        mma_commit(&bars[B_AEMPTY]);
+        TR(31, n5a);
+        ++n5a;
       }
     }
     mma_commit(&bars[B_DONE]);
     mbar_wait(&bars[B_DONE], 0);
   }
-  // ---- drain the whole-kernel accumulators: lane = channel, 32 columns = centroids
+  // ---- drain the whole-kernel accumulator: lane = slot (A_hi, A_lo, r_hi, r_lo x 32 centroids), columns = channels
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp < 4) {
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-#pragma unroll
-    for (int mb = 0; mb < MB; ++mb) {
-      const int c = mb * 128 + warp * 32 + lane;
+    float4* o = reinterpret_cast<float4*>(p.part_p + ((size_t)blockIdx.x * 128 + warp * 32 + lane) * C);
+#pragma unroll 1
+    for (int ch = 0; ch < C / 32; ++ch) {
       float v[32];
+      tmem_ld32(tmem + lane_addr + kColPT + (uint32_t)(ch * 32), v);
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        tmem_ld32(tmem + lane_addr + (which ? kColP2 : kColP1) + (uint32_t)(mb * 32), v);
-        if (c < C) {
-          float4* o = reinterpret_cast<float4*>(p.part_p + (((size_t)blockIdx.x * 2 + which) * C + c) * K);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      }
+      for (int j = 0; j < 8; ++j) o[ch * 8 + j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
   }
   tc_fence_before();
@@ -739,34 +790,51 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, ncols); }
 }
 
-// One warp per channel c, lane = centroid k (K == 32), partials added in fixed order (deterministic):
-//   gcenters[k,c] = sum_b P1[b][c][k] - gamma_c sum_b P2[b][c][k] + (cen[k,c] - beta_c) rcol_k
-//   g_beta[c]  = gamma_c sum_k P2[c,k] + beta_c sum_k rcol_k - sum_k rcol_k cen[k,c]
-//   g_gamma[c] = gamma_c Q[c] + beta_c sum_k P2[c,k] - sum_k cen[k,c] P2[c,k]
+// finalize 1 (block = centroid k, thread = channel c; partials added in fixed order: deterministic):
+//   P1 = sum_b (PT[b][k] + PT[b][32+k]),  P2 = sum_b (PT[b][64+k] + PT[b][96+k]),  rcol_k = sum_b rcol[b]
+//   gcenters[k,c] = P1 - gamma_c P2 + (cen[k,c] - beta_c) rcol_k;   P2 and rcol_k are kept for finalize 2
 __global__ void __launch_bounds__(256)
-cluster_bwd_tc_finalize_kernel(const float* __restrict__ part_p, const float* __restrict__ part_rcol,
-                               const float* __restrict__ part_q, const float* __restrict__ centers,
-                               const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                               int nb, int K, int C, float* __restrict__ gcenters,
-                               float* __restrict__ gw, float* __restrict__ gb) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), k = threadIdx.x & 31;
+cluster_bwd_tc_finalize1_kernel(const float* __restrict__ part_p, const float* __restrict__ part_rcol,
+                                const float* __restrict__ centers, const float* __restrict__ ln_w,
+                                const float* __restrict__ ln_b, int nb, int K, int C,
+                                float* __restrict__ gcenters, float* __restrict__ p2buf, float* __restrict__ rcol) {
+  const int k = blockIdx.x;
+  __shared__ float red[32];
+  float rc = 0.f;
+  for (int b = threadIdx.x; b < 2 * nb; b += blockDim.x) rc += part_rcol[(size_t)b * K + k];
+  rc = block_sum<float>(rc, red);
+  if (threadIdx.x == 0) rcol[k] = rc;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int b = 0; b < nb; ++b) {
+      const float* pp = part_p + (size_t)b * 128 * C + c;
+      s1 += pp[(size_t)k * C] + pp[(size_t)(K + k) * C];
+      s2 += pp[(size_t)(2 * K + k) * C] + pp[(size_t)(3 * K + k) * C];
+    }
+    gcenters[(size_t)k * C + c] = s1 - ln_w[c] * s2 + (centers[(size_t)k * C + c] - ln_b[c]) * rc;
+    p2buf[(size_t)k * C + c] = s2;
+  }
+}
+
+// finalize 2 (thread = channel):
+//   g_beta[c]  = gamma_c sum_k P2[k,c] + beta_c sum_k rcol_k - sum_k rcol_k cen[k,c]
+//   g_gamma[c] = gamma_c Q[c] + beta_c sum_k P2[k,c] - sum_k cen[k,c] P2[k,c]
+__global__ void __launch_bounds__(256)
+cluster_bwd_tc_finalize2_kernel(const float* __restrict__ p2buf, const float* __restrict__ rcol,
+                                const float* __restrict__ part_q, const float* __restrict__ centers,
+                                const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                int nb, int K, int C, float* __restrict__ gw, float* __restrict__ gb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const int KC = K * C;
-  float s1 = 0.f, s2 = 0.f, rc = 0.f, qv = 0.f;
-  for (int b = 0; b < nb; ++b) {
-    s1 += part_p[((size_t)b * 2) * KC + c * K + k];
-    s2 += part_p[((size_t)b * 2 + 1) * KC + c * K + k];
-    rc += part_rcol[((size_t)b * 2) * K + k] + part_rcol[((size_t)b * 2 + 1) * K + k];
+  float sp2 = 0.f, scp = 0.f, src = 0.f, scr = 0.f, qv = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float s2 = p2buf[(size_t)k * C + c], cen = centers[(size_t)k * C + c], rc = rcol[k];
+    sp2 += s2; scp = fmaf(cen, s2, scp); src += rc; scr = fmaf(rc, cen, scr);
   }
-  for (int b = k; b < 2 * nb; b += 32) qv += part_q[(size_t)b * C + c];
-  const float g = ln_w[c], be = ln_b[c], cen = centers[(size_t)k * C + c];
-  gcenters[(size_t)k * C + c] = s1 - g * s2 + (cen - be) * rc;
-  const float sp2 = warp_sum(s2), scp = warp_sum(cen * s2), src = warp_sum(rc), scr = warp_sum(rc * cen);
-  qv = warp_sum(qv);
-  if (k == 0) {
-    gb[c] = g * sp2 + be * src - scr;
-    gw[c] = g * qv + be * sp2 - scp;
-  }
+  for (int b = 0; b < 2 * nb; ++b) qv += part_q[(size_t)b * C + c];
+  const float g = ln_w[c], be = ln_b[c];
+  gb[c] = g * sp2 + be * src - scr;
+  gw[c] = g * qv + be * sp2 - scp;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -821,8 +889,9 @@ size_t bwd_tc_workspace_bytes(long long N, int C, int K) {
   if (!bt::shape_ok(N, C, K)) return 0;
   const size_t g = (size_t)sm_count();
   return align_up((size_t)2 * K * C * 2, 256) + align_up((size_t)3 * K * sizeof(float), 256) +
-         align_up(g * 2 * C * K * sizeof(float), 256) + align_up(g * 2 * K * sizeof(float), 256) +
-         align_up(g * 4 * C * sizeof(float), 256) + 256;
+         align_up(g * 128 * C * sizeof(float), 256) + align_up(g * 2 * K * sizeof(float), 256) +
+         align_up(g * 2 * C * sizeof(float), 256) + align_up((size_t)K * C * sizeof(float), 256) +
+         align_up((size_t)K * sizeof(float), 256) + 256;
 }
 
 int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, const float* ln_w,
@@ -837,9 +906,11 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
   const size_t g = (size_t)sm_count();
   uint8_t* image = ws.take<uint8_t>((size_t)2 * K * C * 2);
   float* cvec = ws.take<float>(3 * K);
-  float* part_p = ws.take<float>(g * 2 * C * K);
+  float* part_p = ws.take<float>(g * 128 * C);
   float* part_rcol = ws.take<float>(g * 2 * K);
-  float* part_ln = ws.take<float>(g * 4 * C);
+  float* part_q = ws.take<float>(g * 2 * C);
+  float* p2buf = ws.take<float>((size_t)K * C);
+  float* rcol = ws.take<float>(K);
   const int grid = (int)std::min<long long>((N + bt::kTok - 1) / bt::kTok, (long long)g);
 
   CUtensorMap mGx;
@@ -853,7 +924,7 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
   const char* trace_path = getenv("VADC_BWD_TRACE");       // debugging only: synchronises and writes a text file
   const size_t trace_bytes = (size_t)16 * 1024 * 2 * sizeof(unsigned long long);
   if (trace_path) { VADC_CUDA(cudaMalloc(&trace, trace_bytes)); VADC_CUDA(cudaMemsetAsync(trace, 0, trace_bytes, st)); }
-  bt::Params p{x, gR, D, A, mu, rstd, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_ln,
+  bt::Params p{x, gR, D, A, mu, rstd, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_q,
                N, alpha, getenv("VADC_BWD_PF") ? atoi(getenv("VADC_BWD_PF")) : 1, trace};
   bool launched = false;
 #define BT_CASE(F4_)                                                                                   \
@@ -882,9 +953,12 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
     free(h);
     cudaFree(trace);
   }
-  bt::cluster_bwd_tc_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part_p, part_rcol, part_ln, centers, ln_w,
-                                                                        ln_b, grid, K, C, gcenters, g_ln_w, g_ln_b);
-  VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize_kernel");
+  bt::cluster_bwd_tc_finalize1_kernel<<<K, 192, 0, st>>>(part_p, part_rcol, centers, ln_w, ln_b, grid, K, C,
+                                                        gcenters, p2buf, rcol);
+  VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize1_kernel");
+  bt::cluster_bwd_tc_finalize2_kernel<<<(C + 63) / 64, 64, 0, st>>>(p2buf, rcol, part_q, centers, ln_w, ln_b, grid, K, C,
+                                                                    g_ln_w, g_ln_b);
+  VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize2_kernel");
   return VADC_OK;
 }
 

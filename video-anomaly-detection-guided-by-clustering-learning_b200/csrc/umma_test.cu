@@ -134,3 +134,60 @@ extern "C" int vadc_debug_umma(const float* A, const float* B, float* out, int N
   VADC_CHECK_LAUNCH("umma_test_kernel");
   return VADC_OK;
 }
+
+// ---------------------------------------------------------------------------
+// issue-rate micro-benchmark: one thread issues `reps` x 8 tcgen05.mma (kind::f16, bf16) of one
+// shape back to back on uninitialised shared memory and waits for the commit; out[0] = cycles.
+// (The fused kernels' tile shapes were chosen from these numbers: scripts/umma_bench.py.)
+// ---------------------------------------------------------------------------
+namespace vadc {
+__global__ void __launch_bounds__(128)
+umma_bench_kernel(int M, int N, int a_mn, int b_mn, int reps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3f803f80u;   // bf16 1.0
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = instr_desc(kFmtBF16, M, N, a_mn, b_mn);
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + 64 * 1024;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        // K-major: 32-byte K slices of [rows x 128 B] blocks; MN-major: 16-row (2 KB) K slices, 8 KB between 64-wide blocks
+        const uint64_t ad = a_mn ? smem_desc_sw128(a0 + (k & 3) * 2048, 8192, 1024) : smem_desc_sw128(a0 + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024);
+        const uint64_t bd = b_mn ? smem_desc_sw128(b0 + (k & 3) * 2048, 8192, 1024) : smem_desc_sw128(b0 + (k >> 2) * 32768 + (k & 3) * 32, 0, 1024);
+        mma_f16(tmem, ad, bd, idesc, (r | k) ? 1u : 0u);
+      }
+    }
+    const long long t1 = clock64();
+    mma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[0] = t2 - t0;
+    out[1] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace vadc
+
+extern "C" int vadc_debug_umma_bench(int M, int N, int a_mn, int b_mn, int reps, long long* out, void* stream) {
+  using namespace vadc;
+  VADC_REQUIRE((M == 64 || M == 128) && N >= 8 && N <= 256 && (N % 8) == 0 && reps > 0, VADC_ERR_BAD_SHAPE);
+  const size_t smem = 161 * 1024 + 1024;
+  VADC_CUDA(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_bench_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(M, N, a_mn, b_mn, reps, out);
+  VADC_CHECK_LAUNCH("umma_bench_kernel");
+  return VADC_OK;
+}
