@@ -68,6 +68,8 @@ unsigned long long vadc_launch_count(void);
  *   A       = exp(-alpha (D - min_k D)) / sum_k     [N,K]
  *   x_rec   = A @ centers                           [N,C]
  *   mu,rstd = LayerNorm statistics                  [N] each (saved for the backward)
+ *   rowstats = per-token sums the backward's closed-form LayerNorm statistics use, [N,4]:
+ *              |f|^2, sum_c f gamma, sum_c f gamma xhat, 0   (may be NULL: not produced)
  *   loss_sq = sum (D*A)^2                           [1]     (sqrt of it is the cluster loss)
  * Constraints: C % 4 == 0, K % 4 == 0.
  * ------------------------------------------------------------------------ */
@@ -76,7 +78,7 @@ int vadc_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
                      const float* centers, int64_t N, int C, int K,
                      float alpha, float eps,
                      float* D, float* A, float* x_rec, float* feature,
-                     int64_t* label, float* mu, float* rstd, float* loss_sq,
+                     int64_t* label, float* mu, float* rstd, float* rowstats, float* loss_sq,
                      void* workspace, size_t workspace_bytes, int impl, void* stream);
 
 /* PosSoftAssign.forward / NegSoftAssign.forward  model/cluster.py:27-55, stand-alone:
@@ -97,7 +99,7 @@ int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int64_t P, int
  * C2: autograd of C1 — the reference's "centroid update" (SURVEY.md D4):
  *     loss.backward()  main_predict.py:296, through cluster.py:84-95.
  *
- * Inputs saved by the forward: x, mu, rstd, feature, D, A.  Upstream grads
+ * Inputs saved by the forward: x, mu, rstd, rowstats (NULL allowed: slower kernel), feature, D, A.  Upstream grads
  * (each may be NULL = zero): gD, gA [N,K]; gR (x_rec) , gF (feature) [N,C].
  * Fused loss gradient (optional): if g_loss_sq != NULL (device scalar, the
  * upstream gradient of the forward's loss_sq = sum (D*A)^2) its contribution
@@ -108,7 +110,7 @@ int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int64_t P, int
  * accumulated).
  * ------------------------------------------------------------------------ */
 size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K);
-int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd,
+int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd, const float* rowstats,
                      const float* feature, const float* ln_w, const float* ln_b,
                      const float* centers,
                      const float* D, const float* A,

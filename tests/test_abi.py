@@ -44,9 +44,9 @@ def test_argument_validation_happens_before_any_cuda_call():
     l = _lib.lib()
     # bad shape (K % 4 != 0) and NULL pointers are rejected on the host
     assert l.vadc_cluster_fwd(None, None, None, None, 8, 192, 30, 16.0, 1e-5, None, None, None, None,
-                              None, None, None, None, None, 0, 0, None) == -1
+                              None, None, None, None, None, None, 0, 0, None) == -1
     assert l.vadc_cluster_fwd(None, None, None, None, 8, 192, 32, 16.0, 1e-5, None, None, None, None,
-                              None, None, None, None, None, 0, 0, None) == -2
+                              None, None, None, None, None, None, 0, 0, None) == -2
     assert l.vadc_pixel_loss(None, None, 0, None, 0, 0, None, None, 0, None) == -1
     assert l.vadc_pixel_loss(None, None, 16, None, 0, 7, None, None, 0, None) == -1
 

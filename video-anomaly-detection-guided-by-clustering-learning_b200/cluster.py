@@ -46,15 +46,16 @@ class _ClusterAssign(torch.autograd.Function):
         label = torch.empty((N,), device=dev, dtype=torch.int64)
         mu = torch.empty((N,), device=dev, dtype=torch.float32)
         rstd = torch.empty((N,), device=dev, dtype=torch.float32)
+        rowstats = torch.empty((N, 4), device=dev, dtype=torch.float32)
         loss_sq = torch.empty((1,), device=dev, dtype=torch.float32)
         l = _lib.lib()
         nb = l.vadc_cluster_fwd_workspace_bytes(N, C, K, impl)
         ws = workspace(nb, dev)
         check(l.vadc_cluster_fwd(ptr(x2), ptr(w), ptr(b), ptr(cen), N, C, K, float(alpha), float(eps),
                                  ptr(D), ptr(A), ptr(R), ptr(F), ptr(label), ptr(mu), ptr(rstd),
-                                 ptr(loss_sq), ptr(ws), ws.numel(), impl, stream()),
+                                 ptr(rowstats), ptr(loss_sq), ptr(ws), ws.numel(), impl, stream()),
               "vadc_cluster_fwd")
-        ctx.save_for_backward(x2, cen, w, b, D, A, F, mu, rstd)
+        ctx.save_for_backward(x2, cen, w, b, D, A, F, mu, rstd, rowstats)
         ctx.alpha, ctx.lead = float(alpha), lead
         ctx.mark_non_differentiable(label)
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero tensors
@@ -62,7 +63,7 @@ class _ClusterAssign(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gD, gA, gR, gF, _glabel, gLsq):
-        x2, cen, w, b, D, A, F, mu, rstd = ctx.saved_tensors
+        x2, cen, w, b, D, A, F, mu, rstd, rowstats = ctx.saved_tensors
         N, C = x2.shape
         K = cen.shape[0]
         dev = x2.device
@@ -79,7 +80,7 @@ class _ClusterAssign(torch.autograd.Function):
         l = _lib.lib()
         nb = l.vadc_cluster_bwd_workspace_bytes(N, C, K)
         ws = workspace(nb, dev)
-        check(l.vadc_cluster_bwd(ptr(x2), ptr(mu), ptr(rstd), ptr(F), ptr(w), ptr(b), ptr(cen), ptr(D), ptr(A),
+        check(l.vadc_cluster_bwd(ptr(x2), ptr(mu), ptr(rstd), ptr(rowstats), ptr(F), ptr(w), ptr(b), ptr(cen), ptr(D), ptr(A),
                                  ptr(gD), ptr(gA), ptr(gR), ptr(gF), ptr(gLsq), N, C, K, ctx.alpha,
                                  ptr(gx), ptr(gc), ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream()),
               "vadc_cluster_bwd")

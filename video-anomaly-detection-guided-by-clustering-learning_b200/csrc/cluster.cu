@@ -221,6 +221,34 @@ using namespace vadc;
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
+namespace vadc {
+// rowstats for the forward paths that do not fuse them: one warp per token,
+// {|f|^2, sum f gamma, sum f gamma xhat, 0} with f = feature row, xhat = (x - mu) rstd
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const float* __restrict__ x, const float* __restrict__ feature, const float* __restrict__ mu,
+                const float* __restrict__ rstd, const float* __restrict__ ln_w, long long N, int C,
+                float* __restrict__ rowstats) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float m = mu[row], rs = rstd[row];
+  float zz = 0.f, p1 = 0.f, p2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float f = feature[row * C + c], xh = (x[row * C + c] - m) * rs, fg = f * ln_w[c];
+    zz = fmaf(f, f, zz); p1 += fg; p2 = fmaf(fg, xh, p2);
+  }
+  zz = warp_sum(zz); p1 = warp_sum(p1); p2 = warp_sum(p2);
+  if (lane == 0) reinterpret_cast<float4*>(rowstats)[row] = make_float4(zz, p1, p2, 0.f);
+}
+static int launch_rowstats(const float* x, const float* feature, const float* mu, const float* rstd,
+                           const float* ln_w, long long N, int C, float* rowstats, cudaStream_t st) {
+  if (!rowstats || N == 0) return VADC_OK;
+  rowstats_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(x, feature, mu, rstd, ln_w, N, C, rowstats);
+  VADC_CHECK_LAUNCH("rowstats_kernel");
+  return VADC_OK;
+}
+}  // namespace vadc
+
 extern "C" size_t vadc_cluster_fwd_workspace_bytes(int64_t N, int C, int K, int impl) {
   (void)impl;
   size_t b = 0;
@@ -234,12 +262,13 @@ extern "C" size_t vadc_cluster_fwd_workspace_bytes(int64_t N, int C, int K, int 
 extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
                                 const float* centers, int64_t N, int C, int K, float alpha,
                                 float eps, float* D, float* A, float* x_rec, float* feature,
-                                int64_t* label, float* mu, float* rstd, float* loss_sq,
+                                int64_t* label, float* mu, float* rstd, float* rowstats, float* loss_sq,
                                 void* workspace, size_t workspace_bytes, int impl, void* stream) {
   VADC_REQUIRE(N >= 0 && C > 0 && K > 0 && (C % 4) == 0 && (K % 4) == 0, VADC_ERR_BAD_SHAPE);
   VADC_REQUIRE(N < (1ll << 31) && C <= 1024, VADC_ERR_UNSUPPORTED);
   VADC_REQUIRE(ln_w && ln_b && centers && loss_sq && workspace, VADC_ERR_NULL_POINTER);
   VADC_REQUIRE(N == 0 || (x && D && A && x_rec && feature && label && mu && rstd), VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(aligned16(rowstats), VADC_ERR_MISALIGNED);
   VADC_REQUIRE(aligned16(x) && aligned16(ln_w) && aligned16(ln_b) && aligned16(centers) &&
                aligned16(D) && aligned16(A) && aligned16(x_rec) && aligned16(feature) &&
                aligned16(workspace), VADC_ERR_MISALIGNED);
@@ -248,12 +277,13 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
 
   if (impl != VADC_IMPL_SIMT && !getenv("VADC_FWD_NO_WS")) {
     int rc = vadc_cluster_fwd_ws(x, ln_w, ln_b, centers, N, C, K, alpha, eps, D, A, x_rec, feature,
-                                 label, mu, rstd, loss_sq, workspace, workspace_bytes, st);
+                                 label, mu, rstd, rowstats, loss_sq, workspace, workspace_bytes, st);
     if (rc != VADC_ERR_UNSUPPORTED) return rc;
   }
   if (impl != VADC_IMPL_SIMT) {
     int rc = vadc_cluster_fwd_tc(x, ln_w, ln_b, centers, N, C, K, alpha, eps, D, A, x_rec, feature,
                                  label, mu, rstd, loss_sq, workspace, workspace_bytes, st);
+    if (rc == VADC_OK) return launch_rowstats(x, feature, mu, rstd, ln_w, N, C, rowstats, st);
     if (rc != VADC_ERR_UNSUPPORTED || impl == VADC_IMPL_TCGEN05) return rc;
   }
   Carver ws(workspace, workspace_bytes);
@@ -271,7 +301,7 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
     cudaError_t e = sgemm_auto((int)N, C, K, Aop, Bop, 0, 0, 1, 1, epi, st);
     if (e != cudaSuccess) return record_cuda_error(e, "x_rec sgemm");
   }
-  return VADC_OK;
+  return launch_rowstats(x, feature, mu, rstd, ln_w, N, C, rowstats, st);
 }
 
 extern "C" size_t vadc_cdist_workspace_bytes(int nb, int64_t R, int64_t P, int C) {
@@ -312,7 +342,7 @@ extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
   return std::max(std::max(b + 256, bwd_fused_workspace_bytes(N, C, K)), bwd_tc_workspace_bytes(N, C, K));
 }
 
-extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd,
+extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd, const float* rowstats,
                                 const float* feature, const float* ln_w, const float* ln_b,
                                 const float* centers,
                                 const float* D, const float* A, const float* gD, const float* gA,
@@ -336,8 +366,8 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
   }
   const char* bimpl = getenv("VADC_BWD_IMPL");            // debugging / A-B runs: tc | fused | generic
   const bool want_tc = !bimpl || !strcmp(bimpl, "tc");
-  if (want_tc && ln_b && gR && !gD && !gA && !gF && bwd_tc_shape_ok(N, C, K))
-    return launch_cluster_bwd_tc(x, mu, rstd, ln_w, ln_b, centers, D, A, gR, g_loss_sq, N, C, K, alpha, gx,
+  if (want_tc && rowstats && ln_b && gR && !gD && !gA && !gF && bwd_tc_shape_ok(N, C, K))
+    return launch_cluster_bwd_tc(x, mu, rstd, rowstats, ln_w, ln_b, centers, D, A, gR, g_loss_sq, N, C, K, alpha, gx,
                                  gcenters, g_ln_w, g_ln_b, workspace, workspace_bytes, st);
   if (bwd_fused_shape_ok(N, C, K) && !getenv("VADC_BWD_GENERIC") && !(bimpl && !strcmp(bimpl, "generic")))
     return launch_cluster_bwd_fused(x, mu, rstd, feature, ln_w, centers, D, A, gD, gA, gR, gF, g_loss_sq,

@@ -31,7 +31,7 @@ int launch_cluster_bwd_fused(const float* x, const float* mu, const float* rstd,
 // tcgen05 warp-specialised backward, K == 32, training-graph case (cluster_bwd_tc.cu)
 bool bwd_tc_shape_ok(long long N, int C, int K);
 size_t bwd_tc_workspace_bytes(long long N, int C, int K);
-int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, const float* ln_w,
+int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, const float* rowstats, const float* ln_w,
                           const float* ln_b, const float* centers, const float* D, const float* A,
                           const float* gR, const float* g_loss_sq, long long N, int C, int K, float alpha,
                           float* gx, float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
@@ -49,4 +49,4 @@ size_t vadc_cluster_ws_extra_workspace_bytes(int64_t N, int C, int K);
 int vadc_cluster_fwd_ws(const float* x, const float* ln_w, const float* ln_b, const float* centers,
                         int64_t N, int C, int K, float alpha, float eps, float* D, float* A,
                         float* x_rec, float* feature, int64_t* label, float* mu, float* rstd,
-                        float* loss_sq, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                        float* rowstats, float* loss_sq, void* workspace, size_t workspace_bytes, cudaStream_t st);

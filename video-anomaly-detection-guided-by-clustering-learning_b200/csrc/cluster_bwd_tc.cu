@@ -70,8 +70,7 @@ constexpr int kMmaWarp = 15;
 constexpr uint32_t kBlk = kTok * 128u;       // one [64 rows x 128 B] operand block
 
 struct Plan {
-  uint32_t x_off, g_off, ta_off, zero_off, tr_off, cen_off, stg_off, prow_off, scal_off, gam_off, bet_off,
-      g2_off, bg_off, cvec_off, misc_off, total;
+  uint32_t x_off, g_off, ta_off, zero_off, tr_off, cen_off, stg_off, scal_off, gam_off, bet_off, cvec_off, misc_off, total;
   uint32_t xbuf, xterm, gterm;
 };
 
@@ -87,13 +86,10 @@ __host__ __device__ inline Plan plan(int C) {
   p.tr_off = off; off += kBlk;                             // [64 tokens x 128 B]: r_hi | r_lo
   p.cen_off = off; off += ncb * kBlk;                      // [C/64][64 rows x 128 B]: rows 0..31 cen_hi, 32..63 cen_lo
   p.stg_off = off; off += 6u * 4096u;                      // per E3 warp: [32 rows x 128 B]
-  p.prow_off = off; off += 2u * 3u * kTok * 4u;            // producer row sums [buf][zz, p1, p2][64]
   p.scal_off = off; off += 2u * 4u * kTok * 4u;            // E1 row scalars [parity][rsum, s1r, s2r, rs][64]
   p.gam_off = off; off += (uint32_t)C * 4u;
   p.bet_off = off; off += (uint32_t)C * 4u;
-  p.g2_off = off; off += (uint32_t)C * 4u;                 // gamma^2
-  p.bg_off = off; off += (uint32_t)C * 4u;                 // beta gamma
-  p.cvec_off = off; off += 3u * kK * 4u;                   // hc = |c|^2/2 - beta.c ; cg = gamma.c ; consts
+  p.cvec_off = off; off += 2u * kK * 4u;                   // hc = |c|^2/2 - beta.c ; cg = gamma.c
   p.misc_off = off; off += 256u;
   p.total = off;
   return p;
@@ -240,6 +236,7 @@ centroid_prep_bwd_kernel(const float* __restrict__ centers, const float* __restr
 
 struct Params {
   const float* x; const float* gR; const float* D; const float* A; const float* mu; const float* rstd;
+  const float* rowstats;                                 // [N,4]: |z|^2, sum z gamma, sum z gamma xhat, 0 (from the forward)
   const float* ln_w; const float* ln_b; const uint8_t* cimage; const float* cvec; const float* g_loss_sq;
   float* part_p; float* part_rcol; float* part_q;        // [grid][128 slots][C], [grid][2][32], [grid][2][C]
   long long N; float alpha; int pf;
@@ -253,15 +250,11 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int C = F4 * 32, K = kK, NCB = C / 64;
   const Plan pl = plan(C);
-  float* sProw = reinterpret_cast<float*>(smem + pl.prow_off);
   float* sScal = reinterpret_cast<float*>(smem + pl.scal_off);
   float* sGam = reinterpret_cast<float*>(smem + pl.gam_off);
   float* sBet = reinterpret_cast<float*>(smem + pl.bet_off);
-  float* sG2 = reinterpret_cast<float*>(smem + pl.g2_off);
-  float* sBG = reinterpret_cast<float*>(smem + pl.bg_off);
   float* sHc = reinterpret_cast<float*>(smem + pl.cvec_off);
   float* sCg = sHc + K;
-  float* sConst = sCg + K;                               // [0] = sum beta gamma, [1] = sum beta^2
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.misc_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.misc_off + 128);
 
@@ -302,17 +295,11 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, ncols);
   for (int c = tid; c < C; c += kThreads) {
     const float g = p.ln_w[c], b = p.ln_b[c];
-    sGam[c] = g; sBet[c] = b; sG2[c] = g * g; sBG[c] = b * g;
+    sGam[c] = g; sBet[c] = b;
   }
   for (int k = tid; k < 2 * K; k += kThreads) sHc[k] = p.cvec[k];
   for (uint32_t i = tid; i < kBlk / 16u; i += kThreads)
     *reinterpret_cast<uint4*>(smem + pl.zero_off + i * 16u) = make_uint4(0, 0, 0, 0);
-  if (warp == 0) {
-    float a = 0.f, b = 0.f;
-    for (int c = lane; c < C; c += 32) { const float g = p.ln_w[c], be = p.ln_b[c]; a += be * g; b += be * be; }
-    a = warp_sum(a); b = warp_sum(b);
-    if (lane == 0) { sConst[0] = a; sConst[1] = b; }
-  }
   fence_async_smem();                                    // the zero block is an MMA operand
   tc_fence_before();
   __syncthreads();
@@ -335,8 +322,6 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     const int lj = lane & 7, lg = lane >> 3;
     const int rsel = (lg & 1) * 4 + (lg >> 1);
     const int nunits = kUnits * nmine;
-    const float cB1 = sConst[0], cB2 = sConst[1];
-    const uint32_t sG2a = smem_u32(sG2) + lj * 16, sBGa = smem_u32(sBG) + lj * 16;
     struct Unit { union { float4 v[F4]; float4 a[8]; }; float rs, nmr; };   // a[]: the 8 float4 of an A unit
     auto issue = [&](Unit& U, int g) {
       if (g >= nunits) return;
@@ -390,62 +375,36 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       const bool isx = u < 16;
       const int buf = it & 1;
       const int r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
-      const uint32_t rx = (uint32_t)(r & 7);
-      const uint32_t rowoff = (uint32_t)r * 128u;
+      // byte offset of this lane's float4 number lj inside its row's first 64-channel block; float4 lj + 8 i sits in
+      // block i/2 at chunk (lj/2 + 4 (i%2)) ^ (r%8): bit 6 of the offset flips with i%2 (all operand bases are 1 KB aligned)
+      const uint32_t e0 = (uint32_t)r * 128u + (((uint32_t)(lj >> 1) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)(lj & 1) * 8u;
       TR(0, it);
       if (isx) {
         // X[buf] is free once S5b and E3 of tile it-2 have finished
         mbar_wait_spin(&bars[B_XEMPTY0 + buf], (uint32_t)(((it >> 1) & 1) ^ 1));
-        const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + r;
-        const bool live = row < p.N;
-        const uint32_t xb = sX32 + buf * pl.xbuf;
-        float q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        const uint32_t xb = sX32 + buf * pl.xbuf + e0;
 #pragma unroll
         for (int i = 0; i < F4; ++i) {
-          const int f = lj + 8 * i;                          // float4 index in the row: channels 4f..4f+3
-          const uint32_t byte = (uint32_t)(f & 15) * 8u;     // 8 bytes of bf16 in the 128-byte row of block f/16
-          const uint32_t off = (uint32_t)(f >> 4) * kBlk + rowoff + ((((byte >> 4) ^ rx) << 4) | (byte & 15u));
           float4 h;
           h.x = fmaf(U.v[i].x, U.rs, U.nmr); h.y = fmaf(U.v[i].y, U.rs, U.nmr);
           h.z = fmaf(U.v[i].z, U.rs, U.nmr); h.w = fmaf(U.v[i].w, U.rs, U.nmr);
-          const float4 g2 = lds128f_const(sG2a + i * 128);
-          const float4 bg = lds128f_const(sBGa + i * 128);
-          float w;
-          w = g2.x * h.x; q1 += w; q2 = fmaf(w, h.x, q2); q3 = fmaf(bg.x, h.x, q3);
-          w = g2.y * h.y; q1 += w; q2 = fmaf(w, h.y, q2); q3 = fmaf(bg.y, h.y, q3);
-          w = g2.z * h.z; q1 += w; q2 = fmaf(w, h.z, q2); q3 = fmaf(bg.z, h.z, q3);
-          w = g2.w * h.w; q1 += w; q2 = fmaf(w, h.w, q2); q3 = fmaf(bg.w, h.w, q3);
           uint32_t a1, a2, b1, b2;
           split2_bf(h.x, h.y, a1, a2);
           split2_bf(h.z, h.w, b1, b2);
-          sts64(xb + off, a1, b1);
-          sts64(xb + pl.xterm + off, a2, b2);
-        }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-          q2 += __shfl_xor_sync(0xffffffffu, q2, o);
-          q3 += __shfl_xor_sync(0xffffffffu, q3, o);
-        }
-        if (lj == 0) {
-          float* prow = sProw + buf * 3 * kTok;
-          prow[r] = live ? q2 + 2.f * q3 + cB2 : 0.f;        // |z|^2
-          prow[kTok + r] = live ? q1 + cB1 : 0.f;            // sum z gamma
-          prow[2 * kTok + r] = live ? q2 + q3 : 0.f;         // sum z gamma xhat
+          sts64((xb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
+          sts64((xb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.xterm, a2, b2);
         }
       } else {
         // G is free once S1 / S5a of the previous tile have completed
         mbar_wait_spin(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));
+        const uint32_t gb = sG32 + e0;
 #pragma unroll
         for (int i = 0; i < F4; ++i) {
-          const int f = lj + 8 * i;
-          const uint32_t byte = (uint32_t)(f & 15) * 8u;
-          const uint32_t off = (uint32_t)(f >> 4) * kBlk + rowoff + ((((byte >> 4) ^ rx) << 4) | (byte & 15u));
           uint32_t a1, a2, b1, b2;
           split2_bf(U.v[i].x, U.v[i].y, a1, a2);
           split2_bf(U.v[i].z, U.v[i].w, b1, b2);
-          sts64(sG32 + off, a1, b1);
-          sts64(sG32 + pl.gterm + off, a2, b2);
+          sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
+          sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.gterm, a2, b2);
         }
       }
       TR(1, it);
@@ -455,13 +414,13 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       if (lane == 0) mbar_arrive(isx ? &bars[B_XFULL0 + buf] : &bars[B_GFULL]);
       TR(2, it);
     };
-    Unit UA, UB;
-    issue(UA, pw);
-    for (int g = pw; g < nunits; g += 2 * kProd) {
-      issue(UB, g + kProd);
-      process(UA, g);
-      issue(UA, g + 2 * kProd);
-      process(UB, g + kProd);
+    Unit cur, nxt;
+    issue(cur, pw);
+#pragma unroll 1
+    for (int g = pw; g < nunits; g += kProd) {           // one copy of the code: four roles share the instruction cache
+      issue(nxt, g + kProd);
+      process(cur, g);
+      cur = nxt;
     }
   } else if (is_e1) {
     // ======================================================================= E1
@@ -473,6 +432,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     float rcol_acc = 0.f;
     float dv[32], av[32];
     float rs_next = 0.f;
+    float4 st_next = make_float4(0, 0, 0, 0);
     auto load_da = [&](int it) {                         // D / A rows of tile `it` (software-pipelined one tile ahead)
       const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + et;
       const bool live = it < nmine && row < p.N;
@@ -486,6 +446,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         av[4 * q] = a4.x; av[4 * q + 1] = a4.y; av[4 * q + 2] = a4.z; av[4 * q + 3] = a4.w;
       }
       rs_next = live ? __ldg(p.rstd + row) : 0.f;
+      st_next = live ? ldg_nc(reinterpret_cast<const float4*>(p.rowstats) + row) : make_float4(0, 0, 0, 0);
     };
     auto prefetch_da = [&](int it) {                     // L2 prefetch of a later tile's D / A rows (8 KB each)
       if (et == 0 && it < nmine) {
@@ -504,15 +465,10 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       const long long row = tile * kTok + et;
       const bool live = row < p.N;
       const float rs = rs_next;
+      const float zz = st_next.x, p1 = st_next.y, p2 = st_next.z;
       TR(10, it);
       prefetch_da(it + 2);
-      // producer row sums of this tile
       const int buf = it & 1;
-      mbar_wait(&bars[B_XFULL0 + buf], (uint32_t)((it >> 1) & 1));
-      TR(13, it);
-      const float zz = sProw[buf * 3 * kTok + et];
-      const float p1 = sProw[buf * 3 * kTok + kTok + et];
-      const float p2 = sProw[buf * 3 * kTok + 2 * kTok + et];
       mbar_wait(&bars[B_G1FULL0 + buf], (uint32_t)((it >> 1) & 1));
       TR(14, it);
       tc_fence_after();
@@ -894,7 +850,7 @@ size_t bwd_tc_workspace_bytes(long long N, int C, int K) {
          align_up((size_t)K * sizeof(float), 256) + 256;
 }
 
-int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, const float* ln_w,
+int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, const float* rowstats, const float* ln_w,
                           const float* ln_b, const float* centers, const float* D, const float* A,
                           const float* gR, const float* g_loss_sq, long long N, int C, int K, float alpha,
                           float* gx, float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
@@ -924,7 +880,7 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
   const char* trace_path = getenv("VADC_BWD_TRACE");       // debugging only: synchronises and writes a text file
   const size_t trace_bytes = (size_t)16 * 1024 * 2 * sizeof(unsigned long long);
   if (trace_path) { VADC_CUDA(cudaMalloc(&trace, trace_bytes)); VADC_CUDA(cudaMemsetAsync(trace, 0, trace_bytes, st)); }
-  bt::Params p{x, gR, D, A, mu, rstd, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_q,
+  bt::Params p{x, gR, D, A, mu, rstd, rowstats, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_q,
                N, alpha, getenv("VADC_BWD_PF") ? atoi(getenv("VADC_BWD_PF")) : 1, trace};
   bool launched = false;
 #define BT_CASE(F4_)                                                                                   \

@@ -199,7 +199,7 @@ centroid_prep_ws_kernel(const float* __restrict__ centers, const float* __restri
 struct Params {
   const float* x; const float* ln_w; const float* ln_b;
   const uint8_t* cimage; const float* cc; const float* scales;
-  float* feature; long long* label; float* mu; float* rstd; double* partial;
+  float* feature; long long* label; float* mu; float* rstd; float* rowstats; double* partial;
   long long N; float alpha, eps; int pf, hint;
 };
 
@@ -320,7 +320,7 @@ cluster_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
         const int r = blk * 8 + rsel + 2 * u;
         const long long row = row0 + r;
         const bool live = row < p.N;
-        float nz = 0.f;
+        float nz = 0.f, p1 = 0.f, p2 = 0.f;                 // |z|^2, sum z gamma, sum z gamma xhat (for the backward)
         const uint32_t rx = (uint32_t)(r & 7);
         const uint32_t zrow = sZ32 + (uint32_t)r * 128u;
         float4* frow = reinterpret_cast<float4*>(p.feature + row * C) + lj;
@@ -328,13 +328,19 @@ cluster_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
         for (int i = 0; i < F4; ++i) {
           const float4 gm = lds128f(sGam32 + i * 128);
           const float4 be = lds128f(sBet32 + i * 128);
-          float4 o;
-          o.x = v[u][i].x * rs[u] * gm.x + be.x;
-          o.y = v[u][i].y * rs[u] * gm.y + be.y;
-          o.z = v[u][i].z * rs[u] * gm.z + be.z;
-          o.w = v[u][i].w * rs[u] * gm.w + be.w;
+          float4 th, o;
+          th.x = v[u][i].x * rs[u]; th.y = v[u][i].y * rs[u]; th.z = v[u][i].z * rs[u]; th.w = v[u][i].w * rs[u];
+          o.x = fmaf(th.x, gm.x, be.x);
+          o.y = fmaf(th.y, gm.y, be.y);
+          o.z = fmaf(th.z, gm.z, be.z);
+          o.w = fmaf(th.w, gm.w, be.w);
           if (live) { if (p.hint & 1) st_hint(frow + 8 * i, o, pol); else frow[8 * i] = o; } else o = make_float4(0, 0, 0, 0);
           nz += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+          if (p.rowstats) {
+            const float gx = o.x * gm.x, gy = o.y * gm.y, gz = o.z * gm.z, gw = o.w * gm.w;
+            p1 += (gx + gy) + (gz + gw);
+            p2 = fmaf(gx, th.x, fmaf(gy, th.y, fmaf(gz, th.z, fmaf(gw, th.w, p2))));
+          }
           uint32_t a1, a2, b1, b2;
           if constexpr (SCALED) {
             split2_h(o.x * s_z, o.y * s_z, a1, a2);
@@ -352,9 +358,19 @@ cluster_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
         nz += __shfl_xor_sync(0xffffffffu, nz, 1);
         nz += __shfl_xor_sync(0xffffffffu, nz, 2);
         nz += __shfl_xor_sync(0xffffffffu, nz, 4);
+        if (p.rowstats) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+            p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+          }
+        }
         if (lj == 0) {
           zzbuf[r] = nz;
-          if (live) { p.mu[row] = mean[u]; p.rstd[row] = rs[u]; }
+          if (live) {
+            p.mu[row] = mean[u]; p.rstd[row] = rs[u];
+            if (p.rowstats) reinterpret_cast<float4*>(p.rowstats)[row] = make_float4(nz, p1, p2, 0.f);
+          }
         }
       }
       fence_async_smem();                                // this block's 8 rows of the tile are in place
@@ -591,7 +607,7 @@ size_t vadc_cluster_ws_extra_workspace_bytes(int64_t N, int C, int K) {
 int vadc_cluster_fwd_ws(const float* x, const float* ln_w, const float* ln_b, const float* centers,
                         int64_t N, int C, int K, float alpha, float eps, float* D, float* A,
                         float* x_rec, float* feature, int64_t* label, float* mu, float* rstd,
-                        float* loss_sq, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                        float* rowstats, float* loss_sq, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (!ws::shape_ok(N, C, K)) return VADC_ERR_UNSUPPORTED;
   if (!vadc_device_ok()) return VADC_ERR_NO_DEVICE;
   if (workspace_bytes < vadc_cluster_ws_extra_workspace_bytes(N, C, K)) return VADC_ERR_WORKSPACE;
@@ -612,7 +628,7 @@ int vadc_cluster_fwd_ws(const float* x, const float* ln_w, const float* ln_b, co
   VADC_CHECK_LAUNCH("centroid_prep_ws_kernel");
 
   const size_t smem = ws::plan(C).total + 1024;
-  ws::Params p{x, ln_w, ln_b, image, cc, scales, feature, reinterpret_cast<long long*>(label), mu, rstd,
+  ws::Params p{x, ln_w, ln_b, image, cc, scales, feature, reinterpret_cast<long long*>(label), mu, rstd, rowstats,
                partial, (long long)N, alpha, eps, getenv("VADC_WS_PF") ? atoi(getenv("VADC_WS_PF")) : -1,
                getenv("VADC_WS_HINT") ? atoi(getenv("VADC_WS_HINT")) : 3};
 #define WS_CASE(F4_)                                                                                   \
