@@ -185,3 +185,99 @@ def test_full_size_properties(impl):
         # fused loss == checksum of the returned tensors
         ref = (D2.double() * A2.double()).pow(2).sum().sqrt()
         assert abs(float(m.fused_cluster_loss()) - float(ref)) < 1e-5 * float(ref)
+
+
+# ---------------------------------------------------------------------------
+# training-graph backward (gradients arrive through x_rec and the fused cluster loss only:
+# model/backbone.py:89-98, main_predict.py:284-296) -> the tcgen05 kernel of cluster_bwd_tc.cu
+# ---------------------------------------------------------------------------
+def _training_graph_backward(Ntok, C, K, alpha, seed, scale_g, loss_w):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((1, 1, 1, Ntok, C)) * 1.7 + 0.3).astype(np.float32)
+    cen = rng.random((K, C)).astype(np.float32)
+    w = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    gR = (scale_g * rng.standard_normal((Ntok, C))).astype(np.float32)
+    m = make_cluster_module(V, C, K, alpha, cen, w, b, V.IMPL_AUTO)
+    xt = T(x, grad=True)
+    D, A, S, R, F, lab = m(xt)
+    torch.autograd.backward([m.fused_cluster_loss() * loss_w, R], [None, T(gR).view_as(R)])
+    f64 = O.cluster_forward(x, cen, w, b, alpha, dtype=np.float64)
+    lD, lA = O.frobenius_loss_grads(f64["D"], f64["A"], loss_w, np.float64)
+    ref = O.cluster_backward(x, cen, w, b, alpha, gD=lD.reshape(Ntok, K), gA=lA.reshape(Ntok, K), gR=gR,
+                             dtype=np.float64)
+    got = (N(xt.grad).reshape(Ntok, C), N(m.cluster_center.grad), N(m.norm.weight.grad), N(m.norm.bias.grad))
+    return got, ref
+
+
+@pytest.mark.parametrize("Ntok,C,K,alpha", [
+    (64, 192, 32, 16.0),          # exactly one tile
+    (1, 192, 32, 16.0),           # a single token
+    (1500, 192, 32, 16.0),        # ragged tail (1500 = 23 * 64 + 28)
+    (777, 128, 32, 32.0),
+    (333, 64, 32, 8.0),
+    (148 * 64 * 3 + 5, 192, 32, 16.0),   # every CTA walks several tiles (buffer recycling) + a one-row tail tile
+])
+def test_training_graph_backward_vs_oracle(Ntok, C, K, alpha):
+    """tolerance 2e-4 of the largest gradient entry; the kernel's operands are two-term bf16 splits
+    (2^-16 per element), the fp32 reference itself is ~2e-5 away from fp64 on these inputs"""
+    got, ref = _training_graph_backward(Ntok, C, K, alpha, seed=Ntok + C, scale_g=1e-2, loss_w=1.3)
+    for g, r, name in zip(got, ref, ("gx", "gcenters", "g_ln_w", "g_ln_b")):
+        assert rel(g, r) < 2e-4, (name, rel(g, r))
+
+
+@pytest.mark.parametrize("scale_g", [1e-12, 1e-6, 1.0, 1e6, 1e12])
+def test_training_graph_backward_has_no_gradient_scale(scale_g):
+    """upstream gradients have no a-priori magnitude: the bf16-split operands keep fp32's exponent range,
+    so the relative error does not depend on the scale of gR (an fp16 operand would overflow / flush)"""
+    got, ref = _training_graph_backward(700, 192, 32, 16.0, seed=5, scale_g=scale_g, loss_w=scale_g * 50)
+    for g, r, name in zip(got, ref, ("gx", "gcenters", "g_ln_w", "g_ln_b")):
+        assert np.isfinite(g).all(), name
+        assert rel(g, r) < 2e-4, (name, scale_g, rel(g, r))
+
+
+def test_training_graph_backward_matches_generic_kernels():
+    """the same backward through the unfused SIMT kernels (VADC_BWD_IMPL=generic) and through the mma.sync
+    fused kernel (VADC_BWD_IMPL=fused): three independent implementations agree"""
+    import os
+    outs = {}
+    for impl in ("tc", "fused", "generic"):
+        os.environ["VADC_BWD_IMPL"] = impl
+        try:
+            outs[impl], _ = _training_graph_backward(2000, 192, 32, 16.0, seed=11, scale_g=1e-2, loss_w=0.7)
+        finally:
+            os.environ.pop("VADC_BWD_IMPL", None)
+    for other in ("fused", "generic"):
+        for a, b_, name in zip(outs["tc"], outs[other], ("gx", "gcenters", "g_ln_w", "g_ln_b")):
+            assert rel(a, b_) < 1e-4, (other, name, rel(a, b_))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("Ntok,C,K", [(700, 192, 32), (130, 64, 32), (90, 768, 64), (300, 192, 1024)])
+def test_forward_rowstats(Ntok, C, K, impl):
+    """the per-token sums the forward hands to the backward: |f|^2, sum f gamma, sum f gamma xhat"""
+    from videoad_b200 import _lib
+    rng = np.random.default_rng(Ntok)
+    x = (rng.standard_normal((Ntok, C)) * 2 + 0.5).astype(np.float32)
+    cen = rng.random((K, C)).astype(np.float32)
+    w = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    l = _lib.lib()
+    t = {k: T(v) for k, v in dict(x=x, cen=cen, w=w, b=b).items()}
+    o = {k: torch.empty(s, device=dev(), dtype=torch.float32) for k, s in
+         dict(D=(Ntok, K), A=(Ntok, K), R=(Ntok, C), F=(Ntok, C), mu=(Ntok,), rstd=(Ntok,), rs=(Ntok, 4), loss=(1,)).items()}
+    lab = torch.empty((Ntok,), device=dev(), dtype=torch.int64)
+    ws = torch.empty(l.vadc_cluster_fwd_workspace_bytes(Ntok, C, K, impl), device=dev(), dtype=torch.uint8)
+    _lib.check(l.vadc_cluster_fwd(_lib.ptr(t["x"]), _lib.ptr(t["w"]), _lib.ptr(t["b"]), _lib.ptr(t["cen"]), Ntok, C, K,
+                                  16.0, 1e-5, _lib.ptr(o["D"]), _lib.ptr(o["A"]), _lib.ptr(o["R"]), _lib.ptr(o["F"]),
+                                  _lib.ptr(lab), _lib.ptr(o["mu"]), _lib.ptr(o["rstd"]), _lib.ptr(o["rs"]),
+                                  _lib.ptr(o["loss"]), _lib.ptr(ws), ws.numel(), impl, _lib.stream()), "fwd")
+    torch.cuda.synchronize()
+    x64 = x.astype(np.float64)
+    mu = x64.mean(1, keepdims=True)
+    xh = (x64 - mu) / np.sqrt(x64.var(1, keepdims=True) + 1e-5)
+    f = xh * w + b
+    want = np.stack([(f * f).sum(1), (f * w).sum(1), (f * w * xh).sum(1)], 1)
+    got = N(o["rs"])
+    assert np.abs(got[:, :3] - want).max() / np.abs(want).max() < 1e-5
+    assert (got[:, 3] == 0).all()

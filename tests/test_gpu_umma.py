@@ -67,23 +67,9 @@ def f16_rne(a):
     return a.astype(np.float16).astype(np.float32)
 
 
-@pytest.mark.parametrize("mode", [2 | 16, 2 | 32, 3 | 16, 7 | 32, 6 | 16])
-def test_umma_mixed_f16_bf16_operands(mode):
-    """one kind::f16 MMA may take an fp16 A with a bf16 B and vice versa (a_format / b_format are
-    independent fields of the instruction descriptor): the fused backward multiplies fp16-split
-    LayerNorm outputs with bf16-split gradients."""
-    Nn, Kd = 64, 128
-    rng = np.random.default_rng(mode)
-    A = rng.standard_normal((128, Kd)).astype(np.float32)
-    B = rng.standard_normal((Nn, Kd)).astype(np.float32)
-    Ain = np.ascontiguousarray(A.T) if mode & 4 else A
-    Bin = np.ascontiguousarray(B.T) if mode & 1 else B
-    got = run(Ain, Bin, Nn, Kd, mode)
-    Ar = f16_rne(A) if mode & 16 else bf16_rne(A)
-    Br = f16_rne(B) if mode & 32 else bf16_rne(B)
-    ref = Ar.astype(np.float64) @ Br.astype(np.float64).T
-    err = np.abs(got - ref).max() / np.abs(ref).max()
-    assert err < 2e-6, err
+# NOTE: one kind::f16 instruction cannot take an fp16 A with a bf16 B (or vice versa): setting different
+# a_format / b_format fields faults the kernel on B200 (tried with vadc_debug_umma mode bits 4 / 5, which remain
+# in the self-test kernel for reference).  This is why the fused backward is bf16 on both sides.
 
 
 @pytest.mark.parametrize("mode", [3, 7])

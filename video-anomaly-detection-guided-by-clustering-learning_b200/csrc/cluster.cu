@@ -304,6 +304,30 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
   return launch_rowstats(x, feature, mu, rstd, ln_w, N, C, rowstats, st);
 }
 
+namespace vadc {
+// cdist of a small problem (the [K,K] centroid self-distance of model/cluster.py:77-79 is 32 x 32 x 192) in ONE
+// launch instead of two norm kernels + a tile GEMM: one warp per output row i, lanes over j, the mm form
+// sqrt(max(0, |a|^2 + |b|^2 - 2 a.b)) with fp32 accumulation
+__global__ void __launch_bounds__(128)
+cdist_small_kernel(const float* __restrict__ a, const float* __restrict__ b, int R, int P, int C,
+                   float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);   // row over all batches
+  const int nbat = blockIdx.y;
+  if (i >= R) return;
+  const float* ar = a + ((size_t)nbat * R + i) * C;
+  for (int j = lane; j < P; j += 32) {
+    const float* br = b + ((size_t)nbat * P + j) * C;
+    float aa = 0.f, bb = 0.f, ab = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float x = ar[c], y = br[c];
+      aa = fmaf(x, x, aa); bb = fmaf(y, y, bb); ab = fmaf(x, y, ab);
+    }
+    out[((size_t)nbat * R + i) * P + j] = sqrtf(fmaxf(aa + bb - 2.f * ab, 0.f));
+  }
+}
+}  // namespace vadc
+
 extern "C" size_t vadc_cdist_workspace_bytes(int nb, int64_t R, int64_t P, int C) {
   (void)C;
   return align_up((size_t)nb * R * sizeof(float), 256) + align_up((size_t)nb * P * sizeof(float), 256) + 256;
@@ -317,6 +341,11 @@ extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int
   VADC_REQUIRE(R < (1ll << 31) && P < (1ll << 31), VADC_ERR_UNSUPPORTED);
   VADC_REQUIRE(workspace_bytes >= vadc_cdist_workspace_bytes(nb, R, P, C), VADC_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((long long)nb * R * P * C <= (1ll << 21) && nb <= 65535) {        // launch-latency-bound sizes
+    cdist_small_kernel<<<dim3((unsigned)((R + 3) / 4), (unsigned)nb), 128, 0, st>>>(a, b, (int)R, (int)P, C, out);
+    VADC_CHECK_LAUNCH("cdist_small_kernel");
+    return VADC_OK;
+  }
   Carver ws(workspace, workspace_bytes);
   float* aa = ws.take<float>((size_t)nb * R);
   float* bb = ws.take<float>((size_t)nb * P);

@@ -746,33 +746,41 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, ncols); }
 }
 
-// finalize 1 (block = centroid k, thread = channel c; partials added in fixed order: deterministic):
+// finalize 1: block = (centroid k, 64-channel chunk), 512 threads = 64 channels x 8 groups of CTAs; every
+// group adds its CTAs' partials in fixed order and the groups are added in fixed order (deterministic):
 //   P1 = sum_b (PT[b][k] + PT[b][32+k]),  P2 = sum_b (PT[b][64+k] + PT[b][96+k]),  rcol_k = sum_b rcol[b]
 //   gcenters[k,c] = P1 - gamma_c P2 + (cen[k,c] - beta_c) rcol_k;   P2 and rcol_k are kept for finalize 2
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 cluster_bwd_tc_finalize1_kernel(const float* __restrict__ part_p, const float* __restrict__ part_rcol,
                                 const float* __restrict__ centers, const float* __restrict__ ln_w,
                                 const float* __restrict__ ln_b, int nb, int K, int C,
                                 float* __restrict__ gcenters, float* __restrict__ p2buf, float* __restrict__ rcol) {
-  const int k = blockIdx.x;
-  __shared__ float red[32];
-  float rc = 0.f;
-  for (int b = threadIdx.x; b < 2 * nb; b += blockDim.x) rc += part_rcol[(size_t)b * K + k];
-  rc = block_sum<float>(rc, red);
-  if (threadIdx.x == 0) rcol[k] = rc;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int b = 0; b < nb; ++b) {
+  const int k = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
+  __shared__ float s1s[8][64], s2s[8][64], rcs[512];
+  float s1 = 0.f, s2 = 0.f, rc = 0.f;
+  for (int b = threadIdx.x; b < 2 * nb; b += 512) rc += part_rcol[(size_t)b * K + k];
+  if (c < C)
+    for (int b = grp; b < nb; b += 8) {
       const float* pp = part_p + (size_t)b * 128 * C + c;
       s1 += pp[(size_t)k * C] + pp[(size_t)(K + k) * C];
       s2 += pp[(size_t)(2 * K + k) * C] + pp[(size_t)(3 * K + k) * C];
     }
-    gcenters[(size_t)k * C + c] = s1 - ln_w[c] * s2 + (centers[(size_t)k * C + c] - ln_b[c]) * rc;
-    p2buf[(size_t)k * C + c] = s2;
+  s1s[grp][threadIdx.x & 63] = s1; s2s[grp][threadIdx.x & 63] = s2; rcs[threadIdx.x] = rc;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    rc = 0.f;
+    for (int i = 0; i < 512; ++i) rc += rcs[i];          // broadcast reads, fixed order
+    s1 = 0.f; s2 = 0.f;
+    for (int g = 0; g < 8; ++g) { s1 += s1s[g][threadIdx.x]; s2 += s2s[g][threadIdx.x]; }
+    if (blockIdx.y == 0 && threadIdx.x == 0) rcol[k] = rc;
+    if (c < C) {
+      gcenters[(size_t)k * C + c] = s1 - ln_w[c] * s2 + (centers[(size_t)k * C + c] - ln_b[c]) * rc;
+      p2buf[(size_t)k * C + c] = s2;
+    }
   }
 }
 
-// finalize 2 (thread = channel):
+// finalize 2: one warp per channel, lane = centroid (K == 32):
 //   g_beta[c]  = gamma_c sum_k P2[k,c] + beta_c sum_k rcol_k - sum_k rcol_k cen[k,c]
 //   g_gamma[c] = gamma_c Q[c] + beta_c sum_k P2[k,c] - sum_k cen[k,c] P2[k,c]
 __global__ void __launch_bounds__(256)
@@ -780,17 +788,18 @@ cluster_bwd_tc_finalize2_kernel(const float* __restrict__ p2buf, const float* __
                                 const float* __restrict__ part_q, const float* __restrict__ centers,
                                 const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                 int nb, int K, int C, float* __restrict__ gw, float* __restrict__ gb) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), k = threadIdx.x & 31;
   if (c >= C) return;
-  float sp2 = 0.f, scp = 0.f, src = 0.f, scr = 0.f, qv = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float s2 = p2buf[(size_t)k * C + c], cen = centers[(size_t)k * C + c], rc = rcol[k];
-    sp2 += s2; scp = fmaf(cen, s2, scp); src += rc; scr = fmaf(rc, cen, scr);
+  const float s2 = p2buf[(size_t)k * C + c], cen = centers[(size_t)k * C + c], rc = rcol[k];
+  float qv = 0.f;
+  for (int b = k; b < 2 * nb; b += 32) qv += part_q[(size_t)b * C + c];
+  const float sp2 = warp_sum(s2), scp = warp_sum(cen * s2), src = warp_sum(rc), scr = warp_sum(rc * cen);
+  qv = warp_sum(qv);
+  if (k == 0) {
+    const float g = ln_w[c], be = ln_b[c];
+    gb[c] = g * sp2 + be * src - scr;
+    gw[c] = g * qv + be * sp2 - scp;
   }
-  for (int b = 0; b < 2 * nb; ++b) qv += part_q[(size_t)b * C + c];
-  const float g = ln_w[c], be = ln_b[c];
-  gb[c] = g * sp2 + be * src - scr;
-  gw[c] = g * qv + be * sp2 - scp;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -909,10 +918,10 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
     free(h);
     cudaFree(trace);
   }
-  bt::cluster_bwd_tc_finalize1_kernel<<<K, 192, 0, st>>>(part_p, part_rcol, centers, ln_w, ln_b, grid, K, C,
+  bt::cluster_bwd_tc_finalize1_kernel<<<dim3(K, (C + 63) / 64), 512, 0, st>>>(part_p, part_rcol, centers, ln_w, ln_b, grid, K, C,
                                                         gcenters, p2buf, rcol);
   VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize1_kernel");
-  bt::cluster_bwd_tc_finalize2_kernel<<<(C + 63) / 64, 64, 0, st>>>(p2buf, rcol, part_q, centers, ln_w, ln_b, grid, K, C,
+  bt::cluster_bwd_tc_finalize2_kernel<<<(C + 7) / 8, 256, 0, st>>>(p2buf, rcol, part_q, centers, ln_w, ln_b, grid, K, C,
                                                                     g_ln_w, g_ln_b);
   VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize2_kernel");
   return VADC_OK;
