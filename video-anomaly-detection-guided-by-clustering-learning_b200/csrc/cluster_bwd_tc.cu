@@ -172,9 +172,14 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
 }
 __device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+__device__ __forceinline__ float2 bf_pair(uint32_t p) { return make_float2(bf_lo(p), bf_hi(p)); }
+__device__ __forceinline__ void split2_bf(float2 v, uint32_t& p1, uint32_t& p2) {
+  p1 = pack_bf2(v.x, v.y);
+  const float2 l = sub2(v, bf_pair(p1));
+  p2 = pack_bf2(l.x, l.y);
+}
 __device__ __forceinline__ void split2_bf(float a, float b, uint32_t& p1, uint32_t& p2) {
-  p1 = pack_bf2(a, b);
-  p2 = pack_bf2(a - bf_lo(p1), b - bf_hi(p1));
+  split2_bf(make_float2(a, b), p1, p2);
 }
 
 // butterfly transpose-reduce over the 32 lanes (rows) of a warp: stages with xor distance >= STOP.
@@ -240,6 +245,7 @@ struct Params {
   const float* ln_w; const float* ln_b; const uint8_t* cimage; const float* cvec; const float* g_loss_sq;
   float* part_p; float* part_rcol; float* part_q;        // [grid][128 slots][C], [grid][2][32], [grid][2][C]
   long long N; float alpha; int pf;
+  int dbg;                                               // timing experiments only (VADC_BWD_DBG): 1 = no producer loads, 2 = no producer stores
   unsigned long long* trace;                             // debugging: per-warp event log of CTA 0 (VADC_BWD_TRACE)
 };
 
@@ -342,13 +348,18 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
         const long long rows = min(8ll, p.N - rn);
         if (rows > 0) prefetch_l2_bulk(src + rn * C, (uint32_t)(rows * C * 4));
+        if (isx && v == 0) {                             // the tile's mu / rstd rows too (their latency is otherwise exposed)
+          const long long t0 = (tile + (long long)p.pf * gridDim.x) * kTok;
+          const long long nr = min((long long)kTok, p.N - t0) & ~3ll;   // bulk prefetch sizes are multiples of 16 bytes
+          if (nr > 0) { prefetch_l2_bulk(p.mu + t0, (uint32_t)(nr * 4)); prefetch_l2_bulk(p.rstd + t0, (uint32_t)(nr * 4)); }
+        }
       }
       const int r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
       const long long row = tile * kTok + r;
       const bool live = row < p.N;
       const float4* sr = reinterpret_cast<const float4*>(src + row * C) + lj;
 #pragma unroll
-      for (int i = 0; i < F4; ++i) U.v[i] = live ? ld_stream(sr + 8 * i) : make_float4(0, 0, 0, 0);
+      for (int i = 0; i < F4; ++i) U.v[i] = (live && !(p.dbg & 1)) ? ld_stream(sr + 8 * i) : make_float4(0, 0, 0, 0);
       U.rs = (isx && live) ? __ldg(p.rstd + row) : 0.f;
       U.nmr = (isx && live) ? -__ldg(p.mu + row) * U.rs : 0.f;
     };
@@ -385,14 +396,14 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         const uint32_t xb = sX32 + buf * pl.xbuf + e0;
 #pragma unroll
         for (int i = 0; i < F4; ++i) {
-          float4 h;
-          h.x = fmaf(U.v[i].x, U.rs, U.nmr); h.y = fmaf(U.v[i].y, U.rs, U.nmr);
-          h.z = fmaf(U.v[i].z, U.rs, U.nmr); h.w = fmaf(U.v[i].w, U.rs, U.nmr);
+          const float2 rs2 = bcast2(U.rs), nm2 = bcast2(U.nmr);
           uint32_t a1, a2, b1, b2;
-          split2_bf(h.x, h.y, a1, a2);
-          split2_bf(h.z, h.w, b1, b2);
+          split2_bf(fma2(make_float2(U.v[i].x, U.v[i].y), rs2, nm2), a1, a2);
+          split2_bf(fma2(make_float2(U.v[i].z, U.v[i].w), rs2, nm2), b1, b2);
+          if (!(p.dbg & 2)) {
           sts64((xb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
           sts64((xb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.xterm, a2, b2);
+          }
         }
       } else {
         // G is free once S1 / S5a of the previous tile have completed
@@ -403,8 +414,10 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
           uint32_t a1, a2, b1, b2;
           split2_bf(U.v[i].x, U.v[i].y, a1, a2);
           split2_bf(U.v[i].z, U.v[i].w, b1, b2);
+          if (!(p.dbg & 2)) {
           sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
           sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.gterm, a2, b2);
+          }
         }
       }
       TR(1, it);
@@ -455,6 +468,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         if (rows > 0) {
           prefetch_l2_bulk(p.D + rn * K, (uint32_t)(rows * K * 4));
           prefetch_l2_bulk(p.A + rn * K, (uint32_t)(rows * K * 4));
+          prefetch_l2_bulk(p.rowstats + rn * 4, (uint32_t)(rows * 16));
         }
       }
     };
@@ -485,29 +499,33 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_G1EMPTY0 + buf]);
       TR(40, it);
-      // softmin backward + cdist ratio
-      float dot0 = 0.f, dot1 = 0.f;
+      // softmin backward + cdist ratio (packed fp32: element pairs k, k+1)
+      const float2 sc2 = bcast2(sc);
+      float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 32; k += 2) {
-        gv[k] = fmaf(sc * dv[k], dv[k] * av[k], gv[k]);              // gA_tot = G1 + sc D^2 A
-        gv[k + 1] = fmaf(sc * dv[k + 1], dv[k + 1] * av[k + 1], gv[k + 1]);
-        dot0 = fmaf(gv[k], av[k], dot0);
-        dot1 = fmaf(gv[k + 1], av[k + 1], dot1);
+        const float2 d2 = make_float2(dv[k], dv[k + 1]), a2 = make_float2(av[k], av[k + 1]);
+        const float2 g2 = fma2(mul2(sc2, d2), mul2(d2, a2), make_float2(gv[k], gv[k + 1]));   // gA_tot = G1 + sc D^2 A
+        gv[k] = g2.x; gv[k + 1] = g2.y;
+        dot2 = fma2(g2, a2, dot2);
       }
-      const float dot = dot0 + dot1;
-      float rsum0 = 0.f, rsum1 = 0.f, sT0 = 0.f, sT1 = 0.f, sG0 = 0.f, sG1 = 0.f;
-      const float hz = 0.5f * zz;
+      const float2 dotb = bcast2(dot2.x + dot2.y), nalpha2 = bcast2(-p.alpha), hz2 = bcast2(0.5f * zz);
+      float2 rsum2 = make_float2(0.f, 0.f), sT2 = rsum2, sG2 = rsum2;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const float gd = av[k] * fmaf(sc * dv[k], av[k], -p.alpha * (gv[k] - dot));
-        float r = gd * fast_rcp(dv[k]);                  // ATen cdist backward: grad / dist, 0 where dist == 0
-        r = (dv[k] == 0.f || !live) ? 0.f : r;
-        gv[k] = r;
-        const float T = fmaf(-0.5f * dv[k], dv[k], hz + lds32f_const(sHc32 + 4 * k));
-        if (k & 1) { rsum1 += r; sT1 = fmaf(r, T, sT1); sG1 = fmaf(r, lds32f_const(sCg32 + 4 * k), sG1); }
-        else { rsum0 += r; sT0 = fmaf(r, T, sT0); sG0 = fmaf(r, lds32f_const(sCg32 + 4 * k), sG0); }
+      for (int k = 0; k < 32; k += 2) {
+        const float2 d2 = make_float2(dv[k], dv[k + 1]), a2 = make_float2(av[k], av[k + 1]);
+        const float2 t = sub2(make_float2(gv[k], gv[k + 1]), dotb);
+        const float2 gd = mul2(a2, fma2(mul2(sc2, d2), a2, mul2(nalpha2, t)));
+        float2 r = mul2(gd, make_float2(fast_rcp(d2.x), fast_rcp(d2.y)));   // ATen cdist backward: grad / dist, 0 where dist == 0
+        r.x = (d2.x == 0.f || !live) ? 0.f : r.x;
+        r.y = (d2.y == 0.f || !live) ? 0.f : r.y;
+        gv[k] = r.x; gv[k + 1] = r.y;
+        const float2 hc = make_float2(lds32f_const(sHc32 + 4 * k), lds32f_const(sHc32 + 4 * k + 4));
+        const float2 cg = make_float2(lds32f_const(sCg32 + 4 * k), lds32f_const(sCg32 + 4 * k + 4));
+        const float2 T = fma2(mul2(d2, bcast2(-0.5f)), d2, add2(hz2, hc));
+        rsum2 = add2(rsum2, r); sT2 = fma2(r, T, sT2); sG2 = fma2(r, cg, sG2);
       }
-      const float rsum = rsum0 + rsum1, sT = sT0 + sT1, sG = sG0 + sG1;
+      const float rsum = rsum2.x + rsum2.y, sT = sT2.x + sT2.y, sG = sG2.x + sG2.y;
       const float s1 = (rsum * p1 - sG) * invC, s2 = (rsum * p2 - sT) * invC;
       TR(41, it);
       // tile R free: S3 / S5b of the previous tile have completed
@@ -576,29 +594,35 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
             const uint32_t off = (((uint32_t)(ch * 4 + j) ^ rx) << 4);
             const uint4 h = lds128u(xrow + off);
             const uint4 l = lds128u(xrow + pl.xterm + off);
-            xh[8 * j + 0] = bf_lo(h.x) + bf_lo(l.x); xh[8 * j + 1] = bf_hi(h.x) + bf_hi(l.x);
-            xh[8 * j + 2] = bf_lo(h.y) + bf_lo(l.y); xh[8 * j + 3] = bf_hi(h.y) + bf_hi(l.y);
-            xh[8 * j + 4] = bf_lo(h.z) + bf_lo(l.z); xh[8 * j + 5] = bf_hi(h.z) + bf_hi(l.z);
-            xh[8 * j + 6] = bf_lo(h.w) + bf_lo(l.w); xh[8 * j + 7] = bf_hi(h.w) + bf_hi(l.w);
+            float2 t;
+            t = add2(bf_pair(h.x), bf_pair(l.x)); xh[8 * j + 0] = t.x; xh[8 * j + 1] = t.y;
+            t = add2(bf_pair(h.y), bf_pair(l.y)); xh[8 * j + 2] = t.x; xh[8 * j + 3] = t.y;
+            t = add2(bf_pair(h.z), bf_pair(l.z)); xh[8 * j + 4] = t.x; xh[8 * j + 5] = t.y;
+            t = add2(bf_pair(h.w), bf_pair(l.w)); xh[8 * j + 6] = t.x; xh[8 * j + 7] = t.y;
           }
           // the TMA store that last read this warp's staging block has finished reading
           if (lane == 0) bulk_wait_read0();
           __syncwarp();
+          // packed fp32 (element pairs): gz = z rsum - acc;  o = (gz gamma) rs - s1 rs - xhat s2 rs;  Q += xhat^2 rsum
+          const float2 nrsum2 = bcast2(-rsum), rsum2 = bcast2(rsum), nrs2 = bcast2(-rs), ns1r2 = bcast2(-s1r), ns2r2 = bcast2(-s2r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 gm = lds128f_const(sGam32 + (uint32_t)(c0 + 4 * j) * 4u);
             const float4 be = lds128f_const(sBet32 + (uint32_t)(c0 + 4 * j) * 4u);
-            float o[4];
-            const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, bev[4] = {be.x, be.y, be.z, be.w};
+            float2 o[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float xhv = xh[4 * j + e];
-              const float z = fmaf(xhv, gmv[e], bev[e]);
-              const float gz = fmaf(z, rsum, -acc[4 * j + e]);
-              o[e] = fmaf(-xhv, s2r, fmaf(gz * gmv[e], rs, -s1r));
-              xh[4 * j + e] = xhv * xhv * rsum;          // Q contribution
+            for (int e = 0; e < 2; ++e) {
+              const float2 g2 = e ? make_float2(gm.z, gm.w) : make_float2(gm.x, gm.y);
+              const float2 b2 = e ? make_float2(be.z, be.w) : make_float2(be.x, be.y);
+              const float2 x2 = make_float2(xh[4 * j + 2 * e], xh[4 * j + 2 * e + 1]);
+              const float2 a2 = make_float2(acc[4 * j + 2 * e], acc[4 * j + 2 * e + 1]);
+              const float2 z = fma2(x2, g2, b2);
+              const float2 ngz = fma2(z, nrsum2, a2);                      // -(gz) = acc - z rsum
+              o[e] = fma2(x2, ns2r2, fma2(mul2(ngz, g2), nrs2, ns1r2));
+              const float2 qq = mul2(mul2(x2, rsum2), x2);                 // Q contribution
+              xh[4 * j + 2 * e] = qq.x; xh[4 * j + 2 * e + 1] = qq.y;
             }
-            sts128f(stg32 + (uint32_t)lane * 128u + ((((uint32_t)j) ^ (uint32_t)(lane & 7)) << 4), o[0], o[1], o[2], o[3]);
+            sts128f(stg32 + (uint32_t)lane * 128u + ((((uint32_t)j) ^ (uint32_t)(lane & 7)) << 4), o[0].x, o[0].y, o[1].x, o[1].y);
           }
           fence_async_smem();
           __syncwarp();
@@ -890,7 +914,8 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
   const size_t trace_bytes = (size_t)16 * 1024 * 2 * sizeof(unsigned long long);
   if (trace_path) { VADC_CUDA(cudaMalloc(&trace, trace_bytes)); VADC_CUDA(cudaMemsetAsync(trace, 0, trace_bytes, st)); }
   bt::Params p{x, gR, D, A, mu, rstd, rowstats, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_q,
-               N, alpha, getenv("VADC_BWD_PF") ? atoi(getenv("VADC_BWD_PF")) : 1, trace};
+               N, alpha, getenv("VADC_BWD_PF") ? atoi(getenv("VADC_BWD_PF")) : 1,
+               getenv("VADC_BWD_DBG") ? atoi(getenv("VADC_BWD_DBG")) : 0, trace};
   bool launched = false;
 #define BT_CASE(F4_)                                                                                   \
   if (C == 32 * F4_) {                                                                                 \

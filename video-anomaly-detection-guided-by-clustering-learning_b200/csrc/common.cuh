@@ -88,4 +88,30 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
   return r;
 }
 
+
+// packed fp32 arithmetic on register pairs (sm_100: FFMA2 / FMUL2 / FADD2 — one issue slot for two lanes of work)
+__device__ __forceinline__ unsigned long long f2_bits(float2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ float2 f2_from(unsigned long long a) { return *reinterpret_cast<float2*>(&a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return f2_from(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(d);
+}
+__device__ __forceinline__ float2 bcast2(float a) { return make_float2(a, a); }
+
 }  // namespace vadc
