@@ -126,8 +126,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // exact two-term fp16 split of a pair: (a, b) = (lo(p1), hi(p1)) + (lo(p2), hi(p2)) + O(2^-22)
 __device__ __forceinline__ void split2_h(float a, float b, uint32_t& p1, uint32_t& p2) {
   p1 = pack_h2(a, b);
-  const float2 f = __half22float2(*reinterpret_cast<__half2*>(&p1));
-  p2 = pack_h2(a - f.x, b - f.y);
+  const float2 l = sub2(make_float2(a, b), __half22float2(*reinterpret_cast<__half2*>(&p1)));
+  p2 = pack_h2(l.x, l.y);
 }
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
@@ -294,19 +294,23 @@ cluster_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
       float mean[2], rs[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        float s = 0.f;
+        float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < F4; ++i) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+        for (int i = 0; i < F4; ++i) s2 = add2(s2, add2(make_float2(v[u][i].x, v[u][i].y), make_float2(v[u][i].z, v[u][i].w)));
+        float s = s2.x + s2.y;
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         mean[u] = s * invC;
-        float q = 0.f;
+        const float2 nm2 = bcast2(-mean[u]);
+        float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < F4; ++i) {
-          v[u][i].x -= mean[u]; v[u][i].y -= mean[u]; v[u][i].z -= mean[u]; v[u][i].w -= mean[u];
-          q += (v[u][i].x * v[u][i].x + v[u][i].y * v[u][i].y) + (v[u][i].z * v[u][i].z + v[u][i].w * v[u][i].w);
+          const float2 a = add2(make_float2(v[u][i].x, v[u][i].y), nm2), b = add2(make_float2(v[u][i].z, v[u][i].w), nm2);
+          v[u][i] = make_float4(a.x, a.y, b.x, b.y);
+          q2 = fma2(a, a, fma2(b, b, q2));
         }
+        float q = q2.x + q2.y;
         q += __shfl_xor_sync(0xffffffffu, q, 1);
         q += __shfl_xor_sync(0xffffffffu, q, 2);
         q += __shfl_xor_sync(0xffffffffu, q, 4);
@@ -320,7 +324,7 @@ cluster_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
         const int r = blk * 8 + rsel + 2 * u;
         const long long row = row0 + r;
         const bool live = row < p.N;
-        float nz = 0.f, p1 = 0.f, p2 = 0.f;                 // |z|^2, sum z gamma, sum z gamma xhat (for the backward)
+        float2 nz2 = make_float2(0.f, 0.f), p12 = nz2, p22 = nz2;   // |z|^2, sum z gamma, sum z gamma xhat (for the backward)
         const uint32_t rx = (uint32_t)(r & 7);
         const uint32_t zrow = sZ32 + (uint32_t)r * 128u;
         float4* frow = reinterpret_cast<float4*>(p.feature + row * C) + lj;
@@ -328,26 +332,31 @@ cluster_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
         for (int i = 0; i < F4; ++i) {
           const float4 gm = lds128f(sGam32 + i * 128);
           const float4 be = lds128f(sBet32 + i * 128);
-          float4 th, o;
-          th.x = v[u][i].x * rs[u]; th.y = v[u][i].y * rs[u]; th.z = v[u][i].z * rs[u]; th.w = v[u][i].w * rs[u];
-          o.x = fmaf(th.x, gm.x, be.x);
-          o.y = fmaf(th.y, gm.y, be.y);
-          o.z = fmaf(th.z, gm.z, be.z);
-          o.w = fmaf(th.w, gm.w, be.w);
-          if (live) { if (p.hint & 1) st_hint(frow + 8 * i, o, pol); else frow[8 * i] = o; } else o = make_float4(0, 0, 0, 0);
-          nz += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+          const float2 rs2 = bcast2(rs[u]);
+          const float2 g01 = make_float2(gm.x, gm.y), g23 = make_float2(gm.z, gm.w);
+          const float2 t01 = mul2(make_float2(v[u][i].x, v[u][i].y), rs2), t23 = mul2(make_float2(v[u][i].z, v[u][i].w), rs2);
+          float2 o01 = fma2(t01, g01, make_float2(be.x, be.y)), o23 = fma2(t23, g23, make_float2(be.z, be.w));
+          if (live) {
+            const float4 o = make_float4(o01.x, o01.y, o23.x, o23.y);
+            if (p.hint & 1) st_hint(frow + 8 * i, o, pol); else frow[8 * i] = o;
+          } else {
+            o01 = make_float2(0.f, 0.f); o23 = o01;
+          }
+          nz2 = fma2(o01, o01, fma2(o23, o23, nz2));
           if (p.rowstats) {
-            const float gx = o.x * gm.x, gy = o.y * gm.y, gz = o.z * gm.z, gw = o.w * gm.w;
-            p1 += (gx + gy) + (gz + gw);
-            p2 = fmaf(gx, th.x, fmaf(gy, th.y, fmaf(gz, th.z, fmaf(gw, th.w, p2))));
+            const float2 og01 = mul2(o01, g01), og23 = mul2(o23, g23);
+            p12 = add2(p12, add2(og01, og23));
+            p22 = fma2(og01, t01, fma2(og23, t23, p22));
           }
           uint32_t a1, a2, b1, b2;
           if constexpr (SCALED) {
-            split2_h(o.x * s_z, o.y * s_z, a1, a2);
-            split2_h(o.z * s_z, o.w * s_z, b1, b2);
+            const float2 sz2 = bcast2(s_z);
+            const float2 w01 = mul2(o01, sz2), w23 = mul2(o23, sz2);
+            split2_h(w01.x, w01.y, a1, a2);
+            split2_h(w23.x, w23.y, b1, b2);
           } else {
-            split2_h(o.x, o.y, a1, a2);
-            split2_h(o.z, o.w, b1, b2);
+            split2_h(o01.x, o01.y, a1, a2);
+            split2_h(o23.x, o23.y, b1, b2);
           }
           const int f = lj + 8 * i;                          // float4 index in the row: channels 4f..4f+3
           const uint32_t byte = (uint32_t)(f & 15) * 8u;     // 8 bytes of fp16 in the 128-byte row of block f/16
@@ -355,6 +364,7 @@ cluster_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_con
           sts64(zrow + off, a1, b1);
           sts64(zrow + zterm + off, a2, b2);
         }
+        float nz = nz2.x + nz2.y, p1 = p12.x + p12.y, p2 = p22.x + p22.y;
         nz += __shfl_xor_sync(0xffffffffu, nz, 1);
         nz += __shfl_xor_sync(0xffffffffu, nz, 2);
         nz += __shfl_xor_sync(0xffffffffu, nz, 4);
