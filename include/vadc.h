@@ -241,6 +241,11 @@ int vadc_memory_separateness(const float* keys, int m, int d, float* out,
  * pin the descriptor encodings the fused kernels rely on.
  * ------------------------------------------------------------------------ */
 int vadc_debug_umma(const float* A, const float* B, float* out, int N, int Kd, int mode, void* stream);
+/* self-test of the TMA-fed tcgen05 GEMM (three-term bf16 split, six products): out [M,N] = A [M,Kd] . B^T with
+ * B [N,Kd] (b_mn = 0) or B [Kd,N] (b_mn = 1). */
+size_t vadc_debug_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t Kd);
+int vadc_debug_tc_gemm(const float* A, const float* B, int64_t M, int64_t N, int64_t Kd, int b_mn,
+                       float* out, void* workspace, size_t workspace_bytes, void* stream);
 /* issue-rate micro-benchmark of one tcgen05.mma shape (bf16, shared-memory operands): `reps` x 8
  * instructions back to back; out[0] = cycles until the commit arrives, out[1] = cycles to issue. */
 int vadc_debug_umma_bench(int M, int N, int a_mn, int b_mn, int reps, long long* out, void* stream);

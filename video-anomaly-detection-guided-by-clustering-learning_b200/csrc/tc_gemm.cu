@@ -1,0 +1,251 @@
+// tc_gemm.cu — fp32-faithful GEMM on tcgen05 / TMEM fed by TMA, for the contractions of the path
+// that are NOT covered by the fused K == 32 kernels and are tensor-bound: the
+// distance / x_rec GEMMs of the cluster head at C = 768 or K >= 64 (BASELINE configs[2], the
+// reference-native K = 1024 head) and the memory score / read GEMMs (m = 2000, d = 768: 244 flop/B).
+//
+//   C[m,n] = sum_k A[m,k] B(n,k)      A [M,Kd] row-major;  B [N,Kd] row-major (K-major) or [Kd,N] row-major (MN-major)
+//
+// fp32 inputs are first split into THREE bf16 terms v = t0 + t1 + t2 (exact: 3 x 8 mantissa bits),
+// written once as bf16 matrices of the same layout (split3_kernel: 6 bytes per element of workspace);
+// the GEMM keeps the six products t0t0, t0t1, t1t0, t0t2, t1t1, t2t0 in the fp32 TMEM accumulator
+// (dropped terms <= 2^-24 relative), which is what keeps argmin bit-exact against the fp32 reference.
+//
+// One CTA = one 128 x BN output tile: warp 0 = TMA producer (3-D tensor maps {cols, rows, term},
+// SWIZZLE_128B boxes land directly as UMMA operand tiles), warp 1 = MMA issuer, warps 2-5 = epilogue
+// (thread = output row = TMEM lane, functor per 32 columns).  Two 96 KB stages.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <stdio.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace vadc {
+using namespace tc;
+
+namespace tg {
+
+constexpr int BM = 128, BK = 64, kStages = 2, kThreads = 192;
+
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ src, long long n4, __nv_bfloat16* __restrict__ t0,
+              __nv_bfloat16* __restrict__ t1, __nv_bfloat16* __restrict__ t2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float a[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[0][j] = __float2bfloat16_rn(a[j]);
+      const float r1 = a[j] - __bfloat162float(h[0][j]);
+      h[1][j] = __float2bfloat16_rn(r1);
+      h[2][j] = __float2bfloat16_rn(r1 - __bfloat162float(h[1][j]));
+    }
+    reinterpret_cast<uint2*>(t0)[i] = *reinterpret_cast<uint2*>(h[0]);
+    reinterpret_cast<uint2*>(t1)[i] = *reinterpret_cast<uint2*>(h[1]);
+    reinterpret_cast<uint2*>(t2)[i] = *reinterpret_cast<uint2*>(h[2]);
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int BN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               int M, int N, int Kd, Epi epi) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t kATerm = BM * 128u, kBTerm = BN * 128u;           // bytes per bf16 term of a stage's operand
+  constexpr uint32_t kStage = 3u * kATerm + 3u * kBTerm;
+  __shared__ uint64_t full[kStages], empty[kStages], accfull;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = (Kd + BK - 1) / BK;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&accfull, 1);
+    fence_mbar_init();
+    prefetch_tmap(&mapA); prefetch_tmap(&mapB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t s0 = smem_u32(smem);
+
+  if (warp == 0 && lane == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(&empty[s], (uint32_t)(((kb / kStages) & 1) ^ 1));
+      mbar_expect_tx(&full[s], kStage);
+      const uint32_t a = s0 + s * kStage, b = a + 3u * kATerm;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        tma_load_3d(&mapA, a + t * kATerm, &full[s], kb * BK, m0, t);
+        if constexpr (!B_MN) {
+          tma_load_3d(&mapB, b + t * kBTerm, &full[s], kb * BK, n0, t);
+        } else {
+#pragma unroll
+          for (int nb = 0; nb < BN / 64; ++nb)                // [64 k-rows x 64 n-cols] boxes, 8 KB apart
+            tma_load_3d(&mapB, b + t * kBTerm + nb * 8192u, &full[s], n0 + nb * 64, kb * BK, t);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, B_MN ? 1 : 0);
+    constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};     // small products first
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(&full[s], (uint32_t)((kb / kStages) & 1));
+      tc_fence_after();
+      const uint32_t a = s0 + s * kStage, b = a + 3u * kATerm;
+#pragma unroll
+      for (int pr = 0; pr < 6; ++pr) {
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t ad = smem_desc_sw128(a + ta[pr] * kATerm + kk * 32u, 0, 1024);
+          const uint64_t bd = B_MN ? smem_desc_sw128(b + tb[pr] * kBTerm + kk * 2048u, 8192, 1024)
+                                   : smem_desc_sw128(b + tb[pr] * kBTerm + kk * 32u, 0, 1024);
+          mma_f16(tmem, ad, bd, idesc, (kb > 0 || pr > 0 || kk > 0) ? 1u : 0u);
+        }
+      }
+      mma_commit(&empty[s]);
+    }
+    mma_commit(&accfull);
+  } else if (warp >= 2) {
+    // ---------------------------------------------------------------- epilogue: thread = row = TMEM lane
+    const int q = warp & 3;
+    const long long m = (long long)m0 + q * 32 + lane;
+    mbar_wait(&accfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int n = n0 + c * 32;
+      if (m < M && n < N) epi(m, n, v, min(32, N - n));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, BN); }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// three bf16 term matrices [rows, cols] stored back to back -> 3-D map {cols, rows, 3}, box {64, box_rows, 1}
+static int make_map3(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return VADC_ERR_CUDA;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+    return VADC_ERR_CUDA;
+  }
+  return VADC_OK;
+}
+
+}  // namespace tg
+
+bool tc_gemm_shape_ok(long long M, long long N, long long Kd, bool b_mn) {
+  if (M < 1 || N < 8 || Kd < 8 || M >= (1ll << 31) || N >= (1ll << 31) || Kd >= (1ll << 31)) return false;
+  if (Kd % 8) return false;                 // TMA row pitch (bf16) must be a multiple of 16 bytes
+  if (b_mn && (N % 8)) return false;
+  return vadc_device_ok() != 0;
+}
+
+size_t tc_gemm_split_bytes(long long rows, long long cols) {
+  return align_up((size_t)3 * rows * cols * sizeof(__nv_bfloat16), 256);
+}
+
+int tc_split3(const float* src, long long rows, long long cols, void* dst, cudaStream_t st) {
+  const long long n = rows * cols;
+  if (n % 4) return VADC_ERR_BAD_SHAPE;
+  __nv_bfloat16* t0 = static_cast<__nv_bfloat16*>(dst);
+  const long long n4 = n / 4;
+  const int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)sm_count() * 8);
+  tg::split3_kernel<<<grid, 256, 0, st>>>(src, n4, t0, t0 + n, t0 + 2 * n);
+  VADC_CHECK_LAUNCH("split3_kernel");
+  return VADC_OK;
+}
+
+template <bool B_MN, class Epi>
+int launch_tc_gemm(const void* a_split, const void* b_split, long long M, long long N, long long Kd, Epi epi,
+                   cudaStream_t st) {
+  constexpr int BN = 128;
+  CUtensorMap mA, mB;
+  int rc;
+  if ((rc = tg::make_map3(&mA, a_split, M, Kd, tg::BM))) return rc;
+  if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64);        // [Kd rows, N cols]: boxes of 64 k-rows x 64 n-cols
+  else rc = tg::make_map3(&mB, b_split, N, Kd, BN);             // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
+  if (rc) return rc;
+  const size_t smem = (size_t)tg::kStages * (3 * tg::BM * 128 + 3 * BN * 128) + 1024;
+  auto kern = tg::tc_gemm_kernel<BN, B_MN, Epi>;
+  VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM));
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, epi);
+  VADC_CHECK_LAUNCH("tc_gemm_kernel");
+  return VADC_OK;
+}
+
+// explicit instantiations for the epilogues of the path
+template int launch_tc_gemm<false, TcStoreEpi>(const void*, const void*, long long, long long, long long, TcStoreEpi, cudaStream_t);
+template int launch_tc_gemm<true, TcStoreEpi>(const void*, const void*, long long, long long, long long, TcStoreEpi, cudaStream_t);
+template int launch_tc_gemm<false, TcDistEpi>(const void*, const void*, long long, long long, long long, TcDistEpi, cudaStream_t);
+template int launch_tc_gemm<true, TcReadEpi>(const void*, const void*, long long, long long, long long, TcReadEpi, cudaStream_t);
+
+}  // namespace vadc
+
+// ---------------------------------------------------------------------------
+// self-test entry: out[M,N] = A[M,Kd] . B^T  (b_mn = 0: B is [N,Kd]; b_mn = 1: B is [Kd,N])
+// ---------------------------------------------------------------------------
+extern "C" size_t vadc_debug_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t Kd) {
+  return vadc::tc_gemm_split_bytes(M, Kd) + vadc::tc_gemm_split_bytes(N, Kd) + 256;
+}
+
+extern "C" int vadc_debug_tc_gemm(const float* A, const float* B, int64_t M, int64_t N, int64_t Kd, int b_mn,
+                                  float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace vadc;
+  VADC_REQUIRE(A && B && out && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(tc_gemm_shape_ok(M, N, Kd, b_mn != 0), VADC_ERR_UNSUPPORTED);
+  VADC_REQUIRE(workspace_bytes >= vadc_debug_tc_gemm_workspace_bytes(M, N, Kd), VADC_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver ws(workspace, workspace_bytes);
+  void* as = ws.take<uint8_t>(tc_gemm_split_bytes(M, Kd));
+  void* bs = ws.take<uint8_t>(tc_gemm_split_bytes(N, Kd));
+  int rc;
+  if ((rc = tc_split3(A, M, Kd, as, st))) return rc;
+  if ((rc = b_mn ? tc_split3(B, Kd, N, bs, st) : tc_split3(B, N, Kd, bs, st))) return rc;
+  TcStoreEpi epi{out, N};
+  return b_mn ? launch_tc_gemm<true>(as, bs, M, N, Kd, epi, st) : launch_tc_gemm<false>(as, bs, M, N, Kd, epi, st);
+}

@@ -1,0 +1,60 @@
+// tc_gemm.cuh — interface of the TMA-fed tcgen05 GEMM (tc_gemm.cu) and its epilogue functors.
+// An epilogue receives 32 consecutive columns of one output row: epi(m, n, v[32], nvalid).
+#pragma once
+#include "common.cuh"
+
+namespace vadc {
+
+bool tc_gemm_shape_ok(long long M, long long N, long long Kd, bool b_mn);
+size_t tc_gemm_split_bytes(long long rows, long long cols);     // workspace of one operand's three bf16 terms
+int tc_split3(const float* src, long long rows, long long cols, void* dst, cudaStream_t st);
+
+// C[m,n] = sum_k A[m,k] B(n,k); a_split / b_split from tc_split3 ([M,Kd]; [N,Kd] or, with B_MN, [Kd,N])
+template <bool B_MN, class Epi>
+int launch_tc_gemm(const void* a_split, const void* b_split, long long M, long long N, long long Kd, Epi epi,
+                   cudaStream_t st);
+
+__device__ __forceinline__ void tc_store_row32(float* o, const float (&v)[32], int nvalid) {
+  if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < nvalid) o[j] = v[j];
+  }
+}
+
+struct TcStoreEpi {
+  float* out; long long ldo;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid) const {
+    tc_store_row32(out + m * ldo + n, v, nvalid);
+  }
+};
+
+// torch.cdist, mm form: sqrt(max(0, |a|^2 + |b|^2 - 2 a.b))
+struct TcDistEpi {
+  float* out; const float* aa; const float* bb; long long ldo;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid) const {
+    const float am = aa[m];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float b = (j < nvalid) ? bb[n + j] : 0.f;
+      v[j] = sqrtf(fmaxf(am + b - 2.0f * v[j], 0.f));
+    }
+    tc_store_row32(out + m * ldo + n, v, nvalid);
+  }
+};
+
+// Memory.read (Memory.py:249-261): uq[m, 0:d] = q[m], uq[m, d:2d] = score_memory @ keys
+struct TcReadEpi {
+  float* uq; const float* q; int d;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid) const {
+    float* o = uq + m * 2 * d;
+    tc_store_row32(o + d + n, v, nvalid);
+    const float* qs = q + m * d + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < nvalid) o[n + j] = qs[j];
+  }
+};
+
+}  // namespace vadc
