@@ -208,8 +208,10 @@ int vadc_memory_score(const float* q, const float* keys, int64_t N, int m, int d
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* read  Memory.py:249-261: updated_query [N,2d] = cat(q, score_memory @ keys) */
+size_t vadc_memory_read_workspace_bytes(int64_t N, int m, int d);
 int vadc_memory_read(const float* q, const float* score_memory, const float* keys,
-                     int64_t N, int m, int d, float* updated_query, void* stream);
+                     int64_t N, int m, int d, float* updated_query,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* gather_loss Memory.py:233-247 (out[0]) and spread_loss :214-231 (out[1],
  * TripletMarginLoss(margin=1,p=2,eps=1e-6)); top2 == NULL skips spread. */

@@ -6,6 +6,7 @@
 #include "sgemm.cuh"
 #include "rows.cuh"
 #include "cluster.h"
+#include "tc_gemm.cuh"
 #include <algorithm>
 #include <stdlib.h>
 
@@ -256,6 +257,8 @@ extern "C" size_t vadc_cluster_fwd_workspace_bytes(int64_t N, int C, int K, int 
   b += align_up((size_t)K * sizeof(float), 256);                         // |c|^2
   b += align_up((size_t)(softmin_blocks(N, K) + 1) * sizeof(double), 256);
   b += std::max(vadc_cluster_tc_extra_workspace_bytes(N, C, K), vadc_cluster_ws_extra_workspace_bytes(N, C, K));
+  if (impl != VADC_IMPL_SIMT && N > 0)                                   // bf16 term copies for the tcgen05 GEMMs
+    b += tc_gemm_split_bytes(N, C) + tc_gemm_split_bytes(K, C) + tc_gemm_split_bytes(N, K);
   return b + 256;
 }
 
@@ -293,6 +296,22 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
   int rc;
   if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, feature, mu, rstd, zz, st))) return rc;
   if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
+  // shapes outside the fused kernels (C = 768, K = 16 / 64 / 256 / 1024): the two contractions run on the
+  // tcgen05 GEMM (three-term bf16 split: fp32-faithful), LayerNorm / softmin stay row kernels
+  const bool use_tc = impl != VADC_IMPL_SIMT && N > 0 && !getenv("VADC_NO_TC_GEMM") &&
+                      tc_gemm_shape_ok(N, K, C, false) && tc_gemm_shape_ok(N, C, K, true);
+  if (use_tc) {
+    void* fs = ws.take<uint8_t>(tc_gemm_split_bytes(N, C));
+    void* cs = ws.take<uint8_t>(tc_gemm_split_bytes(K, C));
+    void* as = ws.take<uint8_t>(tc_gemm_split_bytes(N, K));
+    if ((rc = tc_split3(feature, N, C, fs, st))) return rc;
+    if ((rc = tc_split3(centers, K, C, cs, st))) return rc;
+    if ((rc = launch_tc_gemm<false>(fs, cs, N, K, C, TcDistEpi{D, zz, cc, K}, st))) return rc;
+    if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
+    if ((rc = tc_split3(A, N, K, as, st))) return rc;
+    if ((rc = launch_tc_gemm<true>(as, cs, N, C, K, TcStoreEpi{x_rec, C}, st))) return rc;    // centers [K,C] read MN-major
+    return launch_rowstats(x, feature, mu, rstd, ln_w, N, C, rowstats, st);
+  }
   if ((rc = launch_dist(feature, centers, zz, cc, 1, N, K, C, D, st))) return rc;
   if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
   if (N > 0) {

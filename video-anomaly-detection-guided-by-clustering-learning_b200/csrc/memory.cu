@@ -3,6 +3,7 @@
 // gather / spread losses, weighted segmented update, separateness.
 #include "common.cuh"
 #include "sgemm.cuh"
+#include "tc_gemm.cuh"
 #include "rows.cuh"
 #include "cluster.h"
 
@@ -371,7 +372,8 @@ extern "C" int vadc_memory_prepare_query(const float* query, int B, int d, int64
 extern "C" size_t vadc_memory_score_workspace_bytes(int64_t N, int m, int d) {
   (void)d;
   size_t n = (size_t)(N > 0 ? N : 1);
-  return align_up(n * m * sizeof(float), 256) + 2 * align_up((size_t)col_chunks(N) * m * sizeof(float), 256) + 256;
+  return align_up(n * m * sizeof(float), 256) + 2 * align_up((size_t)col_chunks(N) * m * sizeof(float), 256) +
+         tc_gemm_split_bytes((long long)n, d) + tc_gemm_split_bytes(m, d) + 256;      // bf16 terms of q and keys
 }
 
 extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, int m, int d,
@@ -390,7 +392,15 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
   int chunks = col_chunks(N);
   float* pmax = ws.take<float>((size_t)chunks * m);
   float* psum = ws.take<float>((size_t)chunks * m);
-  {
+  if (tc_gemm_shape_ok(N, m, d, false) && !getenv("VADC_NO_TC_GEMM")) {
+    // q . keys^T on tcgen05 (m = 2000, d = 768 is tensor-bound: 244 flop/B), fp32-faithful three-term split
+    void* qs = ws.take<uint8_t>(tc_gemm_split_bytes(N, d));
+    void* ks = ws.take<uint8_t>(tc_gemm_split_bytes(m, d));
+    int rc;
+    if ((rc = tc_split3(q, N, d, qs, st))) return rc;
+    if ((rc = tc_split3(keys, m, d, ks, st))) return rc;
+    if ((rc = launch_tc_gemm<false>(qs, ks, N, m, d, TcStoreEpi{logits, m}, st))) return rc;
+  } else {
     Operand Aop{q, d, 1}, Bop{keys, 1, d};
     StoreLogits epi{logits, m};
     cudaError_t e = sgemm_auto((int)N, m, d, Aop, Bop, 0, 0, 1, 1, epi, st);
@@ -415,15 +425,33 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
   return VADC_OK;
 }
 
+extern "C" size_t vadc_memory_read_workspace_bytes(int64_t N, int m, int d) {
+  size_t n = (size_t)(N > 0 ? N : 1);
+  return tc_gemm_split_bytes((long long)n, m) + tc_gemm_split_bytes(m, d) + 256;      // bf16 terms of score_memory and keys
+}
+
 extern "C" int vadc_memory_read(const float* q, const float* score_memory, const float* keys,
-                                int64_t N, int m, int d, float* updated_query, void* stream) {
+                                int64_t N, int m, int d, float* updated_query,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   VADC_REQUIRE(N >= 0 && m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
   if (N == 0) return VADC_OK;
   VADC_REQUIRE(q && score_memory && keys && updated_query, VADC_ERR_NULL_POINTER);
   VADC_REQUIRE(N < (1ll << 31), VADC_ERR_UNSUPPORTED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (workspace && workspace_bytes >= vadc_memory_read_workspace_bytes(N, m, d) && tc_gemm_shape_ok(N, d, m, true) &&
+      !getenv("VADC_NO_TC_GEMM")) {
+    // score_memory [N,m] . keys [m,d] (keys read MN-major) on tcgen05
+    Carver ws(workspace, workspace_bytes);
+    void* ss = ws.take<uint8_t>(tc_gemm_split_bytes(N, m));
+    void* ks = ws.take<uint8_t>(tc_gemm_split_bytes(m, d));
+    int rc;
+    if ((rc = tc_split3(score_memory, N, m, ss, st))) return rc;
+    if ((rc = tc_split3(keys, m, d, ks, st))) return rc;
+    return launch_tc_gemm<true>(ss, ks, N, d, m, TcReadEpi{updated_query, q, d}, st);
+  }
   Operand Aop{score_memory, m, 1}, Bop{keys, d, 1};
   ReadEpilogue epi{updated_query, q, d};
-  cudaError_t e = sgemm_auto((int)N, d, m, Aop, Bop, 0, 0, 1, 1, epi, static_cast<cudaStream_t>(stream));
+  cudaError_t e = sgemm_auto((int)N, d, m, Aop, Bop, 0, 0, 1, 1, epi, st);
   if (e != cudaSuccess) return record_cuda_error(e, "memory read sgemm");
   return VADC_OK;
 }

@@ -165,8 +165,10 @@ class Memory(nn.Module):
         B, h, w, d = shp
         N, m = s.q.shape[0], keys.shape[0]
         uq = torch.empty((N, 2 * d), device=s.q.device, dtype=torch.float32)
-        check(_lib.lib().vadc_memory_read(ptr(s.q), ptr(s.score_memory), ptr(keys), N, m, d, ptr(uq), stream()),
-              "vadc_memory_read")
+        l = _lib.lib()
+        ws = workspace(l.vadc_memory_read_workspace_bytes(N, m, d), uq.device)
+        check(l.vadc_memory_read(ptr(s.q), ptr(s.score_memory), ptr(keys), N, m, d, ptr(uq), ptr(ws), ws.numel(),
+                                 stream()), "vadc_memory_read")
         return uq.view(B, h, w, 2 * d).permute(0, 3, 1, 2)          # Memory.py:258-259
 
     def _segmented_update(self, q, keys, score_query, top1):
