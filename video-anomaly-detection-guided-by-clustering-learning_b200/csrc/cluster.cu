@@ -84,11 +84,12 @@ __global__ void zero_kernel(float* p, long long n) {
 // launch helpers shared with space_cluster.cu / memory.cu
 // ---------------------------------------------------------------------------
 int launch_ln_rows(const float* x, const float* w, const float* b, long long N, int C, float eps,
-                   float* z, float* mu, float* rstd, float* zz, cudaStream_t st) {
+                   float* z, float* mu, float* rstd, float* zz, cudaStream_t st, float* rowstats, void* split3) {
   if (N == 0) return VADC_OK;
   const int wpb = 8;
   dim3 grid((unsigned)((N + wpb - 1) / wpb));
-#define LN_CASE(V) ln_rows_kernel<V><<<grid, wpb * 32, 0, st>>>(x, w, b, N, C, eps, z, mu, rstd, zz)
+#define LN_CASE(V) ln_rows_kernel<V><<<grid, wpb * 32, 0, st>>>(x, w, b, N, C, eps, z, mu, rstd, zz, rowstats, \
+                                                              static_cast<__nv_bfloat16*>(split3))
   if (C <= 128) LN_CASE(1);
   else if (C <= 256) LN_CASE(2);
   else if (C <= 512) LN_CASE(4);
@@ -137,7 +138,7 @@ int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* 
     default: softmin_rows_kernel<32><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
   }
   VADC_CHECK_LAUNCH("softmin_rows_kernel");
-  finalize_sum_kernel<<<1, 256, 0, st>>>(partial, nb, loss_sq);
+  finalize_sum_kernel<<<1, 1024, 0, st>>>(partial, nb, loss_sq);
   VADC_CHECK_LAUNCH("finalize_sum_kernel");
   return VADC_OK;
 }
@@ -294,24 +295,25 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
   float* cc = ws.take<float>(K);
   double* partial = ws.take<double>(softmin_blocks(N, K) + 1);
   int rc;
-  if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, feature, mu, rstd, zz, st))) return rc;
-  if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
   // shapes outside the fused kernels (C = 768, K = 16 / 64 / 256 / 1024): the two contractions run on the
-  // tcgen05 GEMM (three-term bf16 split: fp32-faithful), LayerNorm / softmin stay row kernels
+  // tcgen05 GEMM (three-term bf16 split: fp32-faithful); LayerNorm (+ rowstats + the split of z) and softmin
+  // stay row kernels
   const bool use_tc = impl != VADC_IMPL_SIMT && N > 0 && !getenv("VADC_NO_TC_GEMM") &&
                       tc_gemm_shape_ok(N, K, C, false) && tc_gemm_shape_ok(N, C, K, true);
   if (use_tc) {
     void* fs = ws.take<uint8_t>(tc_gemm_split_bytes(N, C));
     void* cs = ws.take<uint8_t>(tc_gemm_split_bytes(K, C));
     void* as = ws.take<uint8_t>(tc_gemm_split_bytes(N, K));
-    if ((rc = tc_split3(feature, N, C, fs, st))) return rc;
+    if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, feature, mu, rstd, zz, st, rowstats, fs))) return rc;
+    if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
     if ((rc = tc_split3(centers, K, C, cs, st))) return rc;
     if ((rc = launch_tc_gemm<false>(fs, cs, N, K, C, TcDistEpi{D, zz, cc, K}, st))) return rc;
     if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
     if ((rc = tc_split3(A, N, K, as, st))) return rc;
-    if ((rc = launch_tc_gemm<true>(as, cs, N, C, K, TcStoreEpi{x_rec, C}, st))) return rc;    // centers [K,C] read MN-major
-    return launch_rowstats(x, feature, mu, rstd, ln_w, N, C, rowstats, st);
+    return launch_tc_gemm<true>(as, cs, N, C, K, TcStoreEpi{x_rec, C}, st);    // centers [K,C] read MN-major
   }
+  if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, feature, mu, rstd, zz, st, rowstats))) return rc;
+  if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
   if ((rc = launch_dist(feature, centers, zz, cc, 1, N, K, C, D, st))) return rc;
   if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
   if (N > 0) {
@@ -320,7 +322,7 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
     cudaError_t e = sgemm_auto((int)N, C, K, Aop, Bop, 0, 0, 1, 1, epi, st);
     if (e != cudaSuccess) return record_cuda_error(e, "x_rec sgemm");
   }
-  return launch_rowstats(x, feature, mu, rstd, ln_w, N, C, rowstats, st);
+  return VADC_OK;
 }
 
 namespace vadc {

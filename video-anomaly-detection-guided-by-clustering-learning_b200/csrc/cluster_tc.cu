@@ -555,7 +555,7 @@ int vadc_cluster_fwd_tc(const float* x, const float* ln_w, const float* ln_b, co
 #undef TC_CASE
   if (!launched) return VADC_ERR_UNSUPPORTED;
   VADC_CHECK_LAUNCH("cluster_fwd_tc_kernel");
-  finalize_sum_kernel<<<1, 256, 0, st>>>(partial, grid, loss_sq);
+  finalize_sum_kernel<<<1, 1024, 0, st>>>(partial, grid, loss_sq);
   VADC_CHECK_LAUNCH("finalize_sum_kernel");
   return VADC_OK;
 }

@@ -2,6 +2,7 @@
 // the memory module: LayerNorm rows, squared row norms, the softmin / argmin /
 // loss row pass, the backward row pass, and deterministic column reductions.
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace vadc {
@@ -16,7 +17,10 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                long long N, int C, float eps, float* __restrict__ z, float* __restrict__ mu,
-               float* __restrict__ rstd, float* __restrict__ zz) {
+               float* __restrict__ rstd, float* __restrict__ zz, float* __restrict__ rowstats,
+               __nv_bfloat16* __restrict__ split) {
+  // optional fused outputs: rowstats [N,4] = {|z|^2, sum z gamma, sum z gamma xhat, 0} (what the tcgen05 backward
+  // uses) and the three bf16 terms of z ([3][N,C], the tcgen05 GEMM's A operand) - saves two more passes over z
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -42,7 +46,8 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
   }
   const float var = warp_sum(q) / (float)C;
   const float rs = 1.0f / sqrtf(var + eps);
-  float nz = 0.f;
+  float nz = 0.f, p1 = 0.f, p2 = 0.f;
+  const long long term = N * (long long)C;
   float4* zr = reinterpret_cast<float4*>(z + row * C);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -57,13 +62,35 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
       o.w = (v[i].w - mean) * rs * g.w + be.w;
       zr[c4] = o;
       nz += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+      if (rowstats) {
+        const float gx = o.x * g.x, gy = o.y * g.y, gz = o.z * g.z, gw = o.w * g.w;
+        p1 += (gx + gy) + (gz + gw);
+        p2 += (gx * ((v[i].x - mean) * rs) + gy * ((v[i].y - mean) * rs)) + (gz * ((v[i].z - mean) * rs) + gw * ((v[i].w - mean) * rs));
+      }
+      if (split) {
+        const float a[4] = {o.x, o.y, o.z, o.w};
+        __nv_bfloat16 h[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[0][j] = __float2bfloat16_rn(a[j]);
+          const float r1 = a[j] - __bfloat162float(h[0][j]);
+          h[1][j] = __float2bfloat16_rn(r1);
+          h[2][j] = __float2bfloat16_rn(r1 - __bfloat162float(h[1][j]));
+        }
+        uint2* sp = reinterpret_cast<uint2*>(split + row * C) + c4;
+        sp[0] = *reinterpret_cast<uint2*>(h[0]);
+        sp[term / 4] = *reinterpret_cast<uint2*>(h[1]);
+        sp[term / 2] = *reinterpret_cast<uint2*>(h[2]);
+      }
     }
   }
   nz = warp_sum(nz);
+  if (rowstats) { p1 = warp_sum(p1); p2 = warp_sum(p2); }
   if (lane == 0) {
     mu[row] = mean;
     rstd[row] = rs;
     if (zz) zz[row] = nz;
+    if (rowstats) reinterpret_cast<float4*>(rowstats)[row] = make_float4(nz, p1, p2, 0.f);
   }
 }
 
@@ -151,12 +178,18 @@ softmin_rows_kernel(const float* __restrict__ D, long long R, int K, float alpha
   if (tid == 0) partial[blockIdx.x] = tot;
 }
 
-// sum `n` doubles (one block), write float out[0] (and out[1] = sqrt if wanted)
-static __global__ void __launch_bounds__(256)
+// sum `n` doubles (one block, 1024 threads: the softmin pass leaves one partial per 256-thread block, 65k of them at
+// cfg2 sizes), write float out[0]; fixed summation order
+static __global__ void __launch_bounds__(1024)
 finalize_sum_kernel(const double* __restrict__ partial, int n, float* __restrict__ out) {
   __shared__ double red[32];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = threadIdx.x;
+  for (; i + 3 * (int)blockDim.x < n; i += 4 * blockDim.x) {           // four independent loads in flight
+    s0 += partial[i]; s1 += partial[i + blockDim.x]; s2 += partial[i + 2 * blockDim.x]; s3 += partial[i + 3 * blockDim.x];
+  }
+  for (; i < n; i += blockDim.x) s0 += partial[i];
+  double s = (s0 + s1) + (s2 + s3);
   s = block_sum<double>(s, red);
   if (threadIdx.x == 0) out[0] = (float)s;
 }

@@ -12,7 +12,8 @@
 //
 // One CTA = one 128 x BN output tile: warp 0 = TMA producer (3-D tensor maps {cols, rows, term},
 // SWIZZLE_128B boxes land directly as UMMA operand tiles), warp 1 = MMA issuer, warps 2-5 = epilogue
-// (thread = output row = TMEM lane, functor per 32 columns).  Two 96 KB stages.
+// (thread = output row = TMEM lane, functor per 32 columns).  One 96 KB stage per CTA and two CTAs per SM
+// (a CTA's load / MMA / epilogue phases overlap with its neighbour's: 1.63 -> 1.30 ms on the C=768, K=256 distance GEMM).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -26,7 +27,7 @@ using namespace tc;
 
 namespace tg {
 
-constexpr int BM = 128, BK = 64, kStages = 2, kThreads = 192;
+constexpr int BM = 128, BK = 64, kStages = 1, kThreads = 192;   // one 96 KB stage per CTA, two CTAs per SM
 
 __global__ void __launch_bounds__(256)
 split3_kernel(const float* __restrict__ src, long long n4, __nv_bfloat16* __restrict__ t0,
@@ -54,7 +55,7 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst,
 }
 
 template <int BN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                int M, int N, int Kd, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
