@@ -306,6 +306,46 @@ def scene_auc(video_mse, video_labels, video_scene):
     return sum(per.values()) / len(per), per
 
 
+def eval_clip_starts(n_frames, frame_num, batch_size):
+    """clip schedule of the reference's evaluation loop (tool/contrast_evaluae.py:185-203): non-overlapping
+    clips of ``frame_num`` frames; a batch opens while ``index + frame_num < T`` and takes up to ``batch_size``
+    clips while ``index + frame_num + 1 < T`` (so the last clip is dropped when it would end exactly at T, and a
+    batch's extra clips stop one frame earlier).  Returns a list of batches, each a list of start indices."""
+    batches, index = [], 0
+    while index + frame_num < n_frames:
+        starts = [index]
+        for _ in range(batch_size - 1):
+            if index + frame_num + 1 < n_frames:
+                index = index + frame_num
+                starts.append(index)
+            else:
+                break
+        index = index + frame_num
+        batches.append(starts)
+    return batches
+
+
+def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size, dtype=np.float64):
+    """tool/contrast_evaluae.py:170-300 (non-predict mode) with a numpy model: for every video [C,T,H,W],
+    clips -> recon = model_fn(clip batch [B,C,D,H,W]) -> per-frame MSE (mean over W, H, C: :232-235) ->
+    psnr (misc/utils.py:124) -> per-video anomly_score (:265) -> per-scene AUC, mean over scenes (:276-298).
+    Returns (auc, per_scene, per_video_scores, per_video_labels)."""
+    vm, vl = [], []
+    for vid, lab in zip(videos, labels):
+        vid = np.asarray(vid, dtype)
+        mses, labs = [], []
+        for starts in eval_clip_starts(vid.shape[1], frame_num, batch_size):
+            clip = np.stack([vid[:, s:s + frame_num] for s in starts])          # [B,C,D,H,W]
+            recon = np.asarray(model_fn(clip), dtype)
+            e = ((recon - clip) ** 2).transpose(0, 2, 1, 3, 4)                   # 'B C D H W -> B D C H W'
+            mses.extend(e.mean(4).mean(3).mean(2).reshape(-1).tolist())
+            for s in starts:
+                labs.extend(np.asarray(lab)[s:s + frame_num].tolist())
+        vm.append(mses); vl.append(labs)
+    auc, per = scene_auc(vm, vl, scenes)
+    return auc, per, [anomly_score(psnr(m)) for m in vm], vl
+
+
 # ----------------------------------------------------------------------------
 # M1-M5: Memory module
 # ----------------------------------------------------------------------------

@@ -173,6 +173,58 @@ def gen_losses_scoring(ref_recon, ref_utils, name, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
 
 
+def gen_eval_loop(ref_utils, name, seed, batch_size, lengths):
+    """run the reference's OWN evaluation loop — the body of ``predict`` in tool/contrast_evaluae.py:170-300,
+    read from the reference tree at run time and exec'd unmodified (the file itself cannot be imported here:
+    it pulls in timm / mmcv / torchvision at module scope) — on a seeded synthetic test set with a small
+    deterministic model, and record the AUCs it prints."""
+    import contextlib
+    import io
+    from einops import rearrange
+    from sklearn.metrics import roc_auc_score
+    src = open(os.path.join(REF, "tool", "contrast_evaluae.py"), encoding="utf-8").read()
+    body = src[src.index("def predict(model, recon_loss, data_loader, dataset, data_iter):"):src.index("if __name__ == '__main__':")]
+    noop = lambda *a, **k: None  # noqa: E731
+    plt = types.SimpleNamespace(title=noop, plot=noop, ylabel=noop, xlabel=noop, show=noop)
+    pd = types.SimpleNamespace(read_csv=lambda *a, **k: types.SimpleNamespace(values=np.zeros((1, 1))))
+    frame_num = 4
+    ns = dict(torch=torch, np=np, rearrange=rearrange, utils=ref_utils, roc_auc_score=roc_auc_score, plt=plt, pd=pd,
+              args=types.SimpleNamespace(frame_num=frame_num, batch_size=batch_size, ispredict=False))
+    exec(compile(body, "tool/contrast_evaluae.py:predict", "exec"), ns)
+
+    class TinyModel(torch.nn.Module):                      # deterministic, elementwise: reproducible in numpy
+        def forward(self, clip):
+            return clip + 0.05 * torch.sin(37.0 * clip) * (1.0 + clip), 0, 0, 0, 0, 0, 0
+
+    g = torch.Generator().manual_seed(seed)
+    scenes = ["01", "02", "01", "03", "02", "03"]
+    videos, labels = [], []
+    for T in lengths:
+        v = torch.rand(3, T, 6, 6, generator=g)
+        lab = np.zeros(T, np.int64)
+        a = int(torch.randint(2, T - 8, (1,), generator=g))
+        lab[a:a + 6] = 1
+        v[:, a:a + 6] = v[:, a:a + 6] * 1.12               # slightly brighter frames -> larger error under TinyModel
+        videos.append(v); labels.append(lab)
+    loader = [(v[None], i, torch.tensor(l)[None], (sc,)) for i, (v, l, sc) in enumerate(zip(videos, labels, scenes))]
+    had_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # CPU-only box (SURVEY.md D5)
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            ns["predict"](TinyModel(), torch.nn.MSELoss(reduction="none"), loader, loader, 0)
+    finally:
+        torch.Tensor.cuda = had_cuda
+    lines = out.getvalue().splitlines()
+    scene_aucs = [float(l.split(":")[-1]) for l in lines if "场景下的auc值为" in l]
+    auc = [float(l.replace("AUC值为", "")) for l in lines if l.startswith("AUC值为")][0]
+    d = {"frame_num": frame_num, "batch_size": batch_size, "auc": auc, "scene_aucs": np.array(scene_aucs),
+         "scenes": np.array(scenes), "lengths": np.array(lengths)}
+    for i, (v, l) in enumerate(zip(videos, labels)):
+        d[f"video{i}"] = t2n(v); d[f"label{i}"] = l
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -185,6 +237,10 @@ def main():
     gen_memory(ref_memory, "memory_d32_m10", 2, 32, 4, 4, 10, 6)
     gen_memory(ref_memory, "memory_d64_m50", 1, 64, 6, 6, 50, 7)
     gen_losses_scoring(ref_recon, ref_utils, "losses_scoring", 8)
+    # batch_size 1 is the reference's default; with batch_size > 1 its loop raises on videos whose length is 2 or 3
+    # mod frame_num (a ragged clip reaches torch.cat), so the batched fixture uses lengths = 0, 1 mod 4
+    gen_eval_loop(ref_utils, "eval_loop_b1", 9, 1, [23, 31, 40, 18, 29, 38])
+    gen_eval_loop(ref_utils, "eval_loop_b3", 10, 3, [24, 33, 40, 17, 29, 36])
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 

@@ -99,3 +99,32 @@ def test_minmax_score_device_and_synthetic_auc():
     auc, _ = V.regularity_auc(mses, labs, scenes)
     oauc, _ = O.scene_auc([m.tolist() for m in mses], labs, scenes)
     assert abs(auc - oauc) < 1e-12 and 0.5 < auc <= 1.0
+
+
+@pytest.mark.parametrize("name", ["eval_loop_b1", "eval_loop_b3"])
+def test_device_resident_evaluation_loop(name):
+    """V.evaluate_videos (videos resident on the GPU, fused per-frame MSE+PSNR, device min-max, one
+    host transfer) against the AUCs of the reference's own loop (golden) and the oracle's per-video scores"""
+    g = load_golden(name)
+    n = len(g["lengths"])
+    videos = [g[f"video{i}"].astype(np.float32) for i in range(n)]
+    labels = [g[f"label{i}"] for i in range(n)]
+    scenes = [str(s) for s in g["scenes"]]
+    fn, bs = int(g["frame_num"]), int(g["batch_size"])
+    auc, per, scores, labs = V.evaluate_videos(lambda c: c + 0.05 * torch.sin(37.0 * c) * (1.0 + c),
+                                               [torch.tensor(v) for v in videos], labels, scenes, fn, bs)
+    assert abs(auc - float(g["auc"])) < 1e-4                      # north_star: frame-level AUC within 1e-4
+    np.testing.assert_allclose(list(per.values()), g["scene_aucs"], atol=1e-4)
+    _, _, oscores, olabs = O.evaluate_videos(lambda c: c + 0.05 * np.sin(37.0 * c) * (1.0 + c), videos, labels, scenes,
+                                             fn, bs, dtype=np.float32)
+    for a, b, la, lb in zip(scores, oscores, labs, olabs):
+        np.testing.assert_allclose(a, b, atol=2e-5)
+        assert list(la) == list(lb)
+
+
+def test_evaluation_loop_ragged_clip_raises_like_the_reference():
+    """with batch_size > 1 the reference's loop raises RuntimeError (torch.cat) on a video whose tail clip is
+    short; the drop-in raises the same exception type from torch.stack"""
+    v = torch.rand(3, 23, 4, 4)
+    with pytest.raises(RuntimeError):
+        V.evaluate_videos(lambda c: c, [v], [np.zeros(23, np.int64)], ["01"], 4, 3)

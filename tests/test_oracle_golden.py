@@ -120,3 +120,26 @@ def test_roc_auc_matches_sklearn_with_ties():
         assert abs(O.roc_auc(y, s) - roc_auc_score(y, s)) < 1e-12
     with pytest.raises(ValueError):
         O.roc_auc(np.ones(5), np.arange(5.0))
+
+
+@pytest.mark.parametrize("name", ["eval_loop_b1", "eval_loop_b3"])
+def test_evaluation_loop_matches_the_references_own_loop(name):
+    """oracle.evaluate_videos vs the AUCs printed by the reference's ``predict`` (tool/contrast_evaluae.py:170-300,
+    exec'd unmodified by tests/golden/make_golden.py::gen_eval_loop) on the same videos and model"""
+    g = load_golden(name)
+    n = len(g["lengths"])
+    videos = [g[f"video{i}"] for i in range(n)]
+    labels = [g[f"label{i}"] for i in range(n)]
+    model = lambda c: c + 0.05 * np.sin(37.0 * c) * (1.0 + c)  # noqa: E731  (TinyModel of the generator)
+    auc, per, _, _ = O.evaluate_videos(model, [v.astype(np.float32) for v in videos], labels, [str(s) for s in g["scenes"]],
+                                       int(g["frame_num"]), int(g["batch_size"]), dtype=np.float32)
+    assert abs(auc - float(g["auc"])) < 1e-12
+    np.testing.assert_allclose(list(per.values()), g["scene_aucs"], atol=1e-12)
+
+
+def test_evaluation_clip_schedule():
+    """tool/contrast_evaluae.py:185-203: strict '<' bounds drop a clip that would end exactly at T"""
+    assert O.eval_clip_starts(8, 4, 1) == [[0]]
+    assert O.eval_clip_starts(9, 4, 1) == [[0], [4]]
+    assert O.eval_clip_starts(24, 4, 3) == [[0, 4, 8], [12, 16, 20]]      # the inner loop's bound is one frame looser
+    assert O.eval_clip_starts(3, 4, 1) == []

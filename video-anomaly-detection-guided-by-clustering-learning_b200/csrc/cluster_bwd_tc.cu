@@ -671,6 +671,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     mbar_wait(&bars[B_CEN], 0);
     int n1 = 0, n5a = 0, n3 = 0, n5b = 0;
     while (n5b < nmine) {
+      const int progress0 = n1 + n3 + n5a + n5b;
       // ---- S3 (feeds E3): acc = r_lo cen_hi + r_hi cen_lo + r_hi cen_hi
       if (n3 < n1 && mbar_try_wait(&bars[B_RFULL], (uint32_t)(n3 & 1)) &&
           mbar_try_wait(&bars[B_ACCEMPTY], (uint32_t)((n3 & 1) ^ 1))) {
@@ -746,6 +747,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         TR(31, n5a);
         ++n5a;
       }
+      if (n1 + n3 + n5a + n5b == progress0) __nanosleep(40);   // nothing was ready: leave the issue slots to the other roles
     }
     mma_commit(&bars[B_DONE]);
     mbar_wait(&bars[B_DONE], 0);

@@ -106,3 +106,67 @@ def regularity_auc(video_mse, video_labels, video_scene):
             scene_dict[sc], scene_label[sc] = predict_label, truth_label
     per = {k: roc_auc_score(scene_label[k], scene_dict[k]) for k in scene_dict}
     return sum(per.values()) / len(per), per
+
+
+def eval_clip_starts(n_frames, frame_num, batch_size):
+    """clip schedule of tool/contrast_evaluae.py:185-203 (host integers only): non-overlapping clips, the
+    reference's strict ``<`` bounds kept (the last clip is dropped when it would end exactly at T)."""
+    batches, index = [], 0
+    while index + frame_num < n_frames:
+        starts = [index]
+        for _ in range(batch_size - 1):
+            if index + frame_num + 1 < n_frames:
+                index = index + frame_num
+                starts.append(index)
+            else:
+                break
+        index = index + frame_num
+        batches.append(starts)
+    return batches
+
+
+@torch.no_grad()
+def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size):
+    """Device-resident evaluation loop with the semantics of
+    tool/contrast_evaluae.py:170-300 (non-predict mode).
+
+    ``videos``: list of [C,T,H,W] tensors (host or device; a host video is copied to the GPU ONCE instead of
+    once per clip), ``labels``: per-video [T] frame labels, ``scenes``: per-video scene id.
+    ``model_fn(clips [B,C,D,H,W]) -> recon [B,C,D,H,W]`` (for the reference's ``Mymodel`` pass
+    ``lambda c: model(c)[0]``).  Per clip batch ONE fused kernel produces per-frame MSE and PSNR on the device
+    (no materialised loss tensor, no ``.tolist()`` sync per clip); per-video min-max normalisation runs on the
+    device over all videos at once; only the final scores cross to the host for the per-scene AUC.
+    Returns (auc, {scene: auc}, [per-video score arrays], [per-video label arrays])."""
+    dev = None
+    ps_chunks, seg, lab_out = [], [0], []
+    for vid, lab in zip(videos, labels):
+        v = vid if vid.is_cuda else vid.cuda(non_blocking=True)
+        dev = v.device
+        lab = np.asarray(lab.cpu() if isinstance(lab, torch.Tensor) else lab).reshape(-1)
+        n, labs = 0, []
+        for starts in eval_clip_starts(v.shape[1], frame_num, batch_size):
+            clip = torch.stack([v[:, s0:s0 + frame_num] for s0 in starts])       # [B,C,D,H,W]
+            recon = model_fn(clip)
+            _, ps = frame_mse(recon, clip, want_psnr=True)                       # [B,D] float64, on the device
+            ps_chunks.append(ps.reshape(-1))
+            n += ps.numel()
+            for s0 in starts:
+                labs.append(lab[s0:s0 + frame_num])
+        seg.append(seg[-1] + n)
+        lab_out.append(np.concatenate(labs) if labs else np.zeros(0, lab.dtype))
+    if dev is None or seg[-1] == 0:
+        raise ValueError("no clips to evaluate")
+    psnr_all = torch.cat(ps_chunks)
+    score = minmax_score_device(psnr_all, torch.tensor(seg, device=dev, dtype=torch.int64)).cpu().numpy()
+    scores = [score[a:b] for a, b in zip(seg[:-1], seg[1:])]
+    scene_dict, scene_label = {}, {}
+    for sc, sv, lv in zip(scenes, scores, lab_out):
+        assert len(sv) == len(lv)
+        if sc in scene_dict:
+            scene_dict[sc] = np.append(scene_dict[sc], sv)
+            scene_label[sc] = np.append(scene_label[sc], lv)
+        else:
+            scene_dict[sc], scene_label[sc] = sv, lv
+    per = {k: roc_auc_score(scene_label[k], scene_dict[k]) for k in scene_dict}
+    return sum(per.values()) / len(per), per, scores, lab_out
+
