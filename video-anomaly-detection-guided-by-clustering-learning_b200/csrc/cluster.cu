@@ -327,24 +327,33 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
 
 namespace vadc {
 // cdist of a small problem (the [K,K] centroid self-distance of model/cluster.py:77-79 is 32 x 32 x 192) in ONE
-// launch instead of two norm kernels + a tile GEMM: one warp per output row i, lanes over j, the mm form
+// launch instead of two norm kernels + a tile GEMM: one block per output row i, 8 lanes per column j, the mm form
 // sqrt(max(0, |a|^2 + |b|^2 - 2 a.b)) with fp32 accumulation
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 cdist_small_kernel(const float* __restrict__ a, const float* __restrict__ b, int R, int P, int C,
                    float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long long i = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);   // row over all batches
-  const int nbat = blockIdx.y;
-  if (i >= R) return;
-  const float* ar = a + ((size_t)nbat * R + i) * C;
-  for (int j = lane; j < P; j += 32) {
-    const float* br = b + ((size_t)nbat * P + j) * C;
+  // block = one row i of one batch; 8 lanes per output column j (lane part p sums the float4 chunks p, p+8, ...)
+  const int i = blockIdx.x, nbat = blockIdx.y, part = threadIdx.x & 7;
+  const float4* ar = reinterpret_cast<const float4*>(a + ((size_t)nbat * R + i) * C);
+  const int nv = C >> 2;
+  for (int j = threadIdx.x >> 3; j < ((P + 31) & ~31); j += 32) {       // whole warps stay in the loop for the shuffles
     float aa = 0.f, bb = 0.f, ab = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float x = ar[c], y = br[c];
-      aa = fmaf(x, x, aa); bb = fmaf(y, y, bb); ab = fmaf(x, y, ab);
+    if (j < P) {
+      const float4* br = reinterpret_cast<const float4*>(b + ((size_t)nbat * P + j) * C);
+      for (int c = part; c < nv; c += 8) {
+        const float4 x = __ldg(ar + c), y = __ldg(br + c);
+        aa += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+        bb += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+        ab += (x.x * y.x + x.y * y.y) + (x.z * y.z + x.w * y.w);
+      }
     }
-    out[((size_t)nbat * R + i) * P + j] = sqrtf(fmaxf(aa + bb - 2.f * ab, 0.f));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      aa += __shfl_xor_sync(0xffffffffu, aa, o);
+      bb += __shfl_xor_sync(0xffffffffu, bb, o);
+      ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    }
+    if (part == 0 && j < P) out[((size_t)nbat * R + i) * P + j] = sqrtf(fmaxf(aa + bb - 2.f * ab, 0.f));
   }
 }
 }  // namespace vadc
@@ -362,8 +371,8 @@ extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int
   VADC_REQUIRE(R < (1ll << 31) && P < (1ll << 31), VADC_ERR_UNSUPPORTED);
   VADC_REQUIRE(workspace_bytes >= vadc_cdist_workspace_bytes(nb, R, P, C), VADC_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((long long)nb * R * P * C <= (1ll << 21) && nb <= 65535) {        // launch-latency-bound sizes
-    cdist_small_kernel<<<dim3((unsigned)((R + 3) / 4), (unsigned)nb), 128, 0, st>>>(a, b, (int)R, (int)P, C, out);
+  if ((long long)nb * R * P * C <= (1ll << 21) && nb <= 65535 && (C % 4) == 0 && aligned16(a) && aligned16(b)) {   // launch-latency-bound sizes
+    cdist_small_kernel<<<dim3((unsigned)R, (unsigned)nb), 256, 0, st>>>(a, b, (int)R, (int)P, C, out);
     VADC_CHECK_LAUNCH("cdist_small_kernel");
     return VADC_OK;
   }

@@ -246,7 +246,8 @@ struct Params {
   float* part_p; float* part_rcol; float* part_q;        // [grid][128 slots][C], [grid][2][32], [grid][2][C]
   long long N; float alpha; int pf;
   int dbg;                                               // timing experiments only (VADC_BWD_DBG): 1 = no producer loads, 2 = no producer stores
-  unsigned long long* trace;                             // debugging: per-warp event log of CTA 0 (VADC_BWD_TRACE)
+  unsigned long long* trace;                             // debugging: per-warp event log of one CTA (VADC_BWD_TRACE)
+  int trace_cta;
 };
 
 template <int F4, bool TRACE>
@@ -270,7 +271,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   int trace_n = 0;
   auto TR = [&](int code, int it) {
     if constexpr (!TRACE) return;
-    if (p.trace && blockIdx.x == 0 && lane == 0 && trace_n < kTraceCap) {
+    if (p.trace && blockIdx.x == p.trace_cta && lane == 0 && trace_n < kTraceCap) {
       unsigned long long* e = p.trace + ((size_t)warp * kTraceCap + trace_n) * 2;
       e[0] = ((unsigned long long)code << 32) | (unsigned)it; e[1] = (unsigned long long)clock64();
       ++trace_n;
@@ -917,7 +918,8 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
   if (trace_path) { VADC_CUDA(cudaMalloc(&trace, trace_bytes)); VADC_CUDA(cudaMemsetAsync(trace, 0, trace_bytes, st)); }
   bt::Params p{x, gR, D, A, mu, rstd, rowstats, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_q,
                N, alpha, getenv("VADC_BWD_PF") ? atoi(getenv("VADC_BWD_PF")) : 1,
-               getenv("VADC_BWD_DBG") ? atoi(getenv("VADC_BWD_DBG")) : 0, trace};
+               getenv("VADC_BWD_DBG") ? atoi(getenv("VADC_BWD_DBG")) : 0, trace,
+               getenv("VADC_BWD_TRACE_CTA") ? atoi(getenv("VADC_BWD_TRACE_CTA")) : 0};
   bool launched = false;
 #define BT_CASE(F4_)                                                                                   \
   if (C == 32 * F4_) {                                                                                 \
