@@ -385,6 +385,18 @@ extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int
   return launch_dist(a, b, aa, bb, nb, R, P, C, out, st);
 }
 
+namespace vadc {
+// split-K factor of the centroid-gradient GEMMs ([K,C] outputs, contraction over the tokens): ~2 CTAs per SM
+static int bwd_tc_splits(long long N, int C, int K) {
+  const long long tiles = (long long)((K + 127) / 128) * ((C + 127) / 128);
+  const long long nkb = (N + 63) / 64;
+  long long s = (2ll * sm_count() + tiles - 1) / tiles;
+  if (s > nkb) s = nkb;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+}  // namespace vadc
+
 extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
   size_t n = (size_t)(N > 0 ? N : 1);
   int tiles = ((K + 63) / 64) * ((C + 63) / 64);
@@ -398,6 +410,9 @@ extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
   b += align_up((size_t)colsum_chunks(N) * K * sizeof(float), 256); // colsum partial
   b += align_up((size_t)K * sizeof(float), 256);             // rcol
   b += align_up((size_t)ln_bwd_blocks(N) * 2 * C * sizeof(float), 256);
+  // generic path on the tcgen05 GEMM: bf16 term copies of gR, feature, A, r and the centroids + split-K partials
+  b += 2 * tc_gemm_split_bytes((long long)n, C) + 2 * tc_gemm_split_bytes((long long)n, K) + tc_gemm_split_bytes(K, C);
+  b += 2 * align_up((size_t)bwd_tc_splits(N, C, K) * K * C * sizeof(float), 256);
   return std::max(std::max(b + 256, bwd_fused_workspace_bytes(N, C, K)), bwd_tc_workspace_bytes(N, C, K));
 }
 
@@ -444,6 +459,38 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
   float* cpart = ws.take<float>((size_t)colsum_chunks(N) * K);
   float* rcol = ws.take<float>(K);
   float* lnpart = ws.take<float>((size_t)ln_bwd_blocks(N) * 2 * C);
+  if (!getenv("VADC_NO_TC_GEMM") && vadc_device_ok() && (K % 8) == 0 && (C % 8) == 0 && K >= 8 && C >= 8) {
+    // ---- the five contractions on the tcgen05 GEMM (three-term bf16 split): G1 = gR c^T; gz = z rsum - r c + gF;
+    //      gcenters = A^T gR - r^T z + c colsum(r) with the token matrices read MN-major and split-K over the tokens
+    const int sk = bwd_tc_splits(N, C, K);
+    void* gRs = ws.take<uint8_t>(tc_gemm_split_bytes(N, C));
+    void* fs = ws.take<uint8_t>(tc_gemm_split_bytes(N, C));
+    void* as = ws.take<uint8_t>(tc_gemm_split_bytes(N, K));
+    void* rs = ws.take<uint8_t>(tc_gemm_split_bytes(N, K));
+    void* cs = ws.take<uint8_t>(tc_gemm_split_bytes(K, C));
+    float* q1 = ws.take<float>((size_t)sk * KC);
+    float* q2 = ws.take<float>((size_t)sk * KC);
+    int rc;
+    if ((rc = tc_split3(centers, K, C, cs, st))) return rc;
+    if (gR) {
+      if ((rc = tc_split3(gR, N, C, gRs, st))) return rc;
+      if ((rc = launch_tc_gemm<false>(gRs, cs, N, K, C, TcStoreEpi{gemm, K}, st))) return rc;
+    }
+    if ((rc = launch_bwd_rows(D, A, gR ? gemm : nullptr, gD, gA, g_loss_sq, N, K, alpha, r, rsum, st))) return rc;
+    if ((rc = tc_split3(r, N, K, rs, st))) return rc;
+    if ((rc = launch_tc_gemm<true>(rs, cs, N, C, K, TcGzEpi{gz, feature, rsum, gF, C}, st))) return rc;
+    if (gR) {
+      if ((rc = tc_split3(A, N, K, as, st))) return rc;
+      if ((rc = launch_tc_gemm_ex<true, true>(as, gRs, K, C, N, sk, TcPartialEpi{q1, C, KC}, st))) return rc;
+    }
+    if ((rc = tc_split3(feature, N, C, fs, st))) return rc;
+    if ((rc = launch_tc_gemm_ex<true, true>(rs, fs, K, C, N, sk, TcPartialEpi{q2, C, KC}, st))) return rc;
+    cudaError_t e2 = launch_colsum(r, N, K, cpart, rcol, st);
+    if (e2 != cudaSuccess) return record_cuda_error(e2, "colsum r");
+    gcenters_finalize_kernel<<<(unsigned)((KC + 255) / 256), 256, 0, st>>>(gR ? q1 : nullptr, q2, sk, centers, rcol, K, C, gcenters);
+    VADC_CHECK_LAUNCH("gcenters_finalize_kernel");
+    return launch_ln_bwd(gz, x, mu, rstd, ln_w, N, C, gx, lnpart, g_ln_w, g_ln_b, st);
+  }
   cudaError_t e;
   int rc;
   // (1) gR . centers^T  -> gemm [N,K]

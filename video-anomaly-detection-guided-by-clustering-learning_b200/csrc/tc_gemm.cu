@@ -54,10 +54,10 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst,
                ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int BN, bool B_MN, class Epi>
+template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kThreads, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               int M, int N, int Kd, Epi epi) {
+               int M, int N, int Kd, int kb_per_split, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t kATerm = BM * 128u, kBTerm = BN * 128u;           // bytes per bf16 term of a stage's operand
@@ -66,7 +66,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb = (Kd + BK - 1) / BK;
+  // split-K: blockIdx.z takes k-blocks [kb0, kb1) and hands its index to the epilogue (partial outputs)
+  const int nkb_all = (Kd + BK - 1) / BK;
+  const int kb0 = blockIdx.z * kb_per_split, kb1 = min(nkb_all, kb0 + kb_per_split);
+  const int nkb = max(kb1 - kb0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&accfull, 1);
@@ -87,21 +90,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&empty[s], (uint32_t)(((kb / kStages) & 1) ^ 1));
       mbar_expect_tx(&full[s], kStage);
       const uint32_t a = s0 + s * kStage, b = a + 3u * kATerm;
+      const int k0 = (kb0 + kb) * BK;
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
-        tma_load_3d(&mapA, a + t * kATerm, &full[s], kb * BK, m0, t);
+        if constexpr (!A_MN) {
+          tma_load_3d(&mapA, a + t * kATerm, &full[s], k0, m0, t);
+        } else {
+#pragma unroll
+          for (int mb = 0; mb < BM / 64; ++mb)                // A given as [Kd, M]: [64 k-rows x 64 m-cols] boxes, 8 KB apart
+            tma_load_3d(&mapA, a + t * kATerm + mb * 8192u, &full[s], m0 + mb * 64, k0, t);
+        }
         if constexpr (!B_MN) {
-          tma_load_3d(&mapB, b + t * kBTerm, &full[s], kb * BK, n0, t);
+          tma_load_3d(&mapB, b + t * kBTerm, &full[s], k0, n0, t);
         } else {
 #pragma unroll
           for (int nb = 0; nb < BN / 64; ++nb)                // [64 k-rows x 64 n-cols] boxes, 8 KB apart
-            tma_load_3d(&mapB, b + t * kBTerm + nb * 8192u, &full[s], n0 + nb * 64, kb * BK, t);
+            tma_load_3d(&mapB, b + t * kBTerm + nb * 8192u, &full[s], n0 + nb * 64, k0, t);
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = instr_desc(kFmtBF16, BM, BN, 0, B_MN ? 1 : 0);
+    const uint32_t idesc = instr_desc(kFmtBF16, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};     // small products first
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
@@ -112,7 +122,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int pr = 0; pr < 6; ++pr) {
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t ad = smem_desc_sw128(a + ta[pr] * kATerm + kk * 32u, 0, 1024);
+          const uint64_t ad = A_MN ? smem_desc_sw128(a + ta[pr] * kATerm + kk * 2048u, 8192, 1024)
+                                   : smem_desc_sw128(a + ta[pr] * kATerm + kk * 32u, 0, 1024);
           const uint64_t bd = B_MN ? smem_desc_sw128(b + tb[pr] * kBTerm + kk * 2048u, 8192, 1024)
                                    : smem_desc_sw128(b + tb[pr] * kBTerm + kk * 32u, 0, 1024);
           mma_f16(tmem, ad, bd, idesc, (kb > 0 || pr > 0 || kk > 0) ? 1u : 0u);
@@ -120,19 +131,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       mma_commit(&empty[s]);
     }
-    mma_commit(&accfull);
+    if (nkb > 0) mma_commit(&accfull);
   } else if (warp >= 2) {
     // ---------------------------------------------------------------- epilogue: thread = row = TMEM lane
     const int q = warp & 3;
     const long long m = (long long)m0 + q * 32 + lane;
-    mbar_wait(&accfull, 0);
-    tc_fence_after();
+    if (nkb > 0) { mbar_wait(&accfull, 0); tc_fence_after(); }
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (nkb > 0) {
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;             // an empty split still writes its (zero) partial
+      }
       const int n = n0 + c * 32;
-      if (m < M && n < N) epi(m, n, v, min(32, N - n));
+      if (m < M && n < N) epi(m, n, v, min(32, N - n), (int)blockIdx.z);
     }
   }
   tc_fence_before();
@@ -200,23 +215,34 @@ int tc_split3(const float* src, long long rows, long long cols, void* dst, cudaS
   return VADC_OK;
 }
 
-template <bool B_MN, class Epi>
-int launch_tc_gemm(const void* a_split, const void* b_split, long long M, long long N, long long Kd, Epi epi,
-                   cudaStream_t st) {
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
+                      Epi epi, cudaStream_t st) {
   constexpr int BN = 128;
   CUtensorMap mA, mB;
   int rc;
-  if ((rc = tg::make_map3(&mA, a_split, M, Kd, tg::BM))) return rc;
+  if (A_MN) rc = tg::make_map3(&mA, a_split, Kd, M, 64);        // [Kd rows, M cols]: boxes of 64 k-rows x 64 m-cols
+  else rc = tg::make_map3(&mA, a_split, M, Kd, tg::BM);
+  if (rc) return rc;
   if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64);        // [Kd rows, N cols]: boxes of 64 k-rows x 64 n-cols
   else rc = tg::make_map3(&mB, b_split, N, Kd, BN);             // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
   if (rc) return rc;
   const size_t smem = (size_t)tg::kStages * (3 * tg::BM * 128 + 3 * BN * 128) + 1024;
-  auto kern = tg::tc_gemm_kernel<BN, B_MN, Epi>;
+  auto kern = tg::tc_gemm_kernel<BN, A_MN, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM));
-  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, epi);
+  const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
+  if (splits < 1) splits = 1;
+  const int per = (nkb + splits - 1) / splits;
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)splits);
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, epi);
   VADC_CHECK_LAUNCH("tc_gemm_kernel");
   return VADC_OK;
+}
+
+template <bool B_MN, class Epi>
+int launch_tc_gemm(const void* a_split, const void* b_split, long long M, long long N, long long Kd, Epi epi,
+                   cudaStream_t st) {
+  return launch_tc_gemm_ex<false, B_MN, Epi>(a_split, b_split, M, N, Kd, 1, epi, st);
 }
 
 // explicit instantiations for the epilogues of the path
@@ -224,6 +250,8 @@ template int launch_tc_gemm<false, TcStoreEpi>(const void*, const void*, long lo
 template int launch_tc_gemm<true, TcStoreEpi>(const void*, const void*, long long, long long, long long, TcStoreEpi, cudaStream_t);
 template int launch_tc_gemm<false, TcDistEpi>(const void*, const void*, long long, long long, long long, TcDistEpi, cudaStream_t);
 template int launch_tc_gemm<true, TcReadEpi>(const void*, const void*, long long, long long, long long, TcReadEpi, cudaStream_t);
+template int launch_tc_gemm<true, TcGzEpi>(const void*, const void*, long long, long long, long long, TcGzEpi, cudaStream_t);
+template int launch_tc_gemm_ex<true, true, TcPartialEpi>(const void*, const void*, long long, long long, long long, int, TcPartialEpi, cudaStream_t);
 
 }  // namespace vadc
 

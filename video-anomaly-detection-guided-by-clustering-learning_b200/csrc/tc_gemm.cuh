@@ -13,6 +13,11 @@ int tc_split3(const float* src, long long rows, long long cols, void* dst, cudaS
 template <bool B_MN, class Epi>
 int launch_tc_gemm(const void* a_split, const void* b_split, long long M, long long N, long long Kd, Epi epi,
                    cudaStream_t st);
+// general form: A_MN = A given as [Kd, M] (e.g. a transposed token matrix), `splits` CTAs along the contraction,
+// each handing its index to the epilogue (split-K partials for the centroid-gradient GEMMs, Kd = tokens)
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
+                      Epi epi, cudaStream_t st);
 
 __device__ __forceinline__ void tc_store_row32(float* o, const float (&v)[32], int nvalid) {
   if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
@@ -26,7 +31,7 @@ __device__ __forceinline__ void tc_store_row32(float* o, const float (&v)[32], i
 
 struct TcStoreEpi {
   float* out; long long ldo;
-  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid) const {
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
     tc_store_row32(out + m * ldo + n, v, nvalid);
   }
 };
@@ -34,7 +39,7 @@ struct TcStoreEpi {
 // torch.cdist, mm form: sqrt(max(0, |a|^2 + |b|^2 - 2 a.b))
 struct TcDistEpi {
   float* out; const float* aa; const float* bb; long long ldo;
-  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid) const {
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
     const float am = aa[m];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -48,12 +53,33 @@ struct TcDistEpi {
 // Memory.read (Memory.py:249-261): uq[m, 0:d] = q[m], uq[m, d:2d] = score_memory @ keys
 struct TcReadEpi {
   float* uq; const float* q; int d;
-  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid) const {
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
     float* o = uq + m * 2 * d;
     tc_store_row32(o + d + n, v, nvalid);
     const float* qs = q + m * d + n;
 #pragma unroll
     for (int j = 0; j < 32; ++j) if (j < nvalid) o[n + j] = qs[j];
+  }
+};
+
+// gz = feature * rsum - r @ centers + gF   (cluster backward, generic path)
+struct TcGzEpi {
+  float* out; const float* feature; const float* rsum; const float* gF; long long ld;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
+    const float rs = rsum[m];
+    const float* f = feature + m * ld + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) v[j] = f[j] * rs - v[j] + (gF ? gF[m * ld + n + j] : 0.f);
+    tc_store_row32(out + m * ld + n, v, nvalid);
+  }
+};
+
+// split-K partial: out[split][m][n]
+struct TcPartialEpi {
+  float* out; long long ld, split_stride;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int split) const {
+    tc_store_row32(out + (long long)split * split_stride + m * ld + n, v, nvalid);
   }
 };
 
