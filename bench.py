@@ -275,9 +275,10 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers ----
     e2e_steps = max(3, args.steps // 4)
-    x_host = torch.randn(shp).pin_memory()
-    g_host = (torch.randn(shp) * 1e-3).pin_memory()
-    out_host = torch.empty(1 + K * C + 2 * C).pin_memory()
+    # pinned staging buffers on the GPU's own NUMA node (far-socket buffers halve the copy rate)
+    x_host = V.pinned_like_local(torch.randn(shp), local)
+    g_host = V.pinned_like_local(torch.randn(shp) * 1e-3, local)
+    out_host = V.pinned_like_local(torch.empty(1 + K * C + 2 * C), local)
     x_dev = torch.empty(shp, device=dev)
 
     def e2e_step():
@@ -325,7 +326,8 @@ def run_ours(args):
         "config": config_dict(world),
         "roofline": dominant,
         "e2e": {"value": world * ntok / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps},
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "h2d_GBps": h2d / (e2e_ms * 1e-3) / 1e9, "host_numa_cpus": len(V.gpu_local_cpus(local))},
         "gpu_launches": int(launches), "clocks": clocks,
         "kernel_family": {0: "auto", 1: "simt", 2: "tcgen05"}[mod.impl],
     }

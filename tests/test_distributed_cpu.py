@@ -93,3 +93,16 @@ def test_single_process_helpers():
     V.fix_random_seeds(31)
     assert torch.equal(a, torch.rand(2))
     assert V.get_sha().startswith("sha:")
+
+
+def test_numa_helpers_cpu():
+    """cpulist parsing and the no-GPU behaviour of the NUMA-local allocation helper"""
+    import os
+    import videoad_b200 as V
+    from videoad_b200.distributed import _parse_cpulist
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    with V.numa_local(0) as ctx:          # no CUDA device here: topology unreadable -> no-op
+        assert ctx.cpus == set() or ctx.cpus <= before
+    assert os.sched_getaffinity(0) == before

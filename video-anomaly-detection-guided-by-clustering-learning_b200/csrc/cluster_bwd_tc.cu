@@ -329,7 +329,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     const int lj = lane & 7, lg = lane >> 3;
     const int rsel = (lg & 1) * 4 + (lg >> 1);
     const int nunits = kUnits * nmine;
-    struct Unit { union { float4 v[F4]; float4 a[8]; }; float rs, nmr; };   // a[]: the 8 float4 of an A unit
+    struct Unit { union { float4 v[F4]; float4 a[8]; }; float rs, mu; };   // a[]: the 8 float4 of an A unit
     auto issue = [&](Unit& U, int g) {
       if (g >= nunits) return;
       const int it = g / kUnits, u = g % kUnits, v = u & 15;
@@ -361,8 +361,8 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       const float4* sr = reinterpret_cast<const float4*>(src + row * C) + lj;
 #pragma unroll
       for (int i = 0; i < F4; ++i) U.v[i] = (live && !(p.dbg & 1)) ? ld_stream(sr + 8 * i) : make_float4(0, 0, 0, 0);
-      U.rs = (isx && live) ? __ldg(p.rstd + row) : 0.f;
-      U.nmr = (isx && live) ? -__ldg(p.mu + row) * U.rs : 0.f;
+      U.rs = (isx && live) ? __ldg(p.rstd + row) : 0.f;   // raw loads only: arithmetic on them here would wait for them
+      U.mu = (isx && live) ? __ldg(p.mu + row) : 0.f;
     };
     auto process = [&](Unit& U, int g) {
       if (g >= nunits) return;
@@ -395,9 +395,9 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         // X[buf] is free once S5b and E3 of tile it-2 have finished
         mbar_wait_spin(&bars[B_XEMPTY0 + buf], (uint32_t)(((it >> 1) & 1) ^ 1));
         const uint32_t xb = sX32 + buf * pl.xbuf + e0;
+        const float2 rs2 = bcast2(U.rs), nm2 = bcast2(-U.mu * U.rs);
 #pragma unroll
         for (int i = 0; i < F4; ++i) {
-          const float2 rs2 = bcast2(U.rs), nm2 = bcast2(U.nmr);
           uint32_t a1, a2, b1, b2;
           split2_bf(fma2(make_float2(U.v[i].x, U.v[i].y), rs2, nm2), a1, a2);
           split2_bf(fma2(make_float2(U.v[i].z, U.v[i].w), rs2, nm2), b1, b2);

@@ -13,6 +13,61 @@ import torch
 import torch.distributed as dist
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_local_cpus(device_index):
+    """CPUs on the NUMA node the GPU's PCIe root hangs off (sysfs local_cpulist), restricted to
+    the CPUs this process may run on; empty set when the topology cannot be read."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as fh:
+            return _parse_cpulist(fh.read()) & set(os.sched_getaffinity(0))
+    except Exception:
+        return set()
+
+
+class numa_local:
+    """Context manager: run the enclosed host allocations on the GPU's own NUMA node.
+
+    Pinned host buffers are placed on the node of the allocating thread; a buffer on the far socket
+    halves host->device copy bandwidth.  The reference keeps whole test videos and every training
+    batch in host memory (dataset/utils_dataset.py:116-135, main_predict.py:241), so the host side
+    of this path allocates its staging buffers inside ``with numa_local(gpu):``.  The previous CPU
+    affinity is restored on exit (the CPU baseline keeps all cores)."""
+
+    def __init__(self, device_index):
+        self.cpus = gpu_local_cpus(device_index)
+        self.prev = None
+
+    def __enter__(self):
+        if self.cpus:
+            self.prev = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, self.cpus)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            os.sched_setaffinity(0, self.prev)
+        return False
+
+
+def pinned_like_local(t, device_index):
+    """pinned host copy of ``t`` allocated on the NUMA node of GPU ``device_index``"""
+    with numa_local(device_index):
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t)
+    return out
+
+
 def setup_for_distributed(is_master):
     """disable printing when not in master process (utils/distritributed_model.py:23-35)"""
     import builtins as __builtin__
