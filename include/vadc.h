@@ -196,6 +196,18 @@ size_t vadc_memory_prepare_query_workspace_bytes(int B, int64_t HW);
 int vadc_memory_prepare_query(const float* query, int B, int d, int64_t HW, float* q,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of Memory.forward with respect to `query` (autograd of Memory.py:145-175; keys are
+ * constants there: every use is .detach()ed or un-graded).  What reaches the query: the first d
+ * channels of g_updated_query [B,2d,HW] (cat :256; the read softmax is detached :255),
+ * g_gather * d MSELoss(q, keys[top1]) (:245), g_spread * d TripletMarginLoss(margin=1,p=2,eps=1e-6)
+ * (q, keys[top1], keys[top2]) (:229), all pulled back through F.normalize(query, dim=1) (:148).
+ * g_updated_query / g_gather / g_spread / top2 may each be NULL (term absent; g_gather and g_spread
+ * are device scalars).  query, g_query [B,d,HW]. */
+int vadc_memory_query_bwd(const float* query, const float* keys, const int64_t* top1,
+                          const int64_t* top2, const float* g_updated_query,
+                          const float* g_gather, const float* g_spread, int B, int d,
+                          int64_t HW, int m, float* g_query, void* stream);
+
 /* get_score  Memory.py:133-143 (+ the top-1 / top-2 of score_memory that
  * gather_loss :241, spread_loss :223 and update :185 take with torch.topk):
  *   logits = q keys^T [N,m]; score_query = softmax over N; score_memory =

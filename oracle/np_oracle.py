@@ -415,6 +415,38 @@ def memory_forward(query, keys, train=True, dtype=np.float32):
     return out
 
 
+def memory_query_backward(query, keys, top1, top2=None, g_updated_query=None, g_gather=None,
+                          g_spread=None, dtype=np.float64):
+    """d/d query of ``Memory.forward`` (autograd of model/Memory.py:145-175).  The reference graph reaches
+    the query through: the first half of ``updated_query`` (cat, :256 -- the read softmax is detached,
+    :255), ``MSELoss(q, keys[top1].detach())`` (:245), ``TripletMarginLoss(margin=1, p=2, eps=1e-6)(q,
+    keys[top1].detach(), keys[top2].detach())`` (:229, train only), then ``F.normalize(query, dim=1)``
+    (:148) and the permute.  query [B,d,h,w]; returns g_query [B,d,h,w]."""
+    query = np.asarray(query, dtype)
+    keys = np.asarray(keys, dtype)
+    B, d, h, w = query.shape
+    N = B * h * w
+    x = query.transpose(0, 2, 3, 1).reshape(N, d)
+    nrm = np.sqrt((x * x).sum(1, keepdims=True))
+    den = np.maximum(nrm, 1e-12)
+    q = x / den
+    g = np.zeros((N, d), dtype)
+    if g_updated_query is not None:
+        g += np.asarray(g_updated_query, dtype)[:, :d].transpose(0, 2, 3, 1).reshape(N, d)
+    k1 = keys[np.asarray(top1).reshape(-1)]
+    if g_gather is not None:
+        g += dtype(g_gather) * 2.0 * (q - k1) / (N * d)
+    if g_spread is not None and top2 is not None:
+        k2 = keys[np.asarray(top2).reshape(-1)]
+        a, e = q - k1 + 1e-6, q - k2 + 1e-6
+        dap, dan = np.sqrt((a * a).sum(1, keepdims=True)), np.sqrt((e * e).sum(1, keepdims=True))
+        active = (dap - dan + 1.0 >= 0).astype(dtype)
+        g += dtype(g_spread) / N * active * (a / np.where(dap > 0, dap, 1.0) - e / np.where(dan > 0, dan, 1.0))
+    dot = np.where(nrm < 1e-12, 0.0, (q * g).sum(1, keepdims=True))
+    gx = (g - q * dot) / den
+    return gx.reshape(B, h, w, d).transpose(0, 3, 1, 2).astype(dtype)
+
+
 def memory_separateness(keys, dtype=np.float32):
     """``MemoryLoss`` (model/Memory.py:52-59)."""
     k = np.asarray(keys, np.float64)

@@ -115,13 +115,24 @@ def gen_memory(ref_memory, name, B, d, h, w, m, seed):
     uq, um, sq, sm, gl, sl = mem(query, keys, train=True)
     uq_t, um_t, sq_t, sm_t, gl_t = mem(query, keys, train=False)
     sep = ref_memory.MemoryLoss(keys)
+    # autograd of the reference module itself: d/d query of <updated_query, W> + 0.7 gather + 0.3 spread
+    g_uq = torch.randn(B, 2 * d, h, w, generator=g)
+    qg = query.clone().requires_grad_(True)
+    o = mem(qg, keys, train=True)
+    ((o[0] * g_uq).sum() + 0.7 * o[4] + 0.3 * o[5]).backward()
+    gq_train = qg.grad.clone()
+    qg = query.clone().requires_grad_(True)
+    o = mem(qg, keys, train=False)
+    ((o[0] * g_uq).sum() + 0.7 * o[4]).backward()
+    gq_test = qg.grad.clone()
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
         query=t2n(query), keys=t2n(keys),
         updated_query=t2n(uq.contiguous()), updated_memory=t2n(um), score_query=t2n(sq),
         score_memory=t2n(sm), gathering_loss=t2n(gl), spreading_loss=t2n(sl),
         test_updated_query=t2n(uq_t.contiguous()), test_updated_memory=t2n(um_t),
-        test_gathering_loss=t2n(gl_t), separateness=t2n(sep))
+        test_gathering_loss=t2n(gl_t), separateness=t2n(sep),
+        g_updated_query=t2n(g_uq), g_query_train=t2n(gq_train), g_query_test=t2n(gq_test))
 
 
 def gen_losses_scoring(ref_recon, ref_utils, name, seed):
@@ -229,6 +240,10 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
     ref_cluster, ref_memory, ref_recon, ref_utils = import_reference()
+    if "--only-memory" in sys.argv:          # regenerate the memory fixtures alone (same seeds)
+        gen_memory(ref_memory, "memory_d32_m10", 2, 32, 4, 4, 10, 6)
+        gen_memory(ref_memory, "memory_d64_m50", 1, 64, 6, 6, 50, 7)
+        return
     gen_cluster(ref_cluster, "cluster_c64_k32", 1, 2, 4, 4, 64, 32, 16.0, False, 1)
     gen_cluster(ref_cluster, "cluster_c32_k16", 2, 2, 4, 4, 32, 16, 32.0, False, 2)
     gen_cluster(ref_cluster, "cluster_c192_k48_peaked", 1, 1, 6, 6, 192, 48, 16.0, True, 3)

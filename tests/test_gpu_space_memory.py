@@ -164,3 +164,52 @@ def test_memory_update_is_deterministic():
     a = mem(T(query), T(keys), train=True)[1]
     b = mem(T(query), T(keys), train=True)[1]
     assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------
+# Memory: gradient with respect to the query (autograd of Memory.py:145-175)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["memory_d32_m10", "memory_d64_m50"])
+def test_memory_backward_golden(name):
+    """d query of <updated_query, W> + 0.7 gathering + 0.3 spreading against the reference module's own
+    autograd (fixture written by tests/golden/make_golden.py); tolerance 2e-5 of the largest entry"""
+    g = load_golden(name)
+    mem = V.Memory(g["keys"].shape[0], g["keys"].shape[1], g["keys"].shape[1], 0.1, 0.1)
+    W = T(g["g_updated_query"])
+    q = T(g["query"]).requires_grad_(True)
+    o = mem(q, T(g["keys"]), train=True)
+    ((o[0] * W).sum() + 0.7 * o[4] + 0.3 * o[5]).backward()
+    assert rel(N(q.grad), g["g_query_train"]) < 2e-5
+    q = T(g["query"]).requires_grad_(True)
+    o = mem(q, T(g["keys"]), train=False)
+    ((o[0] * W).sum() + 0.7 * o[4]).backward()
+    assert rel(N(q.grad), g["g_query_test"]) < 2e-5
+    assert not o[1].requires_grad and not o[2].requires_grad and not o[3].requires_grad
+
+
+@pytest.mark.parametrize("B,d,h,w,m", [(2, 768, 32, 32, 2000), (1, 96, 7, 5, 33), (3, 64, 8, 8, 2)])
+def test_memory_backward_vs_oracle(B, d, h, w, m):
+    """cfg3 shape (m=2000, d=768, N=2048) and ragged shapes against the fp64 oracle; each loss term alone too"""
+    rng = np.random.default_rng(B * 100 + m)
+    keys = rng.random((m, d)).astype(np.float32)
+    keys /= np.linalg.norm(keys, axis=1, keepdims=True)
+    query = rng.standard_normal((B, d, h, w)).astype(np.float32)
+    W = rng.standard_normal((B, 2 * d, h, w)).astype(np.float32)
+    mem = V.Memory(m, d, d, 0.1, 0.1)
+    f = O.memory_forward(query, keys, train=True, dtype=np.float64)
+    for cu, cg, cs in [(1.0, 0.7, 0.3), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (1.0, 0.0, 0.0)]:
+        q = T(query).requires_grad_(True)
+        o = mem(q, T(keys), train=True)
+        loss = 0
+        if cu: loss = loss + cu * (o[0] * T(W)).sum()
+        if cg: loss = loss + cg * o[4]
+        if cs: loss = loss + cs * o[5]
+        loss.backward()
+        ref = O.memory_query_backward(query, keys, f["top1"], f["top2"], W * cu if cu else None,
+                                      cg if cg else None, cs if cs else None)
+        assert rel(N(q.grad), ref) < 2e-5, (cu, cg, cs)
+    # an unused forward leaves no gradient and costs no backward launch
+    q = T(query).requires_grad_(True)
+    o = mem(q, T(keys), train=True)
+    (o[2].sum() * 0 + 1).backward() if o[2].requires_grad else None
+    assert q.grad is None

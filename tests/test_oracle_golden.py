@@ -81,6 +81,11 @@ def test_memory(name):
     np.testing.assert_array_equal(t["updated_memory"], g["test_updated_memory"])
     assert abs(t["gathering_loss"] - g["test_gathering_loss"]) < 1e-5 * abs(g["test_gathering_loss"])
     assert abs(O.memory_separateness(g["keys"]) - g["separateness"]) < 1e-5 * abs(g["separateness"])
+    # gradient with respect to the query against the reference module's own autograd
+    gq = O.memory_query_backward(g["query"], g["keys"], o["top1"], o["top2"], g["g_updated_query"], 0.7, 0.3)
+    assert rel_err(gq, g["g_query_train"]) < 2e-5
+    gq = O.memory_query_backward(g["query"], g["keys"], t["top1"], None, g["g_updated_query"], 0.7, None)
+    assert rel_err(gq, g["g_query_test"]) < 2e-5
 
 
 def test_losses():

@@ -44,6 +44,92 @@ query_transpose_kernel(const float* __restrict__ query, const float* __restrict_
   }
 }
 
+
+// ---- backward of Memory.forward with respect to `query` -------------------
+// autograd of Memory.py:145-175.  What reaches `query` in the reference graph: the first half of
+// updated_query (cat, :256 — the read softmax is .detach()ed, :255), MSELoss(q, keys[top1].detach())
+// (:245) and TripletMarginLoss(margin=1, p=2, eps=1e-6)(q, pos.detach(), neg.detach()) (:229); then
+// F.normalize(query, dim=1) (:148).  Everything is per token, so one kernel does it in the query's own
+// [B, d, HW] layout: lanes run along hw (coalesced), the 8 warps of a block split the channels and meet
+// in shared memory for the three per-token reductions (|x|^2; the two triplet distances; q . g).
+//   g[c]  = gU[b,c,hw] + ag (q - k1) + cp (q - k1 + eps) - cn (q - k2 + eps)
+//   gx[c] = (g[c] - q[c] (q . g)) / |x|            (g / 1e-12 where |x| < 1e-12: the clamp is constant)
+__global__ void __launch_bounds__(256)
+memory_query_bwd_kernel(const float* __restrict__ query, const float* __restrict__ keys,
+                        const long long* __restrict__ top1, const long long* __restrict__ top2,
+                        const float* __restrict__ g_uq, const float* __restrict__ g_gather,
+                        const float* __restrict__ g_spread, int d, long long HW, long long N,
+                        float* __restrict__ gquery) {
+  __shared__ float red[2][8][32];
+  __shared__ float tot[2][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const long long hw = (long long)blockIdx.x * 32 + lane;
+  const bool live = hw < HW;
+  const long long n = (long long)b * HW + hw;
+  const float* xp = query + (long long)b * d * HW + hw;
+  const float* gp = g_uq ? g_uq + (long long)b * 2 * d * HW + hw : nullptr;
+  const float* k1 = live ? keys + top1[n] * d : keys;
+  const float* k2 = (live && top2) ? keys + top2[n] * d : nullptr;
+  const float ag = g_gather ? 2.0f * __ldg(g_gather) / ((float)N * (float)d) : 0.f;
+  const float gs = (g_spread && top2) ? __ldg(g_spread) / (float)N : 0.f;
+  constexpr float kEps = 1e-6f;
+  auto reduce2 = [&](float a, float c) {      // block-wide sums per lane (token) of two values
+    red[0][wid][lane] = a; red[1][wid][lane] = c;
+    __syncthreads();
+    if (wid < 2) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += red[wid][w][lane];
+      tot[wid][lane] = t;
+    }
+    __syncthreads();
+  };
+  // 1: |x|^2
+  float s = 0.f;
+  if (live) for (int c = wid; c < d; c += 8) { const float v = __ldg(xp + (long long)c * HW); s += v * v; }
+  reduce2(s, 0.f);
+  const float nrm = sqrtf(tot[0][lane]);
+  const bool clamped = nrm < 1e-12f;
+  const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+  __syncthreads();
+  // 2: triplet distances
+  float cp = 0.f, cn = 0.f;
+  if (top2 != nullptr) {                       // block-uniform
+    float dp = 0.f, dn = 0.f;
+    if (live) for (int c = wid; c < d; c += 8) {
+      const float q = __ldg(xp + (long long)c * HW) * inv;
+      const float a = q - __ldg(k1 + c) + kEps, e = q - __ldg(k2 + c) + kEps;
+      dp += a * a; dn += e * e;
+    }
+    reduce2(dp, dn);
+    const float dap = sqrtf(tot[0][lane]), dan = sqrtf(tot[1][lane]);
+    const bool active = dap - dan + 1.0f >= 0.f;          // clamp_min(., 0) backward
+    cp = (active && dap > 0.f) ? gs / dap : 0.f;
+    cn = (active && dan > 0.f) ? gs / dan : 0.f;
+    __syncthreads();
+  }
+  auto grad_at = [&](int c, float q) {
+    const float a = q - __ldg(k1 + c);
+    float g = gp ? __ldg(gp + (long long)c * HW) : 0.f;
+    g += ag * a + cp * (a + kEps);
+    if (k2) g -= cn * (q - __ldg(k2 + c) + kEps);
+    return g;
+  };
+  // 3: q . g
+  float dot = 0.f;
+  if (live) for (int c = wid; c < d; c += 8) {
+    const float q = __ldg(xp + (long long)c * HW) * inv;
+    dot += q * grad_at(c, q);
+  }
+  reduce2(dot, 0.f);
+  dot = clamped ? 0.f : tot[0][lane];
+  // 4: through the normalisation
+  if (live) for (int c = wid; c < d; c += 8) {
+    const float q = __ldg(xp + (long long)c * HW) * inv;
+    gquery[((long long)b * d + c) * HW + hw] = (grad_at(c, q) - q * dot) * inv;
+  }
+}
+
 // ---- row softmax over m + top-1 / top-2 (Memory.py:141,185,223,241) -------
 // one warp per token row of logits [N, m]
 __global__ void __launch_bounds__(256)
@@ -366,6 +452,24 @@ extern "C" int vadc_memory_prepare_query(const float* query, int B, int d, int64
   dim3 g2((unsigned)((HW + 31) / 32), (d + 31) / 32, B);
   query_transpose_kernel<<<g2, 256, 0, st>>>(query, inv, d, HW, q);
   VADC_CHECK_LAUNCH("query_transpose_kernel");
+  return VADC_OK;
+}
+
+extern "C" int vadc_memory_query_bwd(const float* query, const float* keys, const int64_t* top1,
+                                     const int64_t* top2, const float* g_updated_query,
+                                     const float* g_gather, const float* g_spread, int B, int d,
+                                     int64_t HW, int m, float* g_query, void* stream) {
+  VADC_REQUIRE(B >= 0 && d > 0 && HW > 0 && m > 0, VADC_ERR_BAD_SHAPE);
+  if (B == 0) return VADC_OK;
+  VADC_REQUIRE(query && keys && top1 && g_query, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(B <= 65535, VADC_ERR_UNSUPPORTED);
+  if (!vadc_device_ok()) return VADC_ERR_NO_DEVICE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((HW + 31) / 32), B);
+  memory_query_bwd_kernel<<<grid, 256, 0, st>>>(query, keys, reinterpret_cast<const long long*>(top1),
+                                                reinterpret_cast<const long long*>(top2), g_updated_query,
+                                                g_gather, g_spread, d, HW, (long long)B * HW, g_query);
+  VADC_CHECK_LAUNCH("memory_query_bwd_kernel");
   return VADC_OK;
 }
 

@@ -52,9 +52,60 @@ def _compute_scores(q, keys, need_query_softmax=True):
     return s
 
 
+class _MemoryForward(torch.autograd.Function):
+    """Memory.forward (Memory.py:145-175) as one autograd node.  Gradients flow to ``query`` exactly where
+    the reference graph lets them: through the first half of ``updated_query`` (the read softmax is
+    ``.detach()``ed, :255), ``gathering_loss`` (:245) and ``spreading_loss`` (:229), back through
+    ``F.normalize`` (:148).  ``keys`` are constants (every use is detached or, for the read product, the
+    caller passes a plain tensor: main.py:131); ``updated_memory`` is detached (:204); the two score
+    matrices are returned for inspection and are not differentiable here."""
+
+    @staticmethod
+    def forward(ctx, mod, query, keys, train):
+        keys_c = f32c(keys)
+        qc = f32c(query)
+        q4 = mod.prepare_query(qc)
+        q, shp = mod._flat(q4)
+        s = _compute_scores(q, keys_c)
+        gathering_loss, spreading_loss = mod._losses(s, keys_c, train)
+        gathering_loss = gathering_loss.clone()           # separate outputs, not two views of one buffer
+        spreading_loss = None if spreading_loss is None else spreading_loss.clone()
+        updated_query = mod._read(s, keys_c, shp)
+        ctx.save_for_backward(qc, keys_c, s.top1, s.top2)
+        ctx.train = bool(train)
+        ctx.set_materialize_grads(False)
+        if train:
+            updated_memory = mod._update(s, keys_c)
+            ctx.mark_non_differentiable(updated_memory, s.score_query, s.score_memory)
+            return (updated_query, updated_memory, s.score_query, s.score_memory,
+                    gathering_loss, spreading_loss)
+        ctx.mark_non_differentiable(s.score_query, s.score_memory)
+        return updated_query, s.score_query, s.score_memory, gathering_loss
+
+    @staticmethod
+    def backward(ctx, *grads):
+        qc, keys_c, top1, top2 = ctx.saved_tensors
+        if ctx.train:
+            g_uq, _, _, _, g_gather, g_spread = grads
+        else:
+            (g_uq, _, _, g_gather), g_spread = grads, None
+        if g_uq is None and g_gather is None and g_spread is None:
+            return None, None, None, None
+        B, d, h, w = qc.shape
+        g_uq = None if g_uq is None else f32c(g_uq)                  # [B,2d,h,w]; the first d channels reach q
+        g_gather = None if g_gather is None else f32c(g_gather).reshape(1)
+        g_spread = None if g_spread is None else f32c(g_spread).reshape(1)
+        gq = torch.empty_like(qc)
+        check(_lib.lib().vadc_memory_query_bwd(ptr(qc), ptr(keys_c), ptr(top1), ptr(top2) if ctx.train else None,
+                                               ptr(g_uq), ptr(g_gather), ptr(g_spread), B, d, h * w,
+                                               keys_c.shape[0], ptr(gq), stream()), "vadc_memory_query_bwd")
+        return None, gq, None, None
+
+
 class Memory(nn.Module):
-    """Drop-in for model/Memory.py:62-261.  Forward-only: outputs are detached
-    (the reference module is not wired into ``Mymodel``)."""
+    """Drop-in for model/Memory.py:62-261.  ``forward`` is differentiable with respect to ``query``
+    (``_MemoryForward``); the stand-alone public methods (``read``, ``gather_loss``, ...) are
+    forward-only.  The reference module is not wired into ``Mymodel``."""
 
     def __init__(self, memory_size, feature_dim, key_dim, temp_update, temp_gather):
         super().__init__()
@@ -95,18 +146,11 @@ class Memory(nn.Module):
 
     def forward(self, query, keys, train=True):
         """Memory.py:145-175.  query [B,d,h,w], keys [m,d]."""
-        with torch.no_grad():
-            keys_c = f32c(keys)
-            q4 = self.prepare_query(query)
-            q, shp = self._flat(q4)
-            s = _compute_scores(q, keys_c)
-            gathering_loss, spreading_loss = self._losses(s, keys_c, train)
-            updated_query = self._read(s, keys_c, shp)
-            if train:
-                updated_memory = self._update(s, keys_c)
-                return (updated_query, updated_memory, s.score_query, s.score_memory,
-                        gathering_loss, spreading_loss)
-            return updated_query, keys, s.score_query, s.score_memory, gathering_loss
+        _lib.require_cuda(query, keys)
+        if train:
+            return _MemoryForward.apply(self, query, keys, True)
+        uq, sq, sm, gl = _MemoryForward.apply(self, query, keys, False)
+        return uq, keys, sq, sm, gl
 
     def update(self, query, keys, train):
         """Memory.py:177-204"""
