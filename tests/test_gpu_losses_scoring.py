@@ -128,3 +128,49 @@ def test_evaluation_loop_ragged_clip_raises_like_the_reference():
     v = torch.rand(3, 23, 4, 4)
     with pytest.raises(RuntimeError):
         V.evaluate_videos(lambda c: c, [v], [np.zeros(23, np.int64)], ["01"], 4, 3)
+
+
+from bench import cfg4_layout          # the synthetic cfg4 layout is shared with bench.py's scoring line
+
+
+def test_cfg4_full_size_scoring_auc():
+    """BASELINE configs[3] at full size (107 videos / 40 791 frames of 3x256x256, 32 GB of clips streamed through
+    the device-resident loop).  The synthetic model adds a known per-frame offset a_f to every pixel, so the
+    per-frame MSE is a_f^2 in closed form: scores and the mean per-scene AUC of the whole pipeline are checked
+    against float64 host arithmetic (north_star: AUC within 1e-4) and against the oracle's AUC on the same MSEs."""
+    fn, bs, S = 8, 16, 256
+    lengths, labels, scenes = cfg4_layout()
+    rng = np.random.default_rng(11)
+    total_scored, all_mse, kept_labels = 0, [], []
+    offsets = [(0.02 + 0.03 * rng.random(T) + 0.02 * lab * rng.random(T)).astype(np.float32)
+               for T, lab in zip(lengths, labels)]
+    state = {"vid": -1, "batches": None}
+
+    def video_iter():
+        for i, T in enumerate(lengths):
+            state["vid"], state["batches"] = i, iter(V.eval_clip_starts(T, fn, bs))
+            yield torch.rand(3, T, S, S, device=dev())           # one video resident at a time (<= 0.5 GB)
+
+    def model_fn(clip):
+        starts = next(state["batches"])
+        off = np.stack([offsets[state["vid"]][s0:s0 + fn] for s0 in starts])          # [B, D]
+        return clip + torch.tensor(off, device=dev())[:, None, :, None, None]
+
+    auc, per, scores, labs = V.evaluate_videos(model_fn, video_iter(), labels, scenes, fn, bs)
+    assert len(scores) == len(lengths) and len(per) == 12
+    exp_mse = []
+    for i, T in enumerate(lengths):
+        keep = np.concatenate([np.arange(s0, s0 + fn) for st in V.eval_clip_starts(T, fn, bs) for s0 in st])
+        assert len(scores[i]) == len(keep) and list(labs[i]) == list(labels[i][keep])
+        assert scores[i].min() == 0.0 and scores[i].max() == 1.0                       # per-video min-max
+        exp_mse.append(offsets[i][keep].astype(np.float64) ** 2)
+        total_scored += len(keep)
+    assert total_scored > 40000
+    # closed form: psnr = 10 log10(1 / a^2) -> 1 - minmax per video -> per-scene AUC -> mean
+    oauc, oper = O.scene_auc([m.tolist() for m in exp_mse], labs, scenes)
+    assert abs(auc - oauc) < 1e-4 and 0.55 < auc < 0.999
+    for k in oper:
+        assert abs(per[k] - oper[k]) < 1e-4
+    for i in (0, 53, 106):                                                             # scores, not only their ranks
+        p = 10 * np.log10(1.0 / exp_mse[i])
+        np.testing.assert_allclose(scores[i], 1 - (p - p.min()) / (p.max() - p.min()), atol=2e-4)
