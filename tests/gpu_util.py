@@ -41,10 +41,12 @@ def assert_labels_match(label, D64, what="label"):
     return bad.size
 
 
-def assert_selfdist_close(S, Sref, tol=2e-5):
+def assert_selfdist_close(S, Sref, tol=5e-5):
     """cdist(centers, centers): compared on the squared distance relative to its
     scale — on the diagonal the mm form leaves fp32 cancellation noise of a few
-    ulp(2|c|^2) that sqrt turns into ~1e-2 (the reference's own diagonal is not 0)"""
+    ulp(2|c|^2) that sqrt turns into ~1e-2 (the reference's own diagonal is not 0).
+    5e-5 of the largest squared distance = 2.5e-5 relative on the distance (north_star: 1e-4); the tcgen05
+    accumulator rounds toward zero, so a 784-long contraction carries ~2x the error of the fp32 FMA chain."""
     S2, R2 = np.asarray(S, np.float64) ** 2, np.asarray(Sref, np.float64) ** 2
     assert np.abs(S2 - R2).max() < tol * R2.max()
 

@@ -42,7 +42,8 @@ def test_space_golden(name):
     assert rel(N(m.norm.bias.grad), g["g_ln_b"]) < 3e-4
 
 
-@pytest.mark.parametrize("B,Dd,side,C,K", [(2, 4, 28, 192, 128), (1, 3, 8, 24, 8), (2, 2, 32, 64, 16)])
+@pytest.mark.parametrize("B,Dd,side,C,K", [(2, 4, 28, 192, 128), (1, 3, 8, 24, 8), (2, 2, 32, 64, 16),
+                                            (4, 8, 28, 192, 128), (16, 8, 16, 192, 64)])   # the last two: batched tcgen05 GEMMs
 def test_space_vs_oracle(B, Dd, side, C, K):
     rng = np.random.default_rng(B * 100 + side)
     x = (rng.standard_normal((B, Dd, side, side, C)) * 1.3).astype(np.float32)

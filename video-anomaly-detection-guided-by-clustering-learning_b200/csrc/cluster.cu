@@ -358,9 +358,20 @@ cdist_small_kernel(const float* __restrict__ a, const float* __restrict__ b, int
 }
 }  // namespace vadc
 
+namespace vadc {
+// batched cdist on the tcgen05 GEMM: tensor-bound sizes only (the split pass costs 10 bytes per operand element)
+static bool cdist_tc_ok(int nb, long long R, long long P, int C) {
+  return nb >= 1 && nb <= 65535 && (C % 8) == 0 && P >= 8 && (long long)nb * R < (1ll << 31) &&
+         (long long)nb * P < (1ll << 31) && (double)nb * R * P * C >= (double)(1ll << 28) &&
+         tc_gemm_shape_ok(R, P, C, false) && !getenv("VADC_NO_TC_GEMM");
+}
+}  // namespace vadc
+
 extern "C" size_t vadc_cdist_workspace_bytes(int nb, int64_t R, int64_t P, int C) {
-  (void)C;
-  return align_up((size_t)nb * R * sizeof(float), 256) + align_up((size_t)nb * P * sizeof(float), 256) + 256;
+  size_t b = align_up((size_t)nb * R * sizeof(float), 256) + align_up((size_t)nb * P * sizeof(float), 256) + 256;
+  if (nb > 0 && R > 0 && P > 0 && C > 0 && (C % 8) == 0)
+    b += tc_gemm_split_bytes((long long)nb * R, C) + tc_gemm_split_bytes((long long)nb * P, C);
+  return b;
 }
 
 extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int64_t P, int C,
@@ -382,6 +393,16 @@ extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int
   int rc;
   if ((rc = launch_row_sqnorm(a, (long long)nb * R, C, aa, st))) return rc;
   if ((rc = launch_row_sqnorm(b, (long long)nb * P, C, bb, st))) return rc;
+  if (cdist_tc_ok(nb, R, P, C)) {
+    // one launch for all batches: A = a as [nb R, C], B = b as [nb P, C], batch z starts z R / z P rows further
+    void* as = ws.take<uint8_t>(tc_gemm_split_bytes((long long)nb * R, C));
+    void* bs = ws.take<uint8_t>(tc_gemm_split_bytes((long long)nb * P, C));
+    if ((rc = tc_split3(a, (long long)nb * R, C, as, st))) return rc;
+    if ((rc = tc_split3(b, (long long)nb * P, C, bs, st))) return rc;
+    TcBatchDistEpi epi{out, aa, bb, P, R * P, R, P};
+    return launch_tc_gemm_batched<false, false>(as, (long long)nb * R, C, bs, (long long)nb * P, C, R, P, C, nb,
+                                                TcBatchOffsets{(int)R, 0, (int)P, 0}, epi, st);
+  }
   return launch_dist(a, b, aa, bb, nb, R, P, C, out, st);
 }
 

@@ -5,6 +5,7 @@
 // batches.
 #include "common.cuh"
 #include "sgemm.cuh"
+#include "tc_gemm.cuh"
 #include "rows.cuh"
 #include "cluster.h"
 
@@ -130,6 +131,15 @@ struct SpaceGcEpilogue {
   }
 };
 
+// The three contractions of the head as batched tcgen05 GEMMs (three-term bf16 split, fp32-faithful): worth it
+// from a few GFLOP up; P, K multiples of 8 for the TMA row pitches, K a multiple of 64 so that a batch's window
+// of the contraction over centroids ends on a k-block boundary (the next batch's columns must not leak in).
+static bool space_tc_ok(long long M, int P, int C, int K) {
+  return M >= 1 && (P % 8) == 0 && (K % 64) == 0 && C <= 65535 && (long long)C * M < (1ll << 31) &&
+         (long long)C * K < (1ll << 31) && (double)M * P * K * C >= (double)(1ll << 28) && vadc_device_ok() != 0 &&
+         !getenv("VADC_NO_TC_GEMM");
+}
+
 static int space_ln_bwd_blocks(long long T) {
   long long b = (T + 31) / 32;
   long long cap = (long long)sm_count() * 2;
@@ -147,7 +157,8 @@ extern "C" size_t vadc_space_cluster_fwd_workspace_bytes(int64_t M, int P, int C
   b += align_up((size_t)C * (M > 0 ? M : 1) * sizeof(float), 256);    // |zt row|^2
   b += align_up((size_t)C * K * sizeof(float), 256);                  // |center row|^2
   b += align_up((size_t)(softmin_blocks(M * C, K) + 1) * sizeof(double), 256);
-  (void)P;
+  if (M > 0 && (P % 8) == 0)
+    b += tc_gemm_split_bytes((long long)C * M, P) + tc_gemm_split_bytes((long long)C * K, P);
   return b + 256;
 }
 
@@ -178,10 +189,20 @@ extern "C" int vadc_space_cluster_fwd(const float* x, const float* ln_w, const f
     if ((rc = launch_row_sqnorm(zt, (long long)C * M, P, zz, st))) return rc;
     if ((rc = launch_row_sqnorm(centers, (long long)C * K, P, cc, st))) return rc;
     // batch c: A = zt[c] [M,P], B = centers[c]^T; out Ds[m, c, k]
-    Operand Aop{zt, P, 1}, Bop{centers, 1, P};
-    SpaceDistEpilogue epi{Ds, zz, cc, (long long)C * K, K, (int)M};
-    cudaError_t e = sgemm_auto((int)M, K, P, Aop, Bop, (long long)M * P, (long long)K * P, C, 1, epi, st);
-    if (e != cudaSuccess) return record_cuda_error(e, "space dist sgemm");
+    if (space_tc_ok(M, P, C, K)) {
+      void* zs = ws.take<uint8_t>(tc_gemm_split_bytes((long long)C * M, P));
+      void* cs = ws.take<uint8_t>(tc_gemm_split_bytes((long long)C * K, P));
+      if ((rc = tc_split3(zt, (long long)C * M, P, zs, st))) return rc;
+      if ((rc = tc_split3(centers, (long long)C * K, P, cs, st))) return rc;
+      TcBatchDistEpi epi{Ds, zz, cc, (long long)C * K, K, M, K};
+      if ((rc = launch_tc_gemm_batched<false, false>(zs, (long long)C * M, P, cs, (long long)C * K, P, M, K, P, C,
+                                                     TcBatchOffsets{(int)M, 0, K, 0}, epi, st))) return rc;
+    } else {
+      Operand Aop{zt, P, 1}, Bop{centers, 1, P};
+      SpaceDistEpilogue epi{Ds, zz, cc, (long long)C * K, K, (int)M};
+      cudaError_t e = sgemm_auto((int)M, K, P, Aop, Bop, (long long)M * P, (long long)K * P, C, 1, epi, st);
+      if (e != cudaSuccess) return record_cuda_error(e, "space dist sgemm");
+    }
   }
   return launch_softmin_rows(Ds, M * (long long)C, K, alpha, As, nullptr, partial, loss_sq, st);
 }
@@ -195,6 +216,9 @@ extern "C" size_t vadc_space_cluster_bwd_workspace_bytes(int64_t M, int P, int C
   b += align_up((size_t)colsum_chunks(M) * C * K * sizeof(float), 256);
   b += align_up((size_t)C * K * sizeof(float), 256);                   // rcol
   b += align_up((size_t)space_ln_bwd_blocks(M * (int64_t)P) * 2 * C * sizeof(float), 256);
+  if ((P % 8) == 0 && (K % 64) == 0)
+    b += tc_gemm_split_bytes((long long)m, (long long)C * K) + tc_gemm_split_bytes((long long)C * K, P) +
+         tc_gemm_split_bytes((long long)C * m, P);
   return b + 256;
 }
 
@@ -223,15 +247,35 @@ extern "C" int vadc_space_cluster_bwd(const float* x, const float* mu, const flo
   int rc;
   cudaError_t e;
   if ((rc = launch_bwd_rows(Ds, As, nullptr, gD, gA, g_loss_sq, M * (long long)C, K, alpha, r, rsum, st))) return rc;
+  const bool tc = space_tc_ok(M, P, C, K);
+  if (tc) {
+    // r as [M, C K] (batch c = its K-column window), centers as [C K, P], zt as [C M, P]: three split passes, then
+    //   gzt[c] = zt[c] rsum[:,c] - r[:,c,:] centers[c]         A K-major (window offset along k), B MN-major
+    //   gcenters[c] = centers[c] rcol[c] - r[:,c,:]^T zt[c]    A MN-major (window offset along m), B MN-major
+    void* rs = ws.take<uint8_t>(tc_gemm_split_bytes(M, (long long)C * K));
+    void* cs = ws.take<uint8_t>(tc_gemm_split_bytes((long long)C * K, P));
+    void* zs = ws.take<uint8_t>(tc_gemm_split_bytes((long long)C * M, P));
+    if ((rc = tc_split3(r, M, (long long)C * K, rs, st))) return rc;
+    if ((rc = tc_split3(centers, (long long)C * K, P, cs, st))) return rc;
+    if ((rc = tc_split3(zt, (long long)C * M, P, zs, st))) return rc;
+    TcSpaceGzEpi egz{gzt, zt, rsum, T, P, C};
+    if ((rc = launch_tc_gemm_batched<false, true>(rs, M, (long long)C * K, cs, (long long)C * K, P, M, P, K, C,
+                                                  TcBatchOffsets{0, K, 0, K}, egz, st))) return rc;
+    e = launch_colsum(r, M, C * K, cpart, rcol, st);
+    if (e != cudaSuccess) return record_cuda_error(e, "space colsum r");
+    TcSpaceGcEpi egc{gcenters, centers, rcol, (long long)K * P, P, K};
+    if ((rc = launch_tc_gemm_batched<true, true>(rs, M, (long long)C * K, zs, (long long)C * M, P, K, P, M, C,
+                                                 TcBatchOffsets{K, 0, 0, (int)M}, egc, st))) return rc;
+  }
   // gzt[c] = zt[c] * rsum[:,c] - r[:,c,:] @ centers[c]
-  {
+  if (!tc) {
     Operand Aop{r, (long long)C * K, 1}, Bop{centers, P, 1};
     SpaceGzEpilogue epi{gzt, zt, rsum, T, P, C};
     e = sgemm_auto((int)M, P, K, Aop, Bop, K, (long long)K * P, C, 1, epi, st);
     if (e != cudaSuccess) return record_cuda_error(e, "space bwd sgemm r.c");
   }
   // gcenters[c] = centers[c] * rcol[c] - r[:,c,:]^T @ zt[c]
-  {
+  if (!tc) {
     e = launch_colsum(r, M, C * K, cpart, rcol, st);
     if (e != cudaSuccess) return record_cuda_error(e, "space colsum r");
     Operand Aop{r, 1, (long long)C * K}, Bop{zt, P, 1};

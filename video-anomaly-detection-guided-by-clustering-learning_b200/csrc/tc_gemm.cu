@@ -29,6 +29,10 @@ namespace tg {
 
 constexpr int BM = 128, BK = 64, kStages = 1, kThreads = 192;   // one 96 KB stage per CTA, two CTAs per SM
 
+// per-blockIdx.z coordinate offsets of a batched launch: output-row / contraction offsets of A, output-column /
+// contraction offsets of B (in elements of the respective tensor-map dimension)
+struct ZOffsets { int batched, a_m, a_k, b_n, b_k; };
+
 __global__ void __launch_bounds__(256)
 split3_kernel(const float* __restrict__ src, long long n4, __nv_bfloat16* __restrict__ t0,
               __nv_bfloat16* __restrict__ t1, __nv_bfloat16* __restrict__ t2) {
@@ -57,7 +61,7 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst,
 template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kThreads, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               int M, int N, int Kd, int kb_per_split, Epi epi) {
+               int M, int N, int Kd, int kb_per_split, const ZOffsets zo, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t kATerm = BM * 128u, kBTerm = BN * 128u;           // bytes per bf16 term of a stage's operand
@@ -66,10 +70,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  // split-K: blockIdx.z takes k-blocks [kb0, kb1) and hands its index to the epilogue (partial outputs)
+  // blockIdx.z is either a split-K slot (k-blocks [kb0, kb1), partial outputs) or, with zo.batched, the index
+  // of an independent problem whose operands sit zo.* coordinates further along the same tensors; either way
+  // the epilogue receives it
   const int nkb_all = (Kd + BK - 1) / BK;
-  const int kb0 = blockIdx.z * kb_per_split, kb1 = min(nkb_all, kb0 + kb_per_split);
+  const int z = blockIdx.z;
+  const int kb0 = zo.batched ? 0 : z * kb_per_split, kb1 = zo.batched ? nkb_all : min(nkb_all, kb0 + kb_per_split);
   const int nkb = max(kb1 - kb0, 0);
+  const int am = m0 + z * zo.a_m, ak = z * zo.a_k, bn = n0 + z * zo.b_n, bk = z * zo.b_k;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&accfull, 1);
@@ -94,18 +102,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
       for (int t = 0; t < 3; ++t) {
         if constexpr (!A_MN) {
-          tma_load_3d(&mapA, a + t * kATerm, &full[s], k0, m0, t);
+          tma_load_3d(&mapA, a + t * kATerm, &full[s], k0 + ak, am, t);
         } else {
 #pragma unroll
           for (int mb = 0; mb < BM / 64; ++mb)                // A given as [Kd, M]: [64 k-rows x 64 m-cols] boxes, 8 KB apart
-            tma_load_3d(&mapA, a + t * kATerm + mb * 8192u, &full[s], m0 + mb * 64, k0, t);
+            tma_load_3d(&mapA, a + t * kATerm + mb * 8192u, &full[s], am + mb * 64, k0 + ak, t);
         }
         if constexpr (!B_MN) {
-          tma_load_3d(&mapB, b + t * kBTerm, &full[s], k0, n0, t);
+          tma_load_3d(&mapB, b + t * kBTerm, &full[s], k0 + bk, bn, t);
         } else {
 #pragma unroll
           for (int nb = 0; nb < BN / 64; ++nb)                // [64 k-rows x 64 n-cols] boxes, 8 KB apart
-            tma_load_3d(&mapB, b + t * kBTerm + nb * 8192u, &full[s], n0 + nb * 64, k0, t);
+            tma_load_3d(&mapB, b + t * kBTerm + nb * 8192u, &full[s], bn + nb * 64, k0 + bk, t);
         }
       }
     }
@@ -234,8 +242,31 @@ int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, lon
   if (splits < 1) splits = 1;
   const int per = (nkb + splits - 1) / splits;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)splits);
-  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, epi);
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0}, epi);
   VADC_CHECK_LAUNCH("tc_gemm_kernel");
+  return VADC_OK;
+}
+
+// nbatch independent [M,N,Kd] problems in ONE launch (blockIdx.z = batch): the operands of batch z start
+// z * off.{m,k} coordinates further along tensors of the given full extents (rows x cols of the split matrices)
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_batched(const void* a_split, long long a_rows, long long a_cols, const void* b_split,
+                           long long b_rows, long long b_cols, long long M, long long N, long long Kd, int nbatch,
+                           TcBatchOffsets off, Epi epi, cudaStream_t st) {
+  constexpr int BN = 128;
+  if (nbatch < 1 || nbatch > 65535) return VADC_ERR_UNSUPPORTED;
+  CUtensorMap mA, mB;
+  int rc;
+  if ((rc = tg::make_map3(&mA, a_split, a_rows, a_cols, A_MN ? 64 : tg::BM))) return rc;
+  if ((rc = tg::make_map3(&mB, b_split, b_rows, b_cols, B_MN ? 64 : BN))) return rc;
+  const size_t smem = (size_t)tg::kStages * (3 * tg::BM * 128 + 3 * BN * 128) + 1024;
+  auto kern = tg::tc_gemm_kernel<BN, A_MN, B_MN, Epi>;
+  VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)nbatch);
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb,
+                                         tg::ZOffsets{1, off.a_m, off.a_k, off.b_n, off.b_k}, epi);
+  VADC_CHECK_LAUNCH("tc_gemm_kernel(batched)");
   return VADC_OK;
 }
 
@@ -252,6 +283,14 @@ template int launch_tc_gemm<false, TcDistEpi>(const void*, const void*, long lon
 template int launch_tc_gemm<true, TcReadEpi>(const void*, const void*, long long, long long, long long, TcReadEpi, cudaStream_t);
 template int launch_tc_gemm<true, TcGzEpi>(const void*, const void*, long long, long long, long long, TcGzEpi, cudaStream_t);
 template int launch_tc_gemm_ex<true, true, TcPartialEpi>(const void*, const void*, long long, long long, long long, int, TcPartialEpi, cudaStream_t);
+#define VADC_TC_BATCHED(AMN, BMN, EPI)                                                                               \
+  template int launch_tc_gemm_batched<AMN, BMN, EPI>(const void*, long long, long long, const void*, long long,       \
+                                                     long long, long long, long long, long long, int, TcBatchOffsets, \
+                                                     EPI, cudaStream_t);
+VADC_TC_BATCHED(false, false, TcBatchDistEpi)
+VADC_TC_BATCHED(false, true, TcSpaceGzEpi)
+VADC_TC_BATCHED(true, true, TcSpaceGcEpi)
+#undef VADC_TC_BATCHED
 
 }  // namespace vadc
 

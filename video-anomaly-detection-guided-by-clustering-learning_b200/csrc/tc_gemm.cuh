@@ -19,6 +19,14 @@ template <bool A_MN, bool B_MN, class Epi>
 int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
                       Epi epi, cudaStream_t st);
 
+// batched form (blockIdx.z = batch): per-batch coordinate offsets along the operands' tensors — a_m / b_n along the
+// output-row / output-column dimension, a_k / b_k along the contraction dimension
+struct TcBatchOffsets { int a_m, a_k, b_n, b_k; };
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_batched(const void* a_split, long long a_rows, long long a_cols, const void* b_split,
+                           long long b_rows, long long b_cols, long long M, long long N, long long Kd, int nbatch,
+                           TcBatchOffsets off, Epi epi, cudaStream_t st);
+
 __device__ __forceinline__ void tc_store_row32(float* o, const float (&v)[32], int nvalid) {
   if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
 #pragma unroll
@@ -47,6 +55,45 @@ struct TcDistEpi {
       v[j] = sqrtf(fmaxf(am + b - 2.0f * v[j], 0.f));
     }
     tc_store_row32(out + m * ldo + n, v, nvalid);
+  }
+};
+
+// batched torch.cdist (mm form): out[z out_z + m ldo + n] from |a|^2 [z aa_z + m], |b|^2 [z bb_z + n]
+struct TcBatchDistEpi {
+  float* out; const float* aa; const float* bb; long long ldo, out_z, aa_z, bb_z;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int z) const {
+    const float am = aa[z * aa_z + m];
+    const float* b = bb + z * bb_z + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float bj = (j < nvalid) ? b[j] : 0.f;
+      v[j] = sqrtf(fmaxf(am + bj - 2.0f * v[j], 0.f));
+    }
+    tc_store_row32(out + z * out_z + m * ldo + n, v, nvalid);
+  }
+};
+
+// space head backward (model/cluster.py:127-149 under autograd): gzt[c,m,p] = zt[c,m,p] rsum[m,c] - (r centers)[m,p]
+struct TcSpaceGzEpi {
+  float* out; const float* zt; const float* rsum; long long MP; int P, C;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int z) const {
+    const long long i = (long long)z * MP + m * P + n;
+    const float rs = rsum[m * C + z];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] = zt[i + j] * rs - v[j];
+    tc_store_row32(out + i, v, nvalid);
+  }
+};
+
+// gcenters[c,k,p] = centers[c,k,p] rcol[c,k] - (r^T zt)[k,p]
+struct TcSpaceGcEpi {
+  float* out; const float* centers; const float* rcol; long long KP; int P, K;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int z) const {
+    const long long i = (long long)z * KP + m * P + n;
+    const float rc = rcol[(long long)z * K + m];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] = centers[i + j] * rc - v[j];
+    tc_store_row32(out + i, v, nvalid);
   }
 };
 
