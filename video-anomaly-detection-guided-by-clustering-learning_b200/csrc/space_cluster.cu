@@ -59,8 +59,10 @@ ln_bwd_transposed_kernel(const float* __restrict__ gzt, const float* __restrict_
     __syncthreads();
     {
       const long long row = t0 + lane;
-      if (row < T)
+      if (row < T) {
+#pragma unroll 8
         for (int c = wid; c < C; c += 8) tile[lane * ld + c] = __ldg(gzt + (long long)c * T + row);
+      }
     }
     __syncthreads();
     for (int rr = wid; rr < 32; rr += 8) {
@@ -142,7 +144,7 @@ static bool space_tc_ok(long long M, int P, int C, int K) {
 
 static int space_ln_bwd_blocks(long long T) {
   long long b = (T + 31) / 32;
-  long long cap = (long long)sm_count() * 2;
+  long long cap = (long long)sm_count() * 6;      // ~37 KB of shared memory per block at C = 192: six resident blocks per SM
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;

@@ -79,8 +79,17 @@ struct TcSpaceGzEpi {
   __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int z) const {
     const long long i = (long long)z * MP + m * P + n;
     const float rs = rsum[m * C + z];
+    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(zt + i) & 15u) == 0) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] = zt[i + j] * rs - v[j];
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(zt + i) + j);
+        v[4 * j] = t.x * rs - v[4 * j]; v[4 * j + 1] = t.y * rs - v[4 * j + 1];
+        v[4 * j + 2] = t.z * rs - v[4 * j + 2]; v[4 * j + 3] = t.w * rs - v[4 * j + 3];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] = zt[i + j] * rs - v[j];
+    }
     tc_store_row32(out + i, v, nvalid);
   }
 };
@@ -91,8 +100,17 @@ struct TcSpaceGcEpi {
   __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int z) const {
     const long long i = (long long)z * KP + m * P + n;
     const float rc = rcol[(long long)z * K + m];
+    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(centers + i) & 15u) == 0) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] = centers[i + j] * rc - v[j];
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(centers + i) + j);
+        v[4 * j] = t.x * rc - v[4 * j]; v[4 * j + 1] = t.y * rc - v[4 * j + 1];
+        v[4 * j + 2] = t.z * rc - v[4 * j + 2]; v[4 * j + 3] = t.w * rc - v[4 * j + 3];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] = centers[i + j] * rc - v[j];
+    }
     tc_store_row32(out + i, v, nvalid);
   }
 };
