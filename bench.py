@@ -476,6 +476,20 @@ def extra_benchmarks(V, dev, peak):
         xs = torch.randn(8, 8, 32, 32, 192, device=dev)
         ms = time_op(lambda: sp(xs), 5, flush)
         out["space_fwd_M64_P1024_C192_K128"] = {"ms": ms, "tokens/s": 65536 / (ms * 1e-3)}
+        del xs
+    # C3 at the full cfg2 batch (B=64: M=512) forward + backward from the space loss (backbone.py:94)
+    xs = torch.randn(64, 8, 32, 32, 192, device=dev, requires_grad=True)
+
+    def space_step():
+        for p_ in sp.parameters():
+            p_.grad = None
+        xs.grad = None
+        sp(xs)
+        sp.fused_cluster_loss().backward()
+    ms = time_op(space_step, 5, flush)
+    alg = 524288 * 192 * 4 * 2 + 192 * 128 * 1024 * 4 * 2 + 4 * 512 * 192 * 128 * 4     # x, gx; centers, gcenters; Ds, As
+    out["space_fwd_bwd_M512_P1024_C192_K128"] = {"ms": ms, "tokens/s": 524288 / (ms * 1e-3),
+                                                 "alg_GB/s": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / peak}
     return out
 
 

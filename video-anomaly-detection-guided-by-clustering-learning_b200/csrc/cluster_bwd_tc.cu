@@ -328,11 +328,13 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     const int pw = warp < 2 ? warp : (warp >> 2) * 2 + (warp & 1);   // warps 0,1,6,7,10,11,14 -> 0..6
     const int lj = lane & 7, lg = lane >> 3;
     const int rsel = (lg & 1) * 4 + (lg >> 1);
-    const int nunits = kUnits * nmine;
     struct Unit { union { float4 v[F4]; float4 a[8]; }; float rs, mu; };   // a[]: the 8 float4 of an A unit
-    auto issue = [&](Unit& U, int g) {
-      if (g >= nunits) return;
-      const int it = g / kUnits, u = g % kUnits, v = u & 15;
+    // (tile, unit) positions advance incrementally: a division by kUnits per unit is ~10 % of a producer's instructions
+    struct Pos { int it, u; };
+    auto advance = [&](Pos& q) { q.u += kProd; if (q.u >= kUnits) { q.u -= kUnits; ++q.it; } };
+    auto issue = [&](Unit& U, const Pos& q) {
+      if (q.it >= nmine) return;
+      const int it = q.it, u = q.u, v = u & 15;
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
       if (u >= 32) {                                     // A rows: 32 rows x 32 centroids, lane = (row, float4)
         const long long rb = tile * kTok + (u - 32) * 32;
@@ -364,9 +366,9 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       U.rs = (isx && live) ? __ldg(p.rstd + row) : 0.f;   // raw loads only: arithmetic on them here would wait for them
       U.mu = (isx && live) ? __ldg(p.mu + row) : 0.f;
     };
-    auto process = [&](Unit& U, int g) {
-      if (g >= nunits) return;
-      const int it = g / kUnits, u = g % kUnits, v = u & 15;
+    auto process = [&](Unit& U, const Pos& q) {
+      if (q.it >= nmine) return;
+      const int it = q.it, u = q.u, v = u & 15;
       if (u >= 32) {
         // tile A is free once S5a of the previous tile has completed
         mbar_wait_spin(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));
@@ -429,12 +431,16 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       TR(2, it);
     };
     Unit cur, nxt;
-    issue(cur, pw);
+    Pos pc{0, pw}, pn{0, pw};                            // kProd < kUnits: every warp owns a unit of tile 0
+    issue(cur, pc);
+    advance(pn);
 #pragma unroll 1
-    for (int g = pw; g < nunits; g += kProd) {           // one copy of the code: four roles share the instruction cache
-      issue(nxt, g + kProd);
-      process(cur, g);
+    while (pc.it < nmine) {                              // one copy of the code: four roles share the instruction cache
+      issue(nxt, pn);
+      process(cur, pc);
       cur = nxt;
+      pc = pn;
+      advance(pn);
     }
   } else if (is_e1) {
     // ======================================================================= E1
