@@ -67,10 +67,11 @@ constexpr int kThreads = 512;
 constexpr int kProd = 7;                     // producer warps
 constexpr int kUnits = 2 * (kTok / 4) + 2;   // producer units per tile: 16 x 4 rows of x, 16 x 4 rows of gR, 2 x 32 rows of A
 constexpr int kMmaWarp = 15;
+constexpr int kDepth = 4;                    // async producers: units in flight per warp
 constexpr uint32_t kBlk = kTok * 128u;       // one [64 rows x 128 B] operand block
 
 struct Plan {
-  uint32_t x_off, g_off, ta_off, zero_off, tr_off, cen_off, stg_off, scal_off, gam_off, bet_off, cvec_off, misc_off, total;
+  uint32_t x_off, g_off, ta_off, zero_off, tr_off, cen_off, stg_off, scal_off, gam_off, bet_off, cvec_off, misc_off, stat_off, total;
   uint32_t xbuf, xterm, gterm;
 };
 
@@ -90,7 +91,8 @@ __host__ __device__ inline Plan plan(int C) {
   p.gam_off = off; off += (uint32_t)C * 4u;
   p.bet_off = off; off += (uint32_t)C * 4u;
   p.cvec_off = off; off += 2u * kK * 4u;                   // hc = |c|^2/2 - beta.c ; cg = gamma.c
-  p.misc_off = off; off += 256u;
+  p.misc_off = off; off += 256u;                           // mbarriers [0,144), TMEM slot at +192
+  p.stat_off = off; off += kProd * kDepth * 4u * 8u;       // async producers: [warp][slot][4 rows] {mu, rstd}
   p.total = off;
   return p;
 }
@@ -142,6 +144,16 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
+// non-blocking phase test (mbarrier.try_wait may suspend the thread for a system-dependent time before it returns false)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
@@ -158,6 +170,22 @@ __device__ __forceinline__ float4 ldg_nc(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
+}
+// Ampere-style asynchronous copies: global -> shared without passing through registers (L2 only for the 16-byte form)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {   // wait until at most n of this thread's groups are pending
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
 }
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
@@ -250,7 +278,7 @@ struct Params {
   int trace_cta;
 };
 
-template <int F4, bool TRACE>
+template <int F4, bool TRACE, bool ASYNC>
 __global__ void __launch_bounds__(kThreads, 1)
 cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -263,7 +291,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   float* sHc = reinterpret_cast<float*>(smem + pl.cvec_off);
   float* sCg = sHc + K;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.misc_off);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.misc_off + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.misc_off + 192);   // (the 18 mbarriers end at +144)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // event trace (debug): entry = {code << 32 | tile, clock64}
@@ -328,6 +356,136 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     const int pw = warp < 2 ? warp : (warp >> 2) * 2 + (warp & 1);   // warps 0,1,6,7,10,11,14 -> 0..6
     const int lj = lane & 7, lg = lane >> 3;
     const int rsel = (lg & 1) * 4 + (lg >> 1);
+    if constexpr (ASYNC) {
+      // ---- asynchronous producers: cp.async brings a unit's raw fp32 rows straight into the unit's OWN destination
+      // in the operand tiles (4 rows x 768 B raw = the bytes of their hi + lo bf16 rows: the float4 a lane owns goes to
+      // the 16-byte chunk that will hold its own and its neighbour's hi halves (even lanes) or lo halves (odd lanes)),
+      // so the loads in flight hold no registers and a warp keeps up to kDepth units in flight behind ONE copy of the
+      // code.  A unit is issued once its buffer is free (non-blocking test: a warp never waits for a buffer while it
+      // still owes converted units to the other roles) and converted in place after its copy group has landed: every
+      // lane reads back its own chunks, the warp synchronises, then the hi / lo halves are written as before.
+      struct Pos { int it, u; };
+      auto advance = [&](Pos& q) { q.u += kProd; if (q.u >= kUnits) { q.u -= kUnits; ++q.it; } };
+      const uint32_t sStat32 = smem_u32(smem + pl.stat_off) + (uint32_t)pw * (kDepth * 4u * 8u);
+      auto buffer_free = [&](const Pos& q) -> bool {
+        if (q.u >= 32) return true;                        // A units are loaded when they are converted
+        return q.u < 16 ? mbar_test(&bars[B_XEMPTY0 + (q.it & 1)], (uint32_t)(((q.it >> 1) & 1) ^ 1))
+                        : mbar_test(&bars[B_GEMPTY], (uint32_t)((q.it & 1) ^ 1));
+      };
+      // staging chunk of this lane's float4 number lj + 8 i of row r (see the class comment): base of the unit's tensor
+      auto unit_base = [&](const Pos& q, int& r, bool& isx) -> uint32_t {
+        const int v = q.u & 15;
+        isx = q.u < 16;
+        r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
+        return (isx ? sX32 + (uint32_t)(q.it & 1) * pl.xbuf : sG32) + (uint32_t)r * 128u +
+               (((uint32_t)(lj >> 1) ^ (uint32_t)(r & 7)) << 4);
+      };
+      auto issue = [&](const Pos& q, int slot) {
+        if (q.u >= 32) { cp_async_commit(); return; }
+        int r; bool isx;
+        const uint32_t b0 = unit_base(q, r, isx);
+        const int v = q.u & 15;
+        const long long tile = (long long)blockIdx.x + (long long)q.it * gridDim.x;
+        const float* src = isx ? p.x : p.gR;
+        if (p.pf > 0 && lane == 0 && (v & 1) == 0 && q.it + p.pf < nmine) {   // L2 prefetch: same 8-row group, pf tiles ahead
+          const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
+          const long long rows = min(8ll, p.N - rn);
+          if (rows > 0) prefetch_l2_bulk(src + rn * C, (uint32_t)(rows * C * 4));
+          if (isx && v == 0) {
+            const long long t0 = (tile + (long long)p.pf * gridDim.x) * kTok;
+            const long long nr = min((long long)kTok, p.N - t0) & ~3ll;
+            if (nr > 0) { prefetch_l2_bulk(p.mu + t0, (uint32_t)(nr * 4)); prefetch_l2_bulk(p.rstd + t0, (uint32_t)(nr * 4)); }
+          }
+        }
+        const long long row = tile * kTok + r;
+        const bool live = row < p.N;
+        const float4* sr = reinterpret_cast<const float4*>(src + row * C) + lj;
+        const uint32_t s0 = b0 + ((lj & 1) ? pl.xterm : 0u);           // even lanes stage in the hi term, odd lanes in the lo term
+#pragma unroll
+        for (int i = 0; i < F4; ++i) {
+          const uint32_t dst = (s0 ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk;
+          if (live) cp_async16(dst, sr + 8 * i);
+          else sts128(dst, 0u, 0u, 0u, 0u);
+        }
+        if (isx && lj == 0) {                                          // the row's LayerNorm statistics ride along
+          const uint32_t st = sStat32 + (uint32_t)(slot * 4 + lg) * 8u;
+          if (live) { cp_async4(st, p.mu + row); cp_async4(st + 4u, p.rstd + row); }
+          else sts64(st, 0u, 0u);
+        }
+        cp_async_commit();
+      };
+      auto process = [&](const Pos& q, int slot) {
+        const int it = q.it;
+        if (q.u >= 32) {                                   // A rows: 32 rows x 32 centroids, lane = (row, float4)
+          const long long rb = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + (q.u - 32) * 32;
+          float4 a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long row = rb + (j >> 1) * 8 + (j & 1) * 2 + rsel;
+            a[j] = row < p.N ? ldg_nc(reinterpret_cast<const float4*>(p.A + row * K) + lj) : make_float4(0, 0, 0, 0);
+          }
+          mbar_wait_spin(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));   // tile A is free once S5a of the previous tile has completed
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t r = (uint32_t)((q.u - 32) * 32 + (j >> 1) * 8 + (j & 1) * 2 + rsel);
+            uint32_t a1, a2, b1, b2;
+            split2_bf(a[j].x, a[j].y, a1, a2);
+            split2_bf(a[j].z, a[j].w, b1, b2);
+            sts64(sTA32 + sw128(r, (uint32_t)lj * 8u), a1, b1);
+            sts64(sTA32 + sw128(r, 64u + (uint32_t)lj * 8u), a2, b2);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_AFULL]);
+          return;
+        }
+        int r; bool isx;
+        const uint32_t b0 = unit_base(q, r, isx);
+        const uint32_t s0 = b0 + ((lj & 1) ? pl.xterm : 0u);
+        TR(0, it);
+        float4 v[F4];
+#pragma unroll
+        for (int i = 0; i < F4; ++i) v[i] = lds128f((s0 ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk);
+        float mu = 0.f, rs = 1.f;
+        if (isx) {
+          const uint32_t st = sStat32 + (uint32_t)(slot * 4 + lg) * 8u;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(mu), "=f"(rs) : "r"(st));
+        }
+        __syncwarp();                                      // every lane holds its chunks: the staging bytes may be overwritten
+        const uint32_t db = b0 + (uint32_t)(lj & 1) * 8u;
+        const float2 rs2 = bcast2(rs), nm2 = bcast2(-mu * rs);
+#pragma unroll
+        for (int i = 0; i < F4; ++i) {
+          uint32_t a1, a2, b1, b2;
+          split2_bf(fma2(make_float2(v[i].x, v[i].y), rs2, nm2), a1, a2);   // gR: v * 1 - 0 (exact)
+          split2_bf(fma2(make_float2(v[i].z, v[i].w), rs2, nm2), b1, b2);
+          sts64((db ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
+          sts64((db ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.xterm, a2, b2);   // xterm == gterm
+        }
+        TR(1, it);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(isx ? &bars[B_XFULL0 + (it & 1)] : &bars[B_GFULL]);
+        TR(2, it);
+      };
+      Pos pi{0, pw}, pp{0, pw};                            // kProd < kUnits: every warp owns a unit of tile 0
+      int pending = 0, si = 0, sp = 0;
+#pragma unroll 1
+      while (pp.it < nmine) {
+        while (pending < kDepth && pi.it < nmine && buffer_free(pi)) {
+          issue(pi, si);
+          advance(pi);
+          si = (si + 1) & (kDepth - 1);
+          ++pending;
+        }
+        if (pending == 0) continue;                        // nothing owed to anybody: poll the buffer of the next unit
+        cp_async_wait_pending(pending - 1);                // the oldest group has landed
+        process(pp, sp);
+        advance(pp);
+        sp = (sp + 1) & (kDepth - 1);
+        --pending;
+      }
+    } else {
     struct Unit { union { float4 v[F4]; float4 a[8]; }; float rs, mu; };   // a[]: the 8 float4 of an A unit
     // (tile, unit) positions advance incrementally: a division by kUnits per unit is ~10 % of a producer's instructions
     struct Pos { int it, u; };
@@ -442,6 +600,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       pc = pn;
       advance(pn);
     }
+    }   // !ASYNC
   } else if (is_e1) {
     // ======================================================================= E1
     const int et = tid - 64;                             // 0..63 = token row; its G1 row sits in TMEM lane 64 + et
@@ -927,9 +1086,14 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
                getenv("VADC_BWD_DBG") ? atoi(getenv("VADC_BWD_DBG")) : 0, trace,
                getenv("VADC_BWD_TRACE_CTA") ? atoi(getenv("VADC_BWD_TRACE_CTA")) : 0};
   bool launched = false;
+  // experiment switch: 1 = cp.async producers staging in place (kept for the trace comparisons in DESIGN.md: parity-equal,
+  // 510 us against 377 us at cfg2 — a unit cannot be requested before its buffer is free, which puts the load latency
+  // behind every buffer release); default = register-staged producers
+  const bool async_prod = getenv("VADC_BWD_ASYNC") && atoi(getenv("VADC_BWD_ASYNC")) == 1;
 #define BT_CASE(F4_)                                                                                   \
   if (C == 32 * F4_) {                                                                                 \
-    auto kern = trace ? bt::cluster_bwd_tc_kernel<F4_, true> : bt::cluster_bwd_tc_kernel<F4_, false>;    \
+    auto kern = trace ? (async_prod ? bt::cluster_bwd_tc_kernel<F4_, true, true> : bt::cluster_bwd_tc_kernel<F4_, true, false>)      \
+                      : (async_prod ? bt::cluster_bwd_tc_kernel<F4_, false, true> : bt::cluster_bwd_tc_kernel<F4_, false, false>);  \
     VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     kern<<<grid, bt::kThreads, smem, st>>>(mGx, p);                                                    \
     launched = true;                                                                                   \
