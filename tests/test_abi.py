@@ -112,3 +112,38 @@ def test_roc_auc_matches_sklearn():
         y = rng.integers(0, 2, n); y[0], y[-1] = 0, 1
         s = np.round(rng.random(n), 2)
         assert abs(V.roc_auc_score(y, s) - roc_auc_score(y, s)) < 1e-12
+
+
+def test_checkpoint_contract_roundtrip(tmp_path):
+    """state_dict names / shapes of the drop-in cluster heads and the DDP 'module.' prefix convention of
+    misc/utils.py:51-76: a checkpoint written the way main_predict.py:204 writes it loads back,
+    unknown keys are skipped, a missing file is a no-op"""
+    import torch
+    import videoad_b200 as V
+
+    class Net(torch.nn.Module):                      # the part of Mymodel the hot path owns (backbone.py:40-41)
+        def __init__(self):
+            super().__init__()
+            self.cluster1 = V.EuclidDistance_Assign_Module(192, 1024, soft_assign_alpha=16.0)
+            self.space_cluster = V.Space_EuclidDistance_Assign_Module(12, 8, space_size=4)
+
+    a, b = Net(), Net()
+    assert {k: tuple(v.shape) for k, v in a.state_dict().items()} == {
+        "cluster1.cluster_center": (1024, 192), "cluster1.identity_matrix": (1024, 1024),
+        "cluster1.norm.weight": (192,), "cluster1.norm.bias": (192,),
+        "space_cluster.cluster_center": (12, 8, 16), "space_cluster.identity_matrix": (12, 8, 8),
+        "space_cluster.norm.weight": (12,), "space_cluster.norm.bias": (12,)}
+    # the reference's substring-based grad toggles (backbone.py:44-72) see the same names
+    assert all(("cluster" in n) for n, _ in a.named_parameters())
+    assert not a.cluster1.identity_matrix.requires_grad and a.cluster1.cluster_center.requires_grad
+    path = str(tmp_path / "checkpoint0.pth")
+    V.save_checkpoint(a, path)
+    sd = torch.load(path)
+    assert all(k.startswith("module.") for k in sd)
+    sd["module.decoder.not_in_this_model"] = torch.zeros(3)
+    torch.save(sd, path)
+    loaded, skipped = V.load_pretrain_model(path, b, map_location="cpu")
+    assert skipped == ["decoder.not_in_this_model"] and len(loaded) == 8
+    for (k, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(va, vb), k
+    assert V.load_pretrain_model(str(tmp_path / "missing.pth"), b) == ([], [])

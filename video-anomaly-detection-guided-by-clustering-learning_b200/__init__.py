@@ -18,7 +18,7 @@ from .scoring import (frame_mse, clip_mse, psnr, anomly_score, roc_auc_score, re
 from .distributed import (init_distributed_mode, fix_random_seeds, setup_for_distributed, get_sha,
                           allreduce_sum_packed, global_frobenius, shard_range,
                           numa_local, pinned_like_local, gpu_local_cpus)
-from .integration import patch_reference
+from .integration import patch_reference, load_pretrain_model, save_checkpoint
 
 __all__ = [
     "EuclidDistance_Assign_Module", "Space_EuclidDistance_Assign_Module", "NegSoftAssign",
@@ -26,6 +26,6 @@ __all__ = [
     "l1_mean", "mse_mean", "e4_norm", "e4_sum", "frame_mse", "clip_mse", "psnr", "anomly_score",
     "roc_auc_score", "regularity_auc", "minmax_score_device", "evaluate_videos", "eval_clip_starts", "init_distributed_mode",
     "fix_random_seeds", "setup_for_distributed", "get_sha", "allreduce_sum_packed",
-    "global_frobenius", "shard_range", "numa_local", "pinned_like_local", "gpu_local_cpus", "patch_reference", "launch_count",
+    "global_frobenius", "shard_range", "numa_local", "pinned_like_local", "gpu_local_cpus", "patch_reference", "load_pretrain_model", "save_checkpoint", "launch_count",
     "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05",
 ]
