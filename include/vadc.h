@@ -242,6 +242,22 @@ int vadc_memory_update(const float* q, const float* keys, const float* score_que
                        float* query_update, float* updated_memory,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Global-batch memory under data parallelism: softmax(score, dim=0) (Memory.py:140) and
+ * max_n score_query[:, i] (:108) span ALL tokens of the batch.  With the tokens sharded over ranks:
+ *   colmax_global = all-reduce MAX of vadc_memory_score's colmax;
+ *   contrib = colsum_local * exp(colmax_local - colmax_global)   (vadc_memory_dp_contrib), S = all-reduce SUM;
+ *   global score_query = local score_query * contrib / S         (vadc_scale_columns, in place);
+ *   this rank's share of the update sums = local query_update * exp(colmax_local - colmax_global)
+ *   (vadc_memory_dp_scale_update, in place), all-reduce SUM, then
+ *   updated_memory = F.normalize(query_update + keys, dim=1)     (vadc_memory_finish_update; Memory.py:193). */
+int vadc_memory_dp_contrib(const float* colmax_local, const float* colsum_local,
+                           const float* colmax_global, int m, float* contrib, void* stream);
+int vadc_scale_columns(float* x, const float* num, const float* den, int64_t N, int m, void* stream);
+int vadc_memory_dp_scale_update(float* query_update, const float* colmax_local,
+                                const float* colmax_global, int m, int d, void* stream);
+int vadc_memory_finish_update(const float* query_update, const float* keys, int m, int d,
+                              float* updated_memory, void* stream);
+
 /* MemoryLoss  Memory.py:52-59: sum |K K^T/2 + 1/2 - I| / (m (m-1)) -> out[0] */
 size_t vadc_memory_separateness_workspace_bytes(int m, int d);
 int vadc_memory_separateness(const float* keys, int m, int d, float* out,

@@ -49,6 +49,10 @@ def _worker(rank, world, port, q):
     out["grad"] = float(v.grad)
     Lc = V.global_frobenius((v.detach() ** 2).sum().reshape(1), ddp_compat=True)
     out["loss_compat"] = float(Lc)
+    # the reductions of the global-batch memory: column maxima (MAX), column sums and update sums (SUM)
+    from videoad_b200.memory import _dist_reduce
+    out["colmax"] = _dist_reduce(torch.tensor([1.0 + rank, 5.0 - 3 * rank, -2.0]), "max").numpy().copy()
+    out["colsum"] = _dist_reduce(torch.tensor([1.0 + rank, 10.0]), "sum").numpy().copy()
     # print is muted on non-master ranks (utils/distritributed_model.py:23-35)
     import builtins
     out["print_wrapped"] = getattr(builtins.print, "_vadc_wrapped", False)
@@ -73,6 +77,9 @@ def test_two_rank_gloo():
         want = res[0]["local"][i] + res[1]["local"][i]
         np.testing.assert_allclose(res[0]["packed"][i], want, rtol=1e-6)
         np.testing.assert_allclose(res[1]["packed"][i], want, rtol=1e-6)
+    for r in (0, 1):
+        np.testing.assert_allclose(res[r]["colmax"], [2.0, 5.0, -2.0])
+        np.testing.assert_allclose(res[r]["colsum"], [3.0, 20.0])
     Lg = (1.0 + 4.0) ** 0.5
     for r in (0, 1):
         assert abs(res[r]["loss"] - Lg) < 1e-6

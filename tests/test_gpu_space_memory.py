@@ -214,3 +214,71 @@ def test_memory_backward_vs_oracle(B, d, h, w, m):
     o = mem(q, T(keys), train=True)
     (o[2].sum() * 0 + 1).backward() if o[2].requires_grad else None
     assert q.grad is None
+
+
+# ---------------------------------------------------------------------------
+# Memory under data parallelism: two "ranks" on one GPU = the full batch
+# ---------------------------------------------------------------------------
+class _TwoRanks:
+    """two python threads stand in for two ranks: a reduction hands each thread the other's tensor (the role of the
+    NCCL all-reduce); a lock lets only one of them enqueue work at a time (they share one stream and workspace)"""
+
+    def __init__(self):
+        import threading
+        self.lock, self.bar, self.slots = threading.Lock(), threading.Barrier(2), [None, None]
+
+    def reducer(self, rank):
+        def reduce(t, op):
+            self.slots[rank] = t
+            self.lock.release()
+            self.bar.wait()
+            other = self.slots[1 - rank]
+            self.bar.wait()
+            self.lock.acquire()
+            return torch.maximum(t, other) if op == "max" else t + other
+        return reduce
+
+
+@pytest.mark.parametrize("d,h,w,m", [(64, 6, 5, 17), (768, 16, 16, 2000)])
+def test_memory_global_batch_two_shards(d, h, w, m):
+    """Memory.global_batch: the batch split over two ranks reproduces the single-process full-batch forward
+    (column softmax over ALL tokens, update sums, loss means) and its gradient — SURVEY 8e 'Memory under DP'"""
+    import threading
+    rng = np.random.default_rng(m)
+    keys = rng.random((m, d)).astype(np.float32)
+    keys /= np.linalg.norm(keys, axis=1, keepdims=True)
+    query = rng.standard_normal((2, d, h, w)).astype(np.float32)
+    query[1] *= 1.7                                        # different column maxima on the two shards
+    W = rng.standard_normal((2, 2 * d, h, w)).astype(np.float32)
+    full = V.Memory(m, d, d, 0.1, 0.1)
+    qf = T(query).requires_grad_(True)
+    of = full(qf, T(keys), train=True)
+    ((of[0] * T(W)).sum() + 0.7 * of[4] + 0.3 * of[5]).backward()
+
+    ranks, out = _TwoRanks(), [None, None]
+
+    def run(rank):
+        ranks.lock.acquire()
+        try:
+            mem = V.Memory(m, d, d, 0.1, 0.1)
+            mem.global_batch, mem._reduce = True, ranks.reducer(rank)
+            q = T(query[rank:rank + 1]).requires_grad_(True)
+            o = mem(q, T(keys), train=True)
+            ((o[0] * T(W[rank:rank + 1])).sum() + 0.7 * o[4] + 0.3 * o[5]).backward()
+            out[rank] = (o, q.grad)
+        finally:
+            ranks.lock.release()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(timeout=120) for t in th]
+    assert out[0] is not None and out[1] is not None
+    n = h * w
+    for r in range(2):
+        o, g = out[r]
+        assert rel(N(o[1]), N(of[1])) < 2e-5                                   # updated_memory: identical on both ranks
+        assert rel(N(o[2]), N(of[2])[r * n:(r + 1) * n]) < 2e-5                # score_query: softmax over ALL tokens
+        assert rel(N(o[3]), N(of[3])[r * n:(r + 1) * n]) < 2e-5
+        assert abs(float(o[4]) - float(of[4])) < 2e-5 * abs(float(of[4]))      # global means
+        assert abs(float(o[5]) - float(of[5])) < 2e-5 * abs(float(of[5]))
+        assert rel(N(g), N(qf.grad)[r:r + 1]) < 2e-5

@@ -1,6 +1,7 @@
 // memory.cu — Memory module (M1-M5), model/Memory.py:62-261 (MNAD memory):
 // addressing scores with the two softmaxes, top-1/top-2 slots, read,
 // gather / spread losses, weighted segmented update, separateness.
+#include <algorithm>
 #include "common.cuh"
 #include "sgemm.cuh"
 #include "tc_gemm.cuh"
@@ -401,6 +402,55 @@ slot_update_kernel(const float* __restrict__ q, const float* __restrict__ keys,
   for (int c = threadIdx.x; c < d; c += 256) updated[(long long)slot * d + c] = sm[c] * s;
 }
 
+// ---- global-batch memory under data parallelism ---------------------------------------
+// softmax(score, dim=0) and max_n score_query[:, i] (Memory.py:140, :108) span ALL tokens of the batch.
+// With the tokens sharded over ranks every rank has its own column maximum cm_l and exp-sum cs_l of the
+// logits; with cm_g = max over ranks (all-reduce MAX) the global column sum is S = sum over ranks of
+// cs_l exp(cm_l - cm_g) (all-reduce SUM of `contrib`), the global score_query is the local one times
+// contrib / S, and the update weight exp(logit - cm_g) is the local weight times exp(cm_l - cm_g).
+__global__ void __launch_bounds__(256)
+memory_dp_contrib_kernel(const float* __restrict__ cm_l, const float* __restrict__ cs_l,
+                         const float* __restrict__ cm_g, int m, float* __restrict__ contrib) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) contrib[i] = cs_l[i] * expf(cm_l[i] - cm_g[i]);
+}
+
+__global__ void __launch_bounds__(256)
+scale_columns_kernel(float* __restrict__ x, const float* __restrict__ num, const float* __restrict__ den,
+                     long long N, int m) {
+  const long long total = N * m;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % m);
+    x[i] *= num[c] / den[c];
+  }
+}
+
+// u[i, :] *= exp(cm_l[i] - cm_g[i])   (local update sums -> this rank's share of the global ones)
+__global__ void __launch_bounds__(256)
+memory_dp_scale_update_kernel(float* __restrict__ u, const float* __restrict__ cm_l,
+                              const float* __restrict__ cm_g, int d) {
+  const int slot = blockIdx.x;
+  const float f = expf(cm_l[slot] - cm_g[slot]);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) u[(long long)slot * d + c] *= f;
+}
+
+// updated_memory[i] = F.normalize(u_i + keys[i])  (Memory.py:193) from already reduced update sums
+__global__ void __launch_bounds__(256)
+memory_finish_update_kernel(const float* __restrict__ u, const float* __restrict__ keys, int d,
+                            float* __restrict__ updated) {
+  __shared__ float red[32];
+  const int slot = blockIdx.x;
+  float nrm = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = u[(long long)slot * d + c] + keys[(long long)slot * d + c];
+    nrm += v * v;
+  }
+  nrm = block_sum<float>(nrm, red);
+  const float s = 1.0f / fmaxf(sqrtf(nrm), 1e-12f);
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    updated[(long long)slot * d + c] = (u[(long long)slot * d + c] + keys[(long long)slot * d + c]) * s;
+}
+
 __global__ void zero_int_kernel(int* p, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0;
@@ -634,6 +684,45 @@ extern "C" int vadc_memory_update(const float* q, const float* keys, const float
     VADC_CUDA(cudaFuncSetAttribute(slot_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   slot_update_kernel<<<m, 256, smem, st>>>(q, keys, score_query, cmax, seg, order, m, d, query_update, updated_memory);
   VADC_CHECK_LAUNCH("slot_update_kernel");
+  return VADC_OK;
+}
+
+extern "C" int vadc_memory_dp_contrib(const float* colmax_local, const float* colsum_local,
+                                      const float* colmax_global, int m, float* contrib, void* stream) {
+  VADC_REQUIRE(m > 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(colmax_local && colsum_local && colmax_global && contrib, VADC_ERR_NULL_POINTER);
+  memory_dp_contrib_kernel<<<(m + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(colmax_local, colsum_local,
+                                                                                          colmax_global, m, contrib);
+  VADC_CHECK_LAUNCH("memory_dp_contrib_kernel");
+  return VADC_OK;
+}
+
+extern "C" int vadc_scale_columns(float* x, const float* num, const float* den, int64_t N, int m, void* stream) {
+  VADC_REQUIRE(N >= 0 && m > 0, VADC_ERR_BAD_SHAPE);
+  if (N == 0) return VADC_OK;
+  VADC_REQUIRE(x && num && den, VADC_ERR_NULL_POINTER);
+  const long long total = (long long)N * m;
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  scale_columns_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, num, den, N, m);
+  VADC_CHECK_LAUNCH("scale_columns_kernel");
+  return VADC_OK;
+}
+
+extern "C" int vadc_memory_dp_scale_update(float* query_update, const float* colmax_local,
+                                           const float* colmax_global, int m, int d, void* stream) {
+  VADC_REQUIRE(m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(query_update && colmax_local && colmax_global, VADC_ERR_NULL_POINTER);
+  memory_dp_scale_update_kernel<<<m, 256, 0, static_cast<cudaStream_t>(stream)>>>(query_update, colmax_local, colmax_global, d);
+  VADC_CHECK_LAUNCH("memory_dp_scale_update_kernel");
+  return VADC_OK;
+}
+
+extern "C" int vadc_memory_finish_update(const float* query_update, const float* keys, int m, int d,
+                                         float* updated_memory, void* stream) {
+  VADC_REQUIRE(m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(query_update && keys && updated_memory, VADC_ERR_NULL_POINTER);
+  memory_finish_update_kernel<<<m, 256, 0, static_cast<cudaStream_t>(stream)>>>(query_update, keys, d, updated_memory);
+  VADC_CHECK_LAUNCH("memory_finish_update_kernel");
   return VADC_OK;
 }
 

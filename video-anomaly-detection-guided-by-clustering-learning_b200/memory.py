@@ -27,6 +27,14 @@ def MemoryLoss(memory):
     return out[0]
 
 
+def _dist_reduce(t, op):
+    """all-reduce over the default process group (NCCL over NVLink); identity when not distributed"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return t
+
+
 class _Scores:
     """everything ``get_score`` + the topk calls derive from one (query, keys) pair"""
     __slots__ = ("q", "score_query", "score_memory", "colmax", "colsum", "top1", "top2")
@@ -71,11 +79,22 @@ class _MemoryForward(torch.autograd.Function):
         gathering_loss = gathering_loss.clone()           # separate outputs, not two views of one buffer
         spreading_loss = None if spreading_loss is None else spreading_loss.clone()
         updated_query = mod._read(s, keys_c, shp)
+        ctx.loss_scale = 1.0
+        glob = mod.global_batch and mod._reduce is not None
+        if glob:
+            # tokens are sharded over ranks: column statistics, losses and update sums become those of the full batch
+            n_all = mod._reduce(torch.tensor([float(q.shape[0])], device=q.device), "sum")
+            ctx.loss_scale = float(q.shape[0]) / float(n_all)         # local mean -> this rank's share of the global mean
+            cm_g, contrib, S = mod._dp_column_stats(s)
+            mod._dp_rescale_scores(s, contrib, S)
+            gathering_loss = mod._reduce(gathering_loss.reshape(1) * ctx.loss_scale, "sum")[0]
+            if spreading_loss is not None:
+                spreading_loss = mod._reduce(spreading_loss.reshape(1) * ctx.loss_scale, "sum")[0]
         ctx.save_for_backward(qc, keys_c, s.top1, s.top2)
         ctx.train = bool(train)
         ctx.set_materialize_grads(False)
         if train:
-            updated_memory = mod._update(s, keys_c)
+            updated_memory = mod._dp_update(s, keys_c, cm_g) if glob else mod._update(s, keys_c)
             ctx.mark_non_differentiable(updated_memory, s.score_query, s.score_memory)
             return (updated_query, updated_memory, s.score_query, s.score_memory,
                     gathering_loss, spreading_loss)
@@ -93,8 +112,9 @@ class _MemoryForward(torch.autograd.Function):
             return None, None, None, None
         B, d, h, w = qc.shape
         g_uq = None if g_uq is None else f32c(g_uq)                  # [B,2d,h,w]; the first d channels reach q
-        g_gather = None if g_gather is None else f32c(g_gather).reshape(1)
-        g_spread = None if g_spread is None else f32c(g_spread).reshape(1)
+        # (global batch: the kernel divides by the local token count; loss_scale turns that into the global mean)
+        g_gather = None if g_gather is None else f32c(g_gather).reshape(1) * ctx.loss_scale
+        g_spread = None if g_spread is None else f32c(g_spread).reshape(1) * ctx.loss_scale
         gq = torch.empty_like(qc)
         check(_lib.lib().vadc_memory_query_bwd(ptr(qc), ptr(keys_c), ptr(top1), ptr(top2) if ctx.train else None,
                                                ptr(g_uq), ptr(g_gather), ptr(g_spread), B, d, h * w,
@@ -114,6 +134,12 @@ class Memory(nn.Module):
         self.key_dim = key_dim
         self.temp_update = temp_update
         self.temp_gather = temp_gather
+        # data parallel, SURVEY 8e: False = every rank treats its shard as the batch (what the reference's DDP run
+        # does); True = column softmax, update sums and loss means over the tokens of ALL ranks, i.e. the
+        # single-process full-batch result: all-reduce MAX of the column maxima [m], SUM of the column sums [m],
+        # SUM of the update sums [m,d] and of three scalars
+        self.global_batch = False
+        self._reduce = _dist_reduce
 
     # -- helpers ------------------------------------------------------------
     @staticmethod
@@ -228,3 +254,34 @@ class Memory(nn.Module):
 
     def _update(self, s, keys):
         return self._segmented_update(s.q, keys, s.score_query, s.top1)[1].detach()
+
+    # -- global batch over ranks (include/vadc.h: vadc_memory_dp_*) -------------
+    def _dp_column_stats(self, s):
+        """(global column maxima, this rank's share of the column sums, the global column sums)"""
+        l = _lib.lib()
+        m = s.colmax.numel()
+        cm_g = self._reduce(s.colmax.clone(), "max")
+        contrib = torch.empty_like(s.colsum)
+        check(l.vadc_memory_dp_contrib(ptr(s.colmax), ptr(s.colsum), ptr(cm_g), m, ptr(contrib), stream()),
+              "vadc_memory_dp_contrib")
+        S = self._reduce(contrib.clone(), "sum")
+        return cm_g, contrib, S
+
+    def _dp_rescale_scores(self, s, contrib, S):
+        """local softmax over this rank's tokens -> softmax over all ranks' tokens, in place"""
+        N, m = s.score_query.shape
+        check(_lib.lib().vadc_scale_columns(ptr(s.score_query), ptr(contrib), ptr(S), N, m, stream()),
+              "vadc_scale_columns")
+
+    def _dp_update(self, s, keys, cm_g):
+        """update sums of this rank (their weights are invariant under the rescaling above), scaled to the global
+        column maximum, summed over ranks, then normalize(u + keys) — identical on every rank"""
+        l = _lib.lib()
+        m, d = keys.shape
+        qu = self._segmented_update(s.q, keys, s.score_query, s.top1)[0]
+        check(l.vadc_memory_dp_scale_update(ptr(qu), ptr(s.colmax), ptr(cm_g), m, d, stream()),
+              "vadc_memory_dp_scale_update")
+        qu = self._reduce(qu, "sum")
+        um = torch.empty_like(qu)
+        check(l.vadc_memory_finish_update(ptr(qu), ptr(keys), m, d, ptr(um), stream()), "vadc_memory_finish_update")
+        return um.detach()
