@@ -3,6 +3,7 @@
 // channel c the M = B*D frames are P-vectors (P = H*W) compared with K
 // centroids of that channel: a batched [M,P] x [P,K] contraction over C
 // batches.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "sgemm.cuh"
 #include "tc_gemm.cuh"
@@ -17,7 +18,8 @@ namespace vadc {
 __global__ void __launch_bounds__(256)
 ln_transpose_kernel(const float* __restrict__ x, const float* __restrict__ w,
                     const float* __restrict__ b, long long T, int C, float eps,
-                    float* __restrict__ zt, float* __restrict__ mu, float* __restrict__ rstd) {
+                    float* __restrict__ zt, float* __restrict__ mu, float* __restrict__ rstd,
+                    __nv_bfloat16* __restrict__ terms /* optional: the three bf16 terms of zt, [3][C*T] */) {
   extern __shared__ float tile[];            // [32][C+1]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long t0 = (long long)blockIdx.x * 32;
@@ -38,8 +40,20 @@ ln_transpose_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }
   __syncthreads();
   const long long row = t0 + lane;
-  if (row < T)
-    for (int c = wid; c < C; c += 8) zt[(long long)c * T + row] = tile[lane * ld + c];
+  if (row < T) {
+    const long long n = (long long)C * T;
+    for (int c = wid; c < C; c += 8) {
+      const float v = tile[lane * ld + c];
+      const long long i = (long long)c * T + row;
+      zt[i] = v;
+      if (terms) {                                // the operand split of the batched tcgen05 GEMM, written in the same pass
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(h0);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+        terms[i] = h0; terms[n + i] = h1; terms[2 * n + i] = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+      }
+    }
+  }
 }
 
 // LayerNorm backward from a transposed upstream gradient gzt [C, T]:
@@ -186,15 +200,15 @@ extern "C" int vadc_space_cluster_fwd(const float* x, const float* ln_w, const f
     size_t smem = (size_t)32 * (C + 1) * sizeof(float);
     if (smem > 48 * 1024)
       VADC_CUDA(cudaFuncSetAttribute(ln_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ln_transpose_kernel<<<(unsigned)((T + 31) / 32), 256, smem, st>>>(x, ln_w, ln_b, T, C, eps, zt, mu, rstd);
+    const bool tc = space_tc_ok(M, P, C, K);
+    __nv_bfloat16* zs = tc ? reinterpret_cast<__nv_bfloat16*>(ws.take<uint8_t>(tc_gemm_split_bytes((long long)C * M, P))) : nullptr;
+    ln_transpose_kernel<<<(unsigned)((T + 31) / 32), 256, smem, st>>>(x, ln_w, ln_b, T, C, eps, zt, mu, rstd, zs);
     VADC_CHECK_LAUNCH("ln_transpose_kernel");
     if ((rc = launch_row_sqnorm(zt, (long long)C * M, P, zz, st))) return rc;
     if ((rc = launch_row_sqnorm(centers, (long long)C * K, P, cc, st))) return rc;
     // batch c: A = zt[c] [M,P], B = centers[c]^T; out Ds[m, c, k]
-    if (space_tc_ok(M, P, C, K)) {
-      void* zs = ws.take<uint8_t>(tc_gemm_split_bytes((long long)C * M, P));
+    if (tc) {
       void* cs = ws.take<uint8_t>(tc_gemm_split_bytes((long long)C * K, P));
-      if ((rc = tc_split3(zt, (long long)C * M, P, zs, st))) return rc;
       if ((rc = tc_split3(centers, (long long)C * K, P, cs, st))) return rc;
       TcBatchDistEpi epi{Ds, zz, cc, (long long)C * K, K, M, K};
       if ((rc = launch_tc_gemm_batched<false, false>(zs, (long long)C * M, P, cs, (long long)C * K, P, M, K, P, C,
