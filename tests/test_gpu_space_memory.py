@@ -282,3 +282,44 @@ def test_memory_global_batch_two_shards(d, h, w, m):
         assert abs(float(o[4]) - float(of[4])) < 2e-5 * abs(float(of[4]))      # global means
         assert abs(float(o[5]) - float(of[5])) < 2e-5 * abs(float(of[5]))
         assert rel(N(g), N(qf.grad)[r:r + 1]) < 2e-5
+
+
+def test_memory_full_size_properties():
+    """cfg3 at a full clip batch: N = 65536 tokens (B=64, 32x32), m = 2000, d = 768 — [N,m] score matrices of 524 MB.
+    The 2e11-MAC contractions are checked on a row sample against float64; everything downstream of the returned
+    scores (top-1 / top-2, losses, segmented update, normalisation) is recomputed on the host for ALL tokens."""
+    B, d, h, w, m = 64, 768, 32, 32, 2000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    query = torch.randn(B, d, h, w, device=dev(), generator=g)
+    keys = torch.nn.functional.normalize(torch.rand(m, d, device=dev(), generator=g), dim=1)
+    mem = V.Memory(m, d, d, 0.1, 0.1)
+    uq, um, sq, sm, gl, sl = mem(query, keys, train=True)
+    Ntok = B * h * w
+    assert sq.shape == (Ntok, m) and sm.shape == (Ntok, m) and uq.shape == (B, 2 * d, h, w)
+    # softmax normalisations (float64 sums on the device tensors, read back as two small vectors)
+    assert float((sm.double().sum(1) - 1).abs().max()) < 1e-5
+    assert float((sq.double().sum(0) - 1).abs().max()) < 1e-4
+    q = O.memory_prepare_query(N(query), np.float64)                          # [N,d] host, float64
+    kn = N(keys).astype(np.float64)
+    rows = np.random.default_rng(0).choice(Ntok, 192, replace=False)
+    logit = q[rows] @ kn.T
+    e = np.exp(logit - logit.max(1, keepdims=True))
+    assert rel(N(sm[torch.as_tensor(rows, device=dev())]), e / e.sum(1, keepdims=True)) < 2e-5
+    uqf = N(uq.permute(0, 2, 3, 1).reshape(Ntok, 2 * d)[torch.as_tensor(rows, device=dev())])
+    assert rel(uqf[:, :d], q[rows]) < 2e-6
+    assert rel(uqf[:, d:], (e / e.sum(1, keepdims=True)) @ kn) < 2e-5
+    # downstream of the scores, all tokens
+    smh, sqh = N(sm), N(sq)
+    part = np.argpartition(-smh, 1, axis=1)[:, :2]
+    first = smh[np.arange(Ntok), part[:, 0]] >= smh[np.arange(Ntok), part[:, 1]]
+    g1 = np.where(first, part[:, 0], part[:, 1]); g2 = np.where(first, part[:, 1], part[:, 0])
+    gather = ((q - kn[g1]) ** 2).mean()
+    dap = np.sqrt(((q - kn[g1] + 1e-6) ** 2).sum(1)); dan = np.sqrt(((q - kn[g2] + 1e-6) ** 2).sum(1))
+    spread = np.maximum(dap - dan + 1.0, 0).mean()
+    assert abs(float(gl) - gather) < 2e-5 * gather and abs(float(sl) - spread) < 2e-5 * spread
+    wgt = sqh[np.arange(Ntok), g1].astype(np.float64) / sqh.max(0).astype(np.float64)[g1]
+    upd = np.zeros((m, d))
+    np.add.at(upd, g1, wgt[:, None] * q)
+    ref = upd + kn
+    ref /= np.maximum(np.linalg.norm(ref, axis=1, keepdims=True), 1e-12)
+    assert rel(N(um), ref) < 2e-5
