@@ -158,12 +158,14 @@ def test_shape_errors_surface_as_exceptions():
         m(torch.zeros((4, 64), device=dev()))                # B, D, H, W, C = x.shape
 
 
-@pytest.mark.parametrize("impl", IMPLS)
-def test_full_size_properties(impl):
-    """BASELINE cfg2 size (B=64,T=16,256x256 -> N=524288 tokens, C=192, K=32):
-    size-independent invariants instead of the (minutes-long) CPU oracle."""
+@pytest.mark.parametrize("impl,C,K", [(i, 192, 32) for i in IMPLS] +
+                         [(V.IMPL_AUTO, 768, 16), (V.IMPL_AUTO, 768, 64), (V.IMPL_AUTO, 768, 256), (V.IMPL_AUTO, 192, 1024)])
+def test_full_size_properties(impl, C, K):
+    """BASELINE cfg2 size (B=64,T=16,256x256 -> N=524288 tokens, C=192, K=32), the cfg3 sweep (C=768, K=16/64/256)
+    and the reference-native head (C=192, K=1024) at the same token count: size-independent invariants instead
+    of the (minutes-long) CPU oracle."""
     torch.manual_seed(0)
-    Ntok, C, K = 524288, 192, 32
+    Ntok = 524288
     m = V.EuclidDistance_Assign_Module(C, K, soft_assign_alpha=16.0).to(dev())
     m.impl = impl
     x = torch.randn(64, 8, 32, 32, C, device=dev())
