@@ -84,12 +84,13 @@ __global__ void zero_kernel(float* p, long long n) {
 // launch helpers shared with space_cluster.cu / memory.cu
 // ---------------------------------------------------------------------------
 int launch_ln_rows(const float* x, const float* w, const float* b, long long N, int C, float eps,
-                   float* z, float* mu, float* rstd, float* zz, cudaStream_t st, float* rowstats, void* split3) {
+                   float* z, float* mu, float* rstd, float* zz, cudaStream_t st, float* rowstats, void* split3,
+                   const float* hscale) {
   if (N == 0) return VADC_OK;
   const int wpb = 8;
   dim3 grid((unsigned)((N + wpb - 1) / wpb));
 #define LN_CASE(V) ln_rows_kernel<V><<<grid, wpb * 32, 0, st>>>(x, w, b, N, C, eps, z, mu, rstd, zz, rowstats, \
-                                                              static_cast<__nv_bfloat16*>(split3))
+                                                              static_cast<__nv_bfloat16*>(split3), hscale)
   if (C <= 128) LN_CASE(1);
   else if (C <= 256) LN_CASE(2);
   else if (C <= 512) LN_CASE(4);
@@ -258,8 +259,8 @@ extern "C" size_t vadc_cluster_fwd_workspace_bytes(int64_t N, int C, int K, int 
   b += align_up((size_t)K * sizeof(float), 256);                         // |c|^2
   b += align_up((size_t)(softmin_blocks(N, K) + 1) * sizeof(double), 256);
   b += std::max(vadc_cluster_tc_extra_workspace_bytes(N, C, K), vadc_cluster_ws_extra_workspace_bytes(N, C, K));
-  if (impl != VADC_IMPL_SIMT && N > 0)                                   // bf16 term copies for the tcgen05 GEMMs
-    b += tc_gemm_split_bytes(N, C) + tc_gemm_split_bytes(K, C) + tc_gemm_split_bytes(N, K);
+  if (impl != VADC_IMPL_SIMT && N > 0)                                   // term copies for the tcgen05 GEMMs + scales
+    b += tc_gemm_split_bytes(N, C) + tc_gemm_split_bytes(K, C) + tc_gemm_split_bytes(N, K) + 256;
   return b + 256;
 }
 
@@ -300,6 +301,23 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
   // stay row kernels
   const bool use_tc = impl != VADC_IMPL_SIMT && N > 0 && !getenv("VADC_NO_TC_GEMM") &&
                       tc_gemm_shape_ok(N, K, C, false) && tc_gemm_shape_ok(N, C, K, true);
+  if (use_tc && !getenv("VADC_TC_BF16X3")) {
+    // every operand of the forward is bounded (LayerNorm output, centroids, softmin weights in [0, 1]): two fp16
+    // terms after a power-of-two scaling carry 22 significant bits (the fused K = 32 kernel's recipe): 2/3 of the
+    // operand bytes and half the MMAs of the three-term bf16 split; the scales stay in device memory (no host sync)
+    void* fs = ws.take<uint8_t>(tc_gemm_split2_bytes(N, C));
+    void* cs = ws.take<uint8_t>(tc_gemm_split2_bytes(K, C));
+    void* as = ws.take<uint8_t>(tc_gemm_split2_bytes(N, K));
+    float* sc = ws.take<float>(8);
+    if ((rc = tc_fwd_scales(centers, ln_w, ln_b, (long long)K * C, C, sc, st))) return rc;
+    if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, feature, mu, rstd, zz, st, rowstats, fs, sc + 0))) return rc;
+    if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
+    if ((rc = tc_split2h(centers, K, C, sc + 1, cs, st))) return rc;
+    if ((rc = launch_tc_gemm_h2<false>(fs, cs, N, K, C, sc + 2, TcDistEpi{D, zz, cc, K}, st))) return rc;
+    if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
+    if ((rc = tc_split2h(A, N, K, sc + 3, as, st))) return rc;
+    return launch_tc_gemm_h2<true>(as, cs, N, C, K, sc + 4, TcStoreEpi{x_rec, C}, st);    // centers [K,C] read MN-major
+  }
   if (use_tc) {
     void* fs = ws.take<uint8_t>(tc_gemm_split_bytes(N, C));
     void* cs = ws.take<uint8_t>(tc_gemm_split_bytes(K, C));
@@ -382,7 +400,10 @@ extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int
   VADC_REQUIRE(R < (1ll << 31) && P < (1ll << 31), VADC_ERR_UNSUPPORTED);
   VADC_REQUIRE(workspace_bytes >= vadc_cdist_workspace_bytes(nb, R, P, C), VADC_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((long long)nb * R * P * C <= (1ll << 21) && nb <= 65535 && (C % 4) == 0 && aligned16(a) && aligned16(b)) {   // launch-latency-bound sizes
+  // launch-latency-bound sizes, and single problems too small to fill the GPU with GEMM tiles (the [K,K] centroid
+  // self-distance at K = 256, C = 768 is 16 tiles: 135 us on the tile GEMM, one row per block does it in ~15 us)
+  const long long macs = (long long)nb * R * P * C;
+  if ((macs <= (1ll << 21) || (nb == 1 && macs <= (1ll << 28))) && nb <= 65535 && (C % 4) == 0 && aligned16(a) && aligned16(b)) {
     cdist_small_kernel<<<dim3((unsigned)R, (unsigned)nb), 256, 0, st>>>(a, b, (int)R, (int)P, C, out);
     VADC_CHECK_LAUNCH("cdist_small_kernel");
     return VADC_OK;

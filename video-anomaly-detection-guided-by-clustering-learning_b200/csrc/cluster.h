@@ -5,7 +5,8 @@
 namespace vadc {
 int launch_ln_rows(const float* x, const float* w, const float* b, long long N, int C, float eps,
                    float* z, float* mu, float* rstd, float* zz, cudaStream_t st,
-                   float* rowstats = nullptr, void* split3 = nullptr);   // optional fused outputs (rows.cuh)
+                   float* rowstats = nullptr, void* split3 = nullptr,    // optional fused outputs (rows.cuh)
+                   const float* hscale = nullptr);                       // split3 then holds two fp16 terms of z * hscale[0]
 int launch_row_sqnorm(const float* a, long long R, int C, float* out, cudaStream_t st);
 int softmin_blocks(long long R, int K);
 int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* A, long long* label,

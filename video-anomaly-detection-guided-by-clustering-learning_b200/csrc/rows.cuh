@@ -2,6 +2,7 @@
 // the memory module: LayerNorm rows, squared row norms, the softmin / argmin /
 // loss row pass, the backward row pass, and deterministic column reductions.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -18,9 +19,11 @@ __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                long long N, int C, float eps, float* __restrict__ z, float* __restrict__ mu,
                float* __restrict__ rstd, float* __restrict__ zz, float* __restrict__ rowstats,
-               __nv_bfloat16* __restrict__ split) {
+               __nv_bfloat16* __restrict__ split, const float* __restrict__ hscale) {
   // optional fused outputs: rowstats [N,4] = {|z|^2, sum z gamma, sum z gamma xhat, 0} (what the tcgen05 backward
-  // uses) and the three bf16 terms of z ([3][N,C], the tcgen05 GEMM's A operand) - saves two more passes over z
+  // uses) and the three bf16 terms of z ([3][N,C], the tcgen05 GEMM's A operand) - saves two more passes over z;
+  // with hscale the split is two fp16 terms of z * hscale[0] instead ([2][N,C]: tc_gemm's two-term mode)
+  const float hs = hscale ? __ldg(hscale) : 1.0f;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -67,7 +70,18 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
         p1 += (gx + gy) + (gz + gw);
         p2 += (gx * ((v[i].x - mean) * rs) + gy * ((v[i].y - mean) * rs)) + (gz * ((v[i].z - mean) * rs) + gw * ((v[i].w - mean) * rs));
       }
-      if (split) {
+      if (split && hscale) {
+        const float a[4] = {o.x * hs, o.y * hs, o.z * hs, o.w * hs};
+        __half h[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[0][j] = __float2half_rn(a[j]);
+          h[1][j] = __float2half_rn(a[j] - __half2float(h[0][j]));
+        }
+        uint2* sp = reinterpret_cast<uint2*>(split + row * C) + c4;
+        sp[0] = *reinterpret_cast<uint2*>(h[0]);
+        sp[term / 4] = *reinterpret_cast<uint2*>(h[1]);
+      } else if (split) {
         const float a[4] = {o.x, o.y, o.z, o.w};
         __nv_bfloat16 h[3][4];
 #pragma unroll

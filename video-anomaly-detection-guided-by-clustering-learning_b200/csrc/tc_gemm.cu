@@ -16,6 +16,7 @@
 // (a CTA's load / MMA / epilogue phases overlap with its neighbour's: 1.63 -> 1.30 ms on the C=768, K=256 distance GEMM).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <stdio.h>
 #include "common.cuh"
@@ -58,14 +59,19 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst,
                ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(kThreads, 2)
+// TERMS = 3: three bf16 terms per operand, six products (fp32-faithful for any fp32 data).
+// TERMS = 2: two fp16 terms of operands pre-scaled by a power of two into fp16's range (bounded data: LayerNorm
+// output, centroids, softmax weights), three products hh + hl + lh (22 significant bits) — two thirds of the operand
+// bytes, half the MMAs, and a 64 KB stage so that three CTAs share an SM; the accumulators are multiplied by
+// *acc_scale (= 1 / (s_a s_b)) before the epilogue sees them.
+template <int BN, int TERMS, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(kThreads, TERMS == 2 ? 3 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               int M, int N, int Kd, int kb_per_split, const ZOffsets zo, Epi epi) {
+               int M, int N, int Kd, int kb_per_split, const ZOffsets zo, const float* __restrict__ acc_scale, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t kATerm = BM * 128u, kBTerm = BN * 128u;           // bytes per bf16 term of a stage's operand
-  constexpr uint32_t kStage = 3u * kATerm + 3u * kBTerm;
+  constexpr uint32_t kStage = (uint32_t)TERMS * (kATerm + kBTerm);
   __shared__ uint64_t full[kStages], empty[kStages], accfull;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,10 +103,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int s = kb % kStages;
       mbar_wait(&empty[s], (uint32_t)(((kb / kStages) & 1) ^ 1));
       mbar_expect_tx(&full[s], kStage);
-      const uint32_t a = s0 + s * kStage, b = a + 3u * kATerm;
+      const uint32_t a = s0 + s * kStage, b = a + (uint32_t)TERMS * kATerm;
       const int k0 = (kb0 + kb) * BK;
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
+      for (int t = 0; t < TERMS; ++t) {
         if constexpr (!A_MN) {
           tma_load_3d(&mapA, a + t * kATerm, &full[s], k0 + ak, am, t);
         } else {
@@ -119,15 +125,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = instr_desc(kFmtBF16, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-    constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};     // small products first
+    const uint32_t idesc = instr_desc(TERMS == 2 ? 0u /* fp16 */ : kFmtBF16, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr int kProducts = TERMS == 2 ? 3 : 6;
+    constexpr int ta[6] = {TERMS == 2 ? 1 : 2, TERMS == 2 ? 0 : 1, 0, 1, 0, 0};   // small products first
+    constexpr int tb[6] = {0, 1, TERMS == 2 ? 0 : 2, 0, 1, 0};
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
       mbar_wait(&full[s], (uint32_t)((kb / kStages) & 1));
       tc_fence_after();
-      const uint32_t a = s0 + s * kStage, b = a + 3u * kATerm;
+      const uint32_t a = s0 + s * kStage, b = a + (uint32_t)TERMS * kATerm;
 #pragma unroll
-      for (int pr = 0; pr < 6; ++pr) {
+      for (int pr = 0; pr < kProducts; ++pr) {
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t ad = A_MN ? smem_desc_sw128(a + ta[pr] * kATerm + kk * 2048u, 8192, 1024)
@@ -145,11 +153,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int q = warp & 3;
     const long long m = (long long)m0 + q * 32 + lane;
     if (nkb > 0) { mbar_wait(&accfull, 0); tc_fence_after(); }
+    const float sc = acc_scale ? __ldg(acc_scale) : 1.0f;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
       if (nkb > 0) {
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        if (TERMS == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= sc;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;             // an empty split still writes its (zero) partial
@@ -182,14 +195,14 @@ static EncodeTiledFn encode_fn() {
 }
 
 // three bf16 term matrices [rows, cols] stored back to back -> 3-D map {cols, rows, 3}, box {64, box_rows, 1}
-static int make_map3(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+static int make_map3(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows, int terms = 3) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return VADC_ERR_CUDA;
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)terms};
   cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(m, terms == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -236,13 +249,13 @@ int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, lon
   else rc = tg::make_map3(&mB, b_split, N, Kd, BN);             // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
   if (rc) return rc;
   const size_t smem = (size_t)tg::kStages * (3 * tg::BM * 128 + 3 * BN * 128) + 1024;
-  auto kern = tg::tc_gemm_kernel<BN, A_MN, B_MN, Epi>;
+  auto kern = tg::tc_gemm_kernel<BN, 3, A_MN, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
   if (splits < 1) splits = 1;
   const int per = (nkb + splits - 1) / splits;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)splits);
-  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0}, epi);
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0}, nullptr, epi);
   VADC_CHECK_LAUNCH("tc_gemm_kernel");
   return VADC_OK;
 }
@@ -260,15 +273,120 @@ int launch_tc_gemm_batched(const void* a_split, long long a_rows, long long a_co
   if ((rc = tg::make_map3(&mA, a_split, a_rows, a_cols, A_MN ? 64 : tg::BM))) return rc;
   if ((rc = tg::make_map3(&mB, b_split, b_rows, b_cols, B_MN ? 64 : BN))) return rc;
   const size_t smem = (size_t)tg::kStages * (3 * tg::BM * 128 + 3 * BN * 128) + 1024;
-  auto kern = tg::tc_gemm_kernel<BN, A_MN, B_MN, Epi>;
+  auto kern = tg::tc_gemm_kernel<BN, 3, A_MN, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)nbatch);
   kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb,
-                                         tg::ZOffsets{1, off.a_m, off.a_k, off.b_n, off.b_k}, epi);
+                                         tg::ZOffsets{1, off.a_m, off.a_k, off.b_n, off.b_k}, nullptr, epi);
   VADC_CHECK_LAUNCH("tc_gemm_kernel(batched)");
   return VADC_OK;
 }
+
+// ---- two-term fp16 mode -------------------------------------------------------------------------
+namespace tg {
+__device__ __forceinline__ float pow2_scale(float bound) {   // power of two s with s * bound in [4, 8); 1 for 0 / non-finite
+  if (!(bound > 0.f) || !isfinite(bound)) return 1.0f;
+  int e;
+  (void)frexpf(bound, &e);
+  e = max(-96, min(96, e));
+  return ldexpf(1.0f, 3 - e);
+}
+
+// scales of the cluster forward (one block): s_z from the LayerNorm bound sqrt(C) max|gamma| + max|beta|, s_c from
+// max|centers|, s_a = 2^13 for the softmin weights in [0, 1]
+//   out[0] = s_z, [1] = s_c, [2] = 1 / (s_z s_c), [3] = s_a, [4] = 1 / (s_a s_c)
+__global__ void __launch_bounds__(1024)
+fwd_scales_kernel(const float* __restrict__ centers, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  long long KC, int C, float* __restrict__ out) {
+  __shared__ float red[3][32];
+  float mc = 0.f, mg = 0.f, mb = 0.f;
+  if ((KC & 3) == 0 && (reinterpret_cast<uintptr_t>(centers) & 15u) == 0) {
+    float m4[4] = {0.f, 0.f, 0.f, 0.f};                      // four independent chains, 16-byte loads
+    for (long long i = threadIdx.x; i < KC / 4; i += blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(centers) + i);
+      m4[0] = fmaxf(m4[0], fabsf(v.x)); m4[1] = fmaxf(m4[1], fabsf(v.y));
+      m4[2] = fmaxf(m4[2], fabsf(v.z)); m4[3] = fmaxf(m4[3], fabsf(v.w));
+    }
+    mc = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  } else {
+    for (long long i = threadIdx.x; i < KC; i += blockDim.x) mc = fmaxf(mc, fabsf(centers[i]));
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { mg = fmaxf(mg, fabsf(ln_w[i])); mb = fmaxf(mb, fabsf(ln_b[i])); }
+  mc = warp_max(mc); mg = warp_max(mg); mb = warp_max(mb);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { red[0][w] = mc; red[1][w] = mg; red[2][w] = mb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 32; ++i) { mc = fmaxf(mc, red[0][i]); mg = fmaxf(mg, red[1][i]); mb = fmaxf(mb, red[2][i]); }
+    mc = fmaxf(mc, red[0][0]); mg = fmaxf(mg, red[1][0]); mb = fmaxf(mb, red[2][0]);
+    const float s_z = pow2_scale(sqrtf((float)C) * mg + mb), s_c = pow2_scale(mc), s_a = 8192.0f;
+    out[0] = s_z; out[1] = s_c; out[2] = 1.0f / (s_z * s_c); out[3] = s_a; out[4] = 1.0f / (s_a * s_c);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split2h_kernel(const float* __restrict__ src, long long n4, const float* __restrict__ scale, __half* __restrict__ t0,
+               __half* __restrict__ t1) {
+  const float s = __ldg(scale);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float a[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+    __half h[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[0][j] = __float2half_rn(a[j]);
+      h[1][j] = __float2half_rn(a[j] - __half2float(h[0][j]));
+    }
+    reinterpret_cast<uint2*>(t0)[i] = *reinterpret_cast<uint2*>(h[0]);
+    reinterpret_cast<uint2*>(t1)[i] = *reinterpret_cast<uint2*>(h[1]);
+  }
+}
+}  // namespace tg
+
+size_t tc_gemm_split2_bytes(long long rows, long long cols) {
+  return align_up((size_t)2 * rows * cols * sizeof(__half), 256);
+}
+
+int tc_fwd_scales(const float* centers, const float* ln_w, const float* ln_b, long long KC, int C, float* out,
+                  cudaStream_t st) {
+  tg::fwd_scales_kernel<<<1, 1024, 0, st>>>(centers, ln_w, ln_b, KC, C, out);
+  VADC_CHECK_LAUNCH("fwd_scales_kernel");
+  return VADC_OK;
+}
+
+int tc_split2h(const float* src, long long rows, long long cols, const float* scale, void* dst, cudaStream_t st) {
+  const long long n = rows * cols;
+  if (n % 4) return VADC_ERR_BAD_SHAPE;
+  __half* t0 = static_cast<__half*>(dst);
+  const long long n4 = n / 4;
+  const int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)sm_count() * 8);
+  tg::split2h_kernel<<<grid, 256, 0, st>>>(src, n4, scale, t0, t0 + n);
+  VADC_CHECK_LAUNCH("split2h_kernel");
+  return VADC_OK;
+}
+
+template <bool B_MN, class Epi>
+int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, long long N, long long Kd,
+                      const float* acc_scale, Epi epi, cudaStream_t st) {
+  constexpr int BN = 128;
+  CUtensorMap mA, mB;
+  int rc;
+  if ((rc = tg::make_map3(&mA, a_split, M, Kd, tg::BM, 2))) return rc;
+  if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64, 2);
+  else rc = tg::make_map3(&mB, b_split, N, Kd, BN, 2);
+  if (rc) return rc;
+  const size_t smem = (size_t)tg::kStages * 2 * (tg::BM * 128 + BN * 128) + 1024;
+  auto kern = tg::tc_gemm_kernel<BN, 2, false, B_MN, Epi>;
+  VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), 1);
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, tg::ZOffsets{0, 0, 0, 0, 0}, acc_scale, epi);
+  VADC_CHECK_LAUNCH("tc_gemm_kernel(fp16 x2)");
+  return VADC_OK;
+}
+template int launch_tc_gemm_h2<false, TcDistEpi>(const void*, const void*, long long, long long, long long, const float*, TcDistEpi, cudaStream_t);
+template int launch_tc_gemm_h2<true, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
 
 template <bool B_MN, class Epi>
 int launch_tc_gemm(const void* a_split, const void* b_split, long long M, long long N, long long Kd, Epi epi,

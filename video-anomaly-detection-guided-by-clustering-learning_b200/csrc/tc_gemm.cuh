@@ -19,6 +19,16 @@ template <bool A_MN, bool B_MN, class Epi>
 int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
                       Epi epi, cudaStream_t st);
 
+// two-term fp16 mode for bounded operands (tc_gemm.cu): operands pre-scaled by powers of two held in device memory,
+// accumulators multiplied by *acc_scale before the epilogue
+size_t tc_gemm_split2_bytes(long long rows, long long cols);
+int tc_fwd_scales(const float* centers, const float* ln_w, const float* ln_b, long long KC, int C, float* out5,
+                  cudaStream_t st);     // out5 = {s_z, s_c, 1/(s_z s_c), s_a, 1/(s_a s_c)}
+int tc_split2h(const float* src, long long rows, long long cols, const float* scale, void* dst, cudaStream_t st);
+template <bool B_MN, class Epi>
+int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, long long N, long long Kd,
+                      const float* acc_scale, Epi epi, cudaStream_t st);
+
 // batched form (blockIdx.z = batch): per-batch coordinate offsets along the operands' tensors — a_m / b_n along the
 // output-row / output-column dimension, a_k / b_k along the contraction dimension
 struct TcBatchOffsets { int a_m, a_k, b_n, b_k; };
