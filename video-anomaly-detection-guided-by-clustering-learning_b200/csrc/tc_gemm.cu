@@ -28,7 +28,15 @@ using namespace tc;
 
 namespace tg {
 
-constexpr int BM = 128, BK = 64, kStages = 1, kThreads = 192;   // one 96 KB stage per CTA, two CTAs per SM
+constexpr int BM = 128, BK = 64, kThreads = 192;
+// bf16 x3: one 96 KB stage per CTA, two CTAs per SM.  fp16 x2: one 64 KB stage, three CTAs per SM — measured against a
+// 3-stage ring in ONE CTA per SM (-DVADC_TC_STAGES_H=3): 169 vs 124 us on the C=768, K=256 distance GEMM and 499 vs 251 us at
+// K=1024: without a second accumulator the lone CTA's epilogue idles the tensor pipe; co-resident CTAs overlap it for free
+#ifndef VADC_TC_STAGES_H
+#define VADC_TC_STAGES_H 1
+#endif
+constexpr int kStagesH = VADC_TC_STAGES_H;
+template <int TERMS> struct StageCfg { static constexpr int stages = TERMS == 2 ? kStagesH : 1; static constexpr int ctas = TERMS == 2 ? (kStagesH == 1 ? 3 : (kStagesH == 2 ? 1 : 1)) : 2; };
 
 // per-blockIdx.z coordinate offsets of a batched launch: output-row / contraction offsets of A, output-column /
 // contraction offsets of B (in elements of the respective tensor-map dimension)
@@ -65,13 +73,14 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst,
 // bytes, half the MMAs, and a 64 KB stage so that three CTAs share an SM; the accumulators are multiplied by
 // *acc_scale (= 1 / (s_a s_b)) before the epilogue sees them.
 template <int BN, int TERMS, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(kThreads, TERMS == 2 ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, StageCfg<TERMS>::ctas)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                int M, int N, int Kd, int kb_per_split, const ZOffsets zo, const float* __restrict__ acc_scale, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t kATerm = BM * 128u, kBTerm = BN * 128u;           // bytes per bf16 term of a stage's operand
   constexpr uint32_t kStage = (uint32_t)TERMS * (kATerm + kBTerm);
+  constexpr int kStages = StageCfg<TERMS>::stages;
   __shared__ uint64_t full[kStages], empty[kStages], accfull;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -248,7 +257,7 @@ int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, lon
   if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64);        // [Kd rows, N cols]: boxes of 64 k-rows x 64 n-cols
   else rc = tg::make_map3(&mB, b_split, N, Kd, BN);             // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
   if (rc) return rc;
-  const size_t smem = (size_t)tg::kStages * (3 * tg::BM * 128 + 3 * BN * 128) + 1024;
+  const size_t smem = (size_t)(3 * tg::BM * 128 + 3 * BN * 128) + 1024;
   auto kern = tg::tc_gemm_kernel<BN, 3, A_MN, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
@@ -272,7 +281,7 @@ int launch_tc_gemm_batched(const void* a_split, long long a_rows, long long a_co
   int rc;
   if ((rc = tg::make_map3(&mA, a_split, a_rows, a_cols, A_MN ? 64 : tg::BM))) return rc;
   if ((rc = tg::make_map3(&mB, b_split, b_rows, b_cols, B_MN ? 64 : BN))) return rc;
-  const size_t smem = (size_t)tg::kStages * (3 * tg::BM * 128 + 3 * BN * 128) + 1024;
+  const size_t smem = (size_t)(3 * tg::BM * 128 + 3 * BN * 128) + 1024;
   auto kern = tg::tc_gemm_kernel<BN, 3, A_MN, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
@@ -376,7 +385,7 @@ int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, lon
   if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64, 2);
   else rc = tg::make_map3(&mB, b_split, N, Kd, BN, 2);
   if (rc) return rc;
-  const size_t smem = (size_t)tg::kStages * 2 * (tg::BM * 128 + BN * 128) + 1024;
+  const size_t smem = (size_t)tg::kStagesH * 2 * (tg::BM * 128 + BN * 128) + 1024;
   auto kern = tg::tc_gemm_kernel<BN, 2, false, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
