@@ -750,7 +750,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         TR(21, it);
         tc_fence_after();
         const uint32_t xrow = sX32 + buf * pl.xbuf + (uint32_t)e3 * kBlk + (uint32_t)rl * 128u;
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = e3 * 64 + ch * 32;
           float acc[32], xh[32];
