@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "vadc.h")
-LIB_PATH = os.path.join(HERE, "libvadc.so")
+LIB_PATH = os.environ.get("VADC_LIB_PATH") or os.path.join(HERE, "libvadc.so")   # override: kernel-variant experiments
 
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 LOSS_L1_MEAN, LOSS_MSE_MEAN, LOSS_E4_NORM = 0, 1, 2

@@ -61,6 +61,13 @@ using namespace tc;
 
 namespace bt {
 
+// the S5 contractions are background work of the MMA thread (nothing waits for their issue): their loops may stay rolled
+#ifdef VADC_BWD_ROLL_S5
+#define VADC_S5_UNROLL _Pragma("unroll 1")
+#else
+#define VADC_S5_UNROLL _Pragma("unroll")
+#endif
+
 constexpr int kTok = 64;                     // tokens per tile
 constexpr int kK = 32;                       // centroids
 constexpr int kThreads = 512;
@@ -750,7 +757,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         TR(21, it);
         tc_fence_after();
         const uint32_t xrow = sX32 + buf * pl.xbuf + (uint32_t)e3 * kBlk + (uint32_t)rl * 128u;
-#pragma unroll 1
+#pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = e3 * 64 + ch * 32;
           float acc[32], xh[32];
@@ -882,9 +889,9 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       if (n5b < n3 && n5b < n5a && mbar_try_wait(&bars[B_XFULL0 + (n5b & 1)], (uint32_t)((n5b >> 1) & 1))) {
         tc_fence_after();
         const uint32_t loX_mn = loX_mn0 + (uint32_t)(n5b & 1) * (pl.xbuf >> 4);
-#pragma unroll
+VADC_S5_UNROLL
         for (int t = 0; t < 2; ++t) {
-#pragma unroll
+VADC_S5_UNROLL
           for (int ks = 0; ks < kTok / 16; ++ks) {
             const uint64_t ad = desc_at(loZR_mn, kHi, (uint32_t)ks * 2048u);
             const uint64_t bd = desc_at(loX_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
@@ -899,9 +906,9 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       // ---- S5a (background): PT[0:64] += [A_hi | A_lo]^T (gR_hi + gR_lo)
       if (n5a < n1 && mbar_try_wait(&bars[B_AFULL], (uint32_t)(n5a & 1))) {
         tc_fence_after();
-#pragma unroll
+VADC_S5_UNROLL
         for (int t = 0; t < 2; ++t) {
-#pragma unroll
+VADC_S5_UNROLL
           for (int ks = 0; ks < kTok / 16; ++ks) {
             const uint64_t ad = desc_at(loTA_mn, kHi, (uint32_t)ks * 2048u);
             const uint64_t bd = desc_at(loG_mn, kHi, (uint32_t)t * pl.gterm + (uint32_t)ks * 2048u);
