@@ -147,3 +147,20 @@ def test_checkpoint_contract_roundtrip(tmp_path):
     for (k, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.equal(va, vb), k
     assert V.load_pretrain_model(str(tmp_path / "missing.pth"), b) == ([], [])
+
+
+def test_clip_schedule_host_logic_matches_oracle_and_cfg4_layout():
+    """the product's clip schedule (host integers, tool/contrast_evaluae.py:185-203) equals the oracle's for every
+    (length, frame_num, batch_size) in a sweep; the synthetic cfg4 layout is one the reference's batched loop accepts"""
+    import videoad_b200 as V
+    from oracle import np_oracle as O
+    import bench
+    for T in list(range(0, 70)) + [381, 720]:
+        for fn in (2, 4, 8, 10):
+            for bs in (1, 3, 16):
+                assert V.eval_clip_starts(T, fn, bs) == O.eval_clip_starts(T, fn, bs), (T, fn, bs)
+    lengths, labels, scenes = bench.cfg4_layout()
+    assert len(lengths) == 107 and sum(lengths) == 40791 and len(set(scenes)) == 12
+    for T, lab in zip(lengths, labels):
+        assert T % 8 in (0, 1) and len(lab) == T and 0 < lab.sum() < T          # both classes in every video
+        assert all(len(b) > 0 for b in V.eval_clip_starts(T, 8, 16))
