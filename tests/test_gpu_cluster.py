@@ -283,3 +283,55 @@ def test_forward_rowstats(Ntok, C, K, impl):
     got = N(o["rs"])
     assert np.abs(got[:, :3] - want).max() / np.abs(want).max() < 1e-5
     assert (got[:, 3] == 0).all()
+
+
+def test_training_step_replays_as_a_cuda_graph():
+    """bench.py replays the whole step as one CUDA graph: the library must call nothing a capture forbids (no
+    allocation, no synchronisation) and a replay on new input values must reproduce the eager result"""
+    C, K = 192, 32
+    main = torch.cuda.Stream()
+    with torch.cuda.stream(main):                     # one non-default stream for every launch (see bench.py)
+        torch.manual_seed(3)
+        m = V.EuclidDistance_Assign_Module(C, K, soft_assign_alpha=16.0).to(dev())
+        x_buf = torch.randn(2, 4, 16, 16, C, device=dev())
+        gR = torch.randn_like(x_buf) * 1e-2
+        params = [m.cluster_center, m.norm.weight, m.norm.bias]
+        out = {}
+
+        def step():
+            for p in params:
+                p.grad = None
+            x = x_buf.detach().requires_grad_(True)
+            D, A, S, R, F, lab = m(x)
+            loss = V.global_frobenius(m.loss_sq)
+            torch.autograd.backward([loss, R], [None, gR])
+            out["loss"], out["gx"], out["lab"] = loss, x.grad, lab
+
+        for _ in range(3):
+            step()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=main):
+            step()
+        cap = {k: v for k, v in out.items()}          # tensors owned by the graph's pool: refreshed by every replay
+        x_buf.copy_(torch.randn_like(x_buf) * 1.5 + 0.2)
+        gR.copy_(torch.randn_like(gR) * 1e-2)
+        g.replay()
+        main.synchronize()
+        got = {k: v.clone() for k, v in cap.items()}
+        gc_graph = m.cluster_center.grad.clone()
+        step()                                        # eager, same inputs
+        main.synchronize()
+        assert torch.equal(got["lab"], out["lab"])
+        assert torch.allclose(got["loss"], out["loss"], rtol=1e-6)
+        assert torch.allclose(got["gx"], out["gx"], rtol=1e-5, atol=1e-9)
+        assert torch.allclose(gc_graph, m.cluster_center.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_numa_local_pinned_buffers():
+    """host staging buffers of the end-to-end path: pinned, equal to their source, CPU affinity restored"""
+    import os
+    before = os.sched_getaffinity(0)
+    src = torch.randn(1000, 7)
+    pin = V.pinned_like_local(src, 0)
+    assert pin.is_pinned() and torch.equal(pin, src) and os.sched_getaffinity(0) == before
+    assert V.gpu_local_cpus(0) <= before
