@@ -56,6 +56,14 @@ int vadc_device_ok(void);                            /* 1 if the current device 
 /* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
 unsigned long long vadc_launch_count(void);
 
+/* Measurement aid: with timing enabled, CUDA events are recorded on the launching stream immediately around
+ * the two dominant kernels (slot 0: the fused K = 32 cluster forward of vadc_cluster_fwd, slot 1: the fused
+ * tcgen05 cluster backward of vadc_cluster_bwd), up to 256 launches per slot.  vadc_timing_read synchronises on
+ * the recorded events and returns the mean kernel duration; enabling resets the counters.  Do not enable while
+ * a stream is being captured into a CUDA graph. */
+int vadc_timing_enable(int on);
+int vadc_timing_read(int slot, float* mean_ms, int* count);
+
 /* ------------------------------------------------------------------------ *
  * C1 + L1: EuclidDistance_Assign_Module.forward   model/cluster.py:81-99
  *          NegSoftAssign.forward                   model/cluster.py:48-55

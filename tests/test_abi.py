@@ -164,3 +164,15 @@ def test_clip_schedule_host_logic_matches_oracle_and_cfg4_layout():
     for T, lab in zip(lengths, labels):
         assert T % 8 in (0, 1) and len(lab) == T and 0 < lab.sum() < T          # both classes in every video
         assert all(len(b) > 0 for b in V.eval_clip_starts(T, 8, 16))
+
+
+def test_timing_api_is_safe_without_a_device():
+    """vadc_timing_enable / vadc_timing_read: no launches recorded -> count 0, no CUDA call"""
+    import ctypes
+    import videoad_b200 as V
+    l = V._lib.lib()
+    ms, cnt = ctypes.c_float(1.0), ctypes.c_int(-1)
+    assert l.vadc_timing_enable(1) == 0 and l.vadc_timing_read(1, ctypes.byref(ms), ctypes.byref(cnt)) == 0
+    assert cnt.value == 0 and ms.value == 0.0
+    assert l.vadc_timing_read(7, ctypes.byref(ms), ctypes.byref(cnt)) != 0
+    assert l.vadc_timing_enable(0) == 0

@@ -1105,8 +1105,10 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
     kern<<<grid, bt::kThreads, smem, st>>>(mGx, p);                                                    \
     launched = true;                                                                                   \
   }
+  timing_begin(VADC_TIMING_CLUSTER_BWD, st);
   BT_CASE(2) BT_CASE(4) BT_CASE(6)
 #undef BT_CASE
+  timing_end(VADC_TIMING_CLUSTER_BWD, st);
   if (!launched) return VADC_ERR_UNSUPPORTED;
   VADC_CHECK_LAUNCH("cluster_bwd_tc_kernel");
   if (trace) {

@@ -649,8 +649,10 @@ int vadc_cluster_fwd_ws(const float* x, const float* ln_w, const float* ln_b, co
     launched = true;                                                                                   \
   }
   bool launched = false;
+  timing_begin(VADC_TIMING_CLUSTER_FWD, st);
   WS_CASE(2) WS_CASE(4) WS_CASE(6)
 #undef WS_CASE
+  timing_end(VADC_TIMING_CLUSTER_FWD, st);
   if (!launched) return VADC_ERR_UNSUPPORTED;
   VADC_CHECK_LAUNCH("cluster_fwd_ws_kernel");
   finalize_sum_kernel<<<1, 1024, 0, st>>>(partial, grid, loss_sq);

@@ -45,6 +45,12 @@ struct Carver {
 };
 
 int sm_count();
+// measurement aid (abi.cu): events around the dominant kernels when vadc_timing_enable(1) is in effect
+#define VADC_TIMING_SLOTS 2
+#define VADC_TIMING_CLUSTER_FWD 0
+#define VADC_TIMING_CLUSTER_BWD 1
+void timing_begin(int slot, cudaStream_t st);
+void timing_end(int slot, cudaStream_t st);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
