@@ -55,6 +55,9 @@ const char* vadc_last_cuda_error(void);              /* text of the last CUDA fa
 int vadc_device_ok(void);                            /* 1 if the current device is sm_100          */
 /* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
 unsigned long long vadc_launch_count(void);
+/* The kernel-variant switches (VADC_BWD_IMPL, VADC_NO_TC_GEMM, ... — A/B runs and debugging) are environment
+ * variables read once per process at their first use; call this after changing one of them at run time. */
+int vadc_refresh_env(void);
 
 /* Measurement aid: with timing enabled, CUDA events are recorded on the launching stream immediately around
  * the two dominant kernels (slot 0: the fused K = 32 cluster forward of vadc_cluster_fwd, slot 1: the fused

@@ -6,6 +6,7 @@ call fails, a RuntimeError is raised."""
 import ctypes
 import os
 import re
+import threading
 
 import torch
 
@@ -51,6 +52,46 @@ def parse_header(path=HEADER):
 
 
 _lib = None
+_tls = threading.local()          # devices of the tensors whose pointers were taken for the call being assembled
+
+
+class _CurrentStream:
+    """placeholder returned by ``stream()``: resolved to the current stream of the DEVICE THE TENSOR ARGUMENTS LIVE
+    ON when the library function is called (libvadc launches on whatever context cudaGetDevice() reports)"""
+
+
+_CUR_STREAM = _CurrentStream()
+
+
+def _guarded(fn, name):
+    """Every kernel-launching entry point runs with the tensors' own device current and on that device's current
+    stream: a module on cuda:1 without set_device, an autograd thread of another device, DataParallel replicas.
+    All tensor arguments of one call must share one device."""
+    def call(*args):
+        devs = getattr(_tls, "devs", None) or ()
+        _tls.devs = []
+        d0 = devs[0] if devs else None
+        if d0 is not None and any(d != d0 for d in devs):
+            raise RuntimeError(f"{name}: tensor arguments live on different CUDA devices {sorted(set(devs))}")
+        if d0 is None and not any(a is _CUR_STREAM for a in args):
+            return fn(*args)                                  # *_workspace_bytes, error strings, counters
+        dev = d0 if d0 is not None else torch.cuda.current_device()
+        with torch.cuda.device(dev):
+            args = tuple(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if a is _CUR_STREAM else a
+                         for a in args)
+            return fn(*args)
+    call.__name__ = name
+    call.raw = fn
+    return call
+
+
+class _Lib:
+    """attribute access returns the device-guarded callables; ``_cdll`` is the raw ctypes handle"""
+
+    def __init__(self, cdll, names):
+        self._cdll = cdll
+        for name in names:
+            setattr(self, name, _guarded(getattr(cdll, name), name))
 
 
 def lib():
@@ -62,12 +103,13 @@ def lib():
             f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
             "(nvcc, sm_100a). videoad_b200 has no CPU or PyTorch fallback.")
     l = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in parse_header().items():
+    protos = parse_header()
+    for name, (res, args) in protos.items():
         fn = getattr(l, name)            # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    _lib = l
-    return l
+    _lib = _Lib(l, protos.keys())
+    return _lib
 
 
 def check(rc, what):
@@ -80,6 +122,7 @@ def check(rc, what):
 
 
 def require_cuda(*tensors):
+    _tls.devs = []                       # a new op starts: forget pointers taken by a call that never happened
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError(
@@ -88,20 +131,33 @@ def require_cuda(*tensors):
 
 
 def ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    """device pointer of ``t`` for the call being assembled; remembers the device for the guard in ``_guarded``"""
+    if t is None:
+        return None
+    if t.is_cuda:
+        devs = getattr(_tls, "devs", None)
+        if devs is None:
+            devs = _tls.devs = []
+        devs.append(t.device.index)
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """the current stream of the device the call's tensors live on (resolved at call time)"""
+    return _CUR_STREAM
 
 
 def f32c(t):
-    """fp32 + contiguous (no copy when already so)"""
+    """fp32 + contiguous + 16-byte aligned base (no copy when already so).  A contiguous view with an odd storage
+    offset (a sliced batch) is cloned: the kernels use 128-bit accesses and TMA."""
     if t is None:
         return None
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
 
 
 _ws_cache = {}

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace vadc {
 thread_local char g_last_cuda_error[256] = "";
@@ -13,18 +14,54 @@ int record_cuda_error(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
+  static int cached[64] = {0};                       // per device: a process may drive several GPUs
   int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess &&
-      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
-    cached = n;
-    return n;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+      if (dev >= 0 && dev < 64) cached[dev] = n;
+      return n;
+    }
   }
   (void)cudaGetLastError();
   return 148;   // B200; only reached on a host without a device (workspace sizing in CPU tests)
 }
+
+// ---- cached environment switches
+struct EnvEntry { char name[48]; char value[64]; bool set; };
+static EnvEntry g_env[32];
+static int g_env_n = 0;
+static volatile int g_env_lock = 0;
+const char* env_str(const char* name) {
+  while (__atomic_exchange_n(&g_env_lock, 1, __ATOMIC_ACQUIRE)) {}
+  const EnvEntry* hit = nullptr;
+  for (int i = 0; i < g_env_n; ++i)
+    if (!strcmp(g_env[i].name, name)) { hit = &g_env[i]; break; }
+  if (!hit && g_env_n < 32) {
+    EnvEntry& e = g_env[g_env_n];
+    snprintf(e.name, sizeof(e.name), "%s", name);
+    const char* v = getenv(name);
+    e.set = v != nullptr;
+    snprintf(e.value, sizeof(e.value), "%s", v ? v : "");
+    hit = &e;
+    ++g_env_n;
+  }
+  __atomic_store_n(&g_env_lock, 0, __ATOMIC_RELEASE);
+  if (!hit) return getenv(name);                     // table full (never with the switches this library knows)
+  return hit->set ? hit->value : nullptr;
+}
+int env_int(const char* name, int dflt) {
+  const char* v = env_str(name);
+  return v ? atoi(v) : dflt;
+}
 }  // namespace vadc
+
+extern "C" int vadc_refresh_env(void) {
+  while (__atomic_exchange_n(&vadc::g_env_lock, 1, __ATOMIC_ACQUIRE)) {}
+  vadc::g_env_n = 0;
+  __atomic_store_n(&vadc::g_env_lock, 0, __ATOMIC_RELEASE);
+  return VADC_OK;
+}
 
 // ---- per-kernel timing (measurement aid): CUDA events recorded on the launching stream right around the two
 // dominant kernels, 256 launches deep, read back after the caller has finished its timed loop

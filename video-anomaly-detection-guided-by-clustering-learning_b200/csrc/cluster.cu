@@ -280,7 +280,7 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
   VADC_REQUIRE(workspace_bytes >= vadc_cluster_fwd_workspace_bytes(N, C, K, impl), VADC_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  if (impl != VADC_IMPL_SIMT && !getenv("VADC_FWD_NO_WS")) {
+  if (impl != VADC_IMPL_SIMT && !env_on("VADC_FWD_NO_WS")) {
     int rc = vadc_cluster_fwd_ws(x, ln_w, ln_b, centers, N, C, K, alpha, eps, D, A, x_rec, feature,
                                  label, mu, rstd, rowstats, loss_sq, workspace, workspace_bytes, st);
     if (rc != VADC_ERR_UNSUPPORTED) return rc;
@@ -299,9 +299,9 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
   // shapes outside the fused kernels (C = 768, K = 16 / 64 / 256 / 1024): the two contractions run on the
   // tcgen05 GEMM (three-term bf16 split: fp32-faithful); LayerNorm (+ rowstats + the split of z) and softmin
   // stay row kernels
-  const bool use_tc = impl != VADC_IMPL_SIMT && N > 0 && !getenv("VADC_NO_TC_GEMM") &&
+  const bool use_tc = impl != VADC_IMPL_SIMT && N > 0 && !env_on("VADC_NO_TC_GEMM") &&
                       tc_gemm_shape_ok(N, K, C, false) && tc_gemm_shape_ok(N, C, K, true);
-  if (use_tc && !getenv("VADC_TC_BF16X3")) {
+  if (use_tc && !env_on("VADC_TC_BF16X3")) {
     // every operand of the forward is bounded (LayerNorm output, centroids, softmin weights in [0, 1]): two fp16
     // terms after a power-of-two scaling carry 22 significant bits (the fused K = 32 kernel's recipe): 2/3 of the
     // operand bytes and half the MMAs of the three-term bf16 split; the scales stay in device memory (no host sync)
@@ -381,7 +381,7 @@ namespace vadc {
 static bool cdist_tc_ok(int nb, long long R, long long P, int C) {
   return nb >= 1 && nb <= 65535 && (C % 8) == 0 && P >= 8 && (long long)nb * R < (1ll << 31) &&
          (long long)nb * P < (1ll << 31) && (double)nb * R * P * C >= (double)(1ll << 28) &&
-         tc_gemm_shape_ok(R, P, C, false) && !getenv("VADC_NO_TC_GEMM");
+         tc_gemm_shape_ok(R, P, C, false) && !env_on("VADC_NO_TC_GEMM");
 }
 }  // namespace vadc
 
@@ -455,7 +455,7 @@ extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
   // generic path on the tcgen05 GEMM: bf16 term copies of gR, feature, A, r and the centroids + split-K partials
   b += 2 * tc_gemm_split_bytes((long long)n, C) + 2 * tc_gemm_split_bytes((long long)n, K) + tc_gemm_split_bytes(K, C);
   b += 2 * align_up((size_t)bwd_tc_splits(N, C, K) * K * C * sizeof(float), 256);
-  return std::max(std::max(b + 256, bwd_fused_workspace_bytes(N, C, K)), bwd_tc_workspace_bytes(N, C, K));
+  return std::max(std::max(b + 256, bwd_fused_workspace_bytes(N, C, K)), std::max(bwd_tc_workspace_bytes(N, C, K), bwd_tc2_workspace_bytes(N, C, K)));
 }
 
 extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd, const float* rowstats,
@@ -480,12 +480,16 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
     VADC_CHECK_LAUNCH("zero_kernel");
     return VADC_OK;
   }
-  const char* bimpl = getenv("VADC_BWD_IMPL");            // debugging / A-B runs: tc | fused | generic
-  const bool want_tc = !bimpl || !strcmp(bimpl, "tc");
-  if (want_tc && rowstats && ln_b && gR && !gD && !gA && !gF && bwd_tc_shape_ok(N, C, K))
-    return launch_cluster_bwd_tc(x, mu, rstd, rowstats, ln_w, ln_b, centers, D, A, gR, g_loss_sq, N, C, K, alpha, gx,
-                                 gcenters, g_ln_w, g_ln_b, workspace, workspace_bytes, st);
-  if (bwd_fused_shape_ok(N, C, K) && !getenv("VADC_BWD_GENERIC") && !(bimpl && !strcmp(bimpl, "generic")))
+  const char* bimpl = env_str("VADC_BWD_IMPL");            // debugging / A-B runs: tc | fused | generic
+  const bool want_tc = !bimpl || !strcmp(bimpl, "tc") || !strcmp(bimpl, "tc1");
+  if (want_tc && rowstats && ln_b && gR && !gD && !gA && !gF && bwd_tc2_shape_ok(N, C, K)) {
+    if (bimpl && !strcmp(bimpl, "tc1"))                      // first generation, kept for same-box A/B runs
+      return launch_cluster_bwd_tc(x, mu, rstd, rowstats, ln_w, ln_b, centers, D, A, gR, g_loss_sq, N, C, K, alpha, gx,
+                                   gcenters, g_ln_w, g_ln_b, workspace, workspace_bytes, st);
+    return launch_cluster_bwd_tc2(x, mu, rstd, rowstats, ln_w, ln_b, centers, D, A, gR, g_loss_sq, N, C, K, alpha, gx,
+                                  gcenters, g_ln_w, g_ln_b, workspace, workspace_bytes, st);
+  }
+  if (bwd_fused_shape_ok(N, C, K) && !env_on("VADC_BWD_GENERIC") && !(bimpl && !strcmp(bimpl, "generic")))
     return launch_cluster_bwd_fused(x, mu, rstd, feature, ln_w, centers, D, A, gD, gA, gR, gF, g_loss_sq,
                                     N, C, K, alpha, gx, gcenters, g_ln_w, g_ln_b, workspace,
                                     workspace_bytes, st);
@@ -501,7 +505,7 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
   float* cpart = ws.take<float>((size_t)colsum_chunks(N) * K);
   float* rcol = ws.take<float>(K);
   float* lnpart = ws.take<float>((size_t)ln_bwd_blocks(N) * 2 * C);
-  if (!getenv("VADC_NO_TC_GEMM") && vadc_device_ok() && (K % 8) == 0 && (C % 8) == 0 && K >= 8 && C >= 8) {
+  if (!env_on("VADC_NO_TC_GEMM") && vadc_device_ok() && (K % 8) == 0 && (C % 8) == 0 && K >= 8 && C >= 8) {
     // ---- the five contractions on the tcgen05 GEMM (three-term bf16 split): G1 = gR c^T; gz = z rsum - r c + gF;
     //      gcenters = A^T gR - r^T z + c colsum(r) with the token matrices read MN-major and split-K over the tokens
     const int sk = bwd_tc_splits(N, C, K);

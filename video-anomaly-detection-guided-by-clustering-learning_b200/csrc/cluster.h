@@ -38,6 +38,14 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
                           const float* gR, const float* g_loss_sq, long long N, int C, int K, float alpha,
                           float* gx, float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
                           size_t workspace_bytes, cudaStream_t st);
+// second generation (cluster_bwd_tc2.cu): x through TMA into the epilogue warps, gR through bulk copies into producer slots
+bool bwd_tc2_shape_ok(long long N, int C, int K);
+size_t bwd_tc2_workspace_bytes(long long N, int C, int K);
+int launch_cluster_bwd_tc2(const float* x, const float* mu, const float* rstd, const float* rowstats, const float* ln_w,
+                           const float* ln_b, const float* centers, const float* D, const float* A,
+                           const float* gR, const float* g_loss_sq, long long N, int C, int K, float alpha,
+                           float* gx, float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st);
 }  // namespace vadc
 
 // tcgen05 path (cluster_tc.cu)

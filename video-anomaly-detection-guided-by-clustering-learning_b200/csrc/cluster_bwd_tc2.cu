@@ -1,52 +1,45 @@
-// cluster_bwd_tc.cu — C2: fused backward of the cluster head on tcgen05 / TMEM, K == 32,
-// training-graph case (gradients arrive through x_rec and the fused cluster loss only).
+// cluster_bwd_tc2.cu — C2: fused backward of the cluster head on tcgen05 / TMEM / TMA, K == 32,
+// training-graph case (gradients arrive through x_rec and the fused cluster loss only).  Second generation.
 //
 //   autograd of model/cluster.py:81-99 + model/backbone.py:98 (loss.backward(), main_predict.py:296)
-//   in ONE persistent warp-specialised kernel; per token it reads x, gR, D, A (+ mu, rstd) once and
-//   writes gx once: 12 C + 8 K bytes (fused-loss variant).  64-token tiles:
+//   in ONE persistent warp-specialised kernel; per token it reads x, gR, D, A (+ mu, rstd, rowstats) once and
+//   writes gx once: 12 C + 8 K bytes (fused-loss variant).  64-token tiles.
 //
-//   warps 0,1,6,7,10,11,14  PRODUCERS  x, gR rows -> xhat = (x - mu) rstd -> two-term bf16 splits of
-//                           xhat and gR into SWIZZLE_128B operand tiles + three row sums of xhat;
-//                           4-row single-tensor units, loads software-pipelined one unit ahead;
-//                           also the bf16 split of the A rows into the [A_hi | A_lo] operand tile
+// What changed against the first generation (cluster_bwd_tc.cu, 0.57 of the HBM roofline: its seven producer warps
+// converted BOTH x and gR through a register pipeline and set the pace of the kernel):
+//   * x never passes through the producers.  Each E3 warp TMA-loads the raw fp32 [32 tokens x 32 channels] boxes it
+//     owns (SWIZZLE_128B, one tile ahead, mbarrier complete_tx), forms xhat = (x - mu) rstd exactly in fp32 for the
+//     LayerNorm backward, writes the two-term bf16 split of xhat into the operand tile of the r^T xhat contraction
+//     (which therefore runs AFTER E3 of its tile: it is background work nothing waits for), and stages gx in the SAME
+//     box it read x from (same swizzled bytes) for the TMA store — the separate 24 KB store staging is gone and the
+//     store's shared-memory read is followed by the next tile's load into the box.
+//   * the producers convert gR (and the A rows) only: half the work.  Their global loads are bulk copies
+//     (cp.async.bulk, mbarrier complete_tx) into a private 4-row slot per warp, issued one unit ahead right after
+//     the slot was read — no load sits in registers, nothing waits on a scoreboard, and a load is never tied to
+//     the availability of the operand tile it will be converted into.
+//   * the r operand tile is double buffered (E1 of tile t+1 must not wait for the r^T xhat contraction of tile t).
+//
+//   warps 0,1,6,7,10,11,14  PRODUCERS  gR rows -> two-term bf16 split into the SWIZZLE_128B operand tile (4-row
+//                           units out of the warp's slot); the bf16 split of the A rows into [A_hi | A_lo]
 //   warp 15 (one thread)    MMA        S1  G1 = gR [cen_hi; cen_lo]^T        [tokens x 2K]  (TMEM, double buffer)
 //                                      S3  acc = r cen                       [tokens x C]
 //                                      S5a PT[0:64]   += [A_hi | A_lo]^T gR  [2K x C]  (TMEM, whole kernel)
 //                                      S5b PT[64:128] += [r_hi | r_lo]^T xhat
-//   warps 2,3               E1         thread = token: softmin backward + cdist ratio -> r; the
-//                                      LayerNorm-backward row statistics in closed form; bf16 split
-//                                      of r into the [r_hi | r_lo] operand tile.  S1's A descriptor
-//                                      starts 64 rows BEFORE the gR tile, so G1 lands in TMEM lanes
-//                                      64..127: E1 runs on the schedulers of warps 2,3 (mod 4) and
-//                                      leaves those of warps 0,1 to E3 (a warp reads lanes 32 (w%4)..)
-//   warps 4,5,8,9,12,13     E3         thread = token x 64 channels: gz = z rsum - acc, LayerNorm
-//                                      backward, gx through swizzled staging + TMA tensor stores,
+//   warps 2,3               E1         thread = token: softmin backward + cdist ratio -> r; the LayerNorm-backward
+//                                      row statistics in closed form; bf16 split of r into [r_hi | r_lo].  S1's A
+//                                      descriptor starts 64 rows BEFORE the gR tile, so G1 lands in TMEM lanes
+//                                      64..127: E1 runs on the schedulers of warps 2,3 (mod 4)
+//   warps 4,5,8,9,12,13     E3         thread = token x 64 channels: raw x box -> xhat; gz = z rsum - acc, LayerNorm
+//                                      backward, gx -> box -> TMA store; xhat hi / lo -> operand tile;
 //                                      Q[c] = sum_n xhat^2 rsum (register butterfly) for g_gamma
 //
-// A small-N tcgen05.mma costs ~80 cycles whatever N is (the 128 x 32 B A-operand fetch from shared
-// memory bounds it; measured with the event trace, VADC_BWD_TRACE), so the contractions are shaped
-// to need few, fat instructions: the two centroid terms are stacked along N for S1 (N = 64), and the
-// centroid-gradient GEMMs take the small [A | r] tiles as the M side (slots, MN-major) and the token
-// tiles as the N side (N = C) with the tokens as the contraction — 62 -> 46 instructions per tile
-// and 7.8k -> ~4k tensor cycles.  S5a / S5b share one accumulator: their A operands are
-// [tileA, ZERO] and [ZERO, tileR] (a constant zero block), so rows 0..63 collect A^T gR and rows
-// 64..127 collect r^T xhat.
-// The token tile is the MMA's M for S1 / S3 (M = 128 with rows 64..127 reading past the tile —
-// their TMEM lanes are never read).  All operands are exact two-term bf16 splits v = h + l (16
-// significant bits, full fp32 exponent range — gradients have no a-priori scale, which rules out
-// fp16; one kind::f16 instruction cannot mix an fp16 with a bf16 operand: it faults); products keep
-// h*h + h*l + l*h (+ l*l where it is free) in the fp32 accumulator (~2^-16 relative per element;
-// the fp32 reference's own error against fp64 is larger, scripts/bwd_algebra_check.py).
-//
-// LayerNorm backward needs the row means of gg = gz*gamma and gg*xhat BEFORE gz exists per thread.
-// They follow in closed form from quantities E1 already has (z = gamma xhat + beta):
+// Contraction shapes, operand precision (exact two-term bf16 splits, fp32 accumulate) and the closed forms of the
+// LayerNorm-backward row means / g_gamma / g_beta are those of the first generation:
 //   sum_c gg        = rsum * sum_c z gamma      - sum_k r_k (cen_k . gamma)
-//   sum_c gg xhat   = rsum * sum_c z gamma xhat - sum_k r_k T_k,  T_k = xhat . (gamma * cen_k)
-//   T_k = z.cen_k - beta.cen_k = (|z|^2 + |cen_k|^2 - D_k^2) / 2 - beta.cen_k      (D is an input)
-// so E3 is a single pass over the accumulator.  With P1 = A^T gR, P2 = r^T xhat, rcol = colsum(r):
-//   gcenters = P1 - gamma * P2 + (cen - beta) rcol
+//   sum_c gg xhat   = rsum * sum_c z gamma xhat - sum_k r_k T_k,  T_k = (|z|^2 + |cen_k|^2 - D_k^2) / 2 - beta.cen_k
+//   gcenters = P1 - gamma * P2 + (cen - beta) rcol,  P1 = A^T gR, P2 = r^T xhat, rcol = colsum(r)
 //   g_beta  = gamma * sum_k P2[k,:] + beta * sum(rcol) - rcol . cen
-//   g_gamma = gamma * Q + beta * sum_k P2[k,:] - sum_k cen[k,:] * P2[k,:]       (no column sums of gz).
+//   g_gamma = gamma * Q + beta * sum_k P2[k,:] - sum_k cen[k,:] * P2[k,:]
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -59,7 +52,7 @@
 namespace vadc {
 using namespace tc;
 
-namespace bt {
+namespace bt2 {
 
 // the S5 contractions are background work of the MMA thread (nothing waits for their issue): their loops may stay rolled
 #ifdef VADC_BWD_ROLL_S5
@@ -72,40 +65,42 @@ constexpr int kTok = 64;                     // tokens per tile
 constexpr int kK = 32;                       // centroids
 constexpr int kThreads = 512;
 constexpr int kProd = 7;                     // producer warps
-constexpr int kUnits = 2 * (kTok / 4) + 2;   // producer units per tile: 16 x 4 rows of x, 16 x 4 rows of gR, 2 x 32 rows of A
+constexpr int kUnits = 2 + kTok / 4;         // producer units per tile: 2 x 32 rows of A, then 16 x 4 rows of gR
 constexpr int kMmaWarp = 15;
-constexpr int kDepth = 4;                    // async producers: units in flight per warp
 constexpr uint32_t kBlk = kTok * 128u;       // one [64 rows x 128 B] operand block
+constexpr uint32_t kBox = 32u * 128u;        // one [32 rows x 128 B] fp32 box (TMA load of x / TMA store of gx)
 
 struct Plan {
-  uint32_t x_off, g_off, ta_off, zero_off, tr_off, cen_off, stg_off, scal_off, gam_off, bet_off, cvec_off, misc_off, stat_off, total;
-  uint32_t xbuf, xterm, gterm;
+  uint32_t xr_off, xh_off, g_off, ta_off, zero_off, tr_off, cen_off, slot_off, scal_off, gam_off, bet_off, cvec_off, misc_off, total;
+  uint32_t xterm, slot;
 };
 
 __host__ __device__ inline Plan plan(int C) {
   Plan p;
   const uint32_t ncb = (uint32_t)C / 64u;
   uint32_t off = 0;
-  p.xterm = ncb * kBlk; p.xbuf = 2u * p.xterm; p.gterm = p.xterm;
-  p.x_off = off; off += 2u * p.xbuf;                       // [2 bufs][2 terms][C/64][64 x 128 B]
-  p.g_off = off; off += 2u * p.gterm;                      // [2 terms][C/64][64 x 128 B]
+  p.xterm = ncb * kBlk; p.slot = 4u * (uint32_t)C * 4u;
+  p.xr_off = off; off += 2u * ncb * 2u * kBox;             // [E3 warp = (channel group, token half)][2 boxes]: raw x, then gx
+  p.xh_off = off; off += 2u * p.xterm;                     // xhat operand [2 terms][C/64][64 x 128 B]
+  p.g_off = off; off += 2u * p.xterm;                      // gR operand   [2 terms][C/64][64 x 128 B]
   p.ta_off = off; off += kBlk;                             // [64 tokens x 128 B]: A_hi (32 slots) | A_lo
   p.zero_off = off; off += kBlk;                           // constant zeros (the other half of S5's M)
-  p.tr_off = off; off += kBlk;                             // [64 tokens x 128 B]: r_hi | r_lo
+  p.tr_off = off; off += 2u * kBlk;                        // [parity][64 tokens x 128 B]: r_hi | r_lo
   p.cen_off = off; off += ncb * kBlk;                      // [C/64][64 rows x 128 B]: rows 0..31 cen_hi, 32..63 cen_lo
-  p.stg_off = off; off += 6u * 4096u;                      // per E3 warp: [32 rows x 128 B]
-  p.scal_off = off; off += 2u * 4u * kTok * 4u;            // E1 row scalars [parity][rsum, s1r, s2r, rs][64]
+  p.slot_off = off; off += kProd * p.slot;                 // per producer warp: 4 raw gR rows
+  p.scal_off = off; off += 2u * 5u * kTok * 4u;            // E1 row scalars [parity][rsum, s1r, s2r, rs, -mu rs][64]
   p.gam_off = off; off += (uint32_t)C * 4u;
   p.bet_off = off; off += (uint32_t)C * 4u;
   p.cvec_off = off; off += 2u * kK * 4u;                   // hc = |c|^2/2 - beta.c ; cg = gamma.c
-  p.misc_off = off; off += 256u;                           // mbarriers [0,144), TMEM slot at +192
-  p.stat_off = off; off += kProd * kDepth * 4u * 8u;       // async producers: [warp][slot][4 rows] {mu, rstd}
+  p.misc_off = off; off += 512u;                           // mbarriers [0, 8 B_COUNT), TMEM slot at +448
   p.total = off;
   return p;
 }
 
-enum { B_CEN = 0, B_XFULL0, B_XFULL1, B_GFULL, B_GEMPTY, B_XEMPTY0, B_XEMPTY1, B_G1FULL0, B_G1FULL1, B_G1EMPTY0, B_G1EMPTY1,
-       B_AFULL, B_AEMPTY, B_RFULL, B_REMPTY, B_ACCFULL, B_ACCEMPTY, B_DONE, B_COUNT };
+enum { B_CEN = 0, B_GFULL, B_GEMPTY, B_G1FULL0, B_G1FULL1, B_G1EMPTY0, B_G1EMPTY1, B_AFULL, B_AEMPTY,
+       B_RFULL0, B_RFULL1, B_REMPTY0, B_REMPTY1, B_ACCFULL, B_ACCEMPTY, B_XHFULL, B_XHEMPTY, B_DONE,
+       B_XR0, B_SLOT0 = B_XR0 + 12, B_COUNT = B_SLOT0 + kProd };
+static_assert(B_COUNT * 8 <= 448, "mbarriers overlap the TMEM slot");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -178,21 +173,13 @@ __device__ __forceinline__ float4 ldg_nc(const float4* p) {
   asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
-// Ampere-style asynchronous copies: global -> shared without passing through registers (L2 only for the 16-byte form)
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void tma_load_2d_u32(const void* tmap, uint32_t smem_dst, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_pending(int n) {   // wait until at most n of this thread's groups are pending
-  switch (n) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-  }
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
@@ -280,14 +267,13 @@ struct Params {
   const float* ln_w; const float* ln_b; const uint8_t* cimage; const float* cvec; const float* g_loss_sq;
   float* part_p; float* part_rcol; float* part_q;        // [grid][128 slots][C], [grid][2][32], [grid][2][C]
   long long N; float alpha; int pf;
-  int dbg;                                               // timing experiments only (VADC_BWD_DBG): 1 = no producer loads, 2 = no producer stores
-  unsigned long long* trace;                             // debugging: per-warp event log of one CTA (VADC_BWD_TRACE)
+  unsigned long long* trace;                             // debugging: per-warp event log of one CTA (VADC_BWD_TRACE builds)
   int trace_cta;
 };
 
-template <int F4, bool TRACE, bool ASYNC>
+template <int F4, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
-cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p) {
+cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_constant__ CUtensorMap mapX, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int C = F4 * 32, K = kK, NCB = C / 64;
@@ -298,7 +284,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   float* sHc = reinterpret_cast<float*>(smem + pl.cvec_off);
   float* sCg = sHc + K;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.misc_off);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.misc_off + 192);   // (the 18 mbarriers end at +144)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.misc_off + 448);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // event trace (debug): entry = {code << 32 | tile, clock64}
@@ -320,19 +306,23 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
 
   if (tid == 0) {
     mbar_init(&bars[B_CEN], 1);
-    mbar_init(&bars[B_XFULL0], 16); mbar_init(&bars[B_XFULL1], 16);
-    mbar_init(&bars[B_GFULL], 16);
+    mbar_init(&bars[B_GFULL], kTok / 4);
     mbar_init(&bars[B_GEMPTY], 1);
-    mbar_init(&bars[B_XEMPTY0], kE3Warps + 1); mbar_init(&bars[B_XEMPTY1], kE3Warps + 1);
     mbar_init(&bars[B_G1FULL0], 1); mbar_init(&bars[B_G1FULL1], 1);
     mbar_init(&bars[B_G1EMPTY0], 2); mbar_init(&bars[B_G1EMPTY1], 2);
     mbar_init(&bars[B_AFULL], 2); mbar_init(&bars[B_AEMPTY], 1);
-    mbar_init(&bars[B_RFULL], 1); mbar_init(&bars[B_REMPTY], 1);
+    mbar_init(&bars[B_RFULL0], 1); mbar_init(&bars[B_RFULL1], 1);
+    mbar_init(&bars[B_REMPTY0], 1); mbar_init(&bars[B_REMPTY1], 1);
     mbar_init(&bars[B_ACCFULL], 1);
     mbar_init(&bars[B_ACCEMPTY], kE3Warps);
+    mbar_init(&bars[B_XHFULL], kE3Warps);
+    mbar_init(&bars[B_XHEMPTY], 1);
     mbar_init(&bars[B_DONE], 1);
+    for (int i = 0; i < 12; ++i) mbar_init(&bars[B_XR0 + i], 1);
+    for (int i = 0; i < kProd; ++i) mbar_init(&bars[B_SLOT0 + i], 1);
     fence_mbar_init();
     prefetch_tmap(&mapGx);
+    prefetch_tmap(&mapX);
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, ncols);
   for (int c = tid; c < C; c += kThreads) {
@@ -347,267 +337,122 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t sX32 = smem_u32(smem + pl.x_off), sG32 = smem_u32(smem + pl.g_off);
+  const uint32_t sXH32 = smem_u32(smem + pl.xh_off), sG32 = smem_u32(smem + pl.g_off);
   const uint32_t sTA32 = smem_u32(smem + pl.ta_off), sTR32 = smem_u32(smem + pl.tr_off);
+  const uint32_t sZero32 = smem_u32(smem + pl.zero_off);
   const uint32_t sCen32 = smem_u32(smem + pl.cen_off);
 
   const bool is_e1 = warp == 2 || warp == 3;
   const bool is_e3 = (warp & 3) < 2 && warp >= 4;
   if (!is_e1 && !is_e3 && warp != kMmaWarp) {
     // ======================================================================= PRODUCERS
-    // 8 lanes per token row (lane j owns float4 chunks j, j+8, ...), 4 rows per warp instruction = one
-    // unit of ONE tensor; the two rows sharing a 16-lane store phase differ by 4 (disjoint banks after
-    // the 128B swizzle): unit v (0..15) of a tile covers rows 8 (v/2) + 2 (v%2) + {0, 4, 1, 5}.
-    // Units 0..15 of a tile are xhat, 16..31 are gR; the loads of a warp's next unit are in flight
-    // while it converts the current one.
+    // Units of a tile: 0, 1 = the A rows (32 rows x 32 centroids each), 2..17 = gR (4 rows each).  A gR unit is four rows
+    // {b, b+1, b+4, b+5}, b = 8 (v/2) + 2 (v%2): 8 lanes per row (lane j owns float4 chunks j, j+8, ...), and the two rows
+    // that share a 16-lane store phase differ by 4 (disjoint banks after the 128B swizzle).  The unit's raw rows arrive in
+    // the warp's private slot by two bulk copies (rows b, b+1 and rows b+4, b+5 are contiguous in global memory) that
+    // were issued while the warp was still converting its previous unit.
     const int pw = warp < 2 ? warp : (warp >> 2) * 2 + (warp & 1);   // warps 0,1,6,7,10,11,14 -> 0..6
     const int lj = lane & 7, lg = lane >> 3;
-    const int rsel = (lg & 1) * 4 + (lg >> 1);
-    if constexpr (ASYNC) {
-      // ---- asynchronous producers: cp.async brings a unit's raw fp32 rows straight into the unit's OWN destination
-      // in the operand tiles (4 rows x 768 B raw = the bytes of their hi + lo bf16 rows: the float4 a lane owns goes to
-      // the 16-byte chunk that will hold its own and its neighbour's hi halves (even lanes) or lo halves (odd lanes)),
-      // so the loads in flight hold no registers and a warp keeps up to kDepth units in flight behind ONE copy of the
-      // code.  A unit is issued once its buffer is free (non-blocking test: a warp never waits for a buffer while it
-      // still owes converted units to the other roles) and converted in place after its copy group has landed: every
-      // lane reads back its own chunks, the warp synchronises, then the hi / lo halves are written as before.
-      struct Pos { int it, u; };
-      auto advance = [&](Pos& q) { q.u += kProd; if (q.u >= kUnits) { q.u -= kUnits; ++q.it; } };
-      const uint32_t sStat32 = smem_u32(smem + pl.stat_off) + (uint32_t)pw * (kDepth * 4u * 8u);
-      auto buffer_free = [&](const Pos& q) -> bool {
-        if (q.u >= 32) return true;                        // A units are loaded when they are converted
-        return q.u < 16 ? mbar_test(&bars[B_XEMPTY0 + (q.it & 1)], (uint32_t)(((q.it >> 1) & 1) ^ 1))
-                        : mbar_test(&bars[B_GEMPTY], (uint32_t)((q.it & 1) ^ 1));
-      };
-      // staging chunk of this lane's float4 number lj + 8 i of row r (see the class comment): base of the unit's tensor
-      auto unit_base = [&](const Pos& q, int& r, bool& isx) -> uint32_t {
-        const int v = q.u & 15;
-        isx = q.u < 16;
-        r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
-        return (isx ? sX32 + (uint32_t)(q.it & 1) * pl.xbuf : sG32) + (uint32_t)r * 128u +
-               (((uint32_t)(lj >> 1) ^ (uint32_t)(r & 7)) << 4);
-      };
-      auto issue = [&](const Pos& q, int slot) {
-        if (q.u >= 32) { cp_async_commit(); return; }
-        int r; bool isx;
-        const uint32_t b0 = unit_base(q, r, isx);
-        const int v = q.u & 15;
-        const long long tile = (long long)blockIdx.x + (long long)q.it * gridDim.x;
-        const float* src = isx ? p.x : p.gR;
-        if (p.pf > 0 && lane == 0 && (v & 1) == 0 && q.it + p.pf < nmine) {   // L2 prefetch: same 8-row group, pf tiles ahead
-          const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
-          const long long rows = min(8ll, p.N - rn);
-          if (rows > 0) prefetch_l2_bulk(src + rn * C, (uint32_t)(rows * C * 4));
-          if (isx && v == 0) {
-            const long long t0 = (tile + (long long)p.pf * gridDim.x) * kTok;
-            const long long nr = min((long long)kTok, p.N - t0) & ~3ll;
-            if (nr > 0) { prefetch_l2_bulk(p.mu + t0, (uint32_t)(nr * 4)); prefetch_l2_bulk(p.rstd + t0, (uint32_t)(nr * 4)); }
-          }
-        }
-        const long long row = tile * kTok + r;
-        const bool live = row < p.N;
-        const float4* sr = reinterpret_cast<const float4*>(src + row * C) + lj;
-        const uint32_t s0 = b0 + ((lj & 1) ? pl.xterm : 0u);           // even lanes stage in the hi term, odd lanes in the lo term
-#pragma unroll
-        for (int i = 0; i < F4; ++i) {
-          const uint32_t dst = (s0 ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk;
-          if (live) cp_async16(dst, sr + 8 * i);
-          else sts128(dst, 0u, 0u, 0u, 0u);
-        }
-        if (isx && lj == 0) {                                          // the row's LayerNorm statistics ride along
-          const uint32_t st = sStat32 + (uint32_t)(slot * 4 + lg) * 8u;
-          if (live) { cp_async4(st, p.mu + row); cp_async4(st + 4u, p.rstd + row); }
-          else sts64(st, 0u, 0u);
-        }
-        cp_async_commit();
-      };
-      auto process = [&](const Pos& q, int slot) {
-        const int it = q.it;
-        if (q.u >= 32) {                                   // A rows: 32 rows x 32 centroids, lane = (row, float4)
-          const long long rb = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + (q.u - 32) * 32;
-          float4 a[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const long long row = rb + (j >> 1) * 8 + (j & 1) * 2 + rsel;
-            a[j] = row < p.N ? ldg_nc(reinterpret_cast<const float4*>(p.A + row * K) + lj) : make_float4(0, 0, 0, 0);
-          }
-          mbar_wait_spin(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));   // tile A is free once S5a of the previous tile has completed
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t r = (uint32_t)((q.u - 32) * 32 + (j >> 1) * 8 + (j & 1) * 2 + rsel);
-            uint32_t a1, a2, b1, b2;
-            split2_bf(a[j].x, a[j].y, a1, a2);
-            split2_bf(a[j].z, a[j].w, b1, b2);
-            sts64(sTA32 + sw128(r, (uint32_t)lj * 8u), a1, b1);
-            sts64(sTA32 + sw128(r, 64u + (uint32_t)lj * 8u), a2, b2);
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[B_AFULL]);
-          return;
-        }
-        int r; bool isx;
-        const uint32_t b0 = unit_base(q, r, isx);
-        const uint32_t s0 = b0 + ((lj & 1) ? pl.xterm : 0u);
-        TR(0, it);
-        float4 v[F4];
-#pragma unroll
-        for (int i = 0; i < F4; ++i) v[i] = lds128f((s0 ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk);
-        float mu = 0.f, rs = 1.f;
-        if (isx) {
-          const uint32_t st = sStat32 + (uint32_t)(slot * 4 + lg) * 8u;
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(mu), "=f"(rs) : "r"(st));
-        }
-        __syncwarp();                                      // every lane holds its chunks: the staging bytes may be overwritten
-        const uint32_t db = b0 + (uint32_t)(lj & 1) * 8u;
-        const float2 rs2 = bcast2(rs), nm2 = bcast2(-mu * rs);
-#pragma unroll
-        for (int i = 0; i < F4; ++i) {
-          uint32_t a1, a2, b1, b2;
-          split2_bf(fma2(make_float2(v[i].x, v[i].y), rs2, nm2), a1, a2);   // gR: v * 1 - 0 (exact)
-          split2_bf(fma2(make_float2(v[i].z, v[i].w), rs2, nm2), b1, b2);
-          sts64((db ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
-          sts64((db ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.xterm, a2, b2);   // xterm == gterm
-        }
-        TR(1, it);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(isx ? &bars[B_XFULL0 + (it & 1)] : &bars[B_GFULL]);
-        TR(2, it);
-      };
-      Pos pi{0, pw}, pp{0, pw};                            // kProd < kUnits: every warp owns a unit of tile 0
-      int pending = 0, si = 0, sp = 0;
-#pragma unroll 1
-      while (pp.it < nmine) {
-        while (pending < kDepth && pi.it < nmine && buffer_free(pi)) {
-          issue(pi, si);
-          advance(pi);
-          si = (si + 1) & (kDepth - 1);
-          ++pending;
-        }
-        if (pending == 0) continue;                        // nothing owed to anybody: poll the buffer of the next unit
-        cp_async_wait_pending(pending - 1);                // the oldest group has landed
-        process(pp, sp);
-        advance(pp);
-        sp = (sp + 1) & (kDepth - 1);
-        --pending;
-      }
-    } else {
-    struct Unit { union { float4 v[F4]; float4 a[8]; }; float rs, mu; };   // a[]: the 8 float4 of an A unit
-    // (tile, unit) positions advance incrementally: a division by kUnits per unit is ~10 % of a producer's instructions
+    const int rsel = (lg & 1) * 4 + (lg >> 1);                       // row of this lane group inside the 8-row group: 0,4,1,5
+    const int srow = (rsel & 1) + (rsel >> 2) * 2;                   // ... and inside the slot (rows b, b+1, b+4, b+5)
+    const uint32_t slot32 = smem_u32(smem + pl.slot_off) + (uint32_t)pw * pl.slot;
+    uint64_t* sbar = &bars[B_SLOT0 + pw];
     struct Pos { int it, u; };
     auto advance = [&](Pos& q) { q.u += kProd; if (q.u >= kUnits) { q.u -= kUnits; ++q.it; } };
-    auto issue = [&](Unit& U, const Pos& q) {
-      if (q.it >= nmine) return;
-      const int it = q.it, u = q.u, v = u & 15;
+    auto next_g = [&](Pos& q) { do { advance(q); } while (q.u < 2); };
+    auto issue_load = [&](const Pos& q) {                           // lane 0: bulk copies of gR unit q into the slot
+      const int v = q.u - 2;
+      const long long tile = (long long)blockIdx.x + (long long)q.it * gridDim.x;
+      const long long r0 = tile * kTok + (v >> 1) * 8 + (v & 1) * 2;
+      const long long n0 = max(0ll, min(2ll, p.N - r0)), n1 = max(0ll, min(2ll, p.N - (r0 + 4)));
+      const uint32_t rowb = (uint32_t)C * 4u;
+      if (n0 + n1 > 0) {
+        mbar_expect_tx(sbar, (uint32_t)(n0 + n1) * rowb);
+        bulk_g2s_u32(slot32, p.gR + r0 * C, (uint32_t)n0 * rowb, sbar);
+        if (n1 > 0) bulk_g2s_u32(slot32 + 2u * rowb, p.gR + (r0 + 4) * C, (uint32_t)n1 * rowb, sbar);
+      } else {
+        mbar_arrive(sbar);                                          // a unit past the end: nothing to copy
+      }
+      if (p.pf > 0 && (v & 1) == 0 && q.it + p.pf < nmine) {        // L2 prefetch: same 8-row group, pf tiles ahead
+        const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
+        const long long rows = min(8ll, p.N - rn);
+        if (rows > 0) prefetch_l2_bulk(p.gR + rn * C, (uint32_t)(rows * C * 4));
+      }
+    };
+    Pos pc{0, pw};
+    {
+      Pos pl0 = pc;
+      if (pl0.u < 2) next_g(pl0);
+      if (lane == 0 && pl0.it < nmine) issue_load(pl0);
+    }
+    uint32_t sphase = 0;
+#pragma unroll 1
+    while (pc.it < nmine) {
+      const int it = pc.it, u = pc.u;
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (u >= 32) {                                     // A rows: 32 rows x 32 centroids, lane = (row, float4)
-        const long long rb = tile * kTok + (u - 32) * 32;
+      if (u < 2) {
+        // ---- A rows: 32 rows x 32 centroids, lane = (row, float4)
+        const long long rb = tile * kTok + u * 32;
+        float4 a[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const long long row = rb + (j >> 1) * 8 + (j & 1) * 2 + rsel;
-          U.a[j] = row < p.N ? ldg_nc(reinterpret_cast<const float4*>(p.A + row * K) + lj) : make_float4(0, 0, 0, 0);
+          a[j] = row < p.N ? ldg_nc(reinterpret_cast<const float4*>(p.A + row * K) + lj) : make_float4(0, 0, 0, 0);
         }
-        return;
-      }
-      const bool isx = u < 16;
-      const float* src = isx ? p.x : p.gR;
-      if (p.pf > 0 && lane == 0 && (v & 1) == 0 && it + p.pf < nmine) {   // L2 prefetch: same 8-row group, pf tiles ahead
-        const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
-        const long long rows = min(8ll, p.N - rn);
-        if (rows > 0) prefetch_l2_bulk(src + rn * C, (uint32_t)(rows * C * 4));
-        if (isx && v == 0) {                             // the tile's mu / rstd rows too (their latency is otherwise exposed)
-          const long long t0 = (tile + (long long)p.pf * gridDim.x) * kTok;
-          const long long nr = min((long long)kTok, p.N - t0) & ~3ll;   // bulk prefetch sizes are multiples of 16 bytes
-          if (nr > 0) { prefetch_l2_bulk(p.mu + t0, (uint32_t)(nr * 4)); prefetch_l2_bulk(p.rstd + t0, (uint32_t)(nr * 4)); }
-        }
-      }
-      const int r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
-      const long long row = tile * kTok + r;
-      const bool live = row < p.N;
-      const float4* sr = reinterpret_cast<const float4*>(src + row * C) + lj;
-#pragma unroll
-      for (int i = 0; i < F4; ++i) U.v[i] = (live && !(p.dbg & 1)) ? ld_stream(sr + 8 * i) : make_float4(0, 0, 0, 0);
-      U.rs = (isx && live) ? __ldg(p.rstd + row) : 0.f;   // raw loads only: arithmetic on them here would wait for them
-      U.mu = (isx && live) ? __ldg(p.mu + row) : 0.f;
-    };
-    auto process = [&](Unit& U, const Pos& q) {
-      if (q.it >= nmine) return;
-      const int it = q.it, u = q.u, v = u & 15;
-      if (u >= 32) {
-        // tile A is free once S5a of the previous tile has completed
-        mbar_wait_spin(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));
+        mbar_wait_spin(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));   // tile A is free once S5a of the previous tile has completed
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t r = (uint32_t)((u - 32) * 32 + (j >> 1) * 8 + (j & 1) * 2 + rsel);
+          const uint32_t r = (uint32_t)(u * 32 + (j >> 1) * 8 + (j & 1) * 2 + rsel);
           uint32_t a1, a2, b1, b2;
-          split2_bf(U.a[j].x, U.a[j].y, a1, a2);
-          split2_bf(U.a[j].z, U.a[j].w, b1, b2);
+          split2_bf(a[j].x, a[j].y, a1, a2);
+          split2_bf(a[j].z, a[j].w, b1, b2);
           sts64(sTA32 + sw128(r, (uint32_t)lj * 8u), a1, b1);            // A_hi: slots 4 lj .. 4 lj + 3
           sts64(sTA32 + sw128(r, 64u + (uint32_t)lj * 8u), a2, b2);      // A_lo
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_AFULL]);
-        return;
-      }
-      const bool isx = u < 16;
-      const int buf = it & 1;
-      const int r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
-      // byte offset of this lane's float4 number lj inside its row's first 64-channel block; float4 lj + 8 i sits in
-      // block i/2 at chunk (lj/2 + 4 (i%2)) ^ (r%8): bit 6 of the offset flips with i%2 (all operand bases are 1 KB aligned)
-      const uint32_t e0 = (uint32_t)r * 128u + (((uint32_t)(lj >> 1) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)(lj & 1) * 8u;
-      TR(0, it);
-      if (isx) {
-        // X[buf] is free once S5b and E3 of tile it-2 have finished
-        mbar_wait_spin(&bars[B_XEMPTY0 + buf], (uint32_t)(((it >> 1) & 1) ^ 1));
-        const uint32_t xb = sX32 + buf * pl.xbuf + e0;
-        const float2 rs2 = bcast2(U.rs), nm2 = bcast2(-U.mu * U.rs);
-#pragma unroll
-        for (int i = 0; i < F4; ++i) {
-          uint32_t a1, a2, b1, b2;
-          split2_bf(fma2(make_float2(U.v[i].x, U.v[i].y), rs2, nm2), a1, a2);
-          split2_bf(fma2(make_float2(U.v[i].z, U.v[i].w), rs2, nm2), b1, b2);
-          if (!(p.dbg & 2)) {
-          sts64((xb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
-          sts64((xb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.xterm, a2, b2);
-          }
-        }
       } else {
+        // ---- gR unit
+        const int v = u - 2;
+        const int r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
+        const bool live = tile * kTok + r < p.N;
+        TR(0, it);
+        mbar_wait_spin(sbar, sphase);
+        sphase ^= 1u;
+        float4 g4[F4];
+        const uint32_t sr = slot32 + (uint32_t)srow * ((uint32_t)C * 4u) + (uint32_t)lj * 16u;
+#pragma unroll
+        for (int i = 0; i < F4; ++i) g4[i] = live ? lds128f(sr + (uint32_t)i * 128u) : make_float4(0, 0, 0, 0);
+        __syncwarp();                                    // every lane holds its chunks: the slot may be refilled
+        {
+          Pos nl = pc;
+          next_g(nl);
+          if (lane == 0 && nl.it < nmine) issue_load(nl);
+        }
+        TR(3, it);
+        // byte offset of this lane's float4 number lj inside its row's first 64-channel block; float4 lj + 8 i sits in
+        // block i/2 at chunk (lj/2 + 4 (i%2)) ^ (r%8): bit 6 of the offset flips with i%2 (all operand bases are 1 KB aligned)
+        const uint32_t e0 = (uint32_t)r * 128u + (((uint32_t)(lj >> 1) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)(lj & 1) * 8u;
         // G is free once S1 / S5a of the previous tile have completed
         mbar_wait_spin(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));
         const uint32_t gb = sG32 + e0;
 #pragma unroll
         for (int i = 0; i < F4; ++i) {
           uint32_t a1, a2, b1, b2;
-          split2_bf(U.v[i].x, U.v[i].y, a1, a2);
-          split2_bf(U.v[i].z, U.v[i].w, b1, b2);
-          if (!(p.dbg & 2)) {
+          split2_bf(g4[i].x, g4[i].y, a1, a2);
+          split2_bf(g4[i].z, g4[i].w, b1, b2);
           sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
-          sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.gterm, a2, b2);
-          }
+          sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.xterm, a2, b2);
         }
+        TR(1, it);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_GFULL]);
+        TR(2, it);
       }
-      TR(1, it);
-      fence_async_smem();
-      __syncwarp();
-      // (one full-barrier per X buffer: an xhat unit of tile it+2 can never arrive into tile it's phase)
-      if (lane == 0) mbar_arrive(isx ? &bars[B_XFULL0 + buf] : &bars[B_GFULL]);
-      TR(2, it);
-    };
-    Unit cur, nxt;
-    Pos pc{0, pw}, pn{0, pw};                            // kProd < kUnits: every warp owns a unit of tile 0
-    issue(cur, pc);
-    advance(pn);
-#pragma unroll 1
-    while (pc.it < nmine) {                              // one copy of the code: four roles share the instruction cache
-      issue(nxt, pn);
-      process(cur, pc);
-      cur = nxt;
-      pc = pn;
-      advance(pn);
+      advance(pc);
     }
-    }   // !ASYNC
   } else if (is_e1) {
     // ======================================================================= E1
     const int et = tid - 64;                             // 0..63 = token row; its G1 row sits in TMEM lane 64 + et
@@ -617,7 +462,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     const uint32_t sHc32 = smem_u32(sHc), sCg32 = smem_u32(sCg);
     float rcol_acc = 0.f;
     float dv[32], av[32];
-    float rs_next = 0.f;
+    float rs_next = 0.f, mu_next = 0.f;
     float4 st_next = make_float4(0, 0, 0, 0);
     auto load_da = [&](int it) {                         // D / A rows of tile `it` (software-pipelined one tile ahead)
       const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + et;
@@ -632,6 +477,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         av[4 * q] = a4.x; av[4 * q + 1] = a4.y; av[4 * q + 2] = a4.z; av[4 * q + 3] = a4.w;
       }
       rs_next = live ? __ldg(p.rstd + row) : 0.f;
+      mu_next = live ? __ldg(p.mu + row) : 0.f;
       st_next = live ? ldg_nc(reinterpret_cast<const float4*>(p.rowstats) + row) : make_float4(0, 0, 0, 0);
     };
     auto prefetch_da = [&](int it) {                     // L2 prefetch of a later tile's D / A rows (8 KB each)
@@ -642,6 +488,8 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
           prefetch_l2_bulk(p.D + rn * K, (uint32_t)(rows * K * 4));
           prefetch_l2_bulk(p.A + rn * K, (uint32_t)(rows * K * 4));
           prefetch_l2_bulk(p.rowstats + rn * 4, (uint32_t)(rows * 16));
+          const long long nr = rows & ~3ll;              // bulk prefetch sizes are multiples of 16 bytes
+          if (nr > 0) { prefetch_l2_bulk(p.mu + rn, (uint32_t)(nr * 4)); prefetch_l2_bulk(p.rstd + rn, (uint32_t)(nr * 4)); }
         }
       }
     };
@@ -651,7 +499,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
       const long long row = tile * kTok + et;
       const bool live = row < p.N;
-      const float rs = rs_next;
+      const float rs = rs_next, nmr = -mu_next * rs_next;
       const float zz = st_next.x, p1 = st_next.y, p2 = st_next.z;
       TR(10, it);
       prefetch_da(it + 2);
@@ -701,27 +549,29 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
       const float rsum = rsum2.x + rsum2.y, sT = sT2.x + sT2.y, sG = sG2.x + sG2.y;
       const float s1 = (rsum * p1 - sG) * invC, s2 = (rsum * p2 - sT) * invC;
       TR(41, it);
-      // tile R free: S3 / S5b of the previous tile have completed
-      mbar_wait(&bars[B_REMPTY], (uint32_t)((it & 1) ^ 1));
+      // tile R[buf] free: S3 / S5b of tile it-2 have completed
+      mbar_wait(&bars[B_REMPTY0 + buf], (uint32_t)(((it >> 1) & 1) ^ 1));
       TR(42, it);
+      const uint32_t tr32 = sTR32 + (uint32_t)buf * kBlk;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t w1[4], w2[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) split2_bf(gv[8 * j + 2 * e], gv[8 * j + 2 * e + 1], w1[e], w2[e]);
-        sts128(sTR32 + sw128((uint32_t)et, (uint32_t)j * 16u), w1[0], w1[1], w1[2], w1[3]);
-        sts128(sTR32 + sw128((uint32_t)et, 64u + (uint32_t)j * 16u), w2[0], w2[1], w2[2], w2[3]);
+        sts128(tr32 + sw128((uint32_t)et, (uint32_t)j * 16u), w1[0], w1[1], w1[2], w1[3]);
+        sts128(tr32 + sw128((uint32_t)et, 64u + (uint32_t)j * 16u), w2[0], w2[1], w2[2], w2[3]);
       }
-      float* scal = sScal + (it & 1) * 4 * kTok;
+      float* scal = sScal + buf * 5 * kTok;
       scal[et] = rsum; scal[kTok + et] = s1 * rs; scal[2 * kTok + et] = s2 * rs; scal[3 * kTok + et] = rs;
+      scal[4 * kTok + et] = nmr;
       TR(43, it);
       fence_async_smem();
       TR(44, it);
       named_bar(1, 64);
-      if (et == 0) mbar_arrive(&bars[B_RFULL]);
+      if (et == 0) mbar_arrive(&bars[B_RFULL0 + buf]);
       TR(15, it);
       // next tile's D / A rows: issued after the fence / barrier above (which would wait for them),
-      // their latency is covered by the butterfly and the wait for tile A
+      // their latency is covered by the butterfly and the wait for the next G1
       load_da(it + 1);
       butterfly<1>(gv, lane);                            // lane l: sum over this warp's 32 rows of r[:, l]
       rcol_acc += gv[0];
@@ -738,81 +588,113 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
 #pragma unroll
       for (int j = 0; j < 8; ++j) accq[c][j] = 0.f;
     if (e3 < NCB) {
+      const int wi = e3 * 2 + q;
       const int rl = q * 32 + lane;                      // token row in the tile = TMEM lane
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       const uint64_t pol = policy_evict_first();
-      const uint32_t stg32 = smem_u32(smem + pl.stg_off) + (uint32_t)(e3 * 2 + q) * 4096u;
-      const uint32_t rx = (uint32_t)(rl & 7);
+      const uint32_t box32 = smem_u32(smem + pl.xr_off) + (uint32_t)wi * 2u * kBox;   // this warp's two boxes (channel halves)
+      uint64_t* xrbar = &bars[B_XR0 + wi * 2];
+      const uint32_t rx = (uint32_t)(lane & 7);          // == rl & 7
+      const uint32_t xhrow = sXH32 + (uint32_t)e3 * kBlk + (uint32_t)rl * 128u;
       const uint32_t sGam32 = smem_u32(sGam), sBet32 = smem_u32(sBet);
+      auto load_boxes = [&](int it) {                    // lane 0: raw x of tile `it`, rows q 32.., channels e3 64.. (two boxes)
+        const long long r0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + q * 32;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          mbar_expect_tx(&xrbar[ch], kBox);
+          tma_load_2d_u32(&mapX, box32 + (uint32_t)ch * kBox, &xrbar[ch], e3 * 64 + ch * 32, (int)r0);
+        }
+      };
+      if (lane == 0) load_boxes(0);
       for (int it = 0; it < nmine; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
         const long long row0 = tile * kTok;
-        const int buf = it & 1;
+        const int par = it & 1;
         TR(19, it);
-        mbar_wait(&bars[B_RFULL], (uint32_t)(it & 1));
+        mbar_wait(&bars[B_RFULL0 + par], (uint32_t)((it >> 1) & 1));
         TR(20, it);
-        const float* scal = sScal + (it & 1) * 4 * kTok;
+        const float* scal = sScal + par * 5 * kTok;
         const float rsum = scal[rl], s1r = scal[kTok + rl], s2r = scal[2 * kTok + rl], rs = scal[3 * kTok + rl];
-        mbar_wait(&bars[B_ACCFULL], (uint32_t)(it & 1));
+        const float nmr = scal[4 * kTok + rl];
+        mbar_wait(&bars[B_ACCFULL], (uint32_t)par);
         TR(21, it);
         tc_fence_after();
-        const uint32_t xrow = sX32 + buf * pl.xbuf + (uint32_t)e3 * kBlk + (uint32_t)rl * 128u;
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = e3 * 64 + ch * 32;
           float acc[32], xh[32];
           tmem_ld32(tmem + lane_addr + kColAcc + (uint32_t)c0, acc);
+          mbar_wait(&xrbar[ch], (uint32_t)par);          // the raw x box of this tile has landed
+          const uint32_t bx = box32 + (uint32_t)ch * kBox + (uint32_t)lane * 128u;
+          {
+            const float2 rs2 = bcast2(rs), nmr2 = bcast2(nmr);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t off = (((uint32_t)(ch * 4 + j) ^ rx) << 4);
-            const uint4 h = lds128u(xrow + off);
-            const uint4 l = lds128u(xrow + pl.xterm + off);
-            float2 t;
-            t = add2(bf_pair(h.x), bf_pair(l.x)); xh[8 * j + 0] = t.x; xh[8 * j + 1] = t.y;
-            t = add2(bf_pair(h.y), bf_pair(l.y)); xh[8 * j + 2] = t.x; xh[8 * j + 3] = t.y;
-            t = add2(bf_pair(h.z), bf_pair(l.z)); xh[8 * j + 4] = t.x; xh[8 * j + 5] = t.y;
-            t = add2(bf_pair(h.w), bf_pair(l.w)); xh[8 * j + 6] = t.x; xh[8 * j + 7] = t.y;
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = lds128f(bx + ((((uint32_t)j) ^ rx) << 4));
+              const float2 a = fma2(make_float2(t.x, t.y), rs2, nmr2), b = fma2(make_float2(t.z, t.w), rs2, nmr2);
+              xh[4 * j] = a.x; xh[4 * j + 1] = a.y; xh[4 * j + 2] = b.x; xh[4 * j + 3] = b.y;   // xhat, exact in fp32
+            }
           }
-          // the TMA store that last read this warp's staging block has finished reading
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
+          // the xhat operand tile is free once S5b of the previous tile has completed
+          if (ch == 0) mbar_wait(&bars[B_XHEMPTY], (uint32_t)(par ^ 1));
           // packed fp32 (element pairs): gz = z rsum - acc;  o = (gz gamma) rs - s1 rs - xhat s2 rs;  Q += xhat^2 rsum
           const float2 nrsum2 = bcast2(-rsum), rsum2 = bcast2(rsum), nrs2 = bcast2(-rs), ns1r2 = bcast2(-s1r), ns2r2 = bcast2(-s2r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 gm = lds128f_const(sGam32 + (uint32_t)(c0 + 4 * j) * 4u);
-            const float4 be = lds128f_const(sBet32 + (uint32_t)(c0 + 4 * j) * 4u);
-            float2 o[2];
+          for (int jj = 0; jj < 4; ++jj) {               // 8 channels per step
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float2 g2 = e ? make_float2(gm.z, gm.w) : make_float2(gm.x, gm.y);
-              const float2 b2 = e ? make_float2(be.z, be.w) : make_float2(be.x, be.y);
-              const float2 x2 = make_float2(xh[4 * j + 2 * e], xh[4 * j + 2 * e + 1]);
-              const float2 a2 = make_float2(acc[4 * j + 2 * e], acc[4 * j + 2 * e + 1]);
-              const float2 z = fma2(x2, g2, b2);
-              const float2 ngz = fma2(z, nrsum2, a2);                      // -(gz) = acc - z rsum
-              o[e] = fma2(x2, ns2r2, fma2(mul2(ngz, g2), nrs2, ns1r2));
-              const float2 qq = mul2(mul2(x2, rsum2), x2);                 // Q contribution
-              xh[4 * j + 2 * e] = qq.x; xh[4 * j + 2 * e + 1] = qq.y;
+            for (int jh = 0; jh < 2; ++jh) {
+              const int j = 2 * jj + jh;
+              const float4 gm = lds128f_const(sGam32 + (uint32_t)(c0 + 4 * j) * 4u);
+              const float4 be = lds128f_const(sBet32 + (uint32_t)(c0 + 4 * j) * 4u);
+              float2 o[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float2 g2 = e ? make_float2(gm.z, gm.w) : make_float2(gm.x, gm.y);
+                const float2 b2 = e ? make_float2(be.z, be.w) : make_float2(be.x, be.y);
+                const float2 x2 = make_float2(xh[4 * j + 2 * e], xh[4 * j + 2 * e + 1]);
+                const float2 a2 = make_float2(acc[4 * j + 2 * e], acc[4 * j + 2 * e + 1]);
+                const float2 z = fma2(x2, g2, b2);
+                const float2 ngz = fma2(z, nrsum2, a2);                      // -(gz) = acc - z rsum
+                o[e] = fma2(x2, ns2r2, fma2(mul2(ngz, g2), nrs2, ns1r2));
+              }
+              // gx goes back into the bytes x was read from (this thread's own row of the box)
+              sts128f(bx + ((((uint32_t)j) ^ rx) << 4), o[0].x, o[0].y, o[1].x, o[1].y);
             }
-            sts128f(stg32 + (uint32_t)lane * 128u + ((((uint32_t)j) ^ (uint32_t)(lane & 7)) << 4), o[0].x, o[0].y, o[1].x, o[1].y);
+            // two-term bf16 split of the 8 xhat values -> one 16-byte chunk of the hi block and of the lo block
+            uint32_t w1[4], w2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split2_bf(xh[8 * jj + 2 * e], xh[8 * jj + 2 * e + 1], w1[e], w2[e]);
+            const uint32_t xo = xhrow + ((((uint32_t)(ch * 4 + jj)) ^ rx) << 4);
+            sts128(xo, w1[0], w1[1], w1[2], w1[3]);
+            sts128(xo + pl.xterm, w2[0], w2[1], w2[2], w2[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {                // Q contributions replace xhat
+              const float2 x2 = make_float2(xh[8 * jj + 2 * e], xh[8 * jj + 2 * e + 1]);
+              const float2 qq = mul2(mul2(x2, rsum2), x2);
+              xh[8 * jj + 2 * e] = qq.x; xh[8 * jj + 2 * e + 1] = qq.y;
+            }
           }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d_hint(&mapGx, stg32, c0, (int)(row0 + q * 32), pol);
+            tma_store_2d_hint(&mapGx, box32 + (uint32_t)ch * kBox, c0, (int)(row0 + q * 32), pol);
             bulk_commit();
           }
-          if (ch == 1) {                                 // accumulator and xhat fully consumed: release them early
+          if (ch == 1) {                                 // accumulator consumed, xhat operand rows written
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&bars[B_ACCEMPTY]); mbar_arrive(&bars[B_XEMPTY0 + buf]); }
+            if (lane == 0) { mbar_arrive(&bars[B_ACCEMPTY]); mbar_arrive(&bars[B_XHFULL]); }
           }
           butterfly<8>(xh, lane);
 #pragma unroll
           for (int j = 0; j < 8; ++j) accq[ch][j] += xh[j];
         }
         TR(22, it);
+        // the stores have finished reading the boxes: fetch the next tile's x into them
+        if (lane == 0) {
+          bulk_wait_read0();
+          if (it + 1 < nmine) load_boxes(it + 1);
+        }
       }
       if (lane == 0) bulk_wait0();
       // finish the butterflies: lane l ends with Q of channel c0 + l over this warp's rows
@@ -836,9 +718,10 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     constexpr uint32_t kLbo = (kBlk >> 4) << 16;                      // 8 KB between the 64-wide blocks of an MN-major operand
     const uint32_t loG_k = (sG32 >> 4) & 0x3FFFu, loG_mn = loG_k | kLbo;
     const uint32_t loG_k64 = loG_k - (kBlk >> 4);                    // S1: MMA rows 64..127 = the tile's rows 0..63
-    const uint32_t loX_mn0 = ((sX32 >> 4) & 0x3FFFu) | kLbo;
+    const uint32_t loX_mn = ((sXH32 >> 4) & 0x3FFFu) | kLbo;
     const uint32_t loTA_mn = ((sTA32 >> 4) & 0x3FFFu) | kLbo;         // blocks: tile A, ZERO
-    const uint32_t loZR_mn = loTA_mn + (kBlk >> 4);                   // blocks: ZERO, tile R
+    const uint32_t loZR_mn0 = ((sZero32 >> 4) & 0x3FFFu) | kLbo;      // blocks: ZERO, tile R[0]
+    const uint32_t loZR_mn1 = ((sZero32 >> 4) & 0x3FFFu) | (2u * kLbo);   //      ZERO, tile R[1] (16 KB further)
     const uint32_t loTR_k = (sTR32 >> 4) & 0x3FFFu;
     const uint32_t loC_k = (sCen32 >> 4) & 0x3FFFu, loC_mn = loC_k | kLbo;
     mbar_wait(&bars[B_CEN], 0);
@@ -846,16 +729,17 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
     while (n5b < nmine) {
       const int progress0 = n1 + n3 + n5a + n5b;
       // ---- S3 (feeds E3): acc = r_lo cen_hi + r_hi cen_lo + r_hi cen_hi
-      if (n3 < n1 && mbar_try_wait(&bars[B_RFULL], (uint32_t)(n3 & 1)) &&
+      if (n3 < n1 && mbar_try_wait(&bars[B_RFULL0 + (n3 & 1)], (uint32_t)((n3 >> 1) & 1)) &&
           mbar_try_wait(&bars[B_ACCEMPTY], (uint32_t)((n3 & 1) ^ 1))) {
         tc_fence_after();
         const uint32_t d = tmem + kColAcc;
+        const uint32_t loTR = loTR_k + (uint32_t)(n3 & 1) * (kBlk >> 4);
         constexpr uint32_t ro[3] = {64u, 0u, 0u}, co[3] = {0u, 4096u, 0u};
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
 #pragma unroll
           for (int ks = 0; ks < K / 16; ++ks) {
-            const uint64_t ad = desc_at(loTR_k, kHi, ro[t] + (uint32_t)ks * 32u);
+            const uint64_t ad = desc_at(loTR, kHi, ro[t] + (uint32_t)ks * 32u);
             const uint64_t bd = desc_at(loC_mn, kHi, co[t] + (uint32_t)(2 * ks) * 1024u);
             mma_f16(d, ad, bd, idesc3, (t > 0 || ks > 0) ? 1u : 0u);
           }
@@ -877,7 +761,7 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         }
 #pragma unroll
         for (int kk = 0; kk < C / 16; ++kk) {
-          const uint64_t ad = desc_at(loG_k64, kHi, pl.gterm + (kk >> 2) * kBlk + (kk & 3) * 32u);
+          const uint64_t ad = desc_at(loG_k64, kHi, pl.xterm + (kk >> 2) * kBlk + (kk & 3) * 32u);
           const uint64_t bd = desc_at(loC_k, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
           mma_f16(d, ad, bd, idesc1b, 1u);
         }
@@ -885,10 +769,10 @@ cluster_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapGx, const Params p)
         TR(30, n1);
         ++n1;
       }
-      // ---- S5b (background): PT[64:128] += [r_hi | r_lo]^T (xhat_hi + xhat_lo)
-      if (n5b < n3 && n5b < n5a && mbar_try_wait(&bars[B_XFULL0 + (n5b & 1)], (uint32_t)((n5b >> 1) & 1))) {
+      // ---- S5b (background, after E3 of its tile): PT[64:128] += [r_hi | r_lo]^T (xhat_hi + xhat_lo)
+      if (n5b < n3 && n5b < n5a && mbar_try_wait(&bars[B_XHFULL], (uint32_t)(n5b & 1))) {
         tc_fence_after();
-        const uint32_t loX_mn = loX_mn0 + (uint32_t)(n5b & 1) * (pl.xbuf >> 4);
+        const uint32_t loZR_mn = (n5b & 1) ? loZR_mn1 : loZR_mn0;
 VADC_S5_UNROLL
         for (int t = 0; t < 2; ++t) {
 VADC_S5_UNROLL
@@ -898,8 +782,8 @@ VADC_S5_UNROLL
             mma_f16(tmem + kColPT, ad, bd, idesc5, 1u);
           }
         }
-        mma_commit(&bars[B_XEMPTY0 + (n5b & 1)]);
-        mma_commit(&bars[B_REMPTY]);
+        mma_commit(&bars[B_XHEMPTY]);
+        mma_commit(&bars[B_REMPTY0 + (n5b & 1)]);
         TR(33, n5b);
         ++n5b;
       }
@@ -911,7 +795,7 @@ VADC_S5_UNROLL
 VADC_S5_UNROLL
           for (int ks = 0; ks < kTok / 16; ++ks) {
             const uint64_t ad = desc_at(loTA_mn, kHi, (uint32_t)ks * 2048u);
-            const uint64_t bd = desc_at(loG_mn, kHi, (uint32_t)t * pl.gterm + (uint32_t)ks * 2048u);
+            const uint64_t bd = desc_at(loG_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
             mma_f16(tmem + kColPT, ad, bd, idesc5, (n5a > 0 || t > 0 || ks > 0) ? 1u : 0u);
           }
         }
@@ -1045,12 +929,12 @@ static bool shape_ok(long long N, int C, int K) {
   return plan(C).total + 1024 <= 227u * 1024u;
 }
 
-}  // namespace bt
+}  // namespace bt2
 
-bool bwd_tc_shape_ok(long long N, int C, int K) { return bt::shape_ok(N, C, K); }
+bool bwd_tc2_shape_ok(long long N, int C, int K) { return bt2::shape_ok(N, C, K); }
 
-size_t bwd_tc_workspace_bytes(long long N, int C, int K) {
-  if (!bt::shape_ok(N, C, K)) return 0;
+size_t bwd_tc2_workspace_bytes(long long N, int C, int K) {
+  if (!bt2::shape_ok(N, C, K)) return 0;
   const size_t g = (size_t)sm_count();
   return align_up((size_t)2 * K * C * 2, 256) + align_up((size_t)3 * K * sizeof(float), 256) +
          align_up(g * 128 * C * sizeof(float), 256) + align_up(g * 2 * K * sizeof(float), 256) +
@@ -1058,14 +942,14 @@ size_t bwd_tc_workspace_bytes(long long N, int C, int K) {
          align_up((size_t)K * sizeof(float), 256) + 256;
 }
 
-int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, const float* rowstats, const float* ln_w,
-                          const float* ln_b, const float* centers, const float* D, const float* A,
-                          const float* gR, const float* g_loss_sq, long long N, int C, int K, float alpha,
-                          float* gx, float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
-                          size_t workspace_bytes, cudaStream_t st) {
-  if (!bt::shape_ok(N, C, K)) return VADC_ERR_UNSUPPORTED;
+int launch_cluster_bwd_tc2(const float* x, const float* mu, const float* rstd, const float* rowstats, const float* ln_w,
+                           const float* ln_b, const float* centers, const float* D, const float* A,
+                           const float* gR, const float* g_loss_sq, long long N, int C, int K, float alpha,
+                           float* gx, float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
+  if (!bt2::shape_ok(N, C, K)) return VADC_ERR_UNSUPPORTED;
   if (!vadc_device_ok()) return VADC_ERR_NO_DEVICE;
-  if (workspace_bytes < bwd_tc_workspace_bytes(N, C, K)) return VADC_ERR_WORKSPACE;
+  if (workspace_bytes < bwd_tc2_workspace_bytes(N, C, K)) return VADC_ERR_WORKSPACE;
   Carver ws(workspace, workspace_bytes);
   const size_t g = (size_t)sm_count();
   uint8_t* image = ws.take<uint8_t>((size_t)2 * K * C * 2);
@@ -1075,42 +959,50 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
   float* part_q = ws.take<float>(g * 2 * C);
   float* p2buf = ws.take<float>((size_t)K * C);
   float* rcol = ws.take<float>(K);
-  const int grid = (int)std::min<long long>((N + bt::kTok - 1) / bt::kTok, (long long)g);
+  const int grid = (int)std::min<long long>((N + bt2::kTok - 1) / bt2::kTok, (long long)g);
 
-  CUtensorMap mGx;
+  CUtensorMap mGx, mX;
   int rc;
-  if ((rc = bt::make_map(&mGx, gx, N, C))) return rc;
-  bt::centroid_prep_bwd_kernel<<<K, 256, 0, st>>>(centers, ln_w, ln_b, K, C, image, cvec);
+  if ((rc = bt2::make_map(&mGx, gx, N, C))) return rc;
+  if ((rc = bt2::make_map(&mX, const_cast<float*>(x), N, C))) return rc;
+  bt2::centroid_prep_bwd_kernel<<<K, 256, 0, st>>>(centers, ln_w, ln_b, K, C, image, cvec);
   VADC_CHECK_LAUNCH("centroid_prep_bwd_kernel");
 
-  const size_t smem = bt::plan(C).total + 1024;
+  const size_t smem = bt2::plan(C).total + 1024;
   unsigned long long* trace = nullptr;
-  const char* trace_path = env_str("VADC_BWD_TRACE");       // debugging only: synchronises and writes a text file
+#ifdef VADC_BWD_TRACE_BUILD
+  // debugging builds only (-DVADC_BWD_TRACE_BUILD): allocates, synchronises and writes a text file — never in the
+  // product library, whose entry points must stay capturable in a CUDA graph
+  const char* trace_path = getenv("VADC_BWD_TRACE");
   const size_t trace_bytes = (size_t)16 * 1024 * 2 * sizeof(unsigned long long);
   if (trace_path) { VADC_CUDA(cudaMalloc(&trace, trace_bytes)); VADC_CUDA(cudaMemsetAsync(trace, 0, trace_bytes, st)); }
-  bt::Params p{x, gR, D, A, mu, rstd, rowstats, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_q,
-               N, alpha, env_int("VADC_BWD_PF", 1),
-               env_int("VADC_BWD_DBG", 0), trace,
-               env_int("VADC_BWD_TRACE_CTA", 0)};
+  const int trace_cta = getenv("VADC_BWD_TRACE_CTA") ? atoi(getenv("VADC_BWD_TRACE_CTA")) : 0;
+#else
+  const int trace_cta = 0;
+#endif
+  bt2::Params p{x, gR, D, A, mu, rstd, rowstats, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_q,
+                N, alpha, env_int("VADC_BWD_PF", 1), trace, trace_cta};
   bool launched = false;
-  // experiment switch: 1 = cp.async producers staging in place (kept for the trace comparisons in DESIGN.md: parity-equal,
-  // 510 us against 377 us at cfg2 — a unit cannot be requested before its buffer is free, which puts the load latency
-  // behind every buffer release); default = register-staged producers
-  const bool async_prod = env_int("VADC_BWD_ASYNC", 0) == 1;
+#ifdef VADC_BWD_TRACE_BUILD
+#define BT_KERN(F4_) (trace ? bt2::cluster_bwd_tc2_kernel<F4_, true> : bt2::cluster_bwd_tc2_kernel<F4_, false>)
+#else
+#define BT_KERN(F4_) bt2::cluster_bwd_tc2_kernel<F4_, false>
+#endif
 #define BT_CASE(F4_)                                                                                   \
   if (C == 32 * F4_) {                                                                                 \
-    auto kern = trace ? (async_prod ? bt::cluster_bwd_tc_kernel<F4_, true, true> : bt::cluster_bwd_tc_kernel<F4_, true, false>)      \
-                      : (async_prod ? bt::cluster_bwd_tc_kernel<F4_, false, true> : bt::cluster_bwd_tc_kernel<F4_, false, false>);  \
+    auto kern = BT_KERN(F4_);                                                                          \
     VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    kern<<<grid, bt::kThreads, smem, st>>>(mGx, p);                                                    \
+    kern<<<grid, bt2::kThreads, smem, st>>>(mGx, mX, p);                                               \
     launched = true;                                                                                   \
   }
   timing_begin(VADC_TIMING_CLUSTER_BWD, st);
   BT_CASE(2) BT_CASE(4) BT_CASE(6)
 #undef BT_CASE
+#undef BT_KERN
   timing_end(VADC_TIMING_CLUSTER_BWD, st);
   if (!launched) return VADC_ERR_UNSUPPORTED;
-  VADC_CHECK_LAUNCH("cluster_bwd_tc_kernel");
+  VADC_CHECK_LAUNCH("cluster_bwd_tc2_kernel");
+#ifdef VADC_BWD_TRACE_BUILD
   if (trace) {
     VADC_CUDA(cudaStreamSynchronize(st));
     unsigned long long* h = (unsigned long long*)malloc(trace_bytes);
@@ -1126,11 +1018,12 @@ int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, co
     free(h);
     cudaFree(trace);
   }
-  bt::cluster_bwd_tc_finalize1_kernel<<<dim3(K, (C + 63) / 64), 512, 0, st>>>(part_p, part_rcol, centers, ln_w, ln_b, grid, K, C,
-                                                        gcenters, p2buf, rcol);
+#endif
+  bt2::cluster_bwd_tc_finalize1_kernel<<<dim3(K, (C + 63) / 64), 512, 0, st>>>(part_p, part_rcol, centers, ln_w, ln_b, grid, K, C,
+                                                         gcenters, p2buf, rcol);
   VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize1_kernel");
-  bt::cluster_bwd_tc_finalize2_kernel<<<(C + 7) / 8, 256, 0, st>>>(p2buf, rcol, part_q, centers, ln_w, ln_b, grid, K, C,
-                                                                    g_ln_w, g_ln_b);
+  bt2::cluster_bwd_tc_finalize2_kernel<<<(C + 7) / 8, 256, 0, st>>>(p2buf, rcol, part_q, centers, ln_w, ln_b, grid, K, C,
+                                                                     g_ln_w, g_ln_b);
   VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize2_kernel");
   return VADC_OK;
 }

@@ -639,8 +639,8 @@ int vadc_cluster_fwd_ws(const float* x, const float* ln_w, const float* ln_b, co
 
   const size_t smem = ws::plan(C).total + 1024;
   ws::Params p{x, ln_w, ln_b, image, cc, scales, feature, reinterpret_cast<long long*>(label), mu, rstd, rowstats,
-               partial, (long long)N, alpha, eps, getenv("VADC_WS_PF") ? atoi(getenv("VADC_WS_PF")) : -1,
-               getenv("VADC_WS_HINT") ? atoi(getenv("VADC_WS_HINT")) : 3};
+               partial, (long long)N, alpha, eps, env_int("VADC_WS_PF", -1),
+               env_int("VADC_WS_HINT", 3)};
 #define WS_CASE(F4_)                                                                                   \
   if (C == 32 * F4_) {                                                                                 \
     VADC_CUDA(cudaFuncSetAttribute(ws::cluster_fwd_ws_kernel<F4_>,                                      \

@@ -45,6 +45,11 @@ struct Carver {
 };
 
 int sm_count();
+// Environment switches (kernel-variant selection for A/B runs and debugging) are read ONCE per process, at their first
+// use: an entry point costs a table lookup, never a getenv().  vadc_refresh_env() (tests) forgets the cached values.
+const char* env_str(const char* name);               // value or nullptr
+inline bool env_on(const char* name) { return env_str(name) != nullptr; }
+int env_int(const char* name, int dflt);
 // measurement aid (abi.cu): events around the dominant kernels when vadc_timing_enable(1) is in effect
 #define VADC_TIMING_SLOTS 2
 #define VADC_TIMING_CLUSTER_FWD 0

@@ -546,7 +546,7 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
   int chunks = col_chunks(N);
   float* pmax = ws.take<float>((size_t)chunks * m);
   float* psum = ws.take<float>((size_t)chunks * m);
-  if (tc_gemm_shape_ok(N, m, d, false) && !getenv("VADC_NO_TC_GEMM")) {
+  if (tc_gemm_shape_ok(N, m, d, false) && !env_on("VADC_NO_TC_GEMM")) {
     // q . keys^T on tcgen05 (m = 2000, d = 768 is tensor-bound: 244 flop/B), fp32-faithful three-term split
     void* qs = ws.take<uint8_t>(tc_gemm_split_bytes(N, d));
     void* ks = ws.take<uint8_t>(tc_gemm_split_bytes(m, d));
@@ -593,7 +593,7 @@ extern "C" int vadc_memory_read(const float* q, const float* score_memory, const
   VADC_REQUIRE(N < (1ll << 31), VADC_ERR_UNSUPPORTED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (workspace && workspace_bytes >= vadc_memory_read_workspace_bytes(N, m, d) && tc_gemm_shape_ok(N, d, m, true) &&
-      !getenv("VADC_NO_TC_GEMM")) {
+      !env_on("VADC_NO_TC_GEMM")) {
     // score_memory [N,m] . keys [m,d] (keys read MN-major) on tcgen05
     Carver ws(workspace, workspace_bytes);
     void* ss = ws.take<uint8_t>(tc_gemm_split_bytes(N, m));

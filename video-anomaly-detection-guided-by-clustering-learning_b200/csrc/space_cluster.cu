@@ -153,7 +153,7 @@ struct SpaceGcEpilogue {
 static bool space_tc_ok(long long M, int P, int C, int K) {
   return M >= 1 && (P % 8) == 0 && (K % 64) == 0 && C <= 65535 && (long long)C * M < (1ll << 31) &&
          (long long)C * K < (1ll << 31) && (double)M * P * K * C >= (double)(1ll << 28) && vadc_device_ok() != 0 &&
-         !getenv("VADC_NO_TC_GEMM");
+         !env_on("VADC_NO_TC_GEMM");
 }
 
 static int space_ln_bwd_blocks(long long T) {
