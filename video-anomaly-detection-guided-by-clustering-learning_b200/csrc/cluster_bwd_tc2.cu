@@ -64,8 +64,7 @@ namespace bt2 {
 constexpr int kTok = 64;                     // tokens per tile
 constexpr int kK = 32;                       // centroids
 constexpr int kThreads = 512;
-constexpr int kProd = 7;                     // producer warps
-constexpr int kUnits = 2 + kTok / 4;         // producer units per tile: 2 x 32 rows of A, then 16 x 4 rows of gR
+constexpr int kProd = 7;                     // producer warps: 6 convert gR, the last one the A rows
 constexpr int kMmaWarp = 15;
 constexpr uint32_t kBlk = kTok * 128u;       // one [64 rows x 128 B] operand block
 constexpr uint32_t kBox = 32u * 128u;        // one [32 rows x 128 B] fp32 box (TMA load of x / TMA store of gx)
@@ -87,7 +86,7 @@ __host__ __device__ inline Plan plan(int C) {
   p.zero_off = off; off += kBlk;                           // constant zeros (the other half of S5's M)
   p.tr_off = off; off += 2u * kBlk;                        // [parity][64 tokens x 128 B]: r_hi | r_lo
   p.cen_off = off; off += ncb * kBlk;                      // [C/64][64 rows x 128 B]: rows 0..31 cen_hi, 32..63 cen_lo
-  p.slot_off = off; off += kProd * p.slot;                 // per producer warp: 4 raw gR rows
+  p.slot_off = off; off += (kProd - 1) * p.slot;           // per gR producer warp: 4 raw gR rows
   p.scal_off = off; off += 2u * 5u * kTok * 4u;            // E1 row scalars [parity][rsum, s1r, s2r, rs, -mu rs][64]
   p.gam_off = off; off += (uint32_t)C * 4u;
   p.bet_off = off; off += (uint32_t)C * 4u;
@@ -156,6 +155,25 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// six non-blocking probes issued back to back: ONE ~150-cycle round trip (separate probes serialise on their predicates)
+__device__ __forceinline__ uint32_t mbar_test6(const uint32_t (&bar)[6], const uint32_t (&parity)[6]) {
+  uint32_t mask;
+  asm volatile(
+      "{\n\t.reg .pred q0, q1, q2, q3, q4, q5;\n\t.reg .u32 t0, t1, t2, t3, t4, t5;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q0, [%1], %7;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q1, [%2], %8;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q2, [%3], %9;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q3, [%4], %10;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q4, [%5], %11;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q5, [%6], %12;\n\t"
+      "selp.u32 t0, 1, 0, q0;\n\tselp.u32 t1, 2, 0, q1;\n\tselp.u32 t2, 4, 0, q2;\n\t"
+      "selp.u32 t3, 8, 0, q3;\n\tselp.u32 t4, 16, 0, q4;\n\tselp.u32 t5, 32, 0, q5;\n\t"
+      "or.b32 t0, t0, t1;\n\tor.b32 t2, t2, t3;\n\tor.b32 t4, t4, t5;\n\tor.b32 t0, t0, t2;\n\tor.b32 %0, t0, t4;\n\t}"
+      : "=r"(mask)
+      : "r"(bar[0]), "r"(bar[1]), "r"(bar[2]), "r"(bar[3]), "r"(bar[4]), "r"(bar[5]),
+        "r"(parity[0]), "r"(parity[1]), "r"(parity[2]), "r"(parity[3]), "r"(parity[4]), "r"(parity[5]) : "memory");
+  return mask;
+}
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
@@ -177,6 +195,7 @@ __device__ __forceinline__ void tma_load_2d_u32(const void* tmap, uint32_t smem_
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -267,6 +286,7 @@ struct Params {
   const float* ln_w; const float* ln_b; const uint8_t* cimage; const float* cvec; const float* g_loss_sq;
   float* part_p; float* part_rcol; float* part_q;        // [grid][128 slots][C], [grid][2][32], [grid][2][C]
   long long N; float alpha; int pf;
+  int mma_sleep;                                         // ns the MMA thread sleeps when nothing is ready (0 = spin)
   unsigned long long* trace;                             // debugging: per-warp event log of one CTA (VADC_BWD_TRACE builds)
   int trace_cta;
 };
@@ -310,7 +330,7 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
     mbar_init(&bars[B_GEMPTY], 1);
     mbar_init(&bars[B_G1FULL0], 1); mbar_init(&bars[B_G1FULL1], 1);
     mbar_init(&bars[B_G1EMPTY0], 2); mbar_init(&bars[B_G1EMPTY1], 2);
-    mbar_init(&bars[B_AFULL], 2); mbar_init(&bars[B_AEMPTY], 1);
+    mbar_init(&bars[B_AFULL], 1); mbar_init(&bars[B_AEMPTY], 1);
     mbar_init(&bars[B_RFULL0], 1); mbar_init(&bars[B_RFULL1], 1);
     mbar_init(&bars[B_REMPTY0], 1); mbar_init(&bars[B_REMPTY1], 1);
     mbar_init(&bars[B_ACCFULL], 1);
@@ -346,63 +366,36 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
   const bool is_e3 = (warp & 3) < 2 && warp >= 4;
   if (!is_e1 && !is_e3 && warp != kMmaWarp) {
     // ======================================================================= PRODUCERS
-    // Units of a tile: 0, 1 = the A rows (32 rows x 32 centroids each), 2..17 = gR (4 rows each).  A gR unit is four rows
-    // {b, b+1, b+4, b+5}, b = 8 (v/2) + 2 (v%2): 8 lanes per row (lane j owns float4 chunks j, j+8, ...), and the two rows
-    // that share a 16-lane store phase differ by 4 (disjoint banks after the 128B swizzle).  The unit's raw rows arrive in
-    // the warp's private slot by two bulk copies (rows b, b+1 and rows b+4, b+5 are contiguous in global memory) that
-    // were issued while the warp was still converting its previous unit.
+    // gR: producer warps 0..5, 16 four-row units per tile (warp w owns units w, w+6, w+12 of every tile).  A unit is the
+    // rows {b, b+1, b+4, b+5}, b = 8 (v/2) + 2 (v%2): 8 lanes per row (lane j owns float4 chunks j, j+8, ...), and the two
+    // rows that share a 16-lane store phase differ by 4 (disjoint banks after the 128B swizzle).  The raw rows arrive in
+    // the warp's private slot by two bulk copies (rows b, b+1 and rows b+4, b+5 are contiguous in global memory).
+    // The gR operand tile is single buffered, so between the release of tile t and the completion of tile t+1 nothing
+    // but conversion should happen: a warp keeps its next TWO units in registers and a third one in (or on its way to) the
+    // slot — all of a tile's units are on chip before the tile is released, whatever the load latency is at that moment
+    // (first version: one unit in registers, one in the slot; every third unit of a warp paid the full latency, 6.7 k
+    // cycles from release to completion in the event trace).
+    // A rows: producer warp 6, two 32-row units per tile, loaded into registers while it waits for the tile.
     const int pw = warp < 2 ? warp : (warp >> 2) * 2 + (warp & 1);   // warps 0,1,6,7,10,11,14 -> 0..6
     const int lj = lane & 7, lg = lane >> 3;
     const int rsel = (lg & 1) * 4 + (lg >> 1);                       // row of this lane group inside the 8-row group: 0,4,1,5
-    const int srow = (rsel & 1) + (rsel >> 2) * 2;                   // ... and inside the slot (rows b, b+1, b+4, b+5)
-    const uint32_t slot32 = smem_u32(smem + pl.slot_off) + (uint32_t)pw * pl.slot;
-    uint64_t* sbar = &bars[B_SLOT0 + pw];
-    struct Pos { int it, u; };
-    auto advance = [&](Pos& q) { q.u += kProd; if (q.u >= kUnits) { q.u -= kUnits; ++q.it; } };
-    auto next_g = [&](Pos& q) { do { advance(q); } while (q.u < 2); };
-    auto issue_load = [&](const Pos& q) {                           // lane 0: bulk copies of gR unit q into the slot
-      const int v = q.u - 2;
-      const long long tile = (long long)blockIdx.x + (long long)q.it * gridDim.x;
-      const long long r0 = tile * kTok + (v >> 1) * 8 + (v & 1) * 2;
-      const long long n0 = max(0ll, min(2ll, p.N - r0)), n1 = max(0ll, min(2ll, p.N - (r0 + 4)));
-      const uint32_t rowb = (uint32_t)C * 4u;
-      if (n0 + n1 > 0) {
-        mbar_expect_tx(sbar, (uint32_t)(n0 + n1) * rowb);
-        bulk_g2s_u32(slot32, p.gR + r0 * C, (uint32_t)n0 * rowb, sbar);
-        if (n1 > 0) bulk_g2s_u32(slot32 + 2u * rowb, p.gR + (r0 + 4) * C, (uint32_t)n1 * rowb, sbar);
-      } else {
-        mbar_arrive(sbar);                                          // a unit past the end: nothing to copy
-      }
-      if (p.pf > 0 && (v & 1) == 0 && q.it + p.pf < nmine) {        // L2 prefetch: same 8-row group, pf tiles ahead
-        const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
-        const long long rows = min(8ll, p.N - rn);
-        if (rows > 0) prefetch_l2_bulk(p.gR + rn * C, (uint32_t)(rows * C * 4));
-      }
-    };
-    Pos pc{0, pw};
-    {
-      Pos pl0 = pc;
-      if (pl0.u < 2) next_g(pl0);
-      if (lane == 0 && pl0.it < nmine) issue_load(pl0);
-    }
-    uint32_t sphase = 0;
-#pragma unroll 1
-    while (pc.it < nmine) {
-      const int it = pc.it, u = pc.u;
-      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (u < 2) {
-        // ---- A rows: 32 rows x 32 centroids, lane = (row, float4)
-        const long long rb = tile * kTok + u * 32;
-        float4 a[8];
+    if (pw == kProd - 1) {
+      float4 a[16];
+      auto load_a = [&](int it) {
+        const long long rb = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const long long row = rb + (j >> 1) * 8 + (j & 1) * 2 + rsel;
-          a[j] = row < p.N ? ldg_nc(reinterpret_cast<const float4*>(p.A + row * K) + lj) : make_float4(0, 0, 0, 0);
+        for (int j = 0; j < 16; ++j) {
+          const long long row = rb + (j >> 3) * 32 + ((j & 7) >> 1) * 8 + (j & 1) * 2 + rsel;
+          a[j] = (it < nmine && row < p.N) ? ldg_nc(reinterpret_cast<const float4*>(p.A + row * K) + lj) : make_float4(0, 0, 0, 0);
         }
+      };
+      load_a(0);
+#pragma unroll 1
+      for (int it = 0; it < nmine; ++it) {
         mbar_wait_spin(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));   // tile A is free once S5a of the previous tile has completed
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t r = (uint32_t)(u * 32 + (j >> 1) * 8 + (j & 1) * 2 + rsel);
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t r = (uint32_t)((j >> 3) * 32 + ((j & 7) >> 1) * 8 + (j & 1) * 2 + rsel);
           uint32_t a1, a2, b1, b2;
           split2_bf(a[j].x, a[j].y, a1, a2);
           split2_bf(a[j].z, a[j].w, b1, b2);
@@ -412,36 +405,68 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_AFULL]);
-      } else {
-        // ---- gR unit
-        const int v = u - 2;
-        const int r = (v >> 1) * 8 + (v & 1) * 2 + rsel;
-        const bool live = tile * kTok + r < p.N;
-        TR(0, it);
+        load_a(it + 1);
+      }
+    } else {
+      const int srow = (rsel & 1) + (rsel >> 2) * 2;                 // this lane group's row inside the slot (rows b, b+1, b+4, b+5)
+      const uint32_t slot32 = smem_u32(smem + pl.slot_off) + (uint32_t)pw * pl.slot;
+      uint64_t* sbar = &bars[B_SLOT0 + pw];
+      struct Pos { int it, v; };
+      auto next = [&](Pos q) { q.v += kProd - 1; if (q.v >= kTok / 4) { q.v = pw; ++q.it; } return q; };
+      auto issue = [&](const Pos& q) {                               // lane 0: bulk copies of gR unit q into the slot
+        if (lane != 0 || q.it >= nmine) return;
+        const int v = q.v;
+        const long long tile = (long long)blockIdx.x + (long long)q.it * gridDim.x;
+        const long long r0 = tile * kTok + (v >> 1) * 8 + (v & 1) * 2;
+        const long long n0 = max(0ll, min(2ll, p.N - r0)), n1 = max(0ll, min(2ll, p.N - (r0 + 4)));
+        const uint32_t rowb = (uint32_t)C * 4u;
+        if (n0 + n1 > 0) {
+          mbar_expect_tx(sbar, (uint32_t)(n0 + n1) * rowb);
+          bulk_g2s_u32(slot32, p.gR + r0 * C, (uint32_t)n0 * rowb, sbar);
+          if (n1 > 0) bulk_g2s_u32(slot32 + 2u * rowb, p.gR + (r0 + 4) * C, (uint32_t)n1 * rowb, sbar);
+        } else {
+          mbar_arrive(sbar);                                         // a unit past the end: nothing to copy
+        }
+        if (p.pf > 0 && (v & 1) == 0 && q.it + p.pf < nmine) {       // L2 prefetch: same 8-row group, pf tiles ahead
+          const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
+          const long long rows = min(8ll, p.N - rn);
+          if (rows > 0) prefetch_l2_bulk(p.gR + rn * C, (uint32_t)(rows * C * 4));
+        }
+      };
+      uint32_t sphase = 0;
+      auto fetch = [&](float4 (&R)[F4], const Pos& q) {              // slot -> registers (the unit's copies were issued before)
+        if (q.it >= nmine) return;
+        const int r = (q.v >> 1) * 8 + (q.v & 1) * 2 + rsel;
+        const bool live = ((long long)blockIdx.x + (long long)q.it * gridDim.x) * kTok + r < p.N;
+        TR(0, q.it);
         mbar_wait_spin(sbar, sphase);
         sphase ^= 1u;
-        float4 g4[F4];
         const uint32_t sr = slot32 + (uint32_t)srow * ((uint32_t)C * 4u) + (uint32_t)lj * 16u;
 #pragma unroll
-        for (int i = 0; i < F4; ++i) g4[i] = live ? lds128f(sr + (uint32_t)i * 128u) : make_float4(0, 0, 0, 0);
-        __syncwarp();                                    // every lane holds its chunks: the slot may be refilled
-        {
-          Pos nl = pc;
-          next_g(nl);
-          if (lane == 0 && nl.it < nmine) issue_load(nl);
-        }
-        TR(3, it);
+        for (int i = 0; i < F4; ++i) R[i] = live ? lds128f(sr + (uint32_t)i * 128u) : make_float4(0, 0, 0, 0);
+        // The slot is refilled by an ASYNC-proxy write (bulk copy) issued by lane 0 right after this: the generic-proxy
+        // reads above must have been performed first.  __syncwarp() alone orders only generic accesses — without the
+        // proxy fence a refill that hit in L2 overtook reads still queued in the load/store unit (stress test: pairs of
+        // gR rows of a tile taken from the NEXT unit, ~1 launch in 20 on ragged multi-CTA shapes).
+        fence_async_smem();
+        __syncwarp();                                                // every lane holds its chunks: the slot may be refilled
+        TR(3, q.it);
+      };
+      auto convert = [&](const float4 (&R)[F4], const Pos& q) {      // registers -> two-term bf16 split in the operand tile
+        const int it = q.it;
+        const int r = (q.v >> 1) * 8 + (q.v & 1) * 2 + rsel;
         // byte offset of this lane's float4 number lj inside its row's first 64-channel block; float4 lj + 8 i sits in
         // block i/2 at chunk (lj/2 + 4 (i%2)) ^ (r%8): bit 6 of the offset flips with i%2 (all operand bases are 1 KB aligned)
         const uint32_t e0 = (uint32_t)r * 128u + (((uint32_t)(lj >> 1) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)(lj & 1) * 8u;
         // G is free once S1 / S5a of the previous tile have completed
         mbar_wait_spin(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));
+        TR(4, it);
         const uint32_t gb = sG32 + e0;
 #pragma unroll
         for (int i = 0; i < F4; ++i) {
           uint32_t a1, a2, b1, b2;
-          split2_bf(g4[i].x, g4[i].y, a1, a2);
-          split2_bf(g4[i].z, g4[i].w, b1, b2);
+          split2_bf(R[i].x, R[i].y, a1, a2);
+          split2_bf(R[i].z, R[i].w, b1, b2);
           sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk, a1, b1);
           sts64((gb ^ ((i & 1) ? 64u : 0u)) + (uint32_t)(i >> 1) * kBlk + pl.xterm, a2, b2);
         }
@@ -450,8 +475,20 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_GFULL]);
         TR(2, it);
+      };
+      float4 RA[F4], RB[F4];
+      Pos pa{0, pw}, pb = next(pa), ps = next(pb), pn = next(ps);   // in RA, in RB, in the slot, next to request
+      issue(pa); fetch(RA, pa);
+      issue(pb); fetch(RB, pb);
+      issue(ps);
+#pragma unroll 1
+      while (pa.it < nmine) {
+        convert(RA, pa);
+        fetch(RA, ps); pa = ps; ps = pn; pn = next(pn); issue(ps);
+        if (pb.it >= nmine) break;
+        convert(RB, pb);
+        fetch(RB, ps); pb = ps; ps = pn; pn = next(pn); issue(ps);
       }
-      advance(pc);
     }
   } else if (is_e1) {
     // ======================================================================= E1
@@ -597,19 +634,19 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
       const uint32_t rx = (uint32_t)(lane & 7);          // == rl & 7
       const uint32_t xhrow = sXH32 + (uint32_t)e3 * kBlk + (uint32_t)rl * 128u;
       const uint32_t sGam32 = smem_u32(sGam), sBet32 = smem_u32(sBet);
-      auto load_boxes = [&](int it) {                    // lane 0: raw x of tile `it`, rows q 32.., channels e3 64.. (two boxes)
+      auto load_box = [&](int it, int ch) {              // lane 0: raw x of tile `it`, rows q 32.., channels e3 64 + ch 32..
         const long long r0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + q * 32;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          mbar_expect_tx(&xrbar[ch], kBox);
-          tma_load_2d_u32(&mapX, box32 + (uint32_t)ch * kBox, &xrbar[ch], e3 * 64 + ch * 32, (int)r0);
-        }
+        mbar_expect_tx(&xrbar[ch], kBox);
+        tma_load_2d_u32(&mapX, box32 + (uint32_t)ch * kBox, &xrbar[ch], e3 * 64 + ch * 32, (int)r0);
       };
-      if (lane == 0) load_boxes(0);
+      if (lane == 0) { load_box(0, 0); load_box(0, 1); }
       for (int it = 0; it < nmine; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
         const long long row0 = tile * kTok;
         const int par = it & 1;
+        // second box of THIS tile: its bytes held gx of the previous tile until that store had read them (the wait
+        // overlaps the wait for this tile's accumulator); the first box was requested before the previous tile ended
+        if (it > 0 && lane == 0) { bulk_wait_read0(); load_box(it, 1); }
         TR(19, it);
         mbar_wait(&bars[B_RFULL0 + par], (uint32_t)((it >> 1) & 1));
         TR(20, it);
@@ -679,22 +716,20 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
           if (lane == 0) {
             tma_store_2d_hint(&mapGx, box32 + (uint32_t)ch * kBox, c0, (int)(row0 + q * 32), pol);
             bulk_commit();
+            // the first box's store was issued half a tile ago: it has read its bytes, the next tile's x may land there
+            if (ch == 1 && it + 1 < nmine) { bulk_wait_read1(); load_box(it + 1, 0); }
           }
           if (ch == 1) {                                 // accumulator consumed, xhat operand rows written
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&bars[B_ACCEMPTY]); mbar_arrive(&bars[B_XHFULL]); }
+            TR(23, it);
           }
           butterfly<8>(xh, lane);
 #pragma unroll
           for (int j = 0; j < 8; ++j) accq[ch][j] += xh[j];
         }
         TR(22, it);
-        // the stores have finished reading the boxes: fetch the next tile's x into them
-        if (lane == 0) {
-          bulk_wait_read0();
-          if (it + 1 < nmine) load_boxes(it + 1);
-        }
       }
       if (lane == 0) bulk_wait0();
       // finish the butterflies: lane l ends with Q of channel c0 + l over this warp's rows
@@ -726,11 +761,26 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
     const uint32_t loC_k = (sCen32 >> 4) & 0x3FFFu, loC_mn = loC_k | kLbo;
     mbar_wait(&bars[B_CEN], 0);
     int n1 = 0, n5a = 0, n3 = 0, n5b = 0;
+    uint32_t last_ready = 0xffffffffu;
+    const uint32_t bar32 = smem_u32(bars);
+    // The issue loop polls SEVERAL barriers: mbarrier.try_wait is a hardware sleep with a time limit (a failed probe costs
+    // ~2 k cycles here: the event trace showed S3 issued 4-5 k cycles after both of its inputs were ready, and E3 — the
+    // busiest role — idle for exactly that long), so every probe is the non-blocking test_wait, and all six sit in ONE asm
+    // block, issued back to back before the first predicate is used (one ~150-cycle round trip per iteration, not six).
     while (n5b < nmine) {
-      const int progress0 = n1 + n3 + n5a + n5b;
+      const uint32_t pb[6] = {bar32 + 8u * (uint32_t)(B_RFULL0 + (n3 & 1)), bar32 + 8u * B_ACCEMPTY, bar32 + 8u * B_GFULL,
+                              bar32 + 8u * (uint32_t)(B_G1EMPTY0 + (n1 & 1)), bar32 + 8u * B_AFULL, bar32 + 8u * B_XHFULL};
+      const uint32_t pp[6] = {(uint32_t)((n3 >> 1) & 1), (uint32_t)((n3 & 1) ^ 1), (uint32_t)(n1 & 1),
+                              (uint32_t)(((n1 >> 1) & 1) ^ 1), (uint32_t)(n5a & 1), (uint32_t)(n5b & 1)};
+      const uint32_t ready = mbar_test6(pb, pp);
+      if constexpr (TRACE) {                             // what the issue thread SEES, and when: one entry per change of the mask
+        if (ready != last_ready) { TR(64 + (int)ready, n3); last_ready = ready; }
+      }
+      const bool rfull = ready & 1u, accempty = ready & 2u, gfull = ready & 4u, g1empty = ready & 8u, afull = ready & 16u,
+                 xhfull = ready & 32u;
+      bool progress = false;
       // ---- S3 (feeds E3): acc = r_lo cen_hi + r_hi cen_lo + r_hi cen_hi
-      if (n3 < n1 && mbar_try_wait(&bars[B_RFULL0 + (n3 & 1)], (uint32_t)((n3 >> 1) & 1)) &&
-          mbar_try_wait(&bars[B_ACCEMPTY], (uint32_t)((n3 & 1) ^ 1))) {
+      if (n3 < n1 && rfull && accempty) {
         tc_fence_after();
         const uint32_t d = tmem + kColAcc;
         const uint32_t loTR = loTR_k + (uint32_t)(n3 & 1) * (kBlk >> 4);
@@ -747,10 +797,10 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
         mma_commit(&bars[B_ACCFULL]);
         TR(32, n3);
         ++n3;
+        progress = true;
       }
       // ---- S1 (feeds E1): G1[:, 0:32] = gR_hi cen_hi + gR_lo cen_hi, G1[:, 32:64] = gR_hi cen_lo
-      if (n1 < nmine && mbar_try_wait(&bars[B_GFULL], (uint32_t)(n1 & 1)) &&
-          mbar_try_wait(&bars[B_G1EMPTY0 + (n1 & 1)], (uint32_t)(((n1 >> 1) & 1) ^ 1))) {
+      if (n1 < nmine && gfull && g1empty) {
         tc_fence_after();
         const uint32_t d = tmem + kColG1 + (uint32_t)((n1 & 1) * 64);
 #pragma unroll
@@ -768,9 +818,28 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
         mma_commit(&bars[B_G1FULL0 + (n1 & 1)]);
         TR(30, n1);
         ++n1;
+        progress = true;
       }
-      // ---- S5b (background, after E3 of its tile): PT[64:128] += [r_hi | r_lo]^T (xhat_hi + xhat_lo)
-      if (n5b < n3 && n5b < n5a && mbar_try_wait(&bars[B_XHFULL], (uint32_t)(n5b & 1))) {
+      // ---- S5a (background; its completion frees the gR tile for the producers): PT[0:64] += [A_hi | A_lo]^T (gR_hi + gR_lo)
+      if (n5a < n1 && afull) {
+        tc_fence_after();
+VADC_S5_UNROLL
+        for (int t = 0; t < 2; ++t) {
+VADC_S5_UNROLL
+          for (int ks = 0; ks < kTok / 16; ++ks) {
+            const uint64_t ad = desc_at(loTA_mn, kHi, (uint32_t)ks * 2048u);
+            const uint64_t bd = desc_at(loG_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
+            mma_f16(tmem + kColPT, ad, bd, idesc5, (n5a > 0 || t > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        mma_commit(&bars[B_GEMPTY]);
+        mma_commit(&bars[B_AEMPTY]);
+        TR(31, n5a);
+        ++n5a;
+        progress = true;
+      }
+      // ---- S5b (background, after E3 of its tile; frees the xhat tile and r[parity]): PT[64:128] += [r_hi | r_lo]^T (xhat_hi + xhat_lo)
+      if (n5b < n3 && n5b < n5a && xhfull) {
         tc_fence_after();
         const uint32_t loZR_mn = (n5b & 1) ? loZR_mn1 : loZR_mn0;
 VADC_S5_UNROLL
@@ -786,25 +855,9 @@ VADC_S5_UNROLL
         mma_commit(&bars[B_REMPTY0 + (n5b & 1)]);
         TR(33, n5b);
         ++n5b;
+        progress = true;
       }
-      // ---- S5a (background): PT[0:64] += [A_hi | A_lo]^T (gR_hi + gR_lo)
-      if (n5a < n1 && mbar_try_wait(&bars[B_AFULL], (uint32_t)(n5a & 1))) {
-        tc_fence_after();
-VADC_S5_UNROLL
-        for (int t = 0; t < 2; ++t) {
-VADC_S5_UNROLL
-          for (int ks = 0; ks < kTok / 16; ++ks) {
-            const uint64_t ad = desc_at(loTA_mn, kHi, (uint32_t)ks * 2048u);
-            const uint64_t bd = desc_at(loG_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
-            mma_f16(tmem + kColPT, ad, bd, idesc5, (n5a > 0 || t > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        mma_commit(&bars[B_GEMPTY]);
-        mma_commit(&bars[B_AEMPTY]);
-        TR(31, n5a);
-        ++n5a;
-      }
-      if (n1 + n3 + n5a + n5b == progress0) __nanosleep(40);   // nothing was ready: leave the issue slots to the other roles
+      if (!progress && p.mma_sleep > 0) __nanosleep((unsigned)p.mma_sleep);   // (a sleep costs far more than its nominal length: default spin)
     }
     mma_commit(&bars[B_DONE]);
     mbar_wait(&bars[B_DONE], 0);
@@ -981,7 +1034,7 @@ int launch_cluster_bwd_tc2(const float* x, const float* mu, const float* rstd, c
   const int trace_cta = 0;
 #endif
   bt2::Params p{x, gR, D, A, mu, rstd, rowstats, ln_w, ln_b, image, cvec, g_loss_sq, part_p, part_rcol, part_q,
-                N, alpha, env_int("VADC_BWD_PF", 1), trace, trace_cta};
+                N, alpha, env_int("VADC_BWD_PF", 1), env_int("VADC_BWD_SLEEP", 0), trace, trace_cta};
   bool launched = false;
 #ifdef VADC_BWD_TRACE_BUILD
 #define BT_KERN(F4_) (trace ? bt2::cluster_bwd_tc2_kernel<F4_, true> : bt2::cluster_bwd_tc2_kernel<F4_, false>)
