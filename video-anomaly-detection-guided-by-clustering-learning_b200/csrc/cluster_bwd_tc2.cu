@@ -70,15 +70,15 @@ constexpr uint32_t kBlk = kTok * 128u;       // one [64 rows x 128 B] operand bl
 constexpr uint32_t kBox = 32u * 128u;        // one [32 rows x 128 B] fp32 box (TMA load of x / TMA store of gx)
 
 struct Plan {
-  uint32_t xr_off, xh_off, g_off, ta_off, zero_off, tr_off, cen_off, slot_off, scal_off, gam_off, bet_off, cvec_off, misc_off, total;
-  uint32_t xterm, slot;
+  uint32_t xr_off, xh_off, g_off, ta_off, zero_off, tr_off, cen_off, da_off, scal_off, gam_off, bet_off, cvec_off, misc_off, total;
+  uint32_t xterm;
 };
 
 __host__ __device__ inline Plan plan(int C) {
   Plan p;
   const uint32_t ncb = (uint32_t)C / 64u;
   uint32_t off = 0;
-  p.xterm = ncb * kBlk; p.slot = 4u * (uint32_t)C * 4u;
+  p.xterm = ncb * kBlk;
   p.xr_off = off; off += 2u * ncb * 2u * kBox;             // [E3 warp = (channel group, token half)][2 boxes]: raw x, then gx
   p.xh_off = off; off += 2u * p.xterm;                     // xhat operand [2 terms][C/64][64 x 128 B]
   p.g_off = off; off += 2u * p.xterm;                      // gR operand   [2 terms][C/64][64 x 128 B]
@@ -86,7 +86,7 @@ __host__ __device__ inline Plan plan(int C) {
   p.zero_off = off; off += kBlk;                           // constant zeros (the other half of S5's M)
   p.tr_off = off; off += 2u * kBlk;                        // [parity][64 tokens x 128 B]: r_hi | r_lo
   p.cen_off = off; off += ncb * kBlk;                      // [C/64][64 rows x 128 B]: rows 0..31 cen_hi, 32..63 cen_lo
-  p.slot_off = off; off += (kProd - 1) * p.slot;           // per gR producer warp: 4 raw gR rows
+  p.da_off = off; off += 2u * kBlk;                        // E1: the tile's D rows and A rows, [64 x 128 B] each (TMA, SWIZZLE_128B)
   p.scal_off = off; off += 2u * 5u * kTok * 4u;            // E1 row scalars [parity][rsum, s1r, s2r, rs, -mu rs][64]
   p.gam_off = off; off += (uint32_t)C * 4u;
   p.bet_off = off; off += (uint32_t)C * 4u;
@@ -98,7 +98,7 @@ __host__ __device__ inline Plan plan(int C) {
 
 enum { B_CEN = 0, B_GFULL, B_GEMPTY, B_G1FULL0, B_G1FULL1, B_G1EMPTY0, B_G1EMPTY1, B_AFULL, B_AEMPTY,
        B_RFULL0, B_RFULL1, B_REMPTY0, B_REMPTY1, B_ACCFULL, B_ACCEMPTY, B_XHFULL, B_XHEMPTY, B_DONE,
-       B_XR0, B_SLOT0 = B_XR0 + 12, B_COUNT = B_SLOT0 + kProd };
+       B_XR0, B_DAFULL = B_XR0 + 12, B_COUNT };
 static_assert(B_COUNT * 8 <= 448, "mbarriers overlap the TMEM slot");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -293,7 +293,8 @@ struct Params {
 
 template <int F4, bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
-cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_constant__ CUtensorMap mapX, const Params p) {
+cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_constant__ CUtensorMap mapX,
+                       const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapA, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int C = F4 * 32, K = kK, NCB = C / 64;
@@ -332,17 +333,19 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
     mbar_init(&bars[B_G1EMPTY0], 2); mbar_init(&bars[B_G1EMPTY1], 2);
     mbar_init(&bars[B_AFULL], 1); mbar_init(&bars[B_AEMPTY], 1);
     mbar_init(&bars[B_RFULL0], 1); mbar_init(&bars[B_RFULL1], 1);
-    mbar_init(&bars[B_REMPTY0], 1); mbar_init(&bars[B_REMPTY1], 1);
+    mbar_init(&bars[B_REMPTY0], 2); mbar_init(&bars[B_REMPTY1], 2);   // S5b's commit + the column sums of producer warp 6
     mbar_init(&bars[B_ACCFULL], 1);
     mbar_init(&bars[B_ACCEMPTY], kE3Warps);
     mbar_init(&bars[B_XHFULL], kE3Warps);
     mbar_init(&bars[B_XHEMPTY], 1);
     mbar_init(&bars[B_DONE], 1);
     for (int i = 0; i < 12; ++i) mbar_init(&bars[B_XR0 + i], 1);
-    for (int i = 0; i < kProd; ++i) mbar_init(&bars[B_SLOT0 + i], 1);
+    mbar_init(&bars[B_DAFULL], 1);
     fence_mbar_init();
     prefetch_tmap(&mapGx);
     prefetch_tmap(&mapX);
+    prefetch_tmap(&mapD);
+    prefetch_tmap(&mapA);
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, ncols);
   for (int c = tid; c < C; c += kThreads) {
@@ -362,6 +365,11 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
   const uint32_t sZero32 = smem_u32(smem + pl.zero_off);
   const uint32_t sCen32 = smem_u32(smem + pl.cen_off);
 
+  // roles by warp (a warp reads TMEM lanes 32 (warp % 4)..; warp % 4 is also its scheduler / sub-partition):
+  //   E1 2,3 (G1 in lanes 64..127)   E3 4,5,8,9,12,13 (accumulator lanes 0..63)   P 0,1,6,7,10,11 gR, 14 A rows   MMA 15
+  // (tried: S3 split in two so that two E3 warps could read lanes 64..127 on the sub-partitions of warps 2,3 — 2+2+1+1
+  //  E3 warps per sub-partition instead of 3+3+0+0: 13 % SLOWER, E1 then shares its sub-partition with an E3 warp and
+  //  becomes the pace setter: the kernel is bound by issue / pipe throughput, moving work between sub-partitions is zero-sum)
   const bool is_e1 = warp == 2 || warp == 3;
   const bool is_e3 = (warp & 3) < 2 && warp >= 4;
   if (!is_e1 && !is_e3 && warp != kMmaWarp) {
@@ -389,10 +397,32 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
           a[j] = (it < nmine && row < p.N) ? ldg_nc(reinterpret_cast<const float4*>(p.A + row * K) + lj) : make_float4(0, 0, 0, 0);
         }
       };
+      // ... and rcol = colsum(r) (for gcenters / g_beta): lane l adds up the 32-bit word l of every row of the r operand
+      // tile, i.e. the slots 2l, 2l+1 of [r_hi | r_lo] (conflict free: a row's 32 words are a permutation of the banks),
+      // instead of a 32 x 32 register butterfly in E1 (2.2 k cycles of E1's 10 k per tile in the event trace).  Order of
+      // work: A rows of tile it+1 (wanted ~2 k cycles after S1 of tile it), then the sums of tile it-1 (its r tile
+      // completes ~5 k cycles after S1 of tile it).
+      float2 rc = make_float2(0.f, 0.f);
+      auto colsum_r = [&](int t) {                       // tile t: wait for E1, add, hand the tile back
+        mbar_wait(&bars[B_RFULL0 + (t & 1)], (uint32_t)((t >> 1) & 1));
+        const uint32_t tr32 = sTR32 + (uint32_t)(t & 1) * kBlk;
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+#pragma unroll 8
+        for (int r = 0; r < kTok; r += 2) {
+          uint32_t w0, w1;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(tr32 + sw128((uint32_t)r, (uint32_t)lane * 4u)));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(tr32 + sw128((uint32_t)r + 1u, (uint32_t)lane * 4u)));
+          acc0 = add2(acc0, bf_pair(w0));
+          acc1 = add2(acc1, bf_pair(w1));
+        }
+        rc = add2(rc, add2(acc0, acc1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_REMPTY0 + (t & 1)]);
+      };
       load_a(0);
 #pragma unroll 1
       for (int it = 0; it < nmine; ++it) {
-        mbar_wait_spin(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));   // tile A is free once S5a of the previous tile has completed
+        mbar_wait(&bars[B_AEMPTY], (uint32_t)((it & 1) ^ 1));        // tile A is free once S5a of the previous tile has completed
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const uint32_t r = (uint32_t)((j >> 3) * 32 + ((j & 7) >> 1) * 8 + (j & 1) * 2 + rsel);
@@ -406,50 +436,39 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_AFULL]);
         load_a(it + 1);
+        if (it >= 2) colsum_r(it - 2);
       }
+      if (nmine >= 2) colsum_r(nmine - 2);
+      colsum_r(nmine - 1);
+      // lanes 0..15 hold the r_hi slots 2l, 2l+1, lanes 16..31 the r_lo slots: rcol_k = hi + lo
+      rc.x += __shfl_down_sync(0xffffffffu, rc.x, 16);
+      rc.y += __shfl_down_sync(0xffffffffu, rc.y, 16);
+      float* pr = p.part_rcol + (size_t)blockIdx.x * 2 * K;
+      if (lane < 16) { pr[2 * lane] = rc.x; pr[2 * lane + 1] = rc.y; }
+      pr[K + lane] = 0.f;
     } else {
-      const int srow = (rsel & 1) + (rsel >> 2) * 2;                 // this lane group's row inside the slot (rows b, b+1, b+4, b+5)
-      const uint32_t slot32 = smem_u32(smem + pl.slot_off) + (uint32_t)pw * pl.slot;
-      uint64_t* sbar = &bars[B_SLOT0 + pw];
+      // gR: plain 128-bit global loads into register sets (one per unit of a tile), no shared-memory staging.  (Second version of this kernel: bulk copies into a private slot per warp.  The event
+      // trace showed the issue of a bulk copy taking 1-2 k cycles, and a TMA store's shared-memory read 2.4 k: every
+      // TMA operation of the CTA — the x boxes, the gx stores, the slots — queues in one unit, and a store that waits
+      // for the memory system blocks the copies behind it.  The x boxes and gx stores stay on TMA, one tile ahead of
+      // their use; the latency-critical gR path does not go through it any more.)
       struct Pos { int it, v; };
-      auto next = [&](Pos q) { q.v += kProd - 1; if (q.v >= kTok / 4) { q.v = pw; ++q.it; } return q; };
-      auto issue = [&](const Pos& q) {                               // lane 0: bulk copies of gR unit q into the slot
-        if (lane != 0 || q.it >= nmine) return;
-        const int v = q.v;
-        const long long tile = (long long)blockIdx.x + (long long)q.it * gridDim.x;
-        const long long r0 = tile * kTok + (v >> 1) * 8 + (v & 1) * 2;
-        const long long n0 = max(0ll, min(2ll, p.N - r0)), n1 = max(0ll, min(2ll, p.N - (r0 + 4)));
-        const uint32_t rowb = (uint32_t)C * 4u;
-        if (n0 + n1 > 0) {
-          mbar_expect_tx(sbar, (uint32_t)(n0 + n1) * rowb);
-          bulk_g2s_u32(slot32, p.gR + r0 * C, (uint32_t)n0 * rowb, sbar);
-          if (n1 > 0) bulk_g2s_u32(slot32 + 2u * rowb, p.gR + (r0 + 4) * C, (uint32_t)n1 * rowb, sbar);
-        } else {
-          mbar_arrive(sbar);                                         // a unit past the end: nothing to copy
-        }
-        if (p.pf > 0 && (v & 1) == 0 && q.it + p.pf < nmine) {       // L2 prefetch: same 8-row group, pf tiles ahead
-          const long long rn = (tile + (long long)p.pf * gridDim.x) * kTok + (v >> 1) * 8;
-          const long long rows = min(8ll, p.N - rn);
-          if (rows > 0) prefetch_l2_bulk(p.gR + rn * C, (uint32_t)(rows * C * 4));
-        }
-      };
-      uint32_t sphase = 0;
-      auto fetch = [&](float4 (&R)[F4], const Pos& q) {              // slot -> registers (the unit's copies were issued before)
+      auto load = [&](float4 (&R)[F4], const Pos& q) {               // global -> registers, asynchronous (scoreboard)
         if (q.it >= nmine) return;
         const int r = (q.v >> 1) * 8 + (q.v & 1) * 2 + rsel;
-        const bool live = ((long long)blockIdx.x + (long long)q.it * gridDim.x) * kTok + r < p.N;
+        const long long row = ((long long)blockIdx.x + (long long)q.it * gridDim.x) * kTok + r;
+        const bool live = row < p.N;
+        const float4* sr = reinterpret_cast<const float4*>(p.gR + row * C) + lj;
         TR(0, q.it);
-        mbar_wait_spin(sbar, sphase);
-        sphase ^= 1u;
-        const uint32_t sr = slot32 + (uint32_t)srow * ((uint32_t)C * 4u) + (uint32_t)lj * 16u;
 #pragma unroll
-        for (int i = 0; i < F4; ++i) R[i] = live ? lds128f(sr + (uint32_t)i * 128u) : make_float4(0, 0, 0, 0);
-        // The slot is refilled by an ASYNC-proxy write (bulk copy) issued by lane 0 right after this: the generic-proxy
-        // reads above must have been performed first.  __syncwarp() alone orders only generic accesses — without the
-        // proxy fence a refill that hit in L2 overtook reads still queued in the load/store unit (stress test: pairs of
-        // gR rows of a tile taken from the NEXT unit, ~1 launch in 20 on ragged multi-CTA shapes).
-        fence_async_smem();
-        __syncwarp();                                                // every lane holds its chunks: the slot may be refilled
+        for (int i = 0; i < F4; ++i) R[i] = live ? ld_stream(sr + 8 * i) : make_float4(0, 0, 0, 0);
+        if (p.pf > 0 && lg == 0 && (q.v & 1) == 0 && q.it + p.pf < nmine) {   // L2 prefetch: same 8-row group, pf tiles ahead
+          const long long rn = ((long long)blockIdx.x + (long long)(q.it + p.pf) * gridDim.x) * kTok + (q.v >> 1) * 8;
+          const char* base = reinterpret_cast<const char*>(p.gR + rn * C);
+          const long long bytes = min(8ll, p.N - rn) * C * 4;
+          for (long long o = (long long)lj * 128; o < bytes; o += 8 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+        }
         TR(3, q.it);
       };
       auto convert = [&](const float4 (&R)[F4], const Pos& q) {      // registers -> two-term bf16 split in the operand tile
@@ -459,7 +478,7 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
         // block i/2 at chunk (lj/2 + 4 (i%2)) ^ (r%8): bit 6 of the offset flips with i%2 (all operand bases are 1 KB aligned)
         const uint32_t e0 = (uint32_t)r * 128u + (((uint32_t)(lj >> 1) ^ (uint32_t)(r & 7)) << 4) + (uint32_t)(lj & 1) * 8u;
         // G is free once S1 / S5a of the previous tile have completed
-        mbar_wait_spin(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));
+        mbar_wait(&bars[B_GEMPTY], (uint32_t)((it & 1) ^ 1));         // (hardware sleep, not a spin: the wait is long)
         TR(4, it);
         const uint32_t gb = sG32 + e0;
 #pragma unroll
@@ -476,18 +495,25 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
         if (lane == 0) mbar_arrive(&bars[B_GFULL]);
         TR(2, it);
       };
-      float4 RA[F4], RB[F4];
-      Pos pa{0, pw}, pb = next(pa), ps = next(pb), pn = next(ps);   // in RA, in RB, in the slot, next to request
-      issue(pa); fetch(RA, pa);
-      issue(pb); fetch(RB, pb);
-      issue(ps);
+      // Tile by tile: ALL of this warp's units of the next tile (warps 0..3: units w, w+6, w+12; warps 4, 5: w, w+6) are
+      // requested right after the current tile's units were converted, so they sit in registers long before the gR tile
+      // is released; after the release only conversions happen (measured with two sets and a rolling order: a load
+      // issued between two conversions stalls for 1-2 k cycles whenever the E3 warps' end-of-tile burst of TMA traffic
+      // has filled the path to L2, and the conversion of a unit that WAS already loaded waited behind it — 6 k cycles
+      // from release to completion of the tile).
+      float4 R0[F4], R1[F4], R2[F4];
+      const bool three = pw + 2 * (kProd - 1) < kTok / 4;
+      load(R0, Pos{0, pw});
+      load(R1, Pos{0, pw + (kProd - 1)});
+      if (three) load(R2, Pos{0, pw + 2 * (kProd - 1)});
 #pragma unroll 1
-      while (pa.it < nmine) {
-        convert(RA, pa);
-        fetch(RA, ps); pa = ps; ps = pn; pn = next(pn); issue(ps);
-        if (pb.it >= nmine) break;
-        convert(RB, pb);
-        fetch(RB, ps); pb = ps; ps = pn; pn = next(pn); issue(ps);
+      for (int it = 0; it < nmine; ++it) {
+        convert(R0, Pos{it, pw});
+        convert(R1, Pos{it, pw + (kProd - 1)});
+        if (three) convert(R2, Pos{it, pw + 2 * (kProd - 1)});
+        load(R0, Pos{it + 1, pw});
+        load(R1, Pos{it + 1, pw + (kProd - 1)});
+        if (three) load(R2, Pos{it + 1, pw + 2 * (kProd - 1)});
       }
     }
   } else if (is_e1) {
@@ -497,41 +523,39 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
     const float sc = p.g_loss_sq ? 2.0f * __ldg(p.g_loss_sq) : 0.f;
     const float invC = 1.0f / (float)C;
     const uint32_t sHc32 = smem_u32(sHc), sCg32 = smem_u32(sCg);
-    float rcol_acc = 0.f;
     float dv[32], av[32];
     float rs_next = 0.f, mu_next = 0.f;
     float4 st_next = make_float4(0, 0, 0, 0);
-    auto load_da = [&](int it) {                         // D / A rows of tile `it` (software-pipelined one tile ahead)
+    // The tile's D and A rows arrive by TMA (two [64 x 32] fp32 boxes, SWIZZLE_128B) one tile ahead and are read from
+    // shared memory, thread = row, conflict free.  (Before: 16 global 128-bit loads per thread with a 128-byte lane stride,
+    // software-pipelined through 64 registers; the event trace showed E1 — 6 k cycles of work per tile — taking 10.6 k per
+    // tile with those loads and setting the pace of the whole kernel once the gR path had been fixed.)
+    const uint32_t sD32 = smem_u32(smem + pl.da_off), sA32 = sD32 + kBlk;
+    auto request_da = [&](int it) {                      // one thread: the boxes of tile `it`
+      const long long r0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok;
+      mbar_expect_tx(&bars[B_DAFULL], 2u * kBlk);
+      tma_load_2d_u32(&mapD, sD32, &bars[B_DAFULL], 0, (int)r0);
+      tma_load_2d_u32(&mapA, sA32, &bars[B_DAFULL], 0, (int)r0);
+    };
+    auto load_row_stats = [&](int it) {                  // rstd, mu, rowstats of tile `it` (three small loads per thread)
       const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok + et;
       const bool live = it < nmine && row < p.N;
-      const float4* dp = reinterpret_cast<const float4*>(p.D + row * K);
-      const float4* ap = reinterpret_cast<const float4*>(p.A + row * K);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 d4 = live ? ldg_nc(dp + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 a4 = live ? ldg_nc(ap + q) : make_float4(0, 0, 0, 0);
-        dv[4 * q] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
-        av[4 * q] = a4.x; av[4 * q + 1] = a4.y; av[4 * q + 2] = a4.z; av[4 * q + 3] = a4.w;
-      }
       rs_next = live ? __ldg(p.rstd + row) : 0.f;
       mu_next = live ? __ldg(p.mu + row) : 0.f;
       st_next = live ? ldg_nc(reinterpret_cast<const float4*>(p.rowstats) + row) : make_float4(0, 0, 0, 0);
     };
-    auto prefetch_da = [&](int it) {                     // L2 prefetch of a later tile's D / A rows (8 KB each)
-      if (et == 0 && it < nmine) {
+    auto prefetch_da = [&](int it) {                     // L2 prefetch of a later tile's row statistics (12 lines, 12 lanes)
+      if (et < 12 && it < nmine) {
         const long long rn = ((long long)blockIdx.x + (long long)it * gridDim.x) * kTok;
-        const long long rows = min((long long)kTok, p.N - rn);
-        if (rows > 0) {
-          prefetch_l2_bulk(p.D + rn * K, (uint32_t)(rows * K * 4));
-          prefetch_l2_bulk(p.A + rn * K, (uint32_t)(rows * K * 4));
-          prefetch_l2_bulk(p.rowstats + rn * 4, (uint32_t)(rows * 16));
-          const long long nr = rows & ~3ll;              // bulk prefetch sizes are multiples of 16 bytes
-          if (nr > 0) { prefetch_l2_bulk(p.mu + rn, (uint32_t)(nr * 4)); prefetch_l2_bulk(p.rstd + rn, (uint32_t)(nr * 4)); }
-        }
+        const char* a = et < 8 ? reinterpret_cast<const char*>(p.rowstats + rn * 4) + et * 128
+                               : reinterpret_cast<const char*>((et < 10 ? p.mu : p.rstd) + rn) + (et & 1) * 128;
+        const long long lim = et < 8 ? (p.N - rn) * 16 - et * 128 : (p.N - rn) * 4 - (et & 1) * 128;
+        if (lim > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
       }
     };
+    if (et == 0) request_da(0);
     prefetch_da(1);
-    load_da(0);
+    load_row_stats(0);
     for (int it = 0; it < nmine; ++it) {
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
       const long long row = tile * kTok + et;
@@ -541,6 +565,21 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
       TR(10, it);
       prefetch_da(it + 2);
       const int buf = it & 1;
+      // D / A rows of this tile: shared memory -> registers; then the boxes go back to the copy engine for the next tile
+      mbar_wait(&bars[B_DAFULL], (uint32_t)(it & 1));
+      {
+        const uint32_t ro = (uint32_t)et * 128u, rx = (uint32_t)(et & 7);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 d4 = lds128f(sD32 + ro + ((((uint32_t)q) ^ rx) << 4));
+          const float4 a4 = lds128f(sA32 + ro + ((((uint32_t)q) ^ rx) << 4));
+          dv[4 * q] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
+          av[4 * q] = a4.x; av[4 * q + 1] = a4.y; av[4 * q + 2] = a4.z; av[4 * q + 3] = a4.w;
+        }
+        fence_async_smem();                              // generic reads before the async-proxy refill (see the note in the producers)
+        named_bar(2, 64);
+        if (et == 0 && it + 1 < nmine) request_da(it + 1);
+      }
       mbar_wait(&bars[B_G1FULL0 + buf], (uint32_t)((it >> 1) & 1));
       TR(14, it);
       tc_fence_after();
@@ -607,14 +646,10 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
       named_bar(1, 64);
       if (et == 0) mbar_arrive(&bars[B_RFULL0 + buf]);
       TR(15, it);
-      // next tile's D / A rows: issued after the fence / barrier above (which would wait for them),
-      // their latency is covered by the butterfly and the wait for the next G1
-      load_da(it + 1);
-      butterfly<1>(gv, lane);                            // lane l: sum over this warp's 32 rows of r[:, l]
-      rcol_acc += gv[0];
-      TR(16, it);
+      // next tile's row statistics: issued after the fence / barrier above (which would wait for them)
+      load_row_stats(it + 1);
+      TR(16, it);                                        // (colsum(r) is taken from the r operand tile by producer warp 6)
     }
-    p.part_rcol[((size_t)blockIdx.x * 2 + (warp - 2)) * K + lane] = rcol_acc;
   } else if (is_e3) {
     // ======================================================================= E3
     const int e3 = (warp >> 2) - 1;                      // 64-channel group
@@ -672,31 +707,45 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
               xh[4 * j] = a.x; xh[4 * j + 1] = a.y; xh[4 * j + 2] = b.x; xh[4 * j + 3] = b.y;   // xhat, exact in fp32
             }
           }
-          // the xhat operand tile is free once S5b of the previous tile has completed
-          if (ch == 0) mbar_wait(&bars[B_XHEMPTY], (uint32_t)(par ^ 1));
-          // packed fp32 (element pairs): gz = z rsum - acc;  o = (gz gamma) rs - s1 rs - xhat s2 rs;  Q += xhat^2 rsum
+          // packed fp32 (element pairs): gz = z rsum - acc;  o = (gz gamma) rs - s1 rs - xhat s2 rs
           const float2 nrsum2 = bcast2(-rsum), rsum2 = bcast2(rsum), nrs2 = bcast2(-rs), ns1r2 = bcast2(-s1r), ns2r2 = bcast2(-s2r);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {               // 8 channels per step
+          for (int j = 0; j < 8; ++j) {
+            const float4 gm = lds128f_const(sGam32 + (uint32_t)(c0 + 4 * j) * 4u);
+            const float4 be = lds128f_const(sBet32 + (uint32_t)(c0 + 4 * j) * 4u);
+            float2 o[2];
 #pragma unroll
-            for (int jh = 0; jh < 2; ++jh) {
-              const int j = 2 * jj + jh;
-              const float4 gm = lds128f_const(sGam32 + (uint32_t)(c0 + 4 * j) * 4u);
-              const float4 be = lds128f_const(sBet32 + (uint32_t)(c0 + 4 * j) * 4u);
-              float2 o[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float2 g2 = e ? make_float2(gm.z, gm.w) : make_float2(gm.x, gm.y);
-                const float2 b2 = e ? make_float2(be.z, be.w) : make_float2(be.x, be.y);
-                const float2 x2 = make_float2(xh[4 * j + 2 * e], xh[4 * j + 2 * e + 1]);
-                const float2 a2 = make_float2(acc[4 * j + 2 * e], acc[4 * j + 2 * e + 1]);
-                const float2 z = fma2(x2, g2, b2);
-                const float2 ngz = fma2(z, nrsum2, a2);                      // -(gz) = acc - z rsum
-                o[e] = fma2(x2, ns2r2, fma2(mul2(ngz, g2), nrs2, ns1r2));
-              }
-              // gx goes back into the bytes x was read from (this thread's own row of the box)
-              sts128f(bx + ((((uint32_t)j) ^ rx) << 4), o[0].x, o[0].y, o[1].x, o[1].y);
+            for (int e = 0; e < 2; ++e) {
+              const float2 g2 = e ? make_float2(gm.z, gm.w) : make_float2(gm.x, gm.y);
+              const float2 b2 = e ? make_float2(be.z, be.w) : make_float2(be.x, be.y);
+              const float2 x2 = make_float2(xh[4 * j + 2 * e], xh[4 * j + 2 * e + 1]);
+              const float2 a2 = make_float2(acc[4 * j + 2 * e], acc[4 * j + 2 * e + 1]);
+              const float2 z = fma2(x2, g2, b2);
+              const float2 ngz = fma2(z, nrsum2, a2);                      // -(gz) = acc - z rsum
+              o[e] = fma2(x2, ns2r2, fma2(mul2(ngz, g2), nrs2, ns1r2));
             }
+            // gx goes back into the bytes x was read from (this thread's own row of the box)
+            sts128f(bx + ((((uint32_t)j) ^ rx) << 4), o[0].x, o[0].y, o[1].x, o[1].y);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d_hint(&mapGx, box32 + (uint32_t)ch * kBox, c0, (int)(row0 + q * 32), pol);
+            bulk_commit();
+            // the first box's store was issued half a tile ago: it has read its bytes, the next tile's x may land there
+            if (ch == 1 && it + 1 < nmine) { bulk_wait_read1(); load_box(it + 1, 0); }
+          }
+          if (ch == 1) {                                 // the accumulator is consumed: S3 of the next tile may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY]);
+            TR(23, it);
+          }
+          // the xhat operand tile is free once S5b of the previous tile has completed — asked for as late as possible: S5b
+          // of tile t-1 is issued after E3 of tile t-1 has ended and shares its issuing thread with S3 of this tile
+          if (ch == 0) mbar_wait(&bars[B_XHEMPTY], (uint32_t)(par ^ 1));
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {               // 8 channels per step
             // two-term bf16 split of the 8 xhat values -> one 16-byte chunk of the hi block and of the lo block
             uint32_t w1[4], w2[4];
 #pragma unroll
@@ -711,19 +760,10 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
               xh[8 * jj + 2 * e] = qq.x; xh[8 * jj + 2 * e + 1] = qq.y;
             }
           }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d_hint(&mapGx, box32 + (uint32_t)ch * kBox, c0, (int)(row0 + q * 32), pol);
-            bulk_commit();
-            // the first box's store was issued half a tile ago: it has read its bytes, the next tile's x may land there
-            if (ch == 1 && it + 1 < nmine) { bulk_wait_read1(); load_box(it + 1, 0); }
-          }
-          if (ch == 1) {                                 // accumulator consumed, xhat operand rows written
-            tc_fence_before();
+          if (ch == 1) {                                 // xhat operand rows written
+            fence_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&bars[B_ACCEMPTY]); mbar_arrive(&bars[B_XHFULL]); }
-            TR(23, it);
+            if (lane == 0) mbar_arrive(&bars[B_XHFULL]);
           }
           butterfly<8>(xh, lane);
 #pragma unroll
@@ -761,103 +801,121 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
     const uint32_t loC_k = (sCen32 >> 4) & 0x3FFFu, loC_mn = loC_k | kLbo;
     mbar_wait(&bars[B_CEN], 0);
     int n1 = 0, n5a = 0, n3 = 0, n5b = 0;
-    uint32_t last_ready = 0xffffffffu;
-    const uint32_t bar32 = smem_u32(bars);
-    // The issue loop polls SEVERAL barriers: mbarrier.try_wait is a hardware sleep with a time limit (a failed probe costs
-    // ~2 k cycles here: the event trace showed S3 issued 4-5 k cycles after both of its inputs were ready, and E3 — the
-    // busiest role — idle for exactly that long), so every probe is the non-blocking test_wait, and all six sit in ONE asm
-    // block, issued back to back before the first predicate is used (one ~150-cycle round trip per iteration, not six).
-    while (n5b < nmine) {
-      const uint32_t pb[6] = {bar32 + 8u * (uint32_t)(B_RFULL0 + (n3 & 1)), bar32 + 8u * B_ACCEMPTY, bar32 + 8u * B_GFULL,
-                              bar32 + 8u * (uint32_t)(B_G1EMPTY0 + (n1 & 1)), bar32 + 8u * B_AFULL, bar32 + 8u * B_XHFULL};
-      const uint32_t pp[6] = {(uint32_t)((n3 >> 1) & 1), (uint32_t)((n3 & 1) ^ 1), (uint32_t)(n1 & 1),
-                              (uint32_t)(((n1 >> 1) & 1) ^ 1), (uint32_t)(n5a & 1), (uint32_t)(n5b & 1)};
-      const uint32_t ready = mbar_test6(pb, pp);
-      if constexpr (TRACE) {                             // what the issue thread SEES, and when: one entry per change of the mask
-        if (ready != last_ready) { TR(64 + (int)ready, n3); last_ready = ready; }
+    // One thread issues every MMA of the CTA.  What the event trace (VADC_BWD_TRACE builds) taught about its loop:
+    //  * mbarrier.try_wait is a hardware sleep with a time limit: a failed probe of one barrier delays the look at the next
+    //    by ~2 k cycles — every probe here is the non-blocking test_wait;
+    //  * test_wait probes of one thread do not overlap (~150 cycles EACH, also when issued back to back from one asm
+    //    block): six probes per look made every reaction ~0.9 k cycles late, and a look between chunks of a contraction
+    //    more than doubled its issue time.  So a condition that has been seen true is remembered until its counter moves,
+    //    and a look probes only what is still unknown and currently decides something (typically one or two barriers);
+    //  * E3 sets the pace and waits for S3, and, a few hundred cycles into its next tile, for the xhat tile that S5b frees:
+    //    priority S3 > S5b > S1 > S5a.
+    enum { kRF = 1, kAE = 2, kGF = 4, kG1E = 8, kAF = 16, kXF = 32 };
+    uint32_t seen = 0;
+    auto probe = [&](uint32_t bit, int b, uint32_t parity) {
+      if (!(seen & bit) && mbar_test(&bars[b], parity)) {
+        seen |= bit;
+        if constexpr (TRACE) TR(64 + (int)seen, n3);
       }
-      const bool rfull = ready & 1u, accempty = ready & 2u, gfull = ready & 4u, g1empty = ready & 8u, afull = ready & 16u,
-                 xhfull = ready & 32u;
-      bool progress = false;
-      // ---- S3 (feeds E3): acc = r_lo cen_hi + r_hi cen_lo + r_hi cen_hi
-      if (n3 < n1 && rfull && accempty) {
-        tc_fence_after();
-        const uint32_t d = tmem + kColAcc;
-        const uint32_t loTR = loTR_k + (uint32_t)(n3 & 1) * (kBlk >> 4);
-        constexpr uint32_t ro[3] = {64u, 0u, 0u}, co[3] = {0u, 4096u, 0u};
+    };
+    while (n5b < nmine) {
+      // ---- S3 (feeds E3, urgent): acc = r_lo cen_hi + r_hi cen_lo + r_hi cen_hi
+      if (n3 < n1) {
+        probe(kRF, B_RFULL0 + (n3 & 1), (uint32_t)((n3 >> 1) & 1));
+        if (seen & kRF) probe(kAE, B_ACCEMPTY, (uint32_t)((n3 & 1) ^ 1));
+        if ((seen & (kRF | kAE)) == (kRF | kAE)) {
+          tc_fence_after();
+          const uint32_t d = tmem + kColAcc;
+          const uint32_t loTR = loTR_k + (uint32_t)(n3 & 1) * (kBlk >> 4);
+          constexpr uint32_t ro[3] = {64u, 0u, 0u}, co[3] = {0u, 4096u, 0u};
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
+          for (int t = 0; t < 3; ++t) {
 #pragma unroll
-          for (int ks = 0; ks < K / 16; ++ks) {
-            const uint64_t ad = desc_at(loTR, kHi, ro[t] + (uint32_t)ks * 32u);
-            const uint64_t bd = desc_at(loC_mn, kHi, co[t] + (uint32_t)(2 * ks) * 1024u);
-            mma_f16(d, ad, bd, idesc3, (t > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < K / 16; ++ks) {
+              const uint64_t ad = desc_at(loTR, kHi, ro[t] + (uint32_t)ks * 32u);
+              const uint64_t bd = desc_at(loC_mn, kHi, co[t] + (uint32_t)(2 * ks) * 1024u);
+              mma_f16(d, ad, bd, idesc3, (t > 0 || ks > 0) ? 1u : 0u);
+            }
           }
+          mma_commit(&bars[B_ACCFULL]);
+          TR(32, n3);
+          ++n3;
+          seen &= ~(uint32_t)(kRF | kAE);
+          continue;
         }
-        mma_commit(&bars[B_ACCFULL]);
-        TR(32, n3);
-        ++n3;
-        progress = true;
+      }
+      // ---- S5b (after E3 of its tile; frees the xhat tile and r[parity]): PT[64:128] += [r_hi | r_lo]^T (xhat_hi + xhat_lo)
+      if (n5b < n3 && n5b < n5a) {
+        probe(kXF, B_XHFULL, (uint32_t)(n5b & 1));
+        if (seen & kXF) {
+          tc_fence_after();
+          const uint32_t loZR_mn = (n5b & 1) ? loZR_mn1 : loZR_mn0;
+VADC_S5_UNROLL
+          for (int t = 0; t < 2; ++t) {
+VADC_S5_UNROLL
+            for (int ks = 0; ks < kTok / 16; ++ks) {
+              const uint64_t ad = desc_at(loZR_mn, kHi, (uint32_t)ks * 2048u);
+              const uint64_t bd = desc_at(loX_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
+              mma_f16(tmem + kColPT, ad, bd, idesc5, 1u);
+            }
+          }
+          mma_commit(&bars[B_XHEMPTY]);
+          mma_commit(&bars[B_REMPTY0 + (n5b & 1)]);
+          TR(33, n5b);
+          ++n5b;
+          seen &= ~(uint32_t)kXF;
+          continue;
+        }
       }
       // ---- S1 (feeds E1): G1[:, 0:32] = gR_hi cen_hi + gR_lo cen_hi, G1[:, 32:64] = gR_hi cen_lo
-      if (n1 < nmine && gfull && g1empty) {
-        tc_fence_after();
-        const uint32_t d = tmem + kColG1 + (uint32_t)((n1 & 1) * 64);
+      if (n1 < nmine) {
+        probe(kGF, B_GFULL, (uint32_t)(n1 & 1));
+        if (seen & kGF) probe(kG1E, B_G1EMPTY0 + (n1 & 1), (uint32_t)(((n1 >> 1) & 1) ^ 1));
+        if ((seen & (kGF | kG1E)) == (kGF | kG1E)) {
+          tc_fence_after();
+          const uint32_t d = tmem + kColG1 + (uint32_t)((n1 & 1) * 64);
 #pragma unroll
-        for (int kk = 0; kk < C / 16; ++kk) {
-          const uint64_t ad = desc_at(loG_k64, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
-          const uint64_t bd = desc_at(loC_k, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
-          mma_f16(d, ad, bd, idesc1a, kk > 0 ? 1u : 0u);
-        }
+          for (int kk = 0; kk < C / 16; ++kk) {
+            const uint64_t ad = desc_at(loG_k64, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
+            const uint64_t bd = desc_at(loC_k, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
+            mma_f16(d, ad, bd, idesc1a, kk > 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int kk = 0; kk < C / 16; ++kk) {
-          const uint64_t ad = desc_at(loG_k64, kHi, pl.xterm + (kk >> 2) * kBlk + (kk & 3) * 32u);
-          const uint64_t bd = desc_at(loC_k, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
-          mma_f16(d, ad, bd, idesc1b, 1u);
+          for (int kk = 0; kk < C / 16; ++kk) {
+            const uint64_t ad = desc_at(loG_k64, kHi, pl.xterm + (kk >> 2) * kBlk + (kk & 3) * 32u);
+            const uint64_t bd = desc_at(loC_k, kHi, (kk >> 2) * kBlk + (kk & 3) * 32u);
+            mma_f16(d, ad, bd, idesc1b, 1u);
+          }
+          mma_commit(&bars[B_G1FULL0 + (n1 & 1)]);
+          TR(30, n1);
+          ++n1;
+          seen &= ~(uint32_t)(kGF | kG1E);
+          continue;
         }
-        mma_commit(&bars[B_G1FULL0 + (n1 & 1)]);
-        TR(30, n1);
-        ++n1;
-        progress = true;
       }
       // ---- S5a (background; its completion frees the gR tile for the producers): PT[0:64] += [A_hi | A_lo]^T (gR_hi + gR_lo)
-      if (n5a < n1 && afull) {
-        tc_fence_after();
+      if (n5a < n1) {
+        probe(kAF, B_AFULL, (uint32_t)(n5a & 1));
+        if (seen & kAF) {
+          tc_fence_after();
 VADC_S5_UNROLL
-        for (int t = 0; t < 2; ++t) {
+          for (int t = 0; t < 2; ++t) {
 VADC_S5_UNROLL
-          for (int ks = 0; ks < kTok / 16; ++ks) {
-            const uint64_t ad = desc_at(loTA_mn, kHi, (uint32_t)ks * 2048u);
-            const uint64_t bd = desc_at(loG_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
-            mma_f16(tmem + kColPT, ad, bd, idesc5, (n5a > 0 || t > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kTok / 16; ++ks) {
+              const uint64_t ad = desc_at(loTA_mn, kHi, (uint32_t)ks * 2048u);
+              const uint64_t bd = desc_at(loG_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
+              mma_f16(tmem + kColPT, ad, bd, idesc5, (n5a > 0 || t > 0 || ks > 0) ? 1u : 0u);
+            }
           }
+          mma_commit(&bars[B_GEMPTY]);
+          mma_commit(&bars[B_AEMPTY]);
+          TR(31, n5a);
+          ++n5a;
+          seen &= ~(uint32_t)kAF;
+          continue;
         }
-        mma_commit(&bars[B_GEMPTY]);
-        mma_commit(&bars[B_AEMPTY]);
-        TR(31, n5a);
-        ++n5a;
-        progress = true;
       }
-      // ---- S5b (background, after E3 of its tile; frees the xhat tile and r[parity]): PT[64:128] += [r_hi | r_lo]^T (xhat_hi + xhat_lo)
-      if (n5b < n3 && n5b < n5a && xhfull) {
-        tc_fence_after();
-        const uint32_t loZR_mn = (n5b & 1) ? loZR_mn1 : loZR_mn0;
-VADC_S5_UNROLL
-        for (int t = 0; t < 2; ++t) {
-VADC_S5_UNROLL
-          for (int ks = 0; ks < kTok / 16; ++ks) {
-            const uint64_t ad = desc_at(loZR_mn, kHi, (uint32_t)ks * 2048u);
-            const uint64_t bd = desc_at(loX_mn, kHi, (uint32_t)t * pl.xterm + (uint32_t)ks * 2048u);
-            mma_f16(tmem + kColPT, ad, bd, idesc5, 1u);
-          }
-        }
-        mma_commit(&bars[B_XHEMPTY]);
-        mma_commit(&bars[B_REMPTY0 + (n5b & 1)]);
-        TR(33, n5b);
-        ++n5b;
-        progress = true;
-      }
-      if (!progress && p.mma_sleep > 0) __nanosleep((unsigned)p.mma_sleep);   // (a sleep costs far more than its nominal length: default spin)
+      if (p.mma_sleep > 0) __nanosleep((unsigned)p.mma_sleep);   // (a sleep costs far more than its nominal length: default spin)
     }
     mma_commit(&bars[B_DONE]);
     mbar_wait(&bars[B_DONE], 0);
@@ -957,13 +1015,13 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, cols] fp32 row-major tensor, box = 32 columns x 32 rows, SWIZZLE_128B
-static int make_map(CUtensorMap* m, float* base, long long rows, int cols) {
+// [rows, cols] fp32 row-major tensor, box = 32 columns x box_rows rows, SWIZZLE_128B
+static int make_map(CUtensorMap* m, float* base, long long rows, int cols, int box_rows = 32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return VADC_ERR_CUDA;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1014,10 +1072,12 @@ int launch_cluster_bwd_tc2(const float* x, const float* mu, const float* rstd, c
   float* rcol = ws.take<float>(K);
   const int grid = (int)std::min<long long>((N + bt2::kTok - 1) / bt2::kTok, (long long)g);
 
-  CUtensorMap mGx, mX;
+  CUtensorMap mGx, mX, mD, mA;
   int rc;
   if ((rc = bt2::make_map(&mGx, gx, N, C))) return rc;
   if ((rc = bt2::make_map(&mX, const_cast<float*>(x), N, C))) return rc;
+  if ((rc = bt2::make_map(&mD, const_cast<float*>(D), N, K, bt2::kTok))) return rc;
+  if ((rc = bt2::make_map(&mA, const_cast<float*>(A), N, K, bt2::kTok))) return rc;
   bt2::centroid_prep_bwd_kernel<<<K, 256, 0, st>>>(centers, ln_w, ln_b, K, C, image, cvec);
   VADC_CHECK_LAUNCH("centroid_prep_bwd_kernel");
 
@@ -1045,7 +1105,7 @@ int launch_cluster_bwd_tc2(const float* x, const float* mu, const float* rstd, c
   if (C == 32 * F4_) {                                                                                 \
     auto kern = BT_KERN(F4_);                                                                          \
     VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    kern<<<grid, bt2::kThreads, smem, st>>>(mGx, mX, p);                                               \
+    kern<<<grid, bt2::kThreads, smem, st>>>(mGx, mX, mD, mA, p);                                               \
     launched = true;                                                                                   \
   }
   timing_begin(VADC_TIMING_CLUSTER_BWD, st);
