@@ -148,6 +148,23 @@ int vadc_space_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
                            float* loss_sq,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Any cluster_num (the reference's constructors take any: model/cluster.py:58-75, :102-122): the kernels address rows
+ * of K fp32 values with 128-bit accesses, so K % 4 == 0 is required; for other sizes the HOST pads the centroids with
+ * K - K_valid trailing rows (any finite values; the Python wrapper uses zeros) and calls these entry points, which exclude
+ * the padding from argmin / softmin / loss (A is exactly 0 there, D holds the finite distance to the padding row).  The
+ * backward entry points need no change: A = 0 makes every gradient through a padded column 0. */
+int vadc_cluster_fwd_padded(const float* x, const float* ln_w, const float* ln_b, const float* centers,
+                            int64_t N, int C, int K, int K_valid, float alpha, float eps,
+                            float* D, float* A, float* x_rec, float* feature, int64_t* label,
+                            float* mu, float* rstd, float* rowstats, float* loss_sq,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int vadc_space_cluster_fwd_padded(const float* x, const float* ln_w, const float* ln_b,
+                                  const float* centers, int64_t M, int P, int C, int K, int K_valid,
+                                  float alpha, float eps,
+                                  float* Ds, float* As, float* zt, float* mu, float* rstd,
+                                  float* loss_sq,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* autograd of C3 (main_predict.py:296). gD/gA [M,C,K] may be NULL; optional
  * fused loss gradient as in vadc_cluster_bwd.  Outputs gx [M*P,C],
  * gcenters [C,K,P], g_ln_w, g_ln_b [C]. */
@@ -190,6 +207,14 @@ size_t vadc_frame_mse_workspace_bytes(int B, int T, int64_t HW, int Cc);
 int vadc_frame_mse(const float* recon, const float* clip, int B, int Cc, int T, int64_t HW,
                    float* mse, double* psnr,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* The same reduction over strided views (strides in ELEMENTS along batch, channel, frame; the H*W plane itself is
+ * contiguous): clip batches are taken out of a device-resident video without a copy — consecutive clips
+ * (tool/contrast_evaluae.py:185-203), clips that overlap by all but one frame (tool/predict_evaluae.py:185-203,
+ * main_predict.py:401-404) — and single frames of a reconstruction (recon[:, :, 0], main_predict.py:417-420). */
+int vadc_frame_mse_strided(const float* recon, int64_t recon_stride_b, int64_t recon_stride_c, int64_t recon_stride_t,
+                           const float* clip, int64_t clip_stride_b, int64_t clip_stride_c, int64_t clip_stride_t,
+                           int B, int Cc, int T, int64_t HW, float* mse, double* psnr,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* E3: anomly_score  misc/utils.py:131-135 — per-video 1 - minmax(psnr).
  * psnr [total] float64, seg_offsets [n_videos+1] int64 (device) -> score [total]

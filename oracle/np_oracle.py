@@ -346,6 +346,63 @@ def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size, dty
     return auc, per, [anomly_score(psnr(m)) for m in vm], vl
 
 
+def eval_clip_starts_stride1(n_frames, frame_num, batch_size):
+    """clip schedule of tool/predict_evaluae.py:185-203 (and, with batch_size 1, main_predict.py:401-404): clips one
+    frame apart, every start s with s + frame_num < T, batched up to ``batch_size``."""
+    batches, index = [], 0
+    while index + frame_num < n_frames:
+        starts = [index]
+        for _ in range(batch_size - 1):
+            if index + frame_num + 1 < n_frames:
+                index = index + 1
+                starts.append(index)
+            else:
+                break
+        index = index + 1
+        batches.append(starts)
+    return batches
+
+
+def evaluate_videos_predict(model_fn, videos, labels, scenes, frame_num, batch_size, ispredict, dtype=np.float64):
+    """tool/predict_evaluae.py:170-284: one score per clip = mean of (recon - target)^2 over W, H, D, C (:233); not
+    ``ispredict``: target = the clip, label = label[index] (:189-190, :208-209, :229-230); ``ispredict``: the model sees
+    the clip's frames 0..3 and the target is its last frame (:204-206, :227-228), label = label[index + frame_num]
+    (:187-188).  Per-video anomly_score, per-scene AUC, mean over scenes (:262-283)."""
+    vm, vl = [], []
+    for vid, lab in zip(videos, labels):
+        vid = np.asarray(vid, dtype)
+        lab = np.asarray(lab)
+        mses, labs = [], []
+        for starts in eval_clip_starts_stride1(vid.shape[1], frame_num, batch_size):
+            clip = np.stack([vid[:, s:s + frame_num] for s in starts])          # [B,C,D,H,W]
+            target, inp = (clip[:, :, -1:], clip[:, :, 0:4]) if ispredict else (clip, clip)
+            recon = np.asarray(model_fn(inp), dtype)
+            e = (recon - target) ** 2
+            mses.extend(e.mean(4).mean(3).mean(2).mean(1).tolist())
+            labs.extend(int(lab[s + frame_num] if ispredict else lab[s]) for s in starts)
+        vm.append(mses); vl.append(labs)
+    auc, per = scene_auc(vm, vl, scenes)
+    return auc, per, [anomly_score(psnr(m)) for m in vm], vl
+
+
+def evaluate_videos_first_frame(model_fn, videos, labels, scenes, frame_num, dtype=np.float64):
+    """main_predict.py:389-457: clips one frame apart, batch 1; score = mean((recon[:, :, 0] - clip[:, :, 0])^2) (:417-421),
+    label = label[index + frame_num] (:403)."""
+    vm, vl = [], []
+    for vid, lab in zip(videos, labels):
+        vid = np.asarray(vid, dtype)
+        lab = np.asarray(lab)
+        mses, labs = [], []
+        for s in range(0, max(vid.shape[1] - frame_num, 0)):
+            clip = vid[None, :, s:s + frame_num]
+            recon = np.asarray(model_fn(clip), dtype)
+            mses.append(float(((recon[:, :, 0] - clip[:, :, 0]) ** 2).mean()))
+            labs.append(int(lab[s + frame_num]))
+        vm.append(mses); vl.append(labs)
+    auc, per = scene_auc(vm, vl, scenes)
+    return auc, per, [anomly_score(psnr(m)) for m in vm], vl
+
+
 # ----------------------------------------------------------------------------
 # M1-M5: Memory module
 # ----------------------------------------------------------------------------

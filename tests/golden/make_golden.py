@@ -236,10 +236,81 @@ def gen_eval_loop(ref_utils, name, seed, batch_size, lengths):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
 
 
+def gen_eval_loop_variant(ref_utils, name, seed, variant, batch_size, ispredict, frame_num, lengths):
+    """the reference's OTHER two evaluation loops, exec'd unmodified like ``gen_eval_loop``:
+    ``variant='predict'``      tool/predict_evaluae.py:170-284 — clips one frame apart, ONE score per clip (mean over
+                               C, D, H, W), label of frame index (+ frame_num when ``ispredict``: the model then sees the
+                               clip's first four frames and predicts its last one);
+    ``variant='first_frame'``  main_predict.py:389-457 — clips one frame apart, batch 1, the score is the error of the
+                               clip's FIRST frame, label of frame index + frame_num."""
+    import contextlib
+    import io
+    from einops import rearrange
+    from sklearn.metrics import roc_auc_score
+    if variant == "predict":
+        src = open(os.path.join(REF, "tool", "predict_evaluae.py"), encoding="utf-8").read()
+        body = src[src.index("def predict(model, recon_loss, data_loader, dataset, data_iter):"):src.index("if __name__ == '__main__':")]
+    else:
+        src = open(os.path.join(REF, "main_predict.py"), encoding="utf-8").read()
+        body = src[src.index("def predict(model, recon_loss, data_loader, dataset):"):src.index("if __name__ == '__main__':")]
+    noop = lambda *a, **k: None  # noqa: E731
+    plt = types.SimpleNamespace(title=noop, plot=noop, ylabel=noop, xlabel=noop, show=noop)
+    pd = types.SimpleNamespace(read_csv=lambda *a, **k: types.SimpleNamespace(values=np.zeros((1, 1))),
+                               DataFrame=lambda *a, **k: types.SimpleNamespace(to_csv=noop))
+    ns = dict(torch=torch, np=np, rearrange=rearrange, utils=ref_utils, roc_auc_score=roc_auc_score, plt=plt, pd=pd,
+              args=types.SimpleNamespace(frame_num=frame_num, batch_size=batch_size, ispredict=ispredict))
+    exec(compile(body, f"{variant}:predict", "exec"), ns)
+
+    class TinyModel(torch.nn.Module):                      # deterministic, elementwise: reproducible anywhere
+        def forward(self, clip):
+            if variant == "predict" and ispredict:         # sees frames 0..3, predicts one frame
+                base = clip[:, :, -1:]
+                out = base + 0.05 * torch.sin(37.0 * base) * (1.0 + clip.mean(dim=2, keepdim=True))
+            else:
+                out = clip + 0.05 * torch.sin(37.0 * clip) * (1.0 + clip)
+            return (out, 0, 0, 0, 0, 0, 0) if variant == "predict" else (out, 0, 0, 0, 0)
+
+    g = torch.Generator().manual_seed(seed)
+    scenes = ["01", "02", "01", "03", "02", "03"]
+    videos, labels = [], []
+    for T in lengths:
+        v = torch.rand(3, T, 6, 6, generator=g)
+        lab = np.zeros(T, np.int64)
+        a = int(torch.randint(2, T - 8, (1,), generator=g))
+        lab[a:a + 6] = 1
+        v[:, a:a + 6] = v[:, a:a + 6] * 1.12
+        videos.append(v); labels.append(lab)
+    loader = [(v[None], i, torch.tensor(l)[None], (sc,)) for i, (v, l, sc) in enumerate(zip(videos, labels, scenes))]
+    had_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            if variant == "predict":
+                ns["predict"](TinyModel(), torch.nn.MSELoss(reduction="none"), loader, loader, 0)
+            else:
+                ns["predict"](TinyModel(), torch.nn.MSELoss(reduction="none"), loader, loader)
+    finally:
+        torch.Tensor.cuda = had_cuda
+    lines = out.getvalue().splitlines()
+    scene_aucs = [float(l.split(":")[-1]) for l in lines if "场景下的auc值为" in l]
+    auc = [float(l.replace("AUC值为", "")) for l in lines if l.startswith("AUC值为")][0]
+    d = {"frame_num": frame_num, "batch_size": batch_size, "ispredict": int(ispredict), "auc": auc,
+         "scene_aucs": np.array(scene_aucs), "scenes": np.array(scenes), "lengths": np.array(lengths)}
+    for i, (v, l) in enumerate(zip(videos, labels)):
+        d[f"video{i}"] = t2n(v); d[f"label{i}"] = l
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
     ref_cluster, ref_memory, ref_recon, ref_utils = import_reference()
+    if "--only-eval-variants" in sys.argv:   # the fixtures added in round 2 alone (the others are unchanged)
+        gen_eval_loop_variant(ref_utils, "eval_predict_b1", 11, "predict", 1, False, 4, [23, 31, 40, 18, 29, 38])
+        gen_eval_loop_variant(ref_utils, "eval_predict_b3_pred", 12, "predict", 3, True, 5, [24, 33, 40, 17, 29, 36])
+        gen_eval_loop_variant(ref_utils, "eval_first_frame", 13, "first_frame", 1, True, 4, [23, 31, 40, 18, 29, 38])
+        return
     if "--only-memory" in sys.argv:          # regenerate the memory fixtures alone (same seeds)
         gen_memory(ref_memory, "memory_d32_m10", 2, 32, 4, 4, 10, 6)
         gen_memory(ref_memory, "memory_d64_m50", 1, 64, 6, 6, 50, 7)
@@ -256,6 +327,9 @@ def main():
     # mod frame_num (a ragged clip reaches torch.cat), so the batched fixture uses lengths = 0, 1 mod 4
     gen_eval_loop(ref_utils, "eval_loop_b1", 9, 1, [23, 31, 40, 18, 29, 38])
     gen_eval_loop(ref_utils, "eval_loop_b3", 10, 3, [24, 33, 40, 17, 29, 36])
+    gen_eval_loop_variant(ref_utils, "eval_predict_b1", 11, "predict", 1, False, 4, [23, 31, 40, 18, 29, 38])
+    gen_eval_loop_variant(ref_utils, "eval_predict_b3_pred", 12, "predict", 3, True, 5, [24, 33, 40, 17, 29, 36])
+    gen_eval_loop_variant(ref_utils, "eval_first_frame", 13, "first_frame", 1, True, 4, [23, 31, 40, 18, 29, 38])
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 

@@ -53,6 +53,12 @@ def _worker(rank, world, port, q):
     from videoad_b200.memory import _dist_reduce
     out["colmax"] = _dist_reduce(torch.tensor([1.0 + rank, 5.0 - 3 * rank, -2.0]), "max").numpy().copy()
     out["colsum"] = _dist_reduce(torch.tensor([1.0 + rank, 10.0]), "sum").numpy().copy()
+    # scoring under data parallelism: every rank scored its own videos (contiguous shard_range), the merged
+    # list comes back in video order on every rank
+    lo, hi = V.shard_range(5)
+    local = [(i, np.full(3, float(i)), np.arange(3) % 2) for i in range(lo, hi)]
+    merged = V.gather_video_scores(local)
+    out["gathered"] = [(i, s_.tolist(), l_.tolist()) for i, s_, l_ in merged]
     # print is muted on non-master ranks (utils/distritributed_model.py:23-35)
     import builtins
     out["print_wrapped"] = getattr(builtins.print, "_vadc_wrapped", False)
@@ -80,6 +86,8 @@ def test_two_rank_gloo():
     for r in (0, 1):
         np.testing.assert_allclose(res[r]["colmax"], [2.0, 5.0, -2.0])
         np.testing.assert_allclose(res[r]["colsum"], [3.0, 20.0])
+    for r in (0, 1):
+        assert res[r]["gathered"] == [(i, [float(i)] * 3, [0, 1, 0]) for i in range(5)]
     Lg = (1.0 + 4.0) ** 0.5
     for r in (0, 1):
         assert abs(res[r]["loss"] - Lg) < 1e-6

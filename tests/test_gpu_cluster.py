@@ -452,3 +452,40 @@ def test_runs_on_the_tensors_device_not_the_current_one():
         assert b.device == d1 and torch.equal(a.cpu(), b.cpu())
     with pytest.raises(RuntimeError):
         m1(x0)
+
+
+@pytest.mark.parametrize("Ntok,C,K,alpha", [(333, 192, 30, 16.0), (200, 64, 6, 32.0), (64, 32, 1, 8.0), (500, 192, 1023, 16.0)])
+def test_any_cluster_num_forward_backward(Ntok, C, K, alpha):
+    """the reference's constructor takes any cluster_num (model/cluster.py:58-75); K % 4 != 0 runs through zero-padded
+    centroids that the device excludes from argmin / softmin / loss (vadc_cluster_fwd_padded): same parity bars as the
+    other shapes, explicit gradients on every output"""
+    rng = np.random.default_rng(K + Ntok)
+    x = (rng.standard_normal((1, 1, 1, Ntok, C)) * 1.3 + 0.2).astype(np.float32)
+    cen = rng.random((K, C)).astype(np.float32)
+    w = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    gR = rng.standard_normal((Ntok, C)).astype(np.float32)
+    gDx = (0.1 * rng.standard_normal((Ntok, K))).astype(np.float32)
+    gAx = rng.standard_normal((Ntok, K)).astype(np.float32)
+    m = make_cluster_module(V, C, K, alpha, cen, w, b)
+    xt = T(x, grad=True)
+    D, A, S, R, F, lab = m(xt)
+    assert D.shape == (1, 1, 1, Ntok, K) and A.shape == D.shape and S.shape == (K, K)
+    o64 = O.cluster_forward(x, cen, w, b, alpha, dtype=np.float64)
+    assert rel(N(D), o64["D"]) < 1e-5
+    assert_labels_match(N(lab), o64["D"])
+    np.testing.assert_allclose(N(A), o64["A"], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(N(A).sum(-1), 1.0, rtol=1e-5)
+    assert rel(N(R), o64["x_rec"]) < 1e-4
+    lo = float(O.frobenius_loss(o64["D"], o64["A"], np.float64))
+    assert abs(float(m.fused_cluster_loss()) - lo) < 1e-4 * lo
+    obj = (D * T(gDx).view_as(D)).sum() + (A * T(gAx).view_as(A)).sum() + (R * T(gR).view_as(R)).sum() + 0.5 * m.fused_cluster_loss()
+    obj.backward()
+    lD, lA = O.frobenius_loss_grads(o64["D"], o64["A"], 0.5, np.float64)
+    gx, gc, gw, gb = O.cluster_backward(x, cen, w, b, alpha, gD=gDx + lD.reshape(Ntok, K), gA=gAx + lA.reshape(Ntok, K),
+                                        gR=gR, dtype=np.float64)
+    assert m.cluster_center.grad.shape == (K, C)
+    assert rel(N(xt.grad).reshape(Ntok, C), gx) < 2e-4
+    assert rel(N(m.cluster_center.grad), gc) < 2e-4
+    assert rel(N(m.norm.weight.grad), gw) < 2e-4
+    assert rel(N(m.norm.bias.grad), gb) < 2e-4

@@ -29,8 +29,10 @@ def _run(model, clip, train_objective):
     grads = None
     if train_objective:
         recon, closs, sloss = out[0], out[1], out[2]
-        # main_predict.py:273-284: ||MSE(none)||_F + cluster loss + space loss
-        loss = torch.norm(torch.nn.MSELoss(reduction="none")(recon, clip)) + closs + sloss
+        # main_predict.py:273-284: ||MSE(none)(recon, predict_frame)||_F + cluster loss + space loss; in predict mode the
+        # decoder returns the frames to predict ([B,3,2,H,W]), the target has their shape
+        target = torch.rand(recon.shape, device=recon.device, generator=torch.Generator(recon.device).manual_seed(7))
+        loss = torch.norm(torch.nn.MSELoss(reduction="none")(recon, target)) + closs + sloss
         model.zero_grad(set_to_none=True)
         loss.backward()
         grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
@@ -64,7 +66,7 @@ def test_mymodel_forward_7tuple_patched_vs_unpatched(train_objective):
     recon_r, closs_r, sloss_r, z3_r, z4_r, feat_r, lab_r = out_ref
     recon_n, closs_n, sloss_n, z3_n, z4_n, feat_n, lab_n = out_new
     assert (z3_n, z4_n) == (z3_r, z4_r) == (0, 0)
-    assert recon_n.shape == recon_r.shape == clip.shape
+    assert recon_n.shape == recon_r.shape and recon_n.shape[:2] == clip.shape[:2] and recon_n.shape[3:] == clip.shape[3:]
     assert rel(N(feat_n), N(feat_r)) < 1e-5                                  # LayerNorm'd tokens [N,192]
     assert abs(float(closs_n) - float(closs_r)) < 1e-4 * float(closs_r)      # north_star: losses within 1e-4 relative
     assert abs(float(sloss_n) - float(sloss_r)) < 1e-4 * float(sloss_r)

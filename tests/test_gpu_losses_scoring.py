@@ -122,6 +122,70 @@ def test_device_resident_evaluation_loop(name):
         assert list(la) == list(lb)
 
 
+def _tiny_t(variant, ispredict):
+    if variant == "predict" and ispredict:
+        return lambda c: c[:, :, -1:] + 0.05 * torch.sin(37.0 * c[:, :, -1:]) * (1.0 + c.mean(dim=2, keepdim=True))
+    return lambda c: c + 0.05 * torch.sin(37.0 * c) * (1.0 + c)
+
+
+def _tiny_n(variant, ispredict):
+    if variant == "predict" and ispredict:
+        return lambda c: c[:, :, -1:] + 0.05 * np.sin(37.0 * c[:, :, -1:]) * (1.0 + c.mean(2, keepdims=True))
+    return lambda c: c + 0.05 * np.sin(37.0 * c) * (1.0 + c)
+
+
+@pytest.mark.parametrize("name,variant", [("eval_predict_b1", "predict"), ("eval_predict_b3_pred", "predict"),
+                                          ("eval_first_frame", "first_frame")])
+def test_other_evaluation_modes(name, variant):
+    """the reference's two other evaluators (tool/predict_evaluae.py:170-284: clips one frame apart, one score per clip,
+    optional frame prediction; main_predict.py:389-457: first-frame error) through the device-resident loop: the AUCs those
+    loops print (golden, exec'd unmodified) within 1e-4, per-video scores against the oracle"""
+    g = load_golden(name)
+    n = len(g["lengths"])
+    videos = [g[f"video{i}"].astype(np.float32) for i in range(n)]
+    labels = [g[f"label{i}"] for i in range(n)]
+    scenes = [str(s) for s in g["scenes"]]
+    fn, bs, isp = int(g["frame_num"]), int(g["batch_size"]), bool(int(g["ispredict"]))
+    auc, per, scores, labs = V.evaluate_videos(_tiny_t(variant, isp), [torch.tensor(v) for v in videos], labels, scenes,
+                                               fn, bs, mode=variant, ispredict=isp)
+    assert abs(auc - float(g["auc"])) < 1e-4
+    if variant == "predict":
+        np.testing.assert_allclose(list(per.values()), g["scene_aucs"], atol=1e-4)
+        _, _, oscores, olabs = O.evaluate_videos_predict(_tiny_n(variant, isp), videos, labels, scenes, fn, bs, isp, dtype=np.float32)
+    else:
+        _, _, oscores, olabs = O.evaluate_videos_first_frame(_tiny_n(variant, isp), videos, labels, scenes, fn, dtype=np.float32)
+    for a, b, la, lb in zip(scores, oscores, labs, olabs):
+        np.testing.assert_allclose(a, b, atol=5e-5)
+        assert list(la) == list(lb)
+
+
+def test_evaluation_loop_degenerate_videos_raise_like_the_reference():
+    """misc/utils.py:128,135: a perfectly reconstructed frame (mse 0) and a video of constant PSNR divide by zero; the
+    device loop raises the same ZeroDivisionError instead of feeding NaN scores to the AUC"""
+    v = torch.rand(3, 13, 8, 8)
+    lab = np.array([0, 1] * 6 + [0])
+    with pytest.raises(ZeroDivisionError):
+        V.evaluate_videos(lambda c: c.clone(), [v], [lab], ["01"], 4, 1)                  # recon == clip: mse = 0
+    const = torch.full((3, 13, 8, 8), 0.25)
+    with pytest.raises(ZeroDivisionError):
+        V.evaluate_videos(lambda c: c + 0.1, [const], [lab], ["01"], 4, 1)                # every frame: mse = 0.01
+
+
+def test_frame_mse_reads_strided_clip_views_in_place():
+    """clip batches are views of the resident video (consecutive or overlapping clips, single frames): same numbers as
+    the contiguous copy, no copy made"""
+    v = torch.rand(3, 40, 16, 20, device=dev())
+    from videoad_b200.scoring import _clip_batch_view, _plane_view
+    for step in (8, 1):
+        view = _clip_batch_view(v, 3, 4, step, 8)
+        assert view.data_ptr() == v[:, 3].data_ptr() and _plane_view(view).data_ptr() == view.data_ptr()
+        ref = torch.stack([v[:, 3 + i * step: 3 + i * step + 8] for i in range(4)])
+        assert torch.equal(view, ref)
+        recon = ref + 0.05 * torch.randn_like(ref)
+        assert torch.equal(V.frame_mse(recon, view), V.frame_mse(recon, ref))
+        assert torch.equal(V.frame_mse(recon[:, :, :1], view[:, :, :1]), V.frame_mse(recon[:, :, :1].contiguous(), ref[:, :, :1].contiguous()))
+
+
 def test_evaluation_loop_ragged_clip_raises_like_the_reference():
     """with batch_size > 1 the reference's loop raises RuntimeError (torch.cat) on a video whose tail clip is
     short; the drop-in raises the same exception type from torch.stack"""

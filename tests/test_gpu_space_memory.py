@@ -21,9 +21,7 @@ def make_space(C, K, side, alpha, centers, w, b):
 @pytest.mark.parametrize("name", ["space_c8_k6_p16", "space_c16_k40_p36"])
 def test_space_golden(name):
     g = load_golden(name)
-    C, K, P = g["centers"].shape
-    if K % 4:
-        pytest.skip("K % 4 != 0 is outside the kernel's documented constraint")
+    C, K, P = g["centers"].shape            # (space_c8_k6_p16: cluster_num = 6 — padded to 8 inside the wrapper)
     side = int(round(P ** 0.5))
     m = make_space(C, K, side, float(g["alpha"]), g["centers"], g["ln_w"], g["ln_b"])
     x = T(g["x"], grad=True)

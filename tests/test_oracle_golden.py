@@ -142,6 +142,31 @@ def test_evaluation_loop_matches_the_references_own_loop(name):
     np.testing.assert_allclose(list(per.values()), g["scene_aucs"], atol=1e-12)
 
 
+def _tiny(variant, ispredict, xp):
+    if variant == "predict" and ispredict:
+        return lambda c: c[:, :, -1:] + 0.05 * xp.sin(37.0 * c[:, :, -1:]) * (1.0 + c.mean(2, keepdims=True))
+    return lambda c: c + 0.05 * xp.sin(37.0 * c) * (1.0 + c)
+
+
+@pytest.mark.parametrize("name,variant", [("eval_predict_b1", "predict"), ("eval_predict_b3_pred", "predict"),
+                                          ("eval_first_frame", "first_frame")])
+def test_other_evaluation_loops_match_the_references_own(name, variant):
+    """oracle restatements of tool/predict_evaluae.py:170-284 and main_predict.py:389-457 vs the AUCs those loops print
+    when exec'd unmodified (make_golden.py::gen_eval_loop_variant)"""
+    g = load_golden(name)
+    n = len(g["lengths"])
+    videos = [g[f"video{i}"].astype(np.float32) for i in range(n)]
+    labels = [g[f"label{i}"] for i in range(n)]
+    scenes = [str(s) for s in g["scenes"]]
+    fn, bs, isp = int(g["frame_num"]), int(g["batch_size"]), bool(int(g["ispredict"]))
+    if variant == "predict":
+        auc, per, _, _ = O.evaluate_videos_predict(_tiny(variant, isp, np), videos, labels, scenes, fn, bs, isp, dtype=np.float32)
+        np.testing.assert_allclose(list(per.values()), g["scene_aucs"], atol=1e-12)
+    else:
+        auc, per, _, _ = O.evaluate_videos_first_frame(_tiny(variant, isp, np), videos, labels, scenes, fn, dtype=np.float32)
+    assert abs(auc - float(g["auc"])) < 1e-12
+
+
 def test_evaluation_clip_schedule():
     """tool/contrast_evaluae.py:185-203: strict '<' bounds drop a clip that would end exactly at T"""
     assert O.eval_clip_starts(8, 4, 1) == [[0]]

@@ -14,7 +14,8 @@ from .cluster import (EuclidDistance_Assign_Module, Space_EuclidDistance_Assign_
 from .memory import Memory, MemoryLoss
 from .losses import Recon_Loss, l1_mean, mse_mean, e4_norm, e4_sum
 from .scoring import (frame_mse, clip_mse, psnr, anomly_score, roc_auc_score, regularity_auc,
-                      minmax_score_device, evaluate_videos, eval_clip_starts)
+                      minmax_score_device, evaluate_videos, eval_clip_starts, eval_clip_starts_stride1,
+                      gather_video_scores)
 from .distributed import (init_distributed_mode, fix_random_seeds, setup_for_distributed, get_sha,
                           allreduce_sum_packed, global_frobenius, shard_range,
                           numa_local, pinned_like_local, gpu_local_cpus)
@@ -24,7 +25,7 @@ __all__ = [
     "EuclidDistance_Assign_Module", "Space_EuclidDistance_Assign_Module", "NegSoftAssign",
     "PosSoftAssign", "cluster_alpha", "cdist", "soft_assign", "Memory", "MemoryLoss", "Recon_Loss",
     "l1_mean", "mse_mean", "e4_norm", "e4_sum", "frame_mse", "clip_mse", "psnr", "anomly_score",
-    "roc_auc_score", "regularity_auc", "minmax_score_device", "evaluate_videos", "eval_clip_starts", "init_distributed_mode",
+    "roc_auc_score", "regularity_auc", "minmax_score_device", "evaluate_videos", "eval_clip_starts", "eval_clip_starts_stride1", "gather_video_scores", "init_distributed_mode",
     "fix_random_seeds", "setup_for_distributed", "get_sha", "allreduce_sum_packed",
     "global_frobenius", "shard_range", "numa_local", "pinned_like_local", "gpu_local_cpus", "patch_reference", "load_pretrain_model", "save_checkpoint", "launch_count",
     "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05",

@@ -39,6 +39,13 @@ class _ClusterAssign(torch.autograd.Function):
         cen, w, b = f32c(centers), f32c(ln_w), f32c(ln_b)
         N = x2.shape[0]
         dev = x2.device
+        # any cluster_num (model/cluster.py:58-75): rows of K values are addressed with 128-bit accesses, so the
+        # centroids are padded with zero rows to a multiple of 4 and the padding is excluded on the device
+        # (vadc_cluster_fwd_padded: A is exactly 0 there); the outputs are cut back to K columns
+        K_valid = K
+        if K % 4:
+            K = K + 4 - K % 4
+            cen = torch.cat([cen, cen.new_zeros((K - K_valid, C))])
         D = torch.empty((N, K), device=dev, dtype=torch.float32)
         A = torch.empty((N, K), device=dev, dtype=torch.float32)
         R = torch.empty((N, C), device=dev, dtype=torch.float32)
@@ -51,14 +58,23 @@ class _ClusterAssign(torch.autograd.Function):
         l = _lib.lib()
         nb = l.vadc_cluster_fwd_workspace_bytes(N, C, K, impl)
         ws = workspace(nb, dev)
-        check(l.vadc_cluster_fwd(ptr(x2), ptr(w), ptr(b), ptr(cen), N, C, K, float(alpha), float(eps),
-                                 ptr(D), ptr(A), ptr(R), ptr(F), ptr(label), ptr(mu), ptr(rstd),
-                                 ptr(rowstats), ptr(loss_sq), ptr(ws), ws.numel(), impl, stream()),
-              "vadc_cluster_fwd")
+        if K_valid == K:
+            check(l.vadc_cluster_fwd(ptr(x2), ptr(w), ptr(b), ptr(cen), N, C, K, float(alpha), float(eps),
+                                     ptr(D), ptr(A), ptr(R), ptr(F), ptr(label), ptr(mu), ptr(rstd),
+                                     ptr(rowstats), ptr(loss_sq), ptr(ws), ws.numel(), impl, stream()),
+                  "vadc_cluster_fwd")
+        else:
+            check(l.vadc_cluster_fwd_padded(ptr(x2), ptr(w), ptr(b), ptr(cen), N, C, K, K_valid, float(alpha), float(eps),
+                                            ptr(D), ptr(A), ptr(R), ptr(F), ptr(label), ptr(mu), ptr(rstd),
+                                            ptr(rowstats), ptr(loss_sq), ptr(ws), ws.numel(), stream()),
+                  "vadc_cluster_fwd_padded")
         ctx.save_for_backward(x2, cen, w, b, D, A, F, mu, rstd, rowstats)
-        ctx.alpha, ctx.lead = float(alpha), lead
+        ctx.alpha, ctx.lead, ctx.K_valid = float(alpha), lead, K_valid
         ctx.mark_non_differentiable(label)
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero tensors
+        if K_valid != K:
+            Dv, Av = D[:, :K_valid].contiguous(), A[:, :K_valid].contiguous()
+            return (Dv.view(*lead, K_valid), Av.view(*lead, K_valid), R.view(*lead, C), F, label, loss_sq)
         return (D.view(*lead, K), A.view(*lead, K), R.view(*lead, C), F, label, loss_sq)
 
     @staticmethod
@@ -68,10 +84,18 @@ class _ClusterAssign(torch.autograd.Function):
         K = cen.shape[0]
         dev = x2.device
 
+        Kv = ctx.K_valid
+
         def prep(g, cols):
             return None if g is None else f32c(g).reshape(-1, cols)
 
-        gD, gA, gR, gF = prep(gD, K), prep(gA, K), prep(gR, C), prep(gF, C)
+        def prep_k(g):                             # gradients of the K_valid real columns; the padding gets zeros
+            if g is None:
+                return None
+            g = f32c(g).reshape(-1, Kv)
+            return g if Kv == K else torch.nn.functional.pad(g, (0, K - Kv))
+
+        gD, gA, gR, gF = prep_k(gD), prep_k(gA), prep(gR, C), prep(gF, C)
         gLsq = None if gLsq is None else f32c(gLsq)
         gx = torch.empty((N, C), device=dev, dtype=torch.float32)
         gc = torch.empty((K, C), device=dev, dtype=torch.float32)
@@ -84,7 +108,7 @@ class _ClusterAssign(torch.autograd.Function):
                                  ptr(gD), ptr(gA), ptr(gR), ptr(gF), ptr(gLsq), N, C, K, ctx.alpha,
                                  ptr(gx), ptr(gc), ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream()),
               "vadc_cluster_bwd")
-        return gx.view(*ctx.lead, C), gc, gw, gb, None, None, None
+        return gx.view(*ctx.lead, C), (gc if Kv == K else gc[:Kv]), gw, gb, None, None, None
 
 
 def cdist(a, b):
@@ -254,6 +278,10 @@ class _SpaceClusterAssign(torch.autograd.Function):
         cen, w, b = f32c(centers), f32c(ln_w), f32c(ln_b)
         M = B * Dd
         dev = x2.device
+        K_valid = K
+        if K % 4:                                  # any cluster_num: zero rows up to a multiple of 4, excluded on the device
+            K = K + 4 - K % 4
+            cen = torch.cat([cen, cen.new_zeros((C, K - K_valid, P))], dim=1)
         Ds = torch.empty((M, C, K), device=dev, dtype=torch.float32)
         As = torch.empty((M, C, K), device=dev, dtype=torch.float32)
         zt = torch.empty((C, M, P), device=dev, dtype=torch.float32)
@@ -263,13 +291,22 @@ class _SpaceClusterAssign(torch.autograd.Function):
         l = _lib.lib()
         nb = l.vadc_space_cluster_fwd_workspace_bytes(M, P, C, K)
         ws = workspace(nb, dev)
-        check(l.vadc_space_cluster_fwd(ptr(x2), ptr(w), ptr(b), ptr(cen), M, P, C, K, float(alpha),
-                                       float(eps), ptr(Ds), ptr(As), ptr(zt), ptr(mu), ptr(rstd),
-                                       ptr(loss_sq), ptr(ws), ws.numel(), stream()),
-              "vadc_space_cluster_fwd")
+        if K_valid == K:
+            check(l.vadc_space_cluster_fwd(ptr(x2), ptr(w), ptr(b), ptr(cen), M, P, C, K, float(alpha),
+                                           float(eps), ptr(Ds), ptr(As), ptr(zt), ptr(mu), ptr(rstd),
+                                           ptr(loss_sq), ptr(ws), ws.numel(), stream()),
+                  "vadc_space_cluster_fwd")
+        else:
+            check(l.vadc_space_cluster_fwd_padded(ptr(x2), ptr(w), ptr(b), ptr(cen), M, P, C, K, K_valid, float(alpha),
+                                                  float(eps), ptr(Ds), ptr(As), ptr(zt), ptr(mu), ptr(rstd),
+                                                  ptr(loss_sq), ptr(ws), ws.numel(), stream()),
+                  "vadc_space_cluster_fwd_padded")
         ctx.save_for_backward(x2, cen, w, Ds, As, zt, mu, rstd)
-        ctx.alpha, ctx.shape = float(alpha), (B, Dd, H, W, C)
+        ctx.alpha, ctx.shape, ctx.K_valid = float(alpha), (B, Dd, H, W, C), K_valid
         ctx.set_materialize_grads(False)
+        if K_valid != K:
+            return (Ds[:, :, :K_valid].contiguous().view(B, Dd, C, K_valid),
+                    As[:, :, :K_valid].contiguous().view(B, Dd, C, K_valid), loss_sq)
         return Ds.view(B, Dd, C, K), As.view(B, Dd, C, K), loss_sq
 
     @staticmethod
@@ -278,8 +315,15 @@ class _SpaceClusterAssign(torch.autograd.Function):
         B, Dd, H, W, C = ctx.shape
         M, P, K = B * Dd, H * W, cen.shape[1]
         dev = x2.device
-        gD = None if gD is None else f32c(gD).reshape(M, C, K)
-        gA = None if gA is None else f32c(gA).reshape(M, C, K)
+        Kv = ctx.K_valid
+
+        def prep_k(g):
+            if g is None:
+                return None
+            g = f32c(g).reshape(M, C, Kv)
+            return g if Kv == K else torch.nn.functional.pad(g, (0, K - Kv))
+
+        gD, gA = prep_k(gD), prep_k(gA)
         gLsq = None if gLsq is None else f32c(gLsq)
         gx = torch.empty((M * P, C), device=dev, dtype=torch.float32)
         gc = torch.empty_like(cen)
@@ -292,7 +336,7 @@ class _SpaceClusterAssign(torch.autograd.Function):
                                        ptr(As), ptr(gD), ptr(gA), ptr(gLsq), M, P, C, K, ctx.alpha,
                                        ptr(gx), ptr(gc), ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream()),
               "vadc_space_cluster_bwd")
-        return gx.view(B, Dd, H, W, C), gc, gw, gb, None, None
+        return gx.view(B, Dd, H, W, C), (gc if Kv == K else gc[:, :Kv].contiguous()), gw, gb, None, None
 
 
 class Space_EuclidDistance_Assign_Module(nn.Module):

@@ -124,7 +124,8 @@ int softmin_blocks(long long R, int K) {
 
 // A, label, loss_sq from D.  partial: softmin_blocks(R,K) doubles.
 int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* A, long long* label,
-                        double* partial, float* loss_sq, cudaStream_t st) {
+                        double* partial, float* loss_sq, cudaStream_t st, int k_valid) {
+  if (k_valid < 0 || k_valid > K) k_valid = K;
   if (R == 0) {
     zero_kernel<<<1, 32, 0, st>>>(loss_sq, 1);
     VADC_CHECK_LAUNCH("zero_kernel");
@@ -133,10 +134,10 @@ int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* 
   int G = group_for(K);
   int nb = softmin_blocks(R, K);
   switch (G) {
-    case 4: softmin_rows_kernel<4><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
-    case 8: softmin_rows_kernel<8><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
-    case 16: softmin_rows_kernel<16><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
-    default: softmin_rows_kernel<32><<<nb, 256, 0, st>>>(D, R, K, alpha, A, label, partial); break;
+    case 4: softmin_rows_kernel<4><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial); break;
+    case 8: softmin_rows_kernel<8><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial); break;
+    case 16: softmin_rows_kernel<16><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial); break;
+    default: softmin_rows_kernel<32><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial); break;
   }
   VADC_CHECK_LAUNCH("softmin_rows_kernel");
   finalize_sum_kernel<<<1, 1024, 0, st>>>(partial, nb, loss_sq);
@@ -264,11 +265,11 @@ extern "C" size_t vadc_cluster_fwd_workspace_bytes(int64_t N, int C, int K, int 
   return b + 256;
 }
 
-extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
-                                const float* centers, int64_t N, int C, int K, float alpha,
-                                float eps, float* D, float* A, float* x_rec, float* feature,
-                                int64_t* label, float* mu, float* rstd, float* rowstats, float* loss_sq,
-                                void* workspace, size_t workspace_bytes, int impl, void* stream) {
+static int cluster_fwd_impl(const float* x, const float* ln_w, const float* ln_b,
+                            const float* centers, int64_t N, int C, int K, int k_valid, float alpha,
+                            float eps, float* D, float* A, float* x_rec, float* feature,
+                            int64_t* label, float* mu, float* rstd, float* rowstats, float* loss_sq,
+                            void* workspace, size_t workspace_bytes, int impl, void* stream) {
   VADC_REQUIRE(N >= 0 && C > 0 && K > 0 && (C % 4) == 0 && (K % 4) == 0, VADC_ERR_BAD_SHAPE);
   VADC_REQUIRE(N < (1ll << 31) && C <= 1024, VADC_ERR_UNSUPPORTED);
   VADC_REQUIRE(ln_w && ln_b && centers && loss_sq && workspace, VADC_ERR_NULL_POINTER);
@@ -333,7 +334,7 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
   if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, feature, mu, rstd, zz, st, rowstats))) return rc;
   if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
   if ((rc = launch_dist(feature, centers, zz, cc, 1, N, K, C, D, st))) return rc;
-  if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
+  if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st, k_valid))) return rc;
   if (N > 0) {
     Operand Aop{A, K, 1}, Bop{centers, C, 1};
     StoreEpilogue epi{x_rec, C};
@@ -341,6 +342,26 @@ extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* 
     if (e != cudaSuccess) return record_cuda_error(e, "x_rec sgemm");
   }
   return VADC_OK;
+}
+
+extern "C" int vadc_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
+                                const float* centers, int64_t N, int C, int K, float alpha,
+                                float eps, float* D, float* A, float* x_rec, float* feature,
+                                int64_t* label, float* mu, float* rstd, float* rowstats, float* loss_sq,
+                                void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  return cluster_fwd_impl(x, ln_w, ln_b, centers, N, C, K, K, alpha, eps, D, A, x_rec, feature, label, mu, rstd, rowstats,
+                          loss_sq, workspace, workspace_bytes, impl, stream);
+}
+
+// any cluster_num: the host pads the centroids to K % 4 == 0 rows; the trailing K - K_valid rows are excluded
+extern "C" int vadc_cluster_fwd_padded(const float* x, const float* ln_w, const float* ln_b,
+                                       const float* centers, int64_t N, int C, int K, int K_valid, float alpha,
+                                       float eps, float* D, float* A, float* x_rec, float* feature,
+                                       int64_t* label, float* mu, float* rstd, float* rowstats, float* loss_sq,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(K_valid >= 1 && K_valid <= K, VADC_ERR_BAD_SHAPE);
+  return cluster_fwd_impl(x, ln_w, ln_b, centers, N, C, K, K_valid, alpha, eps, D, A, x_rec, feature, label, mu, rstd,
+                          rowstats, loss_sq, workspace, workspace_bytes, K_valid == K ? VADC_IMPL_AUTO : VADC_IMPL_SIMT, stream);
 }
 
 namespace vadc {

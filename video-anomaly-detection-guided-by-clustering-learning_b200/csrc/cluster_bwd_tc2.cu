@@ -691,6 +691,9 @@ cluster_bwd_tc2_kernel(const __grid_constant__ CUtensorMap mapGx, const __grid_c
         mbar_wait(&bars[B_ACCFULL], (uint32_t)par);
         TR(21, it);
         tc_fence_after();
+        // (tried: both 32-column halves of the accumulator pulled into registers at once and the accumulator handed back
+        //  immediately, so that S3 of the next tile runs under this tile's epilogue: the S3 gap disappears, but the 64 extra
+        //  live registers cost 204 B of spills and this role's per-tile time went from ~8 k to ~10 k cycles: 341 -> 355 us)
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int c0 = e3 * 64 + ch * 32;

@@ -93,9 +93,11 @@ pixel_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, 
 // one frame; partials go to a [B*T, slices] buffer and are summed in fixed
 // order by the finalize kernel (deterministic, no atomics).
 // ---------------------------------------------------------------------------
+struct FrameStrides { long long rb, rc, rt, cb, cc, ct; };   // element strides of recon / clip along batch, channel, frame
+
 __global__ void __launch_bounds__(256)
 frame_mse_kernel(const float* __restrict__ recon, const float* __restrict__ clip, int Cc, int T,
-                 long long HW, int slices, double* __restrict__ partial) {
+                 long long HW, int slices, const FrameStrides fs, double* __restrict__ partial) {
   __shared__ double red[32];
   const int frame = blockIdx.y;           // b*T + t
   const int b = frame / T, t = frame % T;
@@ -105,9 +107,8 @@ frame_mse_kernel(const float* __restrict__ recon, const float* __restrict__ clip
   const long long v0 = slice * per, v1 = min(nv, v0 + per);
   float acc0 = 0.f, acc1 = 0.f;
   for (int c = 0; c < Cc; ++c) {
-    const long long off = (((long long)b * Cc + c) * T + t) * HW;
-    const float4* r4 = reinterpret_cast<const float4*>(recon + off);
-    const float4* c4 = reinterpret_cast<const float4*>(clip + off);
+    const float4* r4 = reinterpret_cast<const float4*>(recon + b * fs.rb + c * fs.rc + t * fs.rt);
+    const float4* c4 = reinterpret_cast<const float4*>(clip + b * fs.cb + c * fs.cc + t * fs.ct);
     long long i = v0 + threadIdx.x;
     for (; i + 256 < v1; i += 512) {
       float4 a0 = ld_stream(r4 + i), b0 = ld_stream(c4 + i);
@@ -127,14 +128,15 @@ frame_mse_kernel(const float* __restrict__ recon, const float* __restrict__ clip
 // generic (HW % 4 != 0) fallback: scalar loads
 __global__ void __launch_bounds__(256)
 frame_mse_scalar_kernel(const float* __restrict__ recon, const float* __restrict__ clip, int Cc,
-                        int T, long long HW, double* __restrict__ partial) {
+                        int T, long long HW, const FrameStrides fs, double* __restrict__ partial) {
   __shared__ double red[32];
   const int frame = blockIdx.x;
   const int b = frame / T, t = frame % T;
   float acc = 0.f;
   for (int c = 0; c < Cc; ++c) {
-    const long long off = (((long long)b * Cc + c) * T + t) * HW;
-    for (long long i = threadIdx.x; i < HW; i += 256) acc += term<1>(recon[off + i], clip[off + i]);
+    const float* rp = recon + b * fs.rb + c * fs.rc + t * fs.rt;
+    const float* cp = clip + b * fs.cb + c * fs.cc + t * fs.ct;
+    for (long long i = threadIdx.x; i < HW; i += 256) acc += term<1>(rp[i], cp[i]);
   }
   double s = block_sum<double>((double)acc, red);
   if (threadIdx.x == 0) partial[frame] = s;
@@ -244,31 +246,51 @@ extern "C" size_t vadc_frame_mse_workspace_bytes(int B, int T, int64_t HW, int C
   return align_up((size_t)B * T * frame_slices(B * T, HW, Cc) * sizeof(double), 256) + 256;
 }
 
-extern "C" int vadc_frame_mse(const float* recon, const float* clip, int B, int Cc, int T,
-                                 int64_t HW, float* mse, double* psnr, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+static int frame_mse_impl(const float* recon, const float* clip, int B, int Cc, int T, int64_t HW, const FrameStrides fs,
+                          float* mse, double* psnr, void* workspace, size_t workspace_bytes, void* stream) {
   VADC_REQUIRE(B >= 0 && Cc > 0 && T >= 0 && HW > 0, VADC_ERR_BAD_SHAPE);
   if (B == 0 || T == 0) return VADC_OK;
   VADC_REQUIRE(recon && clip && mse && workspace, VADC_ERR_NULL_POINTER);
-  VADC_REQUIRE(aligned16(recon) && aligned16(clip), VADC_ERR_MISALIGNED);
   VADC_REQUIRE((long long)B * T < 65536ll * 1024, VADC_ERR_UNSUPPORTED);
   VADC_REQUIRE(workspace_bytes >= vadc_frame_mse_workspace_bytes(B, T, HW, Cc), VADC_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int frames = B * T;
   double* partial = static_cast<double*>(workspace);
   int slices = 1;
-  if ((HW & 3) == 0 && frames <= 65535) {
+  const bool vec = (HW & 3) == 0 && aligned16(recon) && aligned16(clip) &&
+                   ((fs.rb | fs.rc | fs.rt | fs.cb | fs.cc | fs.ct) & 3) == 0;    // every plane starts on a 16-byte boundary
+  if (vec && frames <= 65535) {
     slices = frame_slices(frames, HW, Cc);
     dim3 grid(slices, frames);
-    frame_mse_kernel<<<grid, 256, 0, st>>>(recon, clip, Cc, T, HW, slices, partial);
+    frame_mse_kernel<<<grid, 256, 0, st>>>(recon, clip, Cc, T, HW, slices, fs, partial);
     VADC_CHECK_LAUNCH("frame_mse_kernel");
   } else {
-    frame_mse_scalar_kernel<<<frames, 256, 0, st>>>(recon, clip, Cc, T, HW, partial);
+    frame_mse_scalar_kernel<<<frames, 256, 0, st>>>(recon, clip, Cc, T, HW, fs, partial);
     VADC_CHECK_LAUNCH("frame_mse_scalar_kernel");
   }
   frame_mse_finalize_kernel<<<(frames + 255) / 256, 256, 0, st>>>(partial, frames, slices, (double)Cc * (double)HW, mse, psnr);
   VADC_CHECK_LAUNCH("frame_mse_finalize_kernel");
   return VADC_OK;
+}
+
+extern "C" int vadc_frame_mse(const float* recon, const float* clip, int B, int Cc, int T,
+                                 int64_t HW, float* mse, double* psnr, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(aligned16(recon) && aligned16(clip), VADC_ERR_MISALIGNED);
+  const FrameStrides fs{(long long)Cc * T * HW, (long long)T * HW, HW, (long long)Cc * T * HW, (long long)T * HW, HW};
+  return frame_mse_impl(recon, clip, B, Cc, T, HW, fs, mse, psnr, workspace, workspace_bytes, stream);
+}
+
+// the same reduction over STRIDED views: clip batches taken out of a device-resident video without a copy (consecutive
+// or overlapping clips), single frames of a reconstruction (recon[:, :, 0]); strides in elements
+extern "C" int vadc_frame_mse_strided(const float* recon, int64_t recon_stride_b, int64_t recon_stride_c, int64_t recon_stride_t,
+                                      const float* clip, int64_t clip_stride_b, int64_t clip_stride_c, int64_t clip_stride_t,
+                                      int B, int Cc, int T, int64_t HW, float* mse, double* psnr,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(recon_stride_b >= 0 && recon_stride_c >= 0 && recon_stride_t >= 0 && clip_stride_b >= 0 &&
+               clip_stride_c >= 0 && clip_stride_t >= 0, VADC_ERR_BAD_SHAPE);
+  const FrameStrides fs{recon_stride_b, recon_stride_c, recon_stride_t, clip_stride_b, clip_stride_c, clip_stride_t};
+  return frame_mse_impl(recon, clip, B, Cc, T, HW, fs, mse, psnr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int vadc_minmax_score(const double* psnr, const int64_t* seg_offsets, int n_videos,

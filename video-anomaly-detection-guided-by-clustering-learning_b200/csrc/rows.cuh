@@ -135,9 +135,22 @@ row_sqnorm_kernel(const float* __restrict__ a, long long R, int C, float* __rest
 //   label = first argmin, A = exp(-alpha (d - dmin)) / sum, part += (d*A)^2.
 // Block partial sums of (d*A)^2 go to `partial[blockIdx.x]` (double).
 // ---------------------------------------------------------------------------
+// columns >= k_valid are padding (the host pads cluster_num to a multiple of 4): excluded from argmin / softmin / loss,
+// their A is exactly 0 (exp(-inf)); D keeps the finite distance to the padding row
+__device__ __forceinline__ float4 mask_pad(float4 v, int k, int k_valid) {
+  if (k + 3 >= k_valid) {
+    if (k >= k_valid) v.x = INFINITY;
+    if (k + 1 >= k_valid) v.y = INFINITY;
+    if (k + 2 >= k_valid) v.z = INFINITY;
+    if (k + 3 >= k_valid) v.w = INFINITY;
+  }
+  return v;
+}
+__device__ __forceinline__ float da_sq(float d, float a) { const float p = a == 0.f ? 0.f : d * a; return p * p; }
+
 template <int G>
 __global__ void __launch_bounds__(256)
-softmin_rows_kernel(const float* __restrict__ D, long long R, int K, float alpha,
+softmin_rows_kernel(const float* __restrict__ D, long long R, int K, int k_valid, float alpha,
                     float* __restrict__ A, long long* __restrict__ label,
                     double* __restrict__ partial) {
   __shared__ double red[32];
@@ -152,8 +165,8 @@ softmin_rows_kernel(const float* __restrict__ D, long long R, int K, float alpha
     float best = INFINITY;
     int bidx = 0x7fffffff;
     for (int i = gl; i < nv; i += G) {
-      float4 v = dr[i];
       int k = i * 4;
+      float4 v = mask_pad(dr[i], k, k_valid);
       if (v.x < best) { best = v.x; bidx = k; }
       if (v.y < best) { best = v.y; bidx = k + 1; }
       if (v.z < best) { best = v.z; bidx = k + 2; }
@@ -167,7 +180,7 @@ softmin_rows_kernel(const float* __restrict__ D, long long R, int K, float alpha
     }
     float s = 0.f;
     for (int i = gl; i < nv; i += G) {
-      float4 v = dr[i];
+      float4 v = mask_pad(dr[i], i * 4, k_valid);
       s += (expf(-alpha * (v.x - best)) + expf(-alpha * (v.y - best))) +
            (expf(-alpha * (v.z - best)) + expf(-alpha * (v.w - best)));
     }
@@ -176,14 +189,13 @@ softmin_rows_kernel(const float* __restrict__ D, long long R, int K, float alpha
     float4* ar = reinterpret_cast<float4*>(A + row * K);
     float l = 0.f;
     for (int i = gl; i < nv; i += G) {
-      float4 v = dr[i], a;
+      float4 v = mask_pad(dr[i], i * 4, k_valid), a;
       a.x = expf(-alpha * (v.x - best)) / s;
       a.y = expf(-alpha * (v.y - best)) / s;
       a.z = expf(-alpha * (v.z - best)) / s;
       a.w = expf(-alpha * (v.w - best)) / s;
       ar[i] = a;
-      float p0 = v.x * a.x, p1 = v.y * a.y, p2 = v.z * a.z, p3 = v.w * a.w;
-      l += (p0 * p0 + p1 * p1) + (p2 * p2 + p3 * p3);
+      l += (da_sq(v.x, a.x) + da_sq(v.y, a.y)) + (da_sq(v.z, a.z) + da_sq(v.w, a.w));
     }
     lsum = (double)l;
     if (gl == 0 && label) label[row] = bidx;

@@ -178,11 +178,11 @@ extern "C" size_t vadc_space_cluster_fwd_workspace_bytes(int64_t M, int P, int C
   return b + 256;
 }
 
-extern "C" int vadc_space_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
-                                      const float* centers, int64_t M, int P, int C, int K,
-                                      float alpha, float eps, float* Ds, float* As, float* zt,
-                                      float* mu, float* rstd, float* loss_sq, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
+static int space_cluster_fwd_impl(const float* x, const float* ln_w, const float* ln_b,
+                                  const float* centers, int64_t M, int P, int C, int K, int k_valid,
+                                  float alpha, float eps, float* Ds, float* As, float* zt,
+                                  float* mu, float* rstd, float* loss_sq, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   VADC_REQUIRE(M >= 0 && P > 0 && C > 0 && K > 0 && (K % 4) == 0, VADC_ERR_BAD_SHAPE);
   VADC_REQUIRE(M * (int64_t)P < (1ll << 31) && M * (int64_t)C < (1ll << 31), VADC_ERR_UNSUPPORTED);
   VADC_REQUIRE(ln_w && ln_b && centers && loss_sq && workspace, VADC_ERR_NULL_POINTER);
@@ -220,7 +220,27 @@ extern "C" int vadc_space_cluster_fwd(const float* x, const float* ln_w, const f
       if (e != cudaSuccess) return record_cuda_error(e, "space dist sgemm");
     }
   }
-  return launch_softmin_rows(Ds, M * (long long)C, K, alpha, As, nullptr, partial, loss_sq, st);
+  return launch_softmin_rows(Ds, M * (long long)C, K, alpha, As, nullptr, partial, loss_sq, st, k_valid);
+}
+
+extern "C" int vadc_space_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
+                                      const float* centers, int64_t M, int P, int C, int K,
+                                      float alpha, float eps, float* Ds, float* As, float* zt,
+                                      float* mu, float* rstd, float* loss_sq, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  return space_cluster_fwd_impl(x, ln_w, ln_b, centers, M, P, C, K, K, alpha, eps, Ds, As, zt, mu, rstd, loss_sq, workspace,
+                                workspace_bytes, stream);
+}
+
+// any cluster_num: centers [C, K, P] padded by the host to K % 4 == 0; the trailing K - K_valid rows of every channel are excluded
+extern "C" int vadc_space_cluster_fwd_padded(const float* x, const float* ln_w, const float* ln_b,
+                                             const float* centers, int64_t M, int P, int C, int K, int K_valid,
+                                             float alpha, float eps, float* Ds, float* As, float* zt,
+                                             float* mu, float* rstd, float* loss_sq, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(K_valid >= 1 && K_valid <= K, VADC_ERR_BAD_SHAPE);
+  return space_cluster_fwd_impl(x, ln_w, ln_b, centers, M, P, C, K, K_valid, alpha, eps, Ds, As, zt, mu, rstd, loss_sq,
+                                workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t vadc_space_cluster_bwd_workspace_bytes(int64_t M, int P, int C, int K) {

@@ -13,23 +13,40 @@ from . import _lib
 from ._lib import check, f32c, ptr, stream, workspace
 
 
-def frame_mse(recon, clip, want_psnr=False):
+def _plane_view(t):
+    """a [B,C,T,H,W] tensor whose H*W planes are contiguous is used as it is (strided batch / channel / frame axes: a
+    clip batch cut out of a resident video, ``recon[:, :, :1]``); anything else is made contiguous"""
+    t = t if t.dtype == torch.float32 else t.float()
+    H, W = t.shape[-2:]
+    ok = (W == 1 or t.stride(-1) == 1) and (H == 1 or t.stride(-2) == W) and all(st >= 0 for st in t.stride())
+    if not ok or t.data_ptr() % 4:
+        t = t.contiguous()
+    return t
+
+
+def frame_mse(recon, clip, want_psnr=False, out_mse=None, out_psnr=None):
     """per-frame MSE of a clip batch: recon, clip [B,C,D,H,W] -> [B,D] fp32
     (``MSELoss(none)`` -> 'B C D H W -> B D C H W' -> mean W, H, C;
     contrast_evaluae.py:232-235).  One pass over both tensors, nothing
-    materialised.  With ``want_psnr`` also returns 10 log10(1/mse) [B,D] float64
-    computed on the device (device-resident evaluation loop)."""
+    materialised; strided views (clips cut out of a resident video) are read in place.  With ``want_psnr`` also returns
+    10 log10(1/mse) [B,D] float64 computed on the device (device-resident evaluation loop).
+    ``out_mse`` / ``out_psnr``: optional contiguous [B*D] destinations (slices of a whole-run buffer)."""
     _lib.require_cuda(recon, clip)
     if recon.shape != clip.shape:
         raise RuntimeError(f"The size of tensor a {tuple(recon.shape)} must match the size of tensor b {tuple(clip.shape)}")
-    r, c = f32c(recon), f32c(clip)
+    r, c = _plane_view(recon), _plane_view(clip)
     B, Cc, T, H, W = r.shape
-    mse = torch.empty((B, T), device=r.device, dtype=torch.float32)
-    ps = torch.empty((B, T), device=r.device, dtype=torch.float64) if want_psnr else None
+    mse = torch.empty((B, T), device=r.device, dtype=torch.float32) if out_mse is None else out_mse
+    ps = None
+    if want_psnr:
+        ps = torch.empty((B, T), device=r.device, dtype=torch.float64) if out_psnr is None else out_psnr
+    if B * T == 0:
+        return (mse, ps) if want_psnr else mse
     l = _lib.lib()
     ws = workspace(l.vadc_frame_mse_workspace_bytes(B, T, H * W, Cc), r.device)
-    check(l.vadc_frame_mse(ptr(r), ptr(c), B, Cc, T, H * W, ptr(mse), ptr(ps), ptr(ws), ws.numel(), stream()),
-          "vadc_frame_mse")
+    check(l.vadc_frame_mse_strided(ptr(r), r.stride(0), r.stride(1), r.stride(2), ptr(c), c.stride(0), c.stride(1), c.stride(2),
+                                   B, Cc, T, H * W, ptr(mse), ptr(ps), ptr(ws), ws.numel(), stream()),
+          "vadc_frame_mse_strided")
     return (mse, ps) if want_psnr else mse
 
 
@@ -125,42 +142,137 @@ def eval_clip_starts(n_frames, frame_num, batch_size):
     return batches
 
 
+def eval_clip_starts_stride1(n_frames, frame_num, batch_size):
+    """clip schedule of tool/predict_evaluae.py:185-203 and (batch 1) main_predict.py:401-404: clips one frame apart"""
+    batches, index = [], 0
+    while index + frame_num < n_frames:
+        starts = [index]
+        for _ in range(batch_size - 1):
+            if index + frame_num + 1 < n_frames:
+                index = index + 1
+                starts.append(index)
+            else:
+                break
+        index = index + 1
+        batches.append(starts)
+    return batches
+
+
+def _clip_batch_view(v, start, nclips, step, frame_num):
+    """[nclips, C, frame_num, H, W] view of the resident video ``v`` [C,T,H,W]: clip i = frames start + i*step ...;
+    no copy (consecutive clips for step = frame_num, overlapping ones for step = 1)"""
+    C, T, H, W = v.shape
+    if start + (nclips - 1) * step + frame_num > T:
+        # the reference concatenates a short tail clip onto full ones (contrast_evaluae.py:196): torch.cat's error
+        raise RuntimeError("Sizes of tensors must match except in dimension 0. Expected size %d but got size %d for tensor "
+                           "number 1 in the list." % (frame_num, T - (start + (nclips - 1) * step)))
+    sc, st, sh, sw = v.stride()
+    return v.as_strided((nclips, C, frame_num, H, W), (step * st, sc, st, sh, sw), v.storage_offset() + start * st)
+
+
+def gather_video_scores(local):
+    """§8e 'scoring under DP': every rank scored its own videos; rank 0 needs all of them in video order for the
+    per-scene AUC.  ``local`` = list of (video_index, scores ndarray, labels ndarray).  Returns the merged, ordered list
+    on every rank (the payload is ~40 k floats for the ShanghaiTech test set: one object all-gather)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return sorted(local, key=lambda t: t[0])
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, local)
+    return sorted((item for part in parts for item in part), key=lambda t: t[0])
+
+
 @torch.no_grad()
-def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size):
-    """Device-resident evaluation loop with the semantics of
-    tool/contrast_evaluae.py:170-300 (non-predict mode).
+def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size, mode="contrast", ispredict=False,
+                    shard=False):
+    """Device-resident evaluation loop with the semantics of the reference's three evaluators:
+
+    ``mode='contrast'``     tool/contrast_evaluae.py:170-300 (non-predict): consecutive clips, one score per FRAME
+    ``mode='predict'``      tool/predict_evaluae.py:170-284: clips one frame apart, one score per CLIP; with
+                            ``ispredict`` the model sees the clip's first four frames and its last frame is the target
+    ``mode='first_frame'``  main_predict.py:389-457: clips one frame apart, the score is the error of the clip's first frame
 
     ``videos``: list of [C,T,H,W] tensors (host or device; a host video is copied to the GPU ONCE instead of
     once per clip), ``labels``: per-video [T] frame labels, ``scenes``: per-video scene id.
-    ``model_fn(clips [B,C,D,H,W]) -> recon [B,C,D,H,W]`` (for the reference's ``Mymodel`` pass
-    ``lambda c: model(c)[0]``).  Per clip batch ONE fused kernel produces per-frame MSE and PSNR on the device
-    (no materialised loss tensor, no ``.tolist()`` sync per clip); per-video min-max normalisation runs on the
-    device over all videos at once; only the final scores cross to the host for the per-scene AUC.
-    Returns (auc, {scene: auc}, [per-video score arrays], [per-video label arrays])."""
-    dev = None
-    ps_chunks, seg, lab_out = [], [0], []
-    for vid, lab in zip(videos, labels):
-        v = vid if vid.is_cuda else vid.cuda(non_blocking=True)
-        dev = v.device
-        lab = np.asarray(lab.cpu() if isinstance(lab, torch.Tensor) else lab).reshape(-1)
-        n, labs = 0, []
-        for starts in eval_clip_starts(v.shape[1], frame_num, batch_size):
-            clip = torch.stack([v[:, s0:s0 + frame_num] for s0 in starts])       # [B,C,D,H,W]
-            recon = model_fn(clip)
-            _, ps = frame_mse(recon, clip, want_psnr=True)                       # [B,D] float64, on the device
-            ps_chunks.append(ps.reshape(-1))
-            n += ps.numel()
-            for s0 in starts:
-                labs.append(lab[s0:s0 + frame_num])
-        seg.append(seg[-1] + n)
-        lab_out.append(np.concatenate(labs) if labs else np.zeros(0, lab.dtype))
-    if dev is None or seg[-1] == 0:
+    ``model_fn(clips [B,C,D,H,W]) -> recon`` (for the reference's ``Mymodel`` pass ``lambda c: model(c)[0]``); the clip
+    batch is a strided VIEW of the resident video (no stack / cat copy).  Per clip batch ONE fused reduction writes MSE
+    and PSNR straight into the whole-run buffers on the device (no materialised loss tensor, no ``.tolist()`` sync per
+    clip); per-video min-max normalisation runs on the device over all videos at once; only the final scores cross to
+    the host for the per-scene AUC.  ``shard=True``: the videos are split over the ranks of the default process group
+    (contiguous ``shard_range``), the scores are gathered and every rank returns the same result (§8e).
+    A video whose PSNR is constant, or a frame reconstructed exactly (MSE 0), raises ZeroDivisionError like
+    misc/utils.py:128,135.  Returns (auc, {scene: auc}, [per-video score arrays], [per-video label arrays])."""
+    if mode not in ("contrast", "predict", "first_frame"):
+        raise ValueError(f"unknown evaluation mode {mode!r}")
+    labels = [np.asarray(l.cpu() if isinstance(l, torch.Tensor) else l).reshape(-1) for l in labels]
+    n_videos = len(labels)
+    lo, hi = 0, n_videos
+    if shard:
+        from .distributed import shard_range
+        lo, hi = shard_range(n_videos)
+    step = frame_num if mode == "contrast" else 1
+    sched = eval_clip_starts if mode == "contrast" else eval_clip_starts_stride1
+    per_clip = frame_num if mode == "contrast" else 1
+    # the schedule of every video of this rank (host integers; a video has as many frames as labels) -> buffer sizes
+    plans, total = {}, 0
+    for i in range(lo, hi):
+        batches = sched(len(labels[i]), frame_num, batch_size)
+        n = sum(len(b) for b in batches) * per_clip
+        plans[i] = (batches, total, n)
+        total += n
+    local = []
+    if total > 0:
+        mse_all = ps_all = None
+        seg, order = [0], []
+        for i, vid in enumerate(videos):
+            if i >= hi:
+                break
+            if i < lo:
+                continue
+            batches, off, n = plans[i]
+            lab = labels[i]
+            if vid.shape[1] != len(lab):
+                raise ValueError(f"video {i}: {vid.shape[1]} frames but {len(lab)} labels")
+            v = f32c(vid if vid.is_cuda else vid.cuda(non_blocking=True))          # resident once, not once per clip
+            if mse_all is None:
+                mse_all = torch.empty((total,), device=v.device, dtype=torch.float32)
+                ps_all = torch.empty((total,), device=v.device, dtype=torch.float64)
+            labs = []
+            for starts in batches:
+                nb = len(starts)
+                clip = _clip_batch_view(v, starts[0], nb, step, frame_num)             # [B,C,D,H,W] view, no copy
+                if mode == "contrast":
+                    k = nb * frame_num
+                    frame_mse(model_fn(clip), clip, want_psnr=True, out_mse=mse_all[off:off + k], out_psnr=ps_all[off:off + k])
+                    labs.extend(lab[s0:s0 + frame_num] for s0 in starts)
+                else:
+                    k = nb
+                    if mode == "first_frame":
+                        recon, target = model_fn(clip)[:, :, :1], clip[:, :, :1]
+                    elif ispredict:
+                        recon, target = model_fn(clip[:, :, 0:4]), clip[:, :, -1:]
+                    else:
+                        recon, target = model_fn(clip), clip
+                    m = frame_mse(recon, target)                                       # [B, D']: mean over C, H, W
+                    cm = m[:, 0] if m.shape[1] == 1 else m.mean(dim=1)                 # ... and over D' (predict_evaluae.py:233)
+                    mse_all[off:off + k] = cm
+                    ps_all[off:off + k] = 10.0 * torch.log10(1.0 / mse_all[off:off + k].double())
+                    labs.append(lab[np.asarray(starts) + (frame_num if (mode == "first_frame" or ispredict) else 0)])
+                off += k
+            seg.append(seg[-1] + n)
+            order.append((i, np.concatenate(labs) if labs else np.zeros(0, lab.dtype)))
+        score = minmax_score_device(ps_all, torch.tensor(seg, device=ps_all.device, dtype=torch.int64)).cpu().numpy()
+        for (i, lv), a, b in zip(order, seg[:-1], seg[1:]):
+            if b > a and not np.isfinite(score[a:b]).all():
+                # constant PSNR (max == min) or an exactly reconstructed frame (mse == 0): misc/utils.py:128,135 divide by zero
+                raise ZeroDivisionError("float division by zero")
+            local.append((i, score[a:b], lv))
+    merged = gather_video_scores(local) if shard else local
+    if not merged or sum(len(m[1]) for m in merged) == 0:
         raise ValueError("no clips to evaluate")
-    psnr_all = torch.cat(ps_chunks)
-    score = minmax_score_device(psnr_all, torch.tensor(seg, device=dev, dtype=torch.int64)).cpu().numpy()
-    scores = [score[a:b] for a, b in zip(seg[:-1], seg[1:])]
     scene_dict, scene_label = {}, {}
-    for sc, sv, lv in zip(scenes, scores, lab_out):
+    for (vi, sv, lv) in merged:
+        sc = scenes[vi]
         assert len(sv) == len(lv)
         if sc in scene_dict:
             scene_dict[sc] = np.append(scene_dict[sc], sv)
@@ -168,5 +280,4 @@ def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size):
         else:
             scene_dict[sc], scene_label[sc] = sv, lv
     per = {k: roc_auc_score(scene_label[k], scene_dict[k]) for k in scene_dict}
-    return sum(per.values()) / len(per), per, scores, lab_out
-
+    return sum(per.values()) / len(per), per, [m[1] for m in merged], [m[2] for m in merged]
