@@ -316,6 +316,19 @@ int vadc_debug_tc_gemm(const float* A, const float* B, int64_t M, int64_t N, int
  * instructions back to back; out[0] = cycles until the commit arrives, out[1] = cycles to issue. */
 int vadc_debug_umma_bench(int M, int N, int a_mn, int b_mn, int reps, long long* out, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * §8e: one-shot all-reduce(sum) of small fp32 messages over NVLink peer memory — replaces the two latency-bound
+ * collectives per training step that utils/distritributed_model.py's gloo DDP (main_predict.py:171) implies for this
+ * path: the scalar sum (D*A)^2 (backbone.py:98, full-batch norm) and [g cluster_center | g gamma | g beta].
+ * peer_blocks_dev: DEVICE array of `world` pointers, one symmetric block per rank: 256 zero-initialised uint32 flag words
+ * followed by 2 * capacity floats, allocated and exchanged once by the host (torch.distributed._symmetric_memory).
+ * Up to four tensors are reduced IN PLACE in one launch; the sum runs in rank order on every rank (bit-identical
+ * results).  Every rank must call with the same sizes in the same order.
+ * ------------------------------------------------------------------------ */
+int vadc_oneshot_allreduce(const void* peer_blocks_dev, int rank, int world,
+                           int64_t capacity, float* t0, int64_t n0, float* t1, int64_t n1, float* t2, int64_t n2,
+                           float* t3, int64_t n3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,6 +161,87 @@ def shard_range(n_items, rank=None, world_size=None):
     return start, start + base + (1 if rank < rem else 0)
 
 
+class _PeerAllReduce:
+    """One-shot all-reduce over NVLink peer memory (csrc/collective.cu): a symmetric block per rank — 256 flag words +
+    2 x capacity floats — allocated and exchanged ONCE through torch.distributed._symmetric_memory (plumbing); after
+    that every all-reduce of up to four small fp32 tensors is a single launch of our own kernel: no NCCL call, no packed
+    staging tensor, capturable in a CUDA graph."""
+
+    FLAG_WORDS = 256
+
+    def __init__(self, capacity, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group or dist.group.WORLD
+        self.capacity = int(capacity)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.block = symm.empty(self.FLAG_WORDS + 2 * self.capacity, dtype=torch.float32, device=self.device)
+        self.block.zero_()
+        self.handle = symm.rendezvous(self.block, group)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        self.peers_dev = int(self.handle.buffer_ptrs_dev)
+        torch.cuda.synchronize()
+        dist.barrier(group)                       # every block is zeroed before the first flag can arrive
+
+    def all_reduce_(self, tensors):
+        from . import _lib
+        ts = [t for t in tensors if t.numel() > 0]
+        padded = sum((t.numel() + 3) // 4 * 4 for t in ts)
+        if len(ts) > 4 or padded > self.capacity or padded * 4 * self.world > 200 * 1024 or any(
+                t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device for t in ts):
+            return False
+        args = []
+        for i in range(4):
+            if i < len(ts):
+                args += [_lib.ptr(ts[i]), ts[i].numel()]
+            else:
+                args += [None, 0]
+        import ctypes
+        _lib.check(_lib.lib().vadc_oneshot_allreduce(ctypes.c_void_p(self.peers_dev), self.rank, self.world, self.capacity,
+                                                     *args, _lib.stream()), "vadc_oneshot_allreduce")
+        return True
+
+
+_peer_ar = None
+_peer_ar_error = None
+
+
+def enable_peer_allreduce(capacity=1 << 16):
+    """switch ``allreduce_sum_packed`` / ``global_frobenius`` from NCCL collectives to the one-shot NVLink kernel for
+    messages of up to ``capacity`` floats (default 256 KB).  Collective: every rank calls it once after
+    ``init_distributed_mode``.  Returns True when the peer path is active; on any failure (no CUDA, one rank, symmetric
+    memory unavailable) NCCL stays in use and the reason is kept in ``peer_allreduce_status()``."""
+    global _peer_ar, _peer_ar_error
+    if not (is_dist() and torch.cuda.is_available()):
+        _peer_ar_error = "not a multi-rank CUDA job"
+        return False
+    ok = torch.zeros(1, device="cuda")
+    try:
+        _peer_ar = _PeerAllReduce(capacity)
+        ok += 1
+    except Exception as e:                      # noqa: BLE001 - the NCCL path is the fallback for the plumbing, not for the math
+        _peer_ar, _peer_ar_error = None, repr(e)[:300]
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks or none
+    if float(ok) < 1:
+        _peer_ar = None
+        _peer_ar_error = _peer_ar_error or "a peer rank could not set up symmetric memory"
+        return False
+    _peer_ar_error = None
+    return True
+
+
+def disable_peer_allreduce():
+    global _peer_ar
+    _peer_ar = None
+
+
+def peer_allreduce_status():
+    return "one-shot NVLink kernel (vadc_oneshot_allreduce)" if _peer_ar is not None else f"NCCL ({_peer_ar_error or 'peer path not enabled'})"
+
+
 def allreduce_sum_packed(tensors, average=False, async_op=False):
     """ONE all-reduce(sum) for a list of tensors: they are packed into a flat
     buffer, reduced, and copied back in place (centroid grads [K,C] + LN grads
@@ -168,6 +249,11 @@ def allreduce_sum_packed(tensors, average=False, async_op=False):
     ``average=True`` divides by world size (DDP-compatible mean).  Returns the
     work handle when ``async_op`` (call ``finish()`` on it)."""
     if not is_dist():
+        return _Done()
+    if _peer_ar is not None and _peer_ar.all_reduce_(tensors):
+        if average:
+            for t in tensors:
+                t.div_(dist.get_world_size())
         return _Done()
     flat = torch.cat([t.reshape(-1) for t in tensors])
     work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op)
@@ -208,7 +294,7 @@ class _AllReduceSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         y = x.clone()
-        if is_dist():
+        if is_dist() and not (_peer_ar is not None and _peer_ar.all_reduce_([y])):
             dist.all_reduce(y, op=dist.ReduceOp.SUM)
         return y
 
