@@ -510,3 +510,33 @@ def memory_separateness(keys, dtype=np.float32):
     m = k.shape[0]
     sim = np.abs(k @ k.T / 2 + 0.5 - np.eye(m))
     return dtype(sim.sum() / (m * (m - 1)))
+
+
+# ----------------------------------------------------------------------------
+# 8f-4: the consumer of feature / feature_label
+# ----------------------------------------------------------------------------
+
+
+def cluster_feature_record(batches, num_clusters=1024):
+    """聚类可视化.py:117-158 restated token by token: ``batches`` = iterable of (feature [N,C], feature_label [N]).
+    Returns (record {label: [n,C]}, label_num [num_clusters], tsne data, tsne label)."""
+    record = {}
+    label_num = np.ones(num_clusters)
+    for feature, feature_label in batches:
+        for data, label in zip(np.asarray(feature), np.asarray(feature_label)):
+            label = int(label)
+            if label in record.keys():
+                record[label] = np.vstack((record[label], data))
+                label_num[label] = label_num[label] + 1
+            else:
+                record.update({label: data})
+    label_max = np.flip(np.argsort(label_num, )[[-5, -4, -3, -6]])
+    data = record[label_max[0]]
+    tag = 1
+    label = np.ones(np.atleast_2d(data).shape[0], dtype='int') * tag
+    for num in label_max[1:]:
+        tag = tag + 1
+        temp = record[num]
+        label = np.concatenate((label, np.ones(np.atleast_2d(temp).shape[0], dtype='int') * tag))
+        data = np.vstack((data, temp))
+    return record, label_num, data, label

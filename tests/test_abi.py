@@ -176,3 +176,29 @@ def test_timing_api_is_safe_without_a_device():
     assert cnt.value == 0 and ms.value == 0.0
     assert l.vadc_timing_read(7, ctypes.byref(ms), ctypes.byref(cnt)) != 0
     assert l.vadc_timing_enable(0) == 0
+
+
+def test_cluster_feature_bank_matches_the_reference_visualisation_loop():
+    """8f-4: the grouped feature dump == the reference's per-token record / label_num / t-SNE selection
+    (聚类可视化.py:117-158, restated in oracle.np_oracle.cluster_feature_record); host logic, runs on CPU tensors"""
+    import numpy as np
+    import torch
+    import videoad_b200 as V
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(0)
+    batches = []
+    for n in (70, 55, 90):
+        lab = rng.choice(12, size=n, p=np.arange(1, 13) / 78.0)          # 12 clusters of distinct popularity
+        batches.append((rng.standard_normal((n, 5)).astype(np.float32), lab))
+    bank = V.ClusterFeatureBank(num_clusters=16)
+    for f, l in batches:
+        bank.add(torch.tensor(f), torch.tensor(l))
+    rec, label_num, data, label = O.cluster_feature_record(batches, 16)
+    np.testing.assert_array_equal(bank.label_num(), label_num)
+    got = bank.record()
+    assert set(got) == set(rec)
+    for k in rec:
+        np.testing.assert_array_equal(got[k], np.atleast_2d(rec[k]))
+    d2, l2 = bank.tsne_selection()
+    np.testing.assert_array_equal(d2, data)
+    np.testing.assert_array_equal(l2, label)

@@ -244,7 +244,7 @@ def test_training_graph_backward_matches_generic_kernels():
     import os
     outs = {}
     from videoad_b200 import _lib
-    for impl in ("tc", "tc1", "fused", "generic"):
+    for impl in ("tc", "fused", "generic"):
         os.environ["VADC_BWD_IMPL"] = impl
         _lib.lib().vadc_refresh_env()                 # the switches are read once per process
         try:
@@ -252,7 +252,7 @@ def test_training_graph_backward_matches_generic_kernels():
         finally:
             os.environ.pop("VADC_BWD_IMPL", None)
             _lib.lib().vadc_refresh_env()
-    for other in ("tc1", "fused", "generic"):
+    for other in ("fused", "generic"):
         for a, b_, name in zip(outs["tc"], outs[other], ("gx", "gcenters", "g_ln_w", "g_ln_b")):
             assert rel(a, b_) < 1e-4, (other, name, rel(a, b_))
 

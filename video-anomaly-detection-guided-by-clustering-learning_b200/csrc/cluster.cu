@@ -476,7 +476,7 @@ extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
   // generic path on the tcgen05 GEMM: bf16 term copies of gR, feature, A, r and the centroids + split-K partials
   b += 2 * tc_gemm_split_bytes((long long)n, C) + 2 * tc_gemm_split_bytes((long long)n, K) + tc_gemm_split_bytes(K, C);
   b += 2 * align_up((size_t)bwd_tc_splits(N, C, K) * K * C * sizeof(float), 256);
-  return std::max(std::max(b + 256, bwd_fused_workspace_bytes(N, C, K)), std::max(bwd_tc_workspace_bytes(N, C, K), bwd_tc2_workspace_bytes(N, C, K)));
+  return std::max(std::max(b + 256, bwd_fused_workspace_bytes(N, C, K)), bwd_tc2_workspace_bytes(N, C, K));
 }
 
 extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd, const float* rowstats,
@@ -502,14 +502,10 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
     return VADC_OK;
   }
   const char* bimpl = env_str("VADC_BWD_IMPL");            // debugging / A-B runs: tc | fused | generic
-  const bool want_tc = !bimpl || !strcmp(bimpl, "tc") || !strcmp(bimpl, "tc1");
-  if (want_tc && rowstats && ln_b && gR && !gD && !gA && !gF && bwd_tc2_shape_ok(N, C, K)) {
-    if (bimpl && !strcmp(bimpl, "tc1"))                      // first generation, kept for same-box A/B runs
-      return launch_cluster_bwd_tc(x, mu, rstd, rowstats, ln_w, ln_b, centers, D, A, gR, g_loss_sq, N, C, K, alpha, gx,
-                                   gcenters, g_ln_w, g_ln_b, workspace, workspace_bytes, st);
+  const bool want_tc = !bimpl || !strcmp(bimpl, "tc");
+  if (want_tc && rowstats && ln_b && gR && !gD && !gA && !gF && bwd_tc2_shape_ok(N, C, K))
     return launch_cluster_bwd_tc2(x, mu, rstd, rowstats, ln_w, ln_b, centers, D, A, gR, g_loss_sq, N, C, K, alpha, gx,
                                   gcenters, g_ln_w, g_ln_b, workspace, workspace_bytes, st);
-  }
   if (bwd_fused_shape_ok(N, C, K) && !env_on("VADC_BWD_GENERIC") && !(bimpl && !strcmp(bimpl, "generic")))
     return launch_cluster_bwd_fused(x, mu, rstd, feature, ln_w, centers, D, A, gD, gA, gR, gF, g_loss_sq,
                                     N, C, K, alpha, gx, gcenters, g_ln_w, g_ln_b, workspace,

@@ -30,15 +30,8 @@ int launch_cluster_bwd_fused(const float* x, const float* mu, const float* rstd,
                              const float* g_loss_sq, long long N, int C, int K, float alpha, float* gx,
                              float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
                              size_t workspace_bytes, cudaStream_t st);
-// tcgen05 warp-specialised backward, K == 32, training-graph case (cluster_bwd_tc.cu)
-bool bwd_tc_shape_ok(long long N, int C, int K);
-size_t bwd_tc_workspace_bytes(long long N, int C, int K);
-int launch_cluster_bwd_tc(const float* x, const float* mu, const float* rstd, const float* rowstats, const float* ln_w,
-                          const float* ln_b, const float* centers, const float* D, const float* A,
-                          const float* gR, const float* g_loss_sq, long long N, int C, int K, float alpha,
-                          float* gx, float* gcenters, float* g_ln_w, float* g_ln_b, void* workspace,
-                          size_t workspace_bytes, cudaStream_t st);
-// second generation (cluster_bwd_tc2.cu): x through TMA into the epilogue warps, gR through bulk copies into producer slots
+// tcgen05 warp-specialised backward, K == 32, training-graph case (cluster_bwd_tc2.cu): x through TMA into the epilogue
+// warps, gR through register sets of the producer warps
 bool bwd_tc2_shape_ok(long long N, int C, int K);
 size_t bwd_tc2_workspace_bytes(long long N, int C, int K);
 int launch_cluster_bwd_tc2(const float* x, const float* mu, const float* rstd, const float* rowstats, const float* ln_w,

@@ -4,6 +4,7 @@ drop-in test of SURVEY.md §4(ii).  Only used where the reference tree exists.""
 import os
 import sys
 
+import numpy as np
 import torch
 
 
@@ -71,3 +72,57 @@ def save_checkpoint(model, path):
     if not all(k.startswith("module.") for k in sd):
         sd = {"module." + k: v for k, v in sd.items()}
     torch.save(sd, path)
+
+
+class ClusterFeatureBank:
+    """The ``feature`` / ``feature_label`` consumer of the reference — 聚类可视化.py:117-160: tokens of
+    every clip are grouped by their cluster label, and the tokens of four well-populated clusters go to t-SNE.
+
+    The reference does this one token at a time on the host (``label.item()`` — a device sync per token — and an
+    ``np.vstack`` per token, quadratic in the number of tokens).  Here ``add`` keeps the batch on the device (one
+    ``bincount`` for the counts), and ``record`` / ``tsne_selection`` group ALL tokens with one stable sort by label and
+    one device-to-host copy; the resulting arrays are identical to the reference's, row order included (tokens of a
+    label stay in arrival order, as the vstack builds them)."""
+
+    def __init__(self, num_clusters=1024):
+        self.num_clusters = num_clusters
+        self._feat, self._lab = [], []
+        self._count = None
+
+    def add(self, feature, feature_label):
+        """feature [N,C], feature_label [N] (int64 or the float zeros ``Mymodel`` returns without clustering)"""
+        lab = feature_label.reshape(-1).to(torch.int64)
+        self._feat.append(feature.detach().reshape(lab.numel(), -1))
+        self._lab.append(lab.to(feature.device))
+        c = torch.bincount(self._lab[-1], minlength=self.num_clusters)
+        self._count = c if self._count is None else self._count + c
+
+    def label_num(self):
+        """the reference's ``label_num`` (:118,:137-138): ones, plus one for every occurrence of a label after its first"""
+        c = np.zeros(self.num_clusters) if self._count is None else self._count.cpu().numpy().astype(np.float64)
+        return np.where(c > 0, c, 1.0)
+
+    def record(self):
+        """{label: [n_label, C] float32 array}, tokens in arrival order (:131-140)"""
+        if not self._feat:
+            return {}
+        feat, lab = torch.cat(self._feat), torch.cat(self._lab)
+        order = torch.argsort(lab, stable=True)
+        feat, lab = feat[order].cpu().numpy(), lab[order].cpu().numpy()
+        cuts = np.flatnonzero(np.diff(lab)) + 1
+        return {int(l[0]): f for l, f in zip(np.split(lab, cuts), np.split(feat, cuts))}
+
+    def tsne_selection(self):
+        """(data [n,C], label [n]) exactly as :142-158 assemble them: the clusters with the 6th, 3rd, 4th and 5th largest
+        token counts (``np.flip(np.argsort(label_num)[[-5, -4, -3, -6]])``), tagged 1..4"""
+        rec = self.record()
+        label_max = np.flip(np.argsort(self.label_num(), )[[-5, -4, -3, -6]])
+        data = rec[int(label_max[0])]
+        tag = 1
+        label = np.ones(data.shape[0], dtype='int') * tag
+        for num in label_max[1:]:
+            tag = tag + 1
+            temp = rec[int(num)]
+            label = np.concatenate((label, np.ones(temp.shape[0], dtype='int') * tag))
+            data = np.vstack((data, temp))
+        return data, label
