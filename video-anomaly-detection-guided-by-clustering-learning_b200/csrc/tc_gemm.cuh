@@ -150,6 +150,20 @@ struct TcGzEpi {
   }
 };
 
+// decoder entry (model/swin_decoder_predict.py:590-602): ConvTranspose3d(C -> C, kernel (2,1,1), stride (2,1,1)) of the
+// channel-last tokens as ONE GEMM [N, C] x [C, 2C]: column j*C + co of token n = (frame f, pixel hw) is channel co of
+// output frame 2f + j, written channel-last: out[((f * 2 + j) * HW + hw) * C + co] + bias[co]
+struct TcTimeDebedEpi {
+  float* out; const float* bias; long long HW; int C;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
+    const int j = n / C, co = n - j * C;
+    const long long f = m / HW, hw = m - f * HW;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += bias[co + i];
+    tc_store_row32(out + ((f * 2 + j) * HW + hw) * C + co, v, nvalid);
+  }
+};
+
 // split-K partial: out[split][m][n]
 struct TcPartialEpi {
   float* out; long long ld, split_stride;
