@@ -613,7 +613,7 @@ def run_ours(args):
         line.update(other)
     else:
         line["strong"] = {"global_clips": CFG["B"], "ms_per_step": ms_step, "speedup_vs_one_gpu": 1.0}
-    if world == 1:
+    if world == 1 and not args.no_reference_legs:
         r = cpu_reference_run(10, 1, budget_s=20.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                 "sample": r["sample"], "ms_per_step": r["ms_per_step"]}
@@ -782,6 +782,8 @@ def main():
                          "Either way the JSON line carries both numbers at N > 1.")
     ap.add_argument("--nccl", action="store_true", help="keep the two per-step all-reduces on NCCL instead of the one-shot NVLink kernel")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-reference-legs", action="store_true",
+                    help="skip the cpu_baseline / gpu_reference legs (ncu launch lists of this repo's kernels only)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph of it")
     args = ap.parse_args()
     if args.impl == "reference":

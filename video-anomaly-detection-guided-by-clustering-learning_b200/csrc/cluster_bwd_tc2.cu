@@ -943,31 +943,47 @@ VADC_S5_UNROLL
   if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem, ncols); }
 }
 
-// finalize 1: block = (centroid k, 64-channel chunk), 512 threads = 64 channels x 8 groups of CTAs; every
-// group adds its CTAs' partials in fixed order and the groups are added in fixed order (deterministic):
+// finalize 1: block = (centroid k, 32-channel chunk), 256 threads = 32 channels x 8 groups of CTAs; every group adds
+// its CTAs' partials in fixed order (four independent accumulation chains: the 14.5 MB of partials are L2-resident and
+// the kernel is latency-bound) and the groups are added in fixed order (deterministic):
 //   P1 = sum_b (PT[b][k] + PT[b][32+k]),  P2 = sum_b (PT[b][64+k] + PT[b][96+k]),  rcol_k = sum_b rcol[b]
 //   gcenters[k,c] = P1 - gamma_c P2 + (cen[k,c] - beta_c) rcol_k;   P2 and rcol_k are kept for finalize 2
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 cluster_bwd_tc_finalize1_kernel(const float* __restrict__ part_p, const float* __restrict__ part_rcol,
                                 const float* __restrict__ centers, const float* __restrict__ ln_w,
                                 const float* __restrict__ ln_b, int nb, int K, int C,
                                 float* __restrict__ gcenters, float* __restrict__ p2buf, float* __restrict__ rcol) {
-  const int k = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
-  __shared__ float s1s[8][64], s2s[8][64], rcs[512];
-  float s1 = 0.f, s2 = 0.f, rc = 0.f;
-  for (int b = threadIdx.x; b < 2 * nb; b += 512) rc += part_rcol[(size_t)b * K + k];
-  if (c < C)
-    for (int b = grp; b < nb; b += 8) {
-      const float* pp = part_p + (size_t)b * 128 * C + c;
-      s1 += pp[(size_t)k * C] + pp[(size_t)(K + k) * C];
-      s2 += pp[(size_t)(2 * K + k) * C] + pp[(size_t)(3 * K + k) * C];
+  const int k = blockIdx.x, cl = threadIdx.x & 31, c = blockIdx.y * 32 + cl, grp = threadIdx.x >> 5;
+  __shared__ float s1s[8][32], s2s[8][32], rcs[256];
+  float rc = 0.f;
+  for (int b = threadIdx.x; b < 2 * nb; b += 256) rc += part_rcol[(size_t)b * K + k];
+  float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    const size_t cta = (size_t)128 * C;
+    const float* base = part_p + c;
+    int b = grp;
+    for (; b + 24 < nb; b += 32) {                       // four CTAs of this group per pass: 16 independent loads
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* pp = base + (size_t)(b + 8 * u) * cta;
+        a1[u] += pp[(size_t)k * C] + pp[(size_t)(K + k) * C];
+        a2[u] += pp[(size_t)(2 * K + k) * C] + pp[(size_t)(3 * K + k) * C];
+      }
     }
-  s1s[grp][threadIdx.x & 63] = s1; s2s[grp][threadIdx.x & 63] = s2; rcs[threadIdx.x] = rc;
+    for (; b < nb; b += 8) {
+      const float* pp = base + (size_t)b * cta;
+      a1[0] += pp[(size_t)k * C] + pp[(size_t)(K + k) * C];
+      a2[0] += pp[(size_t)(2 * K + k) * C] + pp[(size_t)(3 * K + k) * C];
+    }
+  }
+  s1s[grp][cl] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+  s2s[grp][cl] = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+  rcs[threadIdx.x] = rc;
   __syncthreads();
-  if (threadIdx.x < 64) {
+  if (threadIdx.x < 32) {
     rc = 0.f;
-    for (int i = 0; i < 512; ++i) rc += rcs[i];          // broadcast reads, fixed order
-    s1 = 0.f; s2 = 0.f;
+    for (int i = 0; i < 256; ++i) rc += rcs[i];          // broadcast reads, fixed order
+    float s1 = 0.f, s2 = 0.f;
     for (int g = 0; g < 8; ++g) { s1 += s1s[g][threadIdx.x]; s2 += s2s[g][threadIdx.x]; }
     if (blockIdx.y == 0 && threadIdx.x == 0) rcol[k] = rc;
     if (c < C) {
@@ -1135,7 +1151,7 @@ int launch_cluster_bwd_tc2(const float* x, const float* mu, const float* rstd, c
     cudaFree(trace);
   }
 #endif
-  bt2::cluster_bwd_tc_finalize1_kernel<<<dim3(K, (C + 63) / 64), 512, 0, st>>>(part_p, part_rcol, centers, ln_w, ln_b, grid, K, C,
+  bt2::cluster_bwd_tc_finalize1_kernel<<<dim3(K, (C + 31) / 32), 256, 0, st>>>(part_p, part_rcol, centers, ln_w, ln_b, grid, K, C,
                                                          gcenters, p2buf, rcol);
   VADC_CHECK_LAUNCH("cluster_bwd_tc_finalize1_kernel");
   bt2::cluster_bwd_tc_finalize2_kernel<<<(C + 7) / 8, 256, 0, st>>>(p2buf, rcol, part_q, centers, ln_w, ln_b, grid, K, C,
