@@ -234,7 +234,10 @@ def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size, mod
             lab = labels[i]
             if vid.shape[1] != len(lab):
                 raise ValueError(f"video {i}: {vid.shape[1]} frames but {len(lab)} labels")
-            v = f32c(vid if vid.is_cuda else vid.cuda(non_blocking=True))          # resident once, not once per clip
+            v = vid if vid.is_cuda else vid.cuda(non_blocking=True)                # resident once, not once per clip
+            if not (v.dtype == torch.float32 and v.stride(3) == 1 and v.stride(2) == v.shape[3] and v.data_ptr() % 16 == 0
+                    and v.stride(0) % 4 == 0 and v.stride(1) % 4 == 0):
+                v = f32c(v)                         # (a slice [:, :T] of a longer recording keeps its strides: no copy)
             if mse_all is None:
                 mse_all = torch.empty((total,), device=v.device, dtype=torch.float32)
                 ps_all = torch.empty((total,), device=v.device, dtype=torch.float64)
