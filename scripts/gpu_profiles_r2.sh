@@ -2,8 +2,8 @@
 # round-2 profile evidence: bench line, ncu launch list of the same command, full captures of the two dominant kernels
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-python bench.py --steps 20 --warmup 3 --no-extra > gpurun_out/r2_plain.json 2> gpurun_out/r2_plain.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_step.csv python bench.py --steps 2 --warmup 3 --no-extra --no-graph > gpurun_out/r2_ncu_launch.log 2>&1
+python bench.py --steps 20 --warmup 3 --no-extra --no-reference-legs > gpurun_out/r2_plain.json 2> gpurun_out/r2_plain.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_step.csv python bench.py --steps 2 --warmup 3 --no-extra --no-graph --no-reference-legs > gpurun_out/r2_ncu_launch.log 2>&1
 timeout -s KILL 600 bash scripts/prof_bwd.sh r2_bwdtc2 cluster_bwd_tc2_kernel
 python scripts/ncu_summary.py gpurun_out/prof_r2_bwdtc2.ncu-rep 40 > gpurun_out/r2_ncu_prof_bwdtc2.txt 2>&1
 python scripts/ncu_buckets.py gpurun_out/prof_r2_bwdtc2.ncu-rep 100 >> gpurun_out/r2_ncu_prof_bwdtc2.txt 2>&1
