@@ -70,6 +70,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peak():
+    """dense bf16 TFLOP/s: the burst figure of MEASURED_PEAKS.json (kernels timed alone), else the profiling recipe's fallback"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d.get("bf16_tflops", 1590.0))
+    return 1590.0
+
+
 def measured_traffic(kernel):
     """per-launch DRAM bytes of the dominant kernel from the committed ncu capture, or None"""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -739,6 +749,17 @@ def extra_benchmarks(V, dev, peak):
         ms = time_op(lambda: mem(q, keys, train=False), 10, flush)
         out["memory_eval_m2000_d768_n2048"] = {"ms": ms, "tokens/s": 2048 / (ms * 1e-3),
                                                "TFLOP/s": 4 * 2000 * 768 * 2048 / ms / 1e9}
+        # memory module at larger token counts (N = 8192, 65536): tensor-bound (244 flop/B at m=2000, d=768), so
+        # the roofline is the measured dense-bf16 peak; the contractions are fp32-faithful = six bf16 products per flop
+        tpeak = tensor_peak()
+        for nq, (bq, hq) in ((8192, (8, 32)), (65536, (64, 32))):
+            qn = torch.randn(bq, 768, hq, hq, device=dev)
+            ms = time_op(lambda: mem(qn, keys, train=False), 5, flush)
+            tf = 4 * 2000 * 768 * nq / ms / 1e9
+            out[f"memory_eval_m2000_d768_n{nq}"] = {"ms": ms, "tokens/s": nq / (ms * 1e-3), "TFLOP/s": tf,
+                                                    "bf16_product_TFLOP/s": 6 * tf, "frac_tensor": 6 * tf / tpeak,
+                                                    "tensor_peak_TFLOP/s": tpeak}
+            del qn
         # C1 at the reference-native head (C=192, K=1024) and the cfg3 sweep, forward only
         for (C, K, n) in ((192, 1024, 65536), (768, 16, 65536), (768, 64, 65536), (768, 256, 65536)):
             m = V.EuclidDistance_Assign_Module(C, K, soft_assign_alpha=16.0).to(dev)
@@ -754,6 +775,26 @@ def extra_benchmarks(V, dev, peak):
         ms = time_op(lambda: sp(xs), 5, flush)
         out["space_fwd_M64_P1024_C192_K128"] = {"ms": ms, "tokens/s": 65536 / (ms * 1e-3)}
         del xs
+    # C1 + C2 at the reference-native head (C=192, K=1024; model/backbone.py:29-31), forward + backward with the loss spelled
+    # out as the reference does (torch.norm(D * A), backbone.py:87 — the drop-in path: gD / gA reach vadc_cluster_bwd as
+    # tensors, the generic backward), next to the fused-loss form
+    mn = V.EuclidDistance_Assign_Module(192, 1024, soft_assign_alpha=16.0).to(dev)
+    xn = torch.randn(1, 1, 1, 65536, 192, device=dev, requires_grad=True)
+
+    def native_step(fused):
+        for p_ in mn.parameters():
+            p_.grad = None
+        xn.grad = None
+        D_, A_, S_, R_, F_, _ = mn(xn)
+        loss = (mn.fused_cluster_loss() if fused else torch.norm(D_ * A_)) + V.e4_norm(R_, xn.detach())
+        loss.backward()
+    for fused in (False, True):
+        ms = time_op(lambda: native_step(fused), 5, flush)
+        byt = 65536 * (5 * 192 * 4 + 2 * 1024 * 4 * (1 if fused else 3))      # x, R, F, gx + x again; D, A (+ gD, gA, D*A)
+        out["cluster_fwd_bwd_C192_K1024_N65536_" + ("fused_loss" if fused else "explicit_loss")] = {
+            "ms": ms, "tokens/s": 65536 / (ms * 1e-3), "alg_GB/s": byt / ms / 1e6, "frac_hbm": byt / ms / 1e6 / peak,
+            "TFLOP/s": 3 * (4 * 1024 * 192) * 65536 / ms / 1e9}
+    del mn, xn
     # C3 at the full cfg2 batch (B=64: M=512) forward + backward from the space loss (backbone.py:94)
     xs = torch.randn(64, 8, 32, 32, 192, device=dev, requires_grad=True)
 

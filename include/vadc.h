@@ -136,15 +136,21 @@ int vadc_cluster_bwd(const float* x, const float* mu, const float* rstd, const f
  *          torch.norm(xf_distance * xf_assign)          model/backbone.py:94
  *
  * x [M*P, C] tokens (M = B*D clips-frames, P = H*W), centers [C,K,P].
- *   Ds [M,C,K] ('B D C CN'), As [M,C,K], mu/rstd [M*P], loss_sq [1].
- * zt [C,M,P] is the LayerNorm output in the transposed layout the batched
- * cdist consumes (saved for the backward).
+ *   Ds [M,C,K] ('B D C CN'), As [M,C,K], mu/rstd [M*P], loss_sq [1];
+ *   selfdist [C,K,K] = cdist(centers, centers) (model/cluster.py:134), or NULL to skip it.
+ * zt_state (vadc_space_cluster_saved_bytes bytes, 16-byte aligned) keeps the
+ * LayerNorm output in the transposed layout [C,M,P] the batched cdist consumes,
+ * for the backward: opaque to the caller — the three bf16 operand terms of the
+ * tensor-core contractions (their exact sum is the fp32 value) where those run,
+ * plain fp32 otherwise.  The forward and its backward must run under the same
+ * environment (no vadc_refresh_env in between).
  * ------------------------------------------------------------------------ */
+size_t vadc_space_cluster_saved_bytes(int64_t M, int P, int C, int K);
 size_t vadc_space_cluster_fwd_workspace_bytes(int64_t M, int P, int C, int K);
 int vadc_space_cluster_fwd(const float* x, const float* ln_w, const float* ln_b,
                            const float* centers, int64_t M, int P, int C, int K,
                            float alpha, float eps,
-                           float* Ds, float* As, float* zt, float* mu, float* rstd,
+                           float* Ds, float* As, float* selfdist, void* zt_state, float* mu, float* rstd,
                            float* loss_sq,
                            void* workspace, size_t workspace_bytes, void* stream);
 
@@ -161,7 +167,7 @@ int vadc_cluster_fwd_padded(const float* x, const float* ln_w, const float* ln_b
 int vadc_space_cluster_fwd_padded(const float* x, const float* ln_w, const float* ln_b,
                                   const float* centers, int64_t M, int P, int C, int K, int K_valid,
                                   float alpha, float eps,
-                                  float* Ds, float* As, float* zt, float* mu, float* rstd,
+                                  float* Ds, float* As, float* selfdist, void* zt_state, float* mu, float* rstd,
                                   float* loss_sq,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
@@ -170,7 +176,8 @@ int vadc_space_cluster_fwd_padded(const float* x, const float* ln_w, const float
  * gcenters [C,K,P], g_ln_w, g_ln_b [C]. */
 size_t vadc_space_cluster_bwd_workspace_bytes(int64_t M, int P, int C, int K);
 int vadc_space_cluster_bwd(const float* x, const float* mu, const float* rstd,
-                           const float* zt, const float* ln_w, const float* centers,
+                           const void* zt_state, const float* ln_w, const float* ln_b,
+                           const float* centers,
                            const float* Ds, const float* As,
                            const float* gD, const float* gA,
                            const float* g_loss_sq,

@@ -41,7 +41,11 @@ def test_space_golden(name):
 
 
 @pytest.mark.parametrize("B,Dd,side,C,K", [(2, 4, 28, 192, 128), (1, 3, 8, 24, 8), (2, 2, 32, 64, 16),
-                                            (4, 8, 28, 192, 128), (16, 8, 16, 192, 64)])   # the last two: batched tcgen05 GEMMs
+                                            (4, 8, 28, 192, 128), (16, 8, 16, 192, 64),    # these two: batched tcgen05 GEMMs
+                                            (1, 3, 7, 24, 8),        # odd P: token count not a multiple of 4
+                                            (8, 16, 12, 192, 128),   # tcgen05, P = 144: a frame's last 64-token chunk is ragged
+                                            (32, 16, 4, 256, 128),   # tcgen05, P = 16 < one chunk, C at the tiled kernels' limit
+                                            (16, 16, 8, 288, 64)])   # tcgen05, C > 256: the untiled LayerNorm kernels
 def test_space_vs_oracle(B, Dd, side, C, K):
     rng = np.random.default_rng(B * 100 + side)
     x = (rng.standard_normal((B, Dd, side, side, C)) * 1.3).astype(np.float32)
@@ -62,6 +66,26 @@ def test_space_vs_oracle(B, Dd, side, C, K):
     assert rel(N(m.cluster_center.grad), gc) < 3e-4
     assert rel(N(m.norm.weight.grad), gw) < 3e-4
     assert rel(N(m.norm.bias.grad), gb) < 3e-4
+
+
+@pytest.mark.parametrize("B,Dd,side,C,K", [(1, 2, 4, 8, 6), (8, 8, 16, 192, 64)])     # SIMT path with a padded K; tcgen05 path
+def test_space_self_distance_output_and_gradient(B, Dd, side, C, K):
+    """cluster_dist (model/cluster.py:134) comes out of the same call as the distances; a gradient through it reaches
+    the centroids with autograd's cdist formula (the reference's own loss never uses it: backbone.py:95-97)"""
+    rng = np.random.default_rng(K)
+    cen = rng.random((C, K, side * side)).astype(np.float32)
+    m = make_space(C, K, side, 32.0, cen, np.ones(C, np.float32), np.zeros(C, np.float32))
+    x = T(rng.standard_normal((B, Dd, side, side, C)).astype(np.float32))
+    _, _, S, _ = m(x)
+    assert S.shape == (C, K, K)
+    assert_selfdist_close(N(S), O.cdist_mm(cen, cen))
+    assert_selfdist_close(N(m.self_similarity()), O.cdist_mm(cen, cen))
+    wgt = T(rng.random((C, K, K)).astype(np.float32))
+    (S * wgt).sum().backward()
+    cr = torch.tensor(cen, dtype=torch.float64, requires_grad=True)
+    Sr = torch.cdist(cr, cr, compute_mode="donot_use_mm_for_euclid_dist")
+    (Sr * wgt.double().cpu()).sum().backward()
+    assert rel(N(m.cluster_center.grad), cr.grad.numpy()) < 2e-4
 
 
 def test_soft_assign_modules():

@@ -146,9 +146,14 @@ class _SelfDist(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gS):
         c, S = ctx.saved_tensors
-        r = torch.where(S == 0, torch.zeros_like(S), gS / S)
-        r = r + r.transpose(-1, -2)
-        return c * r.sum(-1, keepdim=True) - r @ c
+        return _selfdist_grad(c, S, gS)
+
+
+def _selfdist_grad(c, S, gS):
+    """d cdist(c, c) / dc applied to gS (autograd's own formula on the saved output)"""
+    r = torch.where(S == 0, torch.zeros_like(S), gS / S)
+    r = r + r.transpose(-1, -2)
+    return c * r.sum(-1, keepdim=True) - r @ c
 
 
 class PosSoftAssign(nn.Module):
@@ -284,34 +289,38 @@ class _SpaceClusterAssign(torch.autograd.Function):
             cen = torch.cat([cen, cen.new_zeros((C, K - K_valid, P))], dim=1)
         Ds = torch.empty((M, C, K), device=dev, dtype=torch.float32)
         As = torch.empty((M, C, K), device=dev, dtype=torch.float32)
-        zt = torch.empty((C, M, P), device=dev, dtype=torch.float32)
+        Sd = torch.empty((C, K, K), device=dev, dtype=torch.float32)      # cdist(centers, centers), model/cluster.py:134
         mu = torch.empty((M * P,), device=dev, dtype=torch.float32)
         rstd = torch.empty((M * P,), device=dev, dtype=torch.float32)
         loss_sq = torch.empty((1,), device=dev, dtype=torch.float32)
         l = _lib.lib()
+        # LayerNorm output in the [C, M, P] cdist layout, kept for the backward: opaque (bf16 operand terms or fp32)
+        zt = torch.empty((l.vadc_space_cluster_saved_bytes(M, P, C, K),), device=dev, dtype=torch.uint8)
         nb = l.vadc_space_cluster_fwd_workspace_bytes(M, P, C, K)
         ws = workspace(nb, dev)
         if K_valid == K:
             check(l.vadc_space_cluster_fwd(ptr(x2), ptr(w), ptr(b), ptr(cen), M, P, C, K, float(alpha),
-                                           float(eps), ptr(Ds), ptr(As), ptr(zt), ptr(mu), ptr(rstd),
+                                           float(eps), ptr(Ds), ptr(As), ptr(Sd), ptr(zt), ptr(mu), ptr(rstd),
                                            ptr(loss_sq), ptr(ws), ws.numel(), stream()),
                   "vadc_space_cluster_fwd")
         else:
             check(l.vadc_space_cluster_fwd_padded(ptr(x2), ptr(w), ptr(b), ptr(cen), M, P, C, K, K_valid, float(alpha),
-                                                  float(eps), ptr(Ds), ptr(As), ptr(zt), ptr(mu), ptr(rstd),
+                                                  float(eps), ptr(Ds), ptr(As), ptr(Sd), ptr(zt), ptr(mu), ptr(rstd),
                                                   ptr(loss_sq), ptr(ws), ws.numel(), stream()),
                   "vadc_space_cluster_fwd_padded")
-        ctx.save_for_backward(x2, cen, w, Ds, As, zt, mu, rstd)
+        if K_valid != K:
+            Sd = Sd[:, :K_valid, :K_valid].contiguous()
+        ctx.save_for_backward(x2, cen, w, b, Ds, As, zt, mu, rstd, Sd)
         ctx.alpha, ctx.shape, ctx.K_valid = float(alpha), (B, Dd, H, W, C), K_valid
         ctx.set_materialize_grads(False)
         if K_valid != K:
             return (Ds[:, :, :K_valid].contiguous().view(B, Dd, C, K_valid),
-                    As[:, :, :K_valid].contiguous().view(B, Dd, C, K_valid), loss_sq)
-        return Ds.view(B, Dd, C, K), As.view(B, Dd, C, K), loss_sq
+                    As[:, :, :K_valid].contiguous().view(B, Dd, C, K_valid), loss_sq, Sd)
+        return Ds.view(B, Dd, C, K), As.view(B, Dd, C, K), loss_sq, Sd
 
     @staticmethod
-    def backward(ctx, gD, gA, gLsq):
-        x2, cen, w, Ds, As, zt, mu, rstd = ctx.saved_tensors
+    def backward(ctx, gD, gA, gLsq, gS=None):
+        x2, cen, w, b, Ds, As, zt, mu, rstd, Sd = ctx.saved_tensors
         B, Dd, H, W, C = ctx.shape
         M, P, K = B * Dd, H * W, cen.shape[1]
         dev = x2.device
@@ -332,11 +341,14 @@ class _SpaceClusterAssign(torch.autograd.Function):
         l = _lib.lib()
         nb = l.vadc_space_cluster_bwd_workspace_bytes(M, P, C, K)
         ws = workspace(nb, dev)
-        check(l.vadc_space_cluster_bwd(ptr(x2), ptr(mu), ptr(rstd), ptr(zt), ptr(w), ptr(cen), ptr(Ds),
+        check(l.vadc_space_cluster_bwd(ptr(x2), ptr(mu), ptr(rstd), ptr(zt), ptr(w), ptr(b), ptr(cen), ptr(Ds),
                                        ptr(As), ptr(gD), ptr(gA), ptr(gLsq), M, P, C, K, ctx.alpha,
                                        ptr(gx), ptr(gc), ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream()),
               "vadc_space_cluster_bwd")
-        return gx.view(B, Dd, H, W, C), (gc if Kv == K else gc[:, :Kv].contiguous()), gw, gb, None, None
+        gc = gc if Kv == K else gc[:, :Kv].contiguous()
+        if gS is not None:     # the reference never back-propagates through the self-distance (backbone.py:95-97 are comments)
+            gc = gc + _selfdist_grad(cen[:, :Kv], Sd, gS)
+        return gx.view(B, Dd, H, W, C), gc, gw, gb, None, None
 
 
 class Space_EuclidDistance_Assign_Module(nn.Module):
@@ -371,12 +383,11 @@ class Space_EuclidDistance_Assign_Module(nn.Module):
     def forward(self, x, alpha=None):
         if not alpha == None:  # noqa: E711
             self.assign_func.alpha = alpha
-        Ds, As, loss_sq = _SpaceClusterAssign.apply(
+        Ds, As, loss_sq, cluster_dist = _SpaceClusterAssign.apply(
             x, self.cluster_center, self.norm.weight, self.norm.bias,
-            self.assign_func.alpha, self.norm.eps)
+            self.assign_func.alpha, self.norm.eps)       # cluster_dist = self_similarity(), from the same centroid terms
         self.loss_sq = loss_sq
         x_rec = []
-        cluster_dist = self.self_similarity()
         return Ds, As, cluster_dist, x_rec
 
     def fused_cluster_loss(self):

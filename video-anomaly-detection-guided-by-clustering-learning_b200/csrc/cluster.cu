@@ -433,14 +433,16 @@ extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int
   float* aa = ws.take<float>((size_t)nb * R);
   float* bb = ws.take<float>((size_t)nb * P);
   int rc;
+  const bool self = a == b && R == P;          // centroid self-distance (model/cluster.py:82, :134): one norm pass, one split
+  if (self) bb = aa;
   if ((rc = launch_row_sqnorm(a, (long long)nb * R, C, aa, st))) return rc;
-  if ((rc = launch_row_sqnorm(b, (long long)nb * P, C, bb, st))) return rc;
+  if (!self && (rc = launch_row_sqnorm(b, (long long)nb * P, C, bb, st))) return rc;
   if (cdist_tc_ok(nb, R, P, C)) {
     // one launch for all batches: A = a as [nb R, C], B = b as [nb P, C], batch z starts z R / z P rows further
     void* as = ws.take<uint8_t>(tc_gemm_split_bytes((long long)nb * R, C));
-    void* bs = ws.take<uint8_t>(tc_gemm_split_bytes((long long)nb * P, C));
+    void* bs = self ? as : ws.take<uint8_t>(tc_gemm_split_bytes((long long)nb * P, C));
     if ((rc = tc_split3(a, (long long)nb * R, C, as, st))) return rc;
-    if ((rc = tc_split3(b, (long long)nb * P, C, bs, st))) return rc;
+    if (!self && (rc = tc_split3(b, (long long)nb * P, C, bs, st))) return rc;
     TcBatchDistEpi epi{out, aa, bb, P, R * P, R, P};
     return launch_tc_gemm_batched<false, false>(as, (long long)nb * R, C, bs, (long long)nb * P, C, R, P, C, nb,
                                                 TcBatchOffsets{(int)R, 0, (int)P, 0}, epi, st);

@@ -36,11 +36,13 @@ constexpr int BM = 128, BK = 64, kThreads = 192;
 #define VADC_TC_STAGES_H 1
 #endif
 constexpr int kStagesH = VADC_TC_STAGES_H;
-template <int TERMS> struct StageCfg { static constexpr int stages = TERMS == 2 ? kStagesH : 1; static constexpr int ctas = TERMS == 2 ? (kStagesH == 1 ? 3 : (kStagesH == 2 ? 1 : 1)) : 2; };
+// co-resident CTAs per SM for a ring of STAGES stages: one-stage CTAs share an SM (two at 96 KB, three at 64 KB), a deeper
+// ring owns it (bf16 x3 two-stage ring = 192 KB: opt-in, see launch_tc_gemm_batched).
+template <int TERMS, int STAGES> struct StageCfg { static constexpr int ctas = STAGES > 1 ? 1 : (TERMS == 2 ? 3 : 2); };
 
 // per-blockIdx.z coordinate offsets of a batched launch: output-row / contraction offsets of A, output-column /
 // contraction offsets of B (in elements of the respective tensor-map dimension)
-struct ZOffsets { int batched, a_m, a_k, b_n, b_k; };
+struct ZOffsets { int batched, a_m, a_k, b_n, b_k, pf; };   // pf: k-blocks prefetched into L2 together with every (pf+1)-th load
 
 __global__ void __launch_bounds__(256)
 split3_kernel(const float* __restrict__ src, long long n4, __nv_bfloat16* __restrict__ t0,
@@ -62,6 +64,10 @@ split3_kernel(const float* __restrict__ src, long long n4, __nv_bfloat16* __rest
   }
 }
 
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -72,15 +78,15 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst,
 // output, centroids, softmax weights), three products hh + hl + lh (22 significant bits) — two thirds of the operand
 // bytes, half the MMAs, and a 64 KB stage so that three CTAs share an SM; the accumulators are multiplied by
 // *acc_scale (= 1 / (s_a s_b)) before the epilogue sees them.
-template <int BN, int TERMS, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(kThreads, StageCfg<TERMS>::ctas)
+template <int BN, int TERMS, int STAGES, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(kThreads, StageCfg<TERMS, STAGES>::ctas)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                int M, int N, int Kd, int kb_per_split, const ZOffsets zo, const float* __restrict__ acc_scale, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t kATerm = BM * 128u, kBTerm = BN * 128u;           // bytes per bf16 term of a stage's operand
   constexpr uint32_t kStage = (uint32_t)TERMS * (kATerm + kBTerm);
-  constexpr int kStages = StageCfg<TERMS>::stages;
+  constexpr int kStages = STAGES;
   __shared__ uint64_t full[kStages], empty[kStages], accfull;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,6 +135,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
           for (int nb = 0; nb < BN / 64; ++nb)                // [64 k-rows x 64 n-cols] boxes, 8 KB apart
             tma_load_3d(&mapB, b + t * kBTerm + nb * 8192u, &full[s], bn + nb * 64, k0 + bk, t);
+        }
+      }
+      // K-major operands arrive as 128-byte pieces of rows a whole row pitch apart: a DRAM page is opened for 128 bytes
+      // and closed again long before the next k-block asks for its neighbour.  Ask L2 for the next zo.pf k-blocks of the
+      // same rows NOW, so that DRAM sees (pf + 1) x 128 contiguous bytes per row at once.
+      if (zo.pf > 0 && kb % (zo.pf + 1) == 0) {
+        for (int d = 1; d <= zo.pf && kb + d < nkb; ++d) {
+          const int kp = k0 + d * BK;
+#pragma unroll
+          for (int t = 0; t < TERMS; ++t) {
+            if constexpr (!A_MN) tma_prefetch_3d(&mapA, kp + ak, am, t);
+            if constexpr (!B_MN) tma_prefetch_3d(&mapB, kp + bk, bn, t);
+          }
         }
       }
     }
@@ -258,7 +277,7 @@ int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, lon
   else rc = tg::make_map3(&mB, b_split, N, Kd, BN);             // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
   if (rc) return rc;
   const size_t smem = (size_t)(3 * tg::BM * 128 + 3 * BN * 128) + 1024;
-  auto kern = tg::tc_gemm_kernel<BN, 3, A_MN, B_MN, Epi>;
+  auto kern = tg::tc_gemm_kernel<BN, 3, 1, A_MN, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
   if (splits < 1) splits = 1;
@@ -281,13 +300,23 @@ int launch_tc_gemm_batched(const void* a_split, long long a_rows, long long a_co
   int rc;
   if ((rc = tg::make_map3(&mA, a_split, a_rows, a_cols, A_MN ? 64 : tg::BM))) return rc;
   if ((rc = tg::make_map3(&mB, b_split, b_rows, b_cols, B_MN ? 64 : BN))) return rc;
-  const size_t smem = (size_t)(3 * tg::BM * 128 + 3 * BN * 128) + 1024;
-  auto kern = tg::tc_gemm_kernel<BN, 3, A_MN, B_MN, Epi>;
-  VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
+  const size_t stage = (size_t)(3 * tg::BM * 128 + 3 * BN * 128);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)nbatch);
-  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb,
-                                         tg::ZOffsets{1, off.a_m, off.a_k, off.b_n, off.b_k}, nullptr, epi);
+  const tg::ZOffsets zo{1, off.a_m, off.a_k, off.b_n, off.b_k, nkb >= 4 ? env_int("VADC_TC_PREFETCH", 0) : 0};
+  // two-stage ring, one CTA per SM: measured no better than two co-resident one-stage CTAs on the space head's long
+  // contraction loops (distance GEMM, 16 k-blocks: 251 vs 210 us; gcenters, 8 k-blocks: 218 vs 212 us) — opt-in only
+  if (nkb >= 6 && env_on("VADC_TC_TWO_STAGE")) {
+    auto kern = tg::tc_gemm_kernel<BN, 3, 2, A_MN, B_MN, Epi>;
+    const size_t smem = 2 * stage + 1024;
+    VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, nullptr, epi);
+  } else {
+    auto kern = tg::tc_gemm_kernel<BN, 3, 1, A_MN, B_MN, Epi>;
+    const size_t smem = stage + 1024;
+    VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, nullptr, epi);
+  }
   VADC_CHECK_LAUNCH("tc_gemm_kernel(batched)");
   return VADC_OK;
 }
@@ -386,7 +415,7 @@ int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, lon
   else rc = tg::make_map3(&mB, b_split, N, Kd, BN, 2);
   if (rc) return rc;
   const size_t smem = (size_t)tg::kStagesH * 2 * (tg::BM * 128 + BN * 128) + 1024;
-  auto kern = tg::tc_gemm_kernel<BN, 2, false, B_MN, Epi>;
+  auto kern = tg::tc_gemm_kernel<BN, 2, tg::kStagesH, false, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), 1);
@@ -416,7 +445,7 @@ template int launch_tc_gemm_ex<true, true, TcPartialEpi>(const void*, const void
                                                      long long, long long, long long, long long, int, TcBatchOffsets, \
                                                      EPI, cudaStream_t);
 VADC_TC_BATCHED(false, false, TcBatchDistEpi)
-VADC_TC_BATCHED(false, true, TcSpaceGzEpi)
+VADC_TC_BATCHED(true, false, TcSpaceGzEpi)
 VADC_TC_BATCHED(true, true, TcSpaceGcEpi)
 #undef VADC_TC_BATCHED
 

@@ -1,6 +1,7 @@
 // tc_gemm.cuh — interface of the TMA-fed tcgen05 GEMM (tc_gemm.cu) and its epilogue functors.
 // An epilogue receives 32 consecutive columns of one output row: epi(m, n, v[32], nvalid).
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace vadc {
@@ -47,6 +48,22 @@ __device__ __forceinline__ void tc_store_row32(float* o, const float (&v)[32], i
   }
 }
 
+// t[0..nvalid) = src[0..nvalid), the rest zero; never a predicated load followed by its use inside a branch
+__device__ __forceinline__ void tc_load_row32(const float* src, float (&t)[32], int nvalid) {
+  if (nvalid == 32 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src) + j);
+      t[4 * j] = a.x; t[4 * j + 1] = a.y; t[4 * j + 2] = a.z; t[4 * j + 3] = a.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = __ldg(src + min(j, nvalid - 1));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = j < nvalid ? t[j] : 0.f;
+  }
+}
+
 struct TcStoreEpi {
   float* out; long long ldo;
   __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
@@ -83,24 +100,18 @@ struct TcBatchDistEpi {
   }
 };
 
-// space head backward (model/cluster.py:127-149 under autograd): gzt[c,m,p] = zt[c,m,p] rsum[m,c] - (r centers)[m,p]
+// space head backward (model/cluster.py:127-149 under autograd): gzt[c,m,p] = zt[c,m,p] rsum[m,c] - (r centers)[m,p].
+// The GEMM writes only the contraction, acc[c,m,p] = (r[:,c,:] centers[c])[m,p]; the LayerNorm backward that consumes
+// it forms zt rsum - acc itself from the x-hat it has in registers (zt = x-hat gamma + beta), so nothing is re-read
+// here.  Computed TRANSPOSED — the GEMM's rows (TMEM lanes = epilogue threads) are the positions p, its columns the
+// frames m — so that for every frame a warp stores 32 consecutive p (128 contiguous bytes).
 struct TcSpaceGzEpi {
-  float* out; const float* zt; const float* rsum; long long MP; int P, C;
-  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int z) const {
-    const long long i = (long long)z * MP + m * P + n;
-    const float rs = rsum[m * C + z];
-    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(zt + i) & 15u) == 0) {
+  float* out; long long MP; int P;
+  __device__ __forceinline__ void operator()(long long p, int n, float (&v)[32], int nvalid, int z) const {
+    float* o = out + (long long)z * MP + (long long)n * P + p;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(zt + i) + j);
-        v[4 * j] = t.x * rs - v[4 * j]; v[4 * j + 1] = t.y * rs - v[4 * j + 1];
-        v[4 * j + 2] = t.z * rs - v[4 * j + 2]; v[4 * j + 3] = t.w * rs - v[4 * j + 3];
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] = zt[i + j] * rs - v[j];
-    }
-    tc_store_row32(out + i, v, nvalid);
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) o[(long long)j * P] = v[j];
   }
 };
 
@@ -126,14 +137,17 @@ struct TcSpaceGcEpi {
 };
 
 // Memory.read (Memory.py:249-261): uq[m, 0:d] = q[m], uq[m, d:2d] = score_memory @ keys
+// (the row loads of these two are unconditional — 128-bit where the row is aligned, clamped indices otherwise: a
+// predicated load + use per column compiles to one branch region per column, every load waited for alone)
 struct TcReadEpi {
   float* uq; const float* q; int d;
   __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
     float* o = uq + m * 2 * d;
     tc_store_row32(o + d + n, v, nvalid);
     const float* qs = q + m * d + n;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) if (j < nvalid) o[n + j] = qs[j];
+    float t[32];
+    tc_load_row32(qs, t, nvalid);
+    tc_store_row32(o + n, t, nvalid);
   }
 };
 
@@ -142,10 +156,15 @@ struct TcGzEpi {
   float* out; const float* feature; const float* rsum; const float* gF; long long ld;
   __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
     const float rs = rsum[m];
-    const float* f = feature + m * ld + n;
+    float t[32];
+    tc_load_row32(feature + m * ld + n, t, nvalid);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) v[j] = f[j] * rs - v[j] + (gF ? gF[m * ld + n + j] : 0.f);
+    for (int j = 0; j < 32; ++j) v[j] = t[j] * rs - v[j];
+    if (gF) {
+      tc_load_row32(gF + m * ld + n, t, nvalid);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += t[j];
+    }
     tc_store_row32(out + m * ld + n, v, nvalid);
   }
 };
