@@ -253,38 +253,50 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* src) {
 // shared [C][65] through cp.async (32 consecutive tokens per warp instruction) while the block's x rows — eight tokens
 // per warp, all issued up front — travel to registers; then a warp finishes a token at a time from registers and the
 // conflict-free transposed tile.  The gamma / beta partials stay in registers across a block's tiles.
-template <int CPL>
+// RSUM: the tile holds acc = r centers and the upstream gradient is zt rsum - acc with zt = x-hat gamma + beta (the
+// tensor-core path; needs P >= 64 so that a tile touches two frames at most: their rsum rows ride along into shared
+// memory).  FULL: C == 32 CPL, no per-channel predicates.
+template <int CPL, bool RSUM, bool FULL>
 __global__ void __launch_bounds__(256)
 ln_bwd_transposed_tile_kernel(const float* __restrict__ gzt, const float* __restrict__ x,
                               const float* __restrict__ mu, const float* __restrict__ rstd,
                               const float* __restrict__ w, const float* __restrict__ bias,
-                              const float* __restrict__ rsum /* [T/P, C] or null */, int P, long long T, int C,
+                              const float* __restrict__ rsum /* [T/P, C] */, int P, long long T, int C,
                               float* __restrict__ gx, float* __restrict__ partial /*[grid,2C]*/) {
-  extern __shared__ float tile[];            // [C][65] (>= 8 * 2C floats for the final reduction) + rsum rows [2][C]
-  float* const rs_s = tile + C * kTileLd;
+  extern __shared__ float tile[];            // [32 CPL][65] (rows >= C stay zero) + rsum rows [2][32 CPL]
+  constexpr int CP = 32 * CPL;
+  float* const rs_s = tile + CP * kTileLd;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float aw[CPL], ab[CPL], wv[CPL], bv[CPL];
 #pragma unroll
   for (int q = 0; q < CPL; ++q) {
-    const bool in = lane + 32 * q < C;
-    aw[q] = 0.f; ab[q] = 0.f; wv[q] = in ? __ldg(w + lane + 32 * q) : 0.f; bv[q] = (in && rsum) ? __ldg(bias + lane + 32 * q) : 0.f;
+    const bool in = FULL || lane + 32 * q < C;
+    aw[q] = 0.f; ab[q] = 0.f; wv[q] = in ? __ldg(w + lane + 32 * q) : 0.f; bv[q] = (in && RSUM) ? __ldg(bias + lane + 32 * q) : 0.f;
   }
+  if (!FULL) for (int i = C * kTileLd + threadIdx.x; i < CP * kTileLd + 2 * CP; i += 256) tile[i] = 0.f;
   const long long ntiles = (T + kTileTok - 1) / kTileTok;
   for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
     const long long t0 = tl * kTileTok;
     const int np = (int)min((long long)kTileTok, T - t0);
     __syncthreads();                         // the previous tile has been consumed
-    for (int idx = threadIdx.x; idx < C * kTileTok; idx += 256) {
-      const int c = idx >> 6, k = idx & 63;
-      if (k < np) cp_async4(tile + c * kTileLd + k, gzt + (long long)c * T + t0 + k);
+    {
+      const int k = threadIdx.x & 63;
+      if (k < np) {
+        const float* src = gzt + t0 + k;
+        float* dst = tile + k;
+        for (int c = threadIdx.x >> 6; c < C; c += 4) cp_async4(dst + c * kTileLd, src + (long long)c * T);
+      }
     }
-    // rsum rows of the tile's frames (two at most when P >= 64) ride along into shared memory
-    const long long f0 = rsum ? t0 / P : 0;
-    const int nfr = rsum ? (int)((t0 + np - 1) / P - f0) + 1 : 0;
-    const bool staged = nfr <= 2;
-    const int rem0 = rsum ? (int)(t0 - f0 * P) : 0;      // position of the tile's first token inside frame f0
-    if (rsum && staged)
-      for (int idx = threadIdx.x; idx < nfr * C; idx += 256) cp_async4(rs_s + idx, rsum + f0 * C + idx);
+    int rem0 = 0;
+    if constexpr (RSUM) {
+      const long long f0 = t0 / P;
+      const int nfr = (int)((t0 + np - 1) / P - f0) + 1;            // 1 or 2
+      rem0 = (int)(t0 - f0 * P);                                     // position of the tile's first token inside frame f0
+      for (int idx = threadIdx.x; idx < nfr * C; idx += 256) {
+        const int f = idx >= C ? 1 : 0;
+        cp_async4(rs_s + f * CP + (idx - f * C), rsum + f0 * C + idx);
+      }
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
     float xh[kTokPerWarp][CPL], mr[kTokPerWarp], rr_[kTokPerWarp];
 #pragma unroll
@@ -292,7 +304,7 @@ ln_bwd_transposed_tile_kernel(const float* __restrict__ gzt, const float* __rest
       const long long row = t0 + min(wid + 8 * i, np - 1);
       const float* xr = x + row * C;
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) xh[i][q] = lane + 32 * q < C ? __ldg(xr + lane + 32 * q) : 0.f;
+      for (int q = 0; q < CPL; ++q) xh[i][q] = (FULL || lane + 32 * q < C) ? __ldg(xr + lane + 32 * q) : 0.f;
       mr[i] = __ldg(mu + row); rr_[i] = __ldg(rstd + row);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -301,30 +313,26 @@ ln_bwd_transposed_tile_kernel(const float* __restrict__ gzt, const float* __rest
     for (int i = 0; i < kTokPerWarp; ++i) {
       const int rr = wid + 8 * i;
       const bool on = rr < np;
-      const int rc = on ? rr : 0;
       const float m = mr[i], rs = rr_[i];
-      // with rsum: the tile holds acc = r centers and the upstream gradient is zt rsum - acc, zt = x-hat gamma + beta
-      const bool use = rsum && on;
-      const int df = !use ? 0 : (staged ? (rem0 + rr >= P ? 1 : 0) : (int)((t0 + rr) / P - f0));
-      const float* rsr = use ? rsum + (f0 + df) * C : nullptr;
-      const float* rss = rs_s + df * C;
+      const float* tp = tile + lane * kTileLd + (on ? rr : 0);
+      const float* rss = rs_s + ((RSUM && rem0 + rr >= P) ? CP : 0) + lane;
       float g[CPL], s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int q = 0; q < CPL; ++q) {
-        const int c = lane + 32 * q;
-        float gv = (on && c < C) ? tile[c * kTileLd + rc] : 0.f;
+        float gv = tp[32 * q * kTileLd];
         xh[i][q] = (xh[i][q] - m) * rs;
-        if (rsr && c < C) gv = (xh[i][q] * wv[q] + bv[q]) * (staged ? rss[c] : __ldg(rsr + c)) - gv;
+        if constexpr (RSUM) gv = (xh[i][q] * wv[q] + bv[q]) * rss[32 * q] - gv;
+        gv = on ? gv : 0.f;
         g[q] = gv * wv[q];
         s1 += g[q]; s2 += g[q] * xh[i][q];
         aw[q] += gv * xh[i][q]; ab[q] += gv;
       }
       s1 = warp_sum(s1) / (float)C; s2 = warp_sum(s2) / (float)C;
       if (on) {
-        float* go = gx + (t0 + rr) * C;
+        float* go = gx + (t0 + rr) * C + lane;
 #pragma unroll
         for (int q = 0; q < CPL; ++q)
-          if (lane + 32 * q < C) go[lane + 32 * q] = (g[q] - s1 - xh[i][q] * s2) * rs;
+          if (FULL || lane + 32 * q < C) go[32 * q] = (g[q] - s1 - xh[i][q] * s2) * rs;
       }
     }
   }
@@ -332,7 +340,7 @@ ln_bwd_transposed_tile_kernel(const float* __restrict__ gzt, const float* __rest
 #pragma unroll
   for (int q = 0; q < CPL; ++q) {
     const int c = lane + 32 * q;
-    if (c < C) { tile[wid * 2 * C + c] = aw[q]; tile[wid * 2 * C + C + c] = ab[q]; }
+    if (FULL || c < C) { tile[wid * 2 * C + c] = aw[q]; tile[wid * 2 * C + C + c] = ab[q]; }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += 256) {
@@ -378,10 +386,8 @@ static bool space_tc_ok(long long M, int P, int C, int K) {
          !env_on("VADC_NO_TC_GEMM");
 }
 
-static int space_ln_bwd_blocks(long long T, int C) {
-  // tiled kernel (C <= 256): 64-token tiles, ~50 KB of shared memory per block at C = 192, four resident blocks per SM;
-  // otherwise 32-token tiles, six resident blocks
-  const bool tiled = C <= 32 * kMaxCpl;
+static int space_ln_bwd_blocks(long long T, int C, bool tiled) {
+  // tiled kernel: 64-token tiles, ~50 KB of shared memory per block at C = 192; otherwise 32-token tiles
   long long b = tiled ? (T + kTileTok - 1) / kTileTok : (T + 31) / 32;
   long long cap = (long long)sm_count() * (tiled ? 4 : 6);
   if (b > cap) b = cap;
@@ -449,14 +455,23 @@ template <int CPL>
 static int launch_ln_bwd_tile_cpl(const float* gzt, const float* x, const float* mu, const float* rstd, const float* w,
                                   const float* bias, const float* rsum, int P,
                                   long long T, int C, float* gx, float* partial, int nb, cudaStream_t st) {
-  const size_t need = ((size_t)C * kTileLd + 2 * C) * sizeof(float), red = (size_t)16 * C * sizeof(float);
-  const size_t smem = need > red ? need : red;
-  auto kern = ln_bwd_transposed_tile_kernel<CPL>;
-  if (smem > 48 * 1024) VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<nb, 256, smem, st>>>(gzt, x, mu, rstd, w, bias, rsum, P, T, C, gx, partial);
+  const size_t smem = ((size_t)32 * CPL * kTileLd + 2 * 32 * CPL) * sizeof(float);      // >= 16 C floats for the final reduction
+  const bool full = C == 32 * CPL;
+#define VADC_LB(RS, FU)                                                                                       \
+  {                                                                                                           \
+    auto kern = ln_bwd_transposed_tile_kernel<CPL, RS, FU>;                                                   \
+    if (smem > 48 * 1024) VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<nb, 256, smem, st>>>(gzt, x, mu, rstd, w, bias, rsum, P, T, C, gx, partial);                     \
+  }
+  if (rsum) { if (full) VADC_LB(true, true) else VADC_LB(true, false) }
+  else { if (full) VADC_LB(false, true) else VADC_LB(false, false) }
+#undef VADC_LB
   VADC_CHECK_LAUNCH("ln_bwd_transposed_tile_kernel");
   return VADC_OK;
 }
+
+// tiled LayerNorm backward: C <= 256, and with rsum (tensor-core path) P >= 64
+static bool ln_bwd_tile_ok(int C, int P, bool with_rsum) { return C <= 32 * kMaxCpl && (!with_rsum || P >= kTileTok); }
 
 static int launch_ln_bwd_tile(const float* gzt, const float* x, const float* mu, const float* rstd, const float* w,
                               const float* bias, const float* rsum, int P,
@@ -594,7 +609,7 @@ extern "C" size_t vadc_space_cluster_bwd_workspace_bytes(int64_t M, int P, int C
   b += align_up((size_t)C * m * P * sizeof(float), 256);               // gzt
   b += align_up((size_t)space_colsum_chunks(M, (long long)C * K) * C * K * sizeof(float), 256);
   b += align_up((size_t)C * K * sizeof(float), 256);                   // rcol
-  b += align_up((size_t)space_ln_bwd_blocks(M * (int64_t)P, C) * 2 * C * sizeof(float), 256);
+  b += align_up((size_t)std::max(space_ln_bwd_blocks(M * (int64_t)P, C, true), space_ln_bwd_blocks(M * (int64_t)P, C, false)) * 2 * C * sizeof(float), 256);
   if ((P % 8) == 0 && (K % 64) == 0) b += tc_gemm_split_bytes((long long)m, (long long)C * K);
   return b + 256;
 }
@@ -621,12 +636,13 @@ extern "C" int vadc_space_cluster_bwd(const float* x, const float* mu, const flo
   float* gzt = ws.take<float>((size_t)C * T);
   float* cpart = ws.take<float>((size_t)space_colsum_chunks(M, (long long)C * K) * C * K);
   float* rcol = ws.take<float>((size_t)C * K);
-  int nb = space_ln_bwd_blocks(T, C);
+  const bool tc = space_tc_ok(M, P, C, K);
+  const bool tiled = ln_bwd_tile_ok(C, P, tc);
+  int nb = space_ln_bwd_blocks(T, C, tiled);
   float* lnpart = ws.take<float>((size_t)nb * 2 * C);
   int rc;
   cudaError_t e;
   if ((rc = launch_bwd_rows(Ds, As, nullptr, gD, gA, g_loss_sq, M * (long long)C, K, alpha, r, rsum, st))) return rc;
-  const bool tc = space_tc_ok(M, P, C, K);
   if (tc) {
     // r as [M, C K] (batch c = its K-column window), centers as [C K, P] and zt as [C M, P] (terms the forward kept):
     //   acc[c]^T = centers[c]^T r[:,c,:]^T   (gzt = zt rsum - acc is formed by the LayerNorm backward)   rows = positions p:
@@ -661,7 +677,7 @@ extern "C" int vadc_space_cluster_bwd(const float* x, const float* mu, const flo
     e = sgemm_auto(K, P, (int)M, Aop, Bop, K, T, C, 1, epi, st);
     if (e != cudaSuccess) return record_cuda_error(e, "space bwd sgemm rT.zt");
   }
-  if (C <= 32 * kMaxCpl) {
+  if (tiled) {
     if ((rc = launch_ln_bwd_tile(gzt, x, mu, rstd, ln_w, ln_b, tc ? rsum : nullptr, P, T, C, gx, lnpart, nb, st))) return rc;
   } else {
     size_t smem = ((size_t)32 * (C + 1) + (size_t)8 * 2 * C) * sizeof(float);
