@@ -88,6 +88,21 @@ def test_space_self_distance_output_and_gradient(B, Dd, side, C, K):
     assert rel(N(m.cluster_center.grad), cr.grad.numpy()) < 2e-4
 
 
+def test_three_term_modes_of_the_tensor_core_paths():
+    """the tcgen05 contractions of the space head and the memory module default to two fp16 terms of power-of-two-scaled
+    operands (22 significant bits); VADC_SPACE_TERMS=3 / VADC_MEMORY_TERMS=3 select the fp32-faithful bf16 x3 split"""
+    import os
+    from videoad_b200 import _lib
+    os.environ["VADC_SPACE_TERMS"] = "3"; os.environ["VADC_MEMORY_TERMS"] = "3"
+    _lib.lib().vadc_refresh_env()
+    try:
+        test_space_vs_oracle(4, 8, 28, 192, 128)
+        test_memory_vs_oracle(2, 768, 32, 32, 2000)
+    finally:
+        os.environ.pop("VADC_SPACE_TERMS", None); os.environ.pop("VADC_MEMORY_TERMS", None)
+        _lib.lib().vadc_refresh_env()
+
+
 def test_soft_assign_modules():
     rng = np.random.default_rng(3)
     x = rng.standard_normal((5, 7, 13)).astype(np.float32)

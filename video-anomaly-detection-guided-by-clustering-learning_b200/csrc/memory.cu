@@ -527,7 +527,7 @@ extern "C" size_t vadc_memory_score_workspace_bytes(int64_t N, int m, int d) {
   (void)d;
   size_t n = (size_t)(N > 0 ? N : 1);
   return align_up(n * m * sizeof(float), 256) + 2 * align_up((size_t)col_chunks(N) * m * sizeof(float), 256) +
-         tc_gemm_split_bytes((long long)n, d) + tc_gemm_split_bytes(m, d) + 256;      // bf16 terms of q and keys
+         tc_gemm_split_bytes((long long)n, d) + tc_gemm_split_bytes(m, d) + 1024;     // operand terms of q and keys, scales
 }
 
 extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, int m, int d,
@@ -547,13 +547,26 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
   float* pmax = ws.take<float>((size_t)chunks * m);
   float* psum = ws.take<float>((size_t)chunks * m);
   if (tc_gemm_shape_ok(N, m, d, false) && !env_on("VADC_NO_TC_GEMM")) {
-    // q . keys^T on tcgen05 (m = 2000, d = 768 is tensor-bound: 244 flop/B), fp32-faithful three-term split
+    // q . keys^T on tcgen05 (m = 2000, d = 768 is tensor-bound: 244 flop/B)
     void* qs = ws.take<uint8_t>(tc_gemm_split_bytes(N, d));
     void* ks = ws.take<uint8_t>(tc_gemm_split_bytes(m, d));
     int rc;
-    if ((rc = tc_split3(q, N, d, qs, st))) return rc;
-    if ((rc = tc_split3(keys, m, d, ks, st))) return rc;
-    if ((rc = launch_tc_gemm<false>(qs, ks, N, m, d, TcStoreEpi{logits, m}, st))) return rc;
+    if (env_int("VADC_MEMORY_TERMS", 2) == 3) {            // fp32-faithful three-term bf16 split, six products
+      if ((rc = tc_split3(q, N, d, qs, st))) return rc;
+      if ((rc = tc_split3(keys, m, d, ks, st))) return rc;
+      if ((rc = launch_tc_gemm<false>(qs, ks, N, m, d, TcStoreEpi{logits, m}, st))) return rc;
+    } else {
+      // two fp16 terms of the operands scaled by a power of two from their measured bounds (unit-norm rows in the
+      // module: Memory.py:148, :222), three products, 22 significant bits: 2/3 of the operand bytes, half the MMAs
+      unsigned* bits = ws.take<unsigned>(64);
+      float* sc = ws.take<float>(64);
+      if ((rc = tc_absmax_bits(q, (long long)N * d, bits, st))) return rc;
+      if ((rc = tc_absmax_bits(keys, (long long)m * d, bits + 1, st))) return rc;
+      if ((rc = tc_pair_scales(bits, 0.f, bits + 1, 0.f, sc, st))) return rc;
+      if ((rc = tc_split2h(q, N, d, sc, qs, st))) return rc;
+      if ((rc = tc_split2h(keys, m, d, sc + 1, ks, st))) return rc;
+      if ((rc = launch_tc_gemm_h2<false>(qs, ks, N, m, d, sc + 2, TcStoreEpi{logits, m}, st))) return rc;
+    }
   } else {
     Operand Aop{q, d, 1}, Bop{keys, 1, d};
     StoreLogits epi{logits, m};
@@ -581,7 +594,7 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
 
 extern "C" size_t vadc_memory_read_workspace_bytes(int64_t N, int m, int d) {
   size_t n = (size_t)(N > 0 ? N : 1);
-  return tc_gemm_split_bytes((long long)n, m) + tc_gemm_split_bytes(m, d) + 256;      // bf16 terms of score_memory and keys
+  return tc_gemm_split_bytes((long long)n, m) + tc_gemm_split_bytes(m, d) + 1024;     // operand terms of score_memory and keys, scales
 }
 
 extern "C" int vadc_memory_read(const float* q, const float* score_memory, const float* keys,
@@ -599,9 +612,19 @@ extern "C" int vadc_memory_read(const float* q, const float* score_memory, const
     void* ss = ws.take<uint8_t>(tc_gemm_split_bytes(N, m));
     void* ks = ws.take<uint8_t>(tc_gemm_split_bytes(m, d));
     int rc;
-    if ((rc = tc_split3(score_memory, N, m, ss, st))) return rc;
-    if ((rc = tc_split3(keys, m, d, ks, st))) return rc;
-    return launch_tc_gemm<true>(ss, ks, N, d, m, TcReadEpi{updated_query, q, d}, st);
+    if (env_int("VADC_MEMORY_TERMS", 2) == 3) {
+      if ((rc = tc_split3(score_memory, N, m, ss, st))) return rc;
+      if ((rc = tc_split3(keys, m, d, ks, st))) return rc;
+      return launch_tc_gemm<true>(ss, ks, N, d, m, TcReadEpi{updated_query, q, d}, st);
+    }
+    // fp16 x2: the softmax weights (in [0, 1], Memory.py:139) scaled by 2^13 so that small weights stay normal numbers
+    unsigned* bits = ws.take<unsigned>(64);
+    float* sc = ws.take<float>(64);
+    if ((rc = tc_absmax_bits(keys, (long long)m * d, bits, st))) return rc;
+    if ((rc = tc_pair_scales(nullptr, 8192.0f, bits, 0.f, sc, st))) return rc;
+    if ((rc = tc_split2h(score_memory, N, m, sc, ss, st))) return rc;
+    if ((rc = tc_split2h(keys, m, d, sc + 1, ks, st))) return rc;
+    return launch_tc_gemm_h2<true>(ss, ks, N, d, m, sc + 2, TcReadEpi{updated_query, q, d}, st);
   }
   Operand Aop{score_memory, m, 1}, Bop{keys, d, 1};
   ReadEpilogue epi{updated_query, q, d};

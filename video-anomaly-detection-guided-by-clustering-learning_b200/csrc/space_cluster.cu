@@ -5,6 +5,7 @@
 // batches.
 #include <algorithm>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "sgemm.cuh"
 #include "tc_gemm.cuh"
@@ -143,11 +144,13 @@ constexpr int kTileTok = 64, kTileLd = kTileTok + 1, kMaxCpl = 8, kTokPerWarp = 
 // instruction — either fp32 zt (SIMT contraction path) or the three bf16 operand terms of the batched tcgen05 GEMM plus
 // the chunk's share of |zt[c,m,:]|^2 (sqpart [C*M, chunks]; fp32 zt is then never materialised).
 // CPL = channels per lane (C <= 32 CPL).
-template <bool TERMS, int CPL>
+// NT = 0: fp32 zt; 3: three bf16 terms; 2: two fp16 terms of zt * *scale (a power of two from the LayerNorm bound).
+template <int NT, int CPL>
 __global__ void __launch_bounds__(256)
 ln_transpose_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                          int M, int P, int C, float eps, float* __restrict__ zt, float* __restrict__ mu,
-                         float* __restrict__ rstd, __nv_bfloat16* __restrict__ terms, float* __restrict__ sqpart) {
+                         float* __restrict__ rstd, void* __restrict__ terms_, const float* __restrict__ scale,
+                         float* __restrict__ sqpart) {
   extern __shared__ float tile[];            // [C][65]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int chunks = (P + kTileTok - 1) / kTileTok;
@@ -189,12 +192,13 @@ ln_transpose_tile_kernel(const float* __restrict__ x, const float* __restrict__ 
     }
   }
   __syncthreads();
-  if constexpr (TERMS) {
+  if constexpr (NT != 0) {
     // half a warp per channel, four tokens per lane (np is a multiple of 8 on this path: P % 8 == 0): 8-byte stores
     const long long n = (long long)C * T;
     const int half = lane >> 4, l16 = lane & 15;
     const bool tok = 4 * l16 < np;
-    __nv_bfloat16* const tbase = terms + t0 + 4 * l16;
+    uint16_t* const tbase = static_cast<uint16_t*>(terms_) + t0 + 4 * l16;
+    const float sc = NT == 2 ? __ldg(scale) : 1.0f;
 #pragma unroll 2
     for (int cc = 2 * wid; cc < C; cc += 16) {
       const int c = cc + half;
@@ -204,19 +208,33 @@ ln_transpose_tile_kernel(const float* __restrict__ x, const float* __restrict__ 
         const float* tp = tile + c * kTileLd + 4 * l16;
         v[0] = tp[0]; v[1] = tp[1]; v[2] = tp[2]; v[3] = tp[3];
       }
-      __nv_bfloat162 h[3][2];
+      uint16_t* d = tbase + (long long)c * T;
+      if constexpr (NT == 3) {
+        __nv_bfloat162 h[3][2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        h[0][e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-        const float r0 = v[2 * e] - __low2float(h[0][e]), r1 = v[2 * e + 1] - __high2float(h[0][e]);
-        h[1][e] = __floats2bfloat162_rn(r0, r1);
-        h[2][e] = __floats2bfloat162_rn(r0 - __low2float(h[1][e]), r1 - __high2float(h[1][e]));
-      }
-      if (ok) {
-        __nv_bfloat16* d = tbase + (long long)c * T;
-        *reinterpret_cast<uint2*>(d) = *reinterpret_cast<uint2*>(h[0]);
-        *reinterpret_cast<uint2*>(d + n) = *reinterpret_cast<uint2*>(h[1]);
-        *reinterpret_cast<uint2*>(d + 2 * n) = *reinterpret_cast<uint2*>(h[2]);
+        for (int e = 0; e < 2; ++e) {
+          h[0][e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          const float r0 = v[2 * e] - __low2float(h[0][e]), r1 = v[2 * e + 1] - __high2float(h[0][e]);
+          h[1][e] = __floats2bfloat162_rn(r0, r1);
+          h[2][e] = __floats2bfloat162_rn(r0 - __low2float(h[1][e]), r1 - __high2float(h[1][e]));
+        }
+        if (ok) {
+          *reinterpret_cast<uint2*>(d) = *reinterpret_cast<uint2*>(h[0]);
+          *reinterpret_cast<uint2*>(d + n) = *reinterpret_cast<uint2*>(h[1]);
+          *reinterpret_cast<uint2*>(d + 2 * n) = *reinterpret_cast<uint2*>(h[2]);
+        }
+      } else {
+        __half2 h[2][2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float a0 = v[2 * e] * sc, a1 = v[2 * e + 1] * sc;
+          h[0][e] = __floats2half2_rn(a0, a1);
+          h[1][e] = __floats2half2_rn(a0 - __low2float(h[0][e]), a1 - __high2float(h[0][e]));
+        }
+        if (ok) {
+          *reinterpret_cast<uint2*>(d) = *reinterpret_cast<uint2*>(h[0]);
+          *reinterpret_cast<uint2*>(d + n) = *reinterpret_cast<uint2*>(h[1]);
+        }
       }
       float sq = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
 #pragma unroll
@@ -408,6 +426,14 @@ row_sqnorm_terms_kernel(const __nv_bfloat16* __restrict__ t, long long n, long l
 
 static int space_chunks(int P) { return (P + kTileTok - 1) / kTileTok; }
 
+// operand terms of the tensor-core path: two fp16 terms of power-of-two-scaled operands (22 significant bits: 2/3 of
+// the bytes, half the MMAs) unless VADC_SPACE_TERMS=3 asks for the fp32-faithful three bf16 terms; the untiled
+// LayerNorm kernels (C > 256) only write the latter
+static int space_nt(int C) { return (C > 32 * kMaxCpl || env_int("VADC_SPACE_TERMS", 2) == 3) ? 3 : 2; }
+// saved state of the tensor-core path: [ zt terms | centroid terms | forward scales (256 bytes) ]
+static size_t space_zt_bytes(long long M, int P, int C) { return align_up((size_t)C * M * P * space_nt(C) * 2, 256); }
+static size_t space_cen_bytes(int P, int C, int K) { return align_up((size_t)C * K * P * space_nt(C) * 2, 256); }
+
 // column sums of r [M, C K]: few rows, many columns — split the rows so that the grid covers the SMs a few times
 static int space_colsum_chunks(long long R, long long W) {
   long long want = (4ll * sm_count() + (W + 255) / 256 - 1) / ((W + 255) / 256);
@@ -425,25 +451,27 @@ static cudaError_t launch_space_colsum(const float* a, long long R, int W, float
   return cudaGetLastError();
 }
 
-template <bool TERMS, int CPL>
+template <int NT, int CPL>
 static int launch_ln_transpose_tile_cpl(const float* x, const float* w, const float* b, int M, int P, int C, float eps,
-                                        float* zt, float* mu, float* rstd, __nv_bfloat16* terms, float* sqpart,
+                                        float* zt, float* mu, float* rstd, void* terms, const float* scale, float* sqpart,
                                         cudaStream_t st) {
   const size_t smem = (size_t)C * kTileLd * sizeof(float);
-  auto kern = ln_transpose_tile_kernel<TERMS, CPL>;
+  auto kern = ln_transpose_tile_kernel<NT, CPL>;
   if (smem > 48 * 1024) VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)((long long)M * space_chunks(P)), 256, smem, st>>>(x, w, b, M, P, C, eps, zt, mu, rstd, terms, sqpart);
+  kern<<<(unsigned)((long long)M * space_chunks(P)), 256, smem, st>>>(x, w, b, M, P, C, eps, zt, mu, rstd, terms, scale, sqpart);
   VADC_CHECK_LAUNCH("ln_transpose_tile_kernel");
   return VADC_OK;
 }
 
-// terms != nullptr: bf16 operand terms + sqpart; else fp32 zt
+// nt = 0: fp32 zt; 3: bf16 x3 terms + sqpart; 2: fp16 x2 terms of zt * *scale + sqpart
 static int launch_ln_transpose_tile(const float* x, const float* w, const float* b, int M, int P, int C, float eps,
-                                    float* zt, float* mu, float* rstd, __nv_bfloat16* terms, float* sqpart, cudaStream_t st) {
+                                    float* zt, float* mu, float* rstd, int nt, void* terms, const float* scale,
+                                    float* sqpart, cudaStream_t st) {
   const int cpl = (C + 31) / 32;
-#define VADC_LT(CPL)                                                                                               \
-  return terms ? launch_ln_transpose_tile_cpl<true, CPL>(x, w, b, M, P, C, eps, nullptr, mu, rstd, terms, sqpart, st) \
-               : launch_ln_transpose_tile_cpl<false, CPL>(x, w, b, M, P, C, eps, zt, mu, rstd, nullptr, nullptr, st)
+#define VADC_LT(CPL)                                                                                                   \
+  return nt == 3 ? launch_ln_transpose_tile_cpl<3, CPL>(x, w, b, M, P, C, eps, nullptr, mu, rstd, terms, nullptr, sqpart, st) \
+       : nt == 2 ? launch_ln_transpose_tile_cpl<2, CPL>(x, w, b, M, P, C, eps, nullptr, mu, rstd, terms, scale, sqpart, st)   \
+                 : launch_ln_transpose_tile_cpl<0, CPL>(x, w, b, M, P, C, eps, zt, mu, rstd, nullptr, nullptr, nullptr, st)
   if (cpl <= 2) { VADC_LT(2); }
   if (cpl <= 4) { VADC_LT(4); }
   if (cpl <= 6) { VADC_LT(6); }
@@ -494,7 +522,7 @@ using namespace vadc;
 extern "C" size_t vadc_space_cluster_saved_bytes(int64_t M, int P, int C, int K) {
   const size_t n = (size_t)C * (size_t)(M > 0 ? M : 1) * P;
   if (!space_tc_ok(M, P, C, K)) return align_up(n * sizeof(float), 256);
-  return align_up(n * 3 * sizeof(__nv_bfloat16), 256) + tc_gemm_split_bytes((long long)C * K, P);   // zt terms | centers terms
+  return space_zt_bytes(M > 0 ? M : 1, P, C) + space_cen_bytes(P, C, K) + 256;
 }
 
 extern "C" size_t vadc_space_cluster_fwd_workspace_bytes(int64_t M, int P, int C, int K) {
@@ -531,11 +559,19 @@ static int space_cluster_fwd_impl(const float* x, const float* ln_w, const float
   if (M > 0) {
     const bool tc = space_tc_ok(M, P, C, K);
     const bool tiled = C <= 32 * kMaxCpl;
+    const int nt = tc ? space_nt(C) : 0;
     float* zt = tc ? nullptr : static_cast<float*>(zt_state);
     __nv_bfloat16* zs = tc ? static_cast<__nv_bfloat16*>(zt_state) : nullptr;
+    uint8_t* cs = tc ? static_cast<uint8_t*>(zt_state) + space_zt_bytes(M, P, C) : nullptr;     // the backward reuses both
+    float* sc = tc ? reinterpret_cast<float*>(cs + space_cen_bytes(P, C, K)) : nullptr;
+    if (nt == 2) {                                   // scales: LayerNorm bound, measured max |centers| (device-side)
+      unsigned* bits = reinterpret_cast<unsigned*>(sc + 32);
+      if ((rc = tc_absmax_bits(centers, (long long)C * K * P, bits, st))) return rc;
+      if ((rc = tc_fwd_scales_from_bits(bits, ln_w, ln_b, C, sc, st))) return rc;
+    }
     if (tiled) {
       const long long rows = (long long)C * M;
-      if ((rc = launch_ln_transpose_tile(x, ln_w, ln_b, (int)M, P, C, eps, zt, mu, rstd, zs, sqpart, st))) return rc;
+      if ((rc = launch_ln_transpose_tile(x, ln_w, ln_b, (int)M, P, C, eps, zt, mu, rstd, nt, zs, sc, sqpart, st))) return rc;
       if (tc) {
         sqpart_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(sqpart, rows, space_chunks(P), zz);
         VADC_CHECK_LAUNCH("sqpart_reduce_kernel");
@@ -555,18 +591,24 @@ static int space_cluster_fwd_impl(const float* x, const float* ln_w, const float
     if ((rc = launch_row_sqnorm(centers, (long long)C * K, P, cc, st))) return rc;
     // batch c: A = zt[c] [M,P], B = centers[c]^T; out Ds[m, c, k]
     if (tc) {
-      // the centroids' operand terms live behind the zt terms in the saved state: the backward reuses them
-      void* cs = static_cast<uint8_t*>(zt_state) + align_up((size_t)C * M * P * 3 * sizeof(__nv_bfloat16), 256);
-      if ((rc = tc_split3(centers, (long long)C * K, P, cs, st))) return rc;
       TcBatchDistEpi epi{Ds, zz, cc, (long long)C * K, K, M, K};
-      if ((rc = launch_tc_gemm_batched<false, false>(zs, (long long)C * M, P, cs, (long long)C * K, P, M, K, P, C,
-                                                     TcBatchOffsets{(int)M, 0, K, 0}, epi, st))) return rc;
-      if (selfdist) {     // cdist(centers, centers) (model/cluster.py:134) from the same terms and norms
-        TcBatchDistEpi eps_{selfdist, cc, cc, K, (long long)K * K, K, K};
-        if ((rc = launch_tc_gemm_batched<false, false>(cs, (long long)C * K, P, cs, (long long)C * K, P, K, K, P, C,
-                                                       TcBatchOffsets{K, 0, K, 0}, eps_, st))) return rc;
-        selfdist_done = true;
+      TcBatchDistEpi eps_{selfdist, cc, cc, K, (long long)K * K, K, K};
+      const TcBatchOffsets od{(int)M, 0, K, 0}, os{K, 0, K, 0};
+      if (nt == 2) {
+        if ((rc = tc_split2h(centers, (long long)C * K, P, sc + 1, cs, st))) return rc;
+        if ((rc = launch_tc_gemm_batched_h2<false, false>(zs, (long long)C * M, P, cs, (long long)C * K, P, M, K, P, C, od,
+                                                          sc + 2, epi, st))) return rc;
+        // cdist(centers, centers) (model/cluster.py:134) from the same terms and norms
+        if (selfdist && (rc = launch_tc_gemm_batched_h2<false, false>(cs, (long long)C * K, P, cs, (long long)C * K, P, K, K, P, C,
+                                                                      os, sc + 5, eps_, st))) return rc;
+      } else {
+        if ((rc = tc_split3(centers, (long long)C * K, P, cs, st))) return rc;
+        if ((rc = launch_tc_gemm_batched<false, false>(zs, (long long)C * M, P, cs, (long long)C * K, P, M, K, P, C, od, epi, st)))
+          return rc;
+        if (selfdist && (rc = launch_tc_gemm_batched<false, false>(cs, (long long)C * K, P, cs, (long long)C * K, P, K, K, P, C,
+                                                                   os, eps_, st))) return rc;
       }
+      selfdist_done = true;
     } else {
       Operand Aop{zt, P, 1}, Bop{centers, 1, P};
       SpaceDistEpilogue epi{Ds, zz, cc, (long long)C * K, K, (int)M};
@@ -610,7 +652,7 @@ extern "C" size_t vadc_space_cluster_bwd_workspace_bytes(int64_t M, int P, int C
   b += align_up((size_t)space_colsum_chunks(M, (long long)C * K) * C * K * sizeof(float), 256);
   b += align_up((size_t)C * K * sizeof(float), 256);                   // rcol
   b += align_up((size_t)std::max(space_ln_bwd_blocks(M * (int64_t)P, C, true), space_ln_bwd_blocks(M * (int64_t)P, C, false)) * 2 * C * sizeof(float), 256);
-  if ((P % 8) == 0 && (K % 64) == 0) b += tc_gemm_split_bytes((long long)m, (long long)C * K);
+  if ((P % 8) == 0 && (K % 64) == 0) b += tc_gemm_split_bytes((long long)m, (long long)C * K) + 512;     // r terms, scales
   return b + 256;
 }
 
@@ -649,17 +691,33 @@ extern "C" int vadc_space_cluster_bwd(const float* x, const float* mu, const flo
     //                                        A = centers MN-major, B = r K-major
     //   gcenters[c] = centers[c] rcol[c] - r[:,c,:]^T zt[c]    A MN-major (window offset along m), B MN-major
     void* rs = ws.take<uint8_t>(tc_gemm_split_bytes(M, (long long)C * K));
-    const __nv_bfloat16* zs = static_cast<const __nv_bfloat16*>(zt_state);
-    const void* cs = static_cast<const uint8_t*>(zt_state) + align_up((size_t)C * M * P * 3 * sizeof(__nv_bfloat16), 256);
-    if ((rc = tc_split3(r, M, (long long)C * K, rs, st))) return rc;
+    const int nt = space_nt(C);
+    const void* zs = zt_state;
+    const uint8_t* cs = static_cast<const uint8_t*>(zt_state) + space_zt_bytes(M, P, C);
+    const float* fsc = reinterpret_cast<const float*>(cs + space_cen_bytes(P, C, K));
     TcSpaceGzEpi egz{gzt, T, P};                   // gzt <- r centers; the LayerNorm backward below forms zt rsum - that
-    if ((rc = launch_tc_gemm_batched<true, false>(cs, (long long)C * K, P, rs, M, (long long)C * K, P, M, K, C,
-                                                  TcBatchOffsets{0, K, 0, K}, egz, st))) return rc;
+    TcSpaceGcEpi egc{gcenters, centers, rcol, (long long)K * P, P, K};
+    const TcBatchOffsets oz{0, K, 0, K}, oc{K, 0, 0, (int)M};
     e = launch_space_colsum(r, M, C * K, cpart, rcol, st);
     if (e != cudaSuccess) return record_cuda_error(e, "space colsum r");
-    TcSpaceGcEpi egc{gcenters, centers, rcol, (long long)K * P, P, K};
-    if ((rc = launch_tc_gemm_batched<true, true>(rs, M, (long long)C * K, zs, (long long)C * M, P, K, P, M, C,
-                                                 TcBatchOffsets{K, 0, 0, (int)M}, egc, st))) return rc;
+    if (nt == 2) {
+      // r has no a-priori bound: scale from its measured max (device-side, no host sync)
+      unsigned* bits = ws.take<unsigned>(64);
+      float* bsc = ws.take<float>(64);
+      if ((rc = tc_absmax_bits(r, (long long)M * C * K, bits, st))) return rc;
+      if ((rc = tc_space_bwd_scales(bits, fsc, bsc, st))) return rc;
+      if ((rc = tc_split2h(r, M, (long long)C * K, bsc, rs, st))) return rc;
+      if ((rc = launch_tc_gemm_batched_h2<true, false>(cs, (long long)C * K, P, rs, M, (long long)C * K, P, M, K, C, oz, bsc + 1,
+                                                       egz, st))) return rc;
+      if ((rc = launch_tc_gemm_batched_h2<true, true>(rs, M, (long long)C * K, zs, (long long)C * M, P, K, P, M, C, oc, bsc + 2,
+                                                      egc, st))) return rc;
+    } else {
+      if ((rc = tc_split3(r, M, (long long)C * K, rs, st))) return rc;
+      if ((rc = launch_tc_gemm_batched<true, false>(cs, (long long)C * K, P, rs, M, (long long)C * K, P, M, K, C, oz, egz, st)))
+        return rc;
+      if ((rc = launch_tc_gemm_batched<true, true>(rs, M, (long long)C * K, zs, (long long)C * M, P, K, P, M, C, oc, egc, st)))
+        return rc;
+    }
   } else {
     const float* zt = static_cast<const float*>(zt_state);
     // gzt[c] = zt[c] * rsum[:,c] - r[:,c,:] @ centers[c]

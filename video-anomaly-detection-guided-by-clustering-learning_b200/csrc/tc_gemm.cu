@@ -290,35 +290,53 @@ int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, lon
 
 // nbatch independent [M,N,Kd] problems in ONE launch (blockIdx.z = batch): the operands of batch z start
 // z * off.{m,k} coordinates further along tensors of the given full extents (rows x cols of the split matrices)
-template <bool A_MN, bool B_MN, class Epi>
-int launch_tc_gemm_batched(const void* a_split, long long a_rows, long long a_cols, const void* b_split,
-                           long long b_rows, long long b_cols, long long M, long long N, long long Kd, int nbatch,
-                           TcBatchOffsets off, Epi epi, cudaStream_t st) {
+// TERMS = 3: bf16 x3 operands from tc_split3; TERMS = 2: fp16 x2 operands from tc_split2h, accumulators scaled by *acc_scale
+template <int TERMS, bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_batched_t(const void* a_split, long long a_rows, long long a_cols, const void* b_split,
+                             long long b_rows, long long b_cols, long long M, long long N, long long Kd, int nbatch,
+                             TcBatchOffsets off, const float* acc_scale, Epi epi, cudaStream_t st) {
   constexpr int BN = 128;
   if (nbatch < 1 || nbatch > 65535) return VADC_ERR_UNSUPPORTED;
+  if (TERMS == 2 && !acc_scale) return VADC_ERR_NULL_POINTER;
   CUtensorMap mA, mB;
   int rc;
-  if ((rc = tg::make_map3(&mA, a_split, a_rows, a_cols, A_MN ? 64 : tg::BM))) return rc;
-  if ((rc = tg::make_map3(&mB, b_split, b_rows, b_cols, B_MN ? 64 : BN))) return rc;
+  if ((rc = tg::make_map3(&mA, a_split, a_rows, a_cols, A_MN ? 64 : tg::BM, TERMS))) return rc;
+  if ((rc = tg::make_map3(&mB, b_split, b_rows, b_cols, B_MN ? 64 : BN, TERMS))) return rc;
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
-  const size_t stage = (size_t)(3 * tg::BM * 128 + 3 * BN * 128);
+  const size_t stage = (size_t)TERMS * (tg::BM * 128 + BN * 128);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)nbatch);
   const tg::ZOffsets zo{1, off.a_m, off.a_k, off.b_n, off.b_k, nkb >= 4 ? env_int("VADC_TC_PREFETCH", 0) : 0};
   // two-stage ring, one CTA per SM: measured no better than two co-resident one-stage CTAs on the space head's long
   // contraction loops (distance GEMM, 16 k-blocks: 251 vs 210 us; gcenters, 8 k-blocks: 218 vs 212 us) — opt-in only
-  if (nkb >= 6 && env_on("VADC_TC_TWO_STAGE")) {
-    auto kern = tg::tc_gemm_kernel<BN, 3, 2, A_MN, B_MN, Epi>;
+  if (TERMS == 3 && nkb >= 6 && env_on("VADC_TC_TWO_STAGE")) {
+    auto kern = tg::tc_gemm_kernel<BN, TERMS, 2, A_MN, B_MN, Epi>;
     const size_t smem = 2 * stage + 1024;
     VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, nullptr, epi);
+    kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, acc_scale, epi);
   } else {
-    auto kern = tg::tc_gemm_kernel<BN, 3, 1, A_MN, B_MN, Epi>;
+    auto kern = tg::tc_gemm_kernel<BN, TERMS, 1, A_MN, B_MN, Epi>;
     const size_t smem = stage + 1024;
     VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, nullptr, epi);
+    kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, acc_scale, epi);
   }
   VADC_CHECK_LAUNCH("tc_gemm_kernel(batched)");
   return VADC_OK;
+}
+
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_batched(const void* a_split, long long a_rows, long long a_cols, const void* b_split,
+                           long long b_rows, long long b_cols, long long M, long long N, long long Kd, int nbatch,
+                           TcBatchOffsets off, Epi epi, cudaStream_t st) {
+  return launch_tc_gemm_batched_t<3, A_MN, B_MN, Epi>(a_split, a_rows, a_cols, b_split, b_rows, b_cols, M, N, Kd, nbatch, off,
+                                                      nullptr, epi, st);
+}
+
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_batched_h2(const void* a_split, long long a_rows, long long a_cols, const void* b_split,
+                              long long b_rows, long long b_cols, long long M, long long N, long long Kd, int nbatch,
+                              TcBatchOffsets off, const float* acc_scale, Epi epi, cudaStream_t st) {
+  return launch_tc_gemm_batched_t<2, A_MN, B_MN, Epi>(a_split, a_rows, a_cols, b_split, b_rows, b_cols, M, N, Kd, nbatch, off,
+                                                      acc_scale, epi, st);
 }
 
 // ---- two-term fp16 mode -------------------------------------------------------------------------
@@ -333,7 +351,7 @@ __device__ __forceinline__ float pow2_scale(float bound) {   // power of two s w
 
 // scales of the cluster forward (one block): s_z from the LayerNorm bound sqrt(C) max|gamma| + max|beta|, s_c from
 // max|centers|, s_a = 2^13 for the softmin weights in [0, 1]
-//   out[0] = s_z, [1] = s_c, [2] = 1 / (s_z s_c), [3] = s_a, [4] = 1 / (s_a s_c)
+//   out[0] = s_z, [1] = s_c, [2] = 1 / (s_z s_c), [3] = s_a, [4] = 1 / (s_a s_c), [5] = 1 / (s_c s_c)
 __global__ void __launch_bounds__(1024)
 fwd_scales_kernel(const float* __restrict__ centers, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                   long long KC, int C, float* __restrict__ out) {
@@ -360,6 +378,7 @@ fwd_scales_kernel(const float* __restrict__ centers, const float* __restrict__ l
     mc = fmaxf(mc, red[0][0]); mg = fmaxf(mg, red[1][0]); mb = fmaxf(mb, red[2][0]);
     const float s_z = pow2_scale(sqrtf((float)C) * mg + mb), s_c = pow2_scale(mc), s_a = 8192.0f;
     out[0] = s_z; out[1] = s_c; out[2] = 1.0f / (s_z * s_c); out[3] = s_a; out[4] = 1.0f / (s_a * s_c);
+    out[5] = 1.0f / (s_c * s_c);                             // centroid self-distance
   }
 }
 
@@ -404,6 +423,84 @@ int tc_split2h(const float* src, long long rows, long long cols, const float* sc
   return VADC_OK;
 }
 
+namespace tg {
+// max |src| as the bit pattern of a non-negative float (ordered like unsigned integers): deterministic atomicMax
+__global__ void __launch_bounds__(256)
+absmax_bits_kernel(const float* __restrict__ src, long long n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  const long long n4 = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) ? n / 4 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(src[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f && isfinite(m)) atomicMax(out, __float_as_uint(m));
+}
+
+// out[0] = s_a, out[1] = s_b, out[2] = 1 / (s_a s_b); a scale comes from a measured bound (bits) or is given
+__global__ void pair_scales_kernel(const unsigned* a_bits, float a_given, const unsigned* b_bits, float b_given, float* out) {
+  const float sa = a_bits ? pow2_scale(__uint_as_float(*a_bits)) : a_given;
+  const float sb = b_bits ? pow2_scale(__uint_as_float(*b_bits)) : b_given;
+  out[0] = sa; out[1] = sb; out[2] = 1.0f / (sa * sb);
+}
+}  // namespace tg
+
+// space head backward: r scaled from its measured bound, against the forward's s_z, s_c (fwd_sc = tc_fwd_scales output)
+//   out[0] = s_r, [1] = 1 / (s_c s_r), [2] = 1 / (s_r s_z)
+namespace tg {
+__global__ void space_bwd_scales_kernel(const unsigned* r_bits, const float* fwd_sc, float* out) {
+  const float sr = pow2_scale(__uint_as_float(*r_bits));
+  out[0] = sr; out[1] = 1.0f / (fwd_sc[1] * sr); out[2] = 1.0f / (sr * fwd_sc[0]);
+}
+}  // namespace tg
+int tc_space_bwd_scales(const unsigned* r_bits, const float* fwd_sc, float* out3, cudaStream_t st) {
+  tg::space_bwd_scales_kernel<<<1, 1, 0, st>>>(r_bits, fwd_sc, out3);
+  VADC_CHECK_LAUNCH("space_bwd_scales_kernel");
+  return VADC_OK;
+}
+
+// the forward scales (layout of fwd_scales_kernel) from an already measured max |centers| (tc_absmax_bits: every SM
+// takes part — the one-block scan of fwd_scales_kernel is for the cluster head's small [K, C] centroid matrix)
+namespace tg {
+__global__ void __launch_bounds__(256)
+fwd_scales_from_bits_kernel(const unsigned* cen_bits, const float* __restrict__ ln_w, const float* __restrict__ ln_b, int C,
+                            float* __restrict__ out) {
+  __shared__ float red[2][8];
+  float mg = 0.f, mb = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { mg = fmaxf(mg, fabsf(ln_w[i])); mb = fmaxf(mb, fabsf(ln_b[i])); }
+  mg = warp_max(mg); mb = warp_max(mb);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = mg; red[1][threadIdx.x >> 5] = mb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) { mg = fmaxf(mg, red[0][i]); mb = fmaxf(mb, red[1][i]); }
+    const float s_z = pow2_scale(sqrtf((float)C) * mg + mb), s_c = pow2_scale(__uint_as_float(*cen_bits)), s_a = 8192.0f;
+    out[0] = s_z; out[1] = s_c; out[2] = 1.0f / (s_z * s_c); out[3] = s_a; out[4] = 1.0f / (s_a * s_c);
+    out[5] = 1.0f / (s_c * s_c);
+  }
+}
+}  // namespace tg
+int tc_fwd_scales_from_bits(const unsigned* cen_bits, const float* ln_w, const float* ln_b, int C, float* out, cudaStream_t st) {
+  tg::fwd_scales_from_bits_kernel<<<1, 256, 0, st>>>(cen_bits, ln_w, ln_b, C, out);
+  VADC_CHECK_LAUNCH("fwd_scales_from_bits_kernel");
+  return VADC_OK;
+}
+
+int tc_absmax_bits(const float* src, long long n, unsigned* out, cudaStream_t st) {
+  VADC_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned), st));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 8));
+  tg::absmax_bits_kernel<<<grid, 256, 0, st>>>(src, n, out);
+  VADC_CHECK_LAUNCH("absmax_bits_kernel");
+  return VADC_OK;
+}
+
+int tc_pair_scales(const unsigned* a_bits, float a_given, const unsigned* b_bits, float b_given, float* out3, cudaStream_t st) {
+  tg::pair_scales_kernel<<<1, 1, 0, st>>>(a_bits, a_given, b_bits, b_given, out3);
+  VADC_CHECK_LAUNCH("pair_scales_kernel");
+  return VADC_OK;
+}
+
 template <bool B_MN, class Epi>
 int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, long long N, long long Kd,
                       const float* acc_scale, Epi epi, cudaStream_t st) {
@@ -425,6 +522,8 @@ int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, lon
 }
 template int launch_tc_gemm_h2<false, TcDistEpi>(const void*, const void*, long long, long long, long long, const float*, TcDistEpi, cudaStream_t);
 template int launch_tc_gemm_h2<true, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
+template int launch_tc_gemm_h2<false, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
+template int launch_tc_gemm_h2<true, TcReadEpi>(const void*, const void*, long long, long long, long long, const float*, TcReadEpi, cudaStream_t);
 
 template <bool B_MN, class Epi>
 int launch_tc_gemm(const void* a_split, const void* b_split, long long M, long long N, long long Kd, Epi epi,
@@ -448,6 +547,14 @@ VADC_TC_BATCHED(false, false, TcBatchDistEpi)
 VADC_TC_BATCHED(true, false, TcSpaceGzEpi)
 VADC_TC_BATCHED(true, true, TcSpaceGcEpi)
 #undef VADC_TC_BATCHED
+#define VADC_TC_BATCHED_H2(AMN, BMN, EPI)                                                                              \
+  template int launch_tc_gemm_batched_h2<AMN, BMN, EPI>(const void*, long long, long long, const void*, long long,      \
+                                                        long long, long long, long long, long long, int, TcBatchOffsets, \
+                                                        const float*, EPI, cudaStream_t);
+VADC_TC_BATCHED_H2(false, false, TcBatchDistEpi)
+VADC_TC_BATCHED_H2(true, false, TcSpaceGzEpi)
+VADC_TC_BATCHED_H2(true, true, TcSpaceGcEpi)
+#undef VADC_TC_BATCHED_H2
 
 }  // namespace vadc
 

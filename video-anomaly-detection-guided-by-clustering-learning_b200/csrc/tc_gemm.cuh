@@ -24,11 +24,18 @@ int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, lon
 // accumulators multiplied by *acc_scale before the epilogue
 size_t tc_gemm_split2_bytes(long long rows, long long cols);
 int tc_fwd_scales(const float* centers, const float* ln_w, const float* ln_b, long long KC, int C, float* out5,
-                  cudaStream_t st);     // out5 = {s_z, s_c, 1/(s_z s_c), s_a, 1/(s_a s_c)}
+                  cudaStream_t st);     // out (6 floats) = {s_z, s_c, 1/(s_z s_c), s_a, 1/(s_a s_c), 1/(s_c s_c)}
 int tc_split2h(const float* src, long long rows, long long cols, const float* scale, void* dst, cudaStream_t st);
 template <bool B_MN, class Epi>
 int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, long long N, long long Kd,
                       const float* acc_scale, Epi epi, cudaStream_t st);
+
+// scales for operands whose bound has to be measured: max |src| as float bits (memset + atomicMax), then
+// out3 = {s_a, s_b, 1 / (s_a s_b)} with s = the power of two that puts the bound in [4, 8), or the given constant
+int tc_absmax_bits(const float* src, long long n, unsigned* out, cudaStream_t st);
+int tc_pair_scales(const unsigned* a_bits, float a_given, const unsigned* b_bits, float b_given, float* out3, cudaStream_t st);
+int tc_fwd_scales_from_bits(const unsigned* cen_bits, const float* ln_w, const float* ln_b, int C, float* out6, cudaStream_t st);
+int tc_space_bwd_scales(const unsigned* r_bits, const float* fwd_sc, float* out3, cudaStream_t st);   // {s_r, 1/(s_c s_r), 1/(s_r s_z)}
 
 // batched form (blockIdx.z = batch): per-batch coordinate offsets along the operands' tensors — a_m / b_n along the
 // output-row / output-column dimension, a_k / b_k along the contraction dimension
@@ -37,6 +44,11 @@ template <bool A_MN, bool B_MN, class Epi>
 int launch_tc_gemm_batched(const void* a_split, long long a_rows, long long a_cols, const void* b_split,
                            long long b_rows, long long b_cols, long long M, long long N, long long Kd, int nbatch,
                            TcBatchOffsets off, Epi epi, cudaStream_t st);
+
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_batched_h2(const void* a_split, long long a_rows, long long a_cols, const void* b_split,
+                              long long b_rows, long long b_cols, long long M, long long N, long long Kd, int nbatch,
+                              TcBatchOffsets off, const float* acc_scale, Epi epi, cudaStream_t st);
 
 __device__ __forceinline__ void tc_store_row32(float* o, const float (&v)[32], int nvalid) {
   if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
