@@ -255,16 +255,21 @@ int vadc_memory_query_bwd(const float* query, const float* keys, const int64_t* 
  * gather_loss :241, spread_loss :223 and update :185 take with torch.topk):
  *   logits = q keys^T [N,m]; score_query = softmax over N; score_memory =
  *   softmax over m; colmax[m] = max_n logits; colsum[m] = sum_n exp(logit-colmax);
- *   top1/top2 [N] int64. */
+ *   top1/top2 [N] int64.
+ * score_memory_terms (optional, 4*N*m bytes, 16-byte aligned, or NULL): the operand terms of score_memory for the
+ * read contraction, written in the softmax pass; hand the same buffer to vadc_memory_read to skip its split pass. */
 size_t vadc_memory_score_workspace_bytes(int64_t N, int m, int d);
 int vadc_memory_score(const float* q, const float* keys, int64_t N, int m, int d,
                       float* score_query, float* score_memory,
                       float* colmax, float* colsum, int64_t* top1, int64_t* top2,
+                      void* score_memory_terms,
                       void* workspace, size_t workspace_bytes, void* stream);
 
-/* read  Memory.py:249-261: updated_query [N,2d] = cat(q, score_memory @ keys) */
+/* read  Memory.py:249-261: updated_query [N,2d] = cat(q, score_memory @ keys); score_memory holds softmax weights
+ * (values in [0, 1]: the fp16 x2 operand terms scale them by 2^13) */
 size_t vadc_memory_read_workspace_bytes(int64_t N, int m, int d);
-int vadc_memory_read(const float* q, const float* score_memory, const float* keys,
+int vadc_memory_read(const float* q, const float* score_memory, const void* score_memory_terms,
+                     const float* keys,
                      int64_t N, int m, int d, float* updated_query,
                      void* workspace, size_t workspace_bytes, void* stream);
 

@@ -124,7 +124,8 @@ int softmin_blocks(long long R, int K) {
 
 // A, label, loss_sq from D.  partial: softmin_blocks(R,K) doubles.
 int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* A, long long* label,
-                        double* partial, float* loss_sq, cudaStream_t st, int k_valid) {
+                        double* partial, float* loss_sq, cudaStream_t st, int k_valid, void* terms_h2, float sa) {
+  __half* th = static_cast<__half*>(terms_h2);
   if (k_valid < 0 || k_valid > K) k_valid = K;
   if (R == 0) {
     zero_kernel<<<1, 32, 0, st>>>(loss_sq, 1);
@@ -134,10 +135,10 @@ int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* 
   int G = group_for(K);
   int nb = softmin_blocks(R, K);
   switch (G) {
-    case 4: softmin_rows_kernel<4><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial); break;
-    case 8: softmin_rows_kernel<8><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial); break;
-    case 16: softmin_rows_kernel<16><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial); break;
-    default: softmin_rows_kernel<32><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial); break;
+    case 4: softmin_rows_kernel<4><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial, th, sa); break;
+    case 8: softmin_rows_kernel<8><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial, th, sa); break;
+    case 16: softmin_rows_kernel<16><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial, th, sa); break;
+    default: softmin_rows_kernel<32><<<nb, 256, 0, st>>>(D, R, K, k_valid, alpha, A, label, partial, th, sa); break;
   }
   VADC_CHECK_LAUNCH("softmin_rows_kernel");
   finalize_sum_kernel<<<1, 1024, 0, st>>>(partial, nb, loss_sq);
@@ -315,8 +316,8 @@ static int cluster_fwd_impl(const float* x, const float* ln_w, const float* ln_b
     if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
     if ((rc = tc_split2h(centers, K, C, sc + 1, cs, st))) return rc;
     if ((rc = launch_tc_gemm_h2<false>(fs, cs, N, K, C, sc + 2, TcDistEpi{D, zz, cc, K}, st))) return rc;
-    if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
-    if ((rc = tc_split2h(A, N, K, sc + 3, as, st))) return rc;
+    // softmin writes A and, in the same pass, its two fp16 terms scaled by s_a = 2^13 (the value fwd_scales_kernel puts in sc[3])
+    if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st, k_valid, as, 8192.0f))) return rc;
     return launch_tc_gemm_h2<true>(as, cs, N, C, K, sc + 4, TcStoreEpi{x_rec, C}, st);    // centers [K,C] read MN-major
   }
   if (use_tc) {
@@ -327,7 +328,7 @@ static int cluster_fwd_impl(const float* x, const float* ln_w, const float* ln_b
     if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
     if ((rc = tc_split3(centers, K, C, cs, st))) return rc;
     if ((rc = launch_tc_gemm<false>(fs, cs, N, K, C, TcDistEpi{D, zz, cc, K}, st))) return rc;
-    if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st))) return rc;
+    if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st, k_valid))) return rc;
     if ((rc = tc_split3(A, N, K, as, st))) return rc;
     return launch_tc_gemm<true>(as, cs, N, C, K, TcStoreEpi{x_rec, C}, st);    // centers [K,C] read MN-major
   }
@@ -424,7 +425,9 @@ extern "C" int vadc_cdist(const float* a, const float* b, int nb, int64_t R, int
   // launch-latency-bound sizes, and single problems too small to fill the GPU with GEMM tiles (the [K,K] centroid
   // self-distance at K = 256, C = 768 is 16 tiles: 135 us on the tile GEMM, one row per block does it in ~15 us)
   const long long macs = (long long)nb * R * P * C;
-  if ((macs <= (1ll << 21) || (nb == 1 && macs <= (1ll << 28))) && nb <= 65535 && (C % 4) == 0 && aligned16(a) && aligned16(b)) {
+  const long long tiles = ((R + 127) / 128) * ((P + 127) / 128);       // 32 tiles and more keep the tile GEMM busy enough
+  if ((macs <= (1ll << 21) || (nb == 1 && macs <= (1ll << 28) && tiles < 32)) && nb <= 65535 && (C % 4) == 0 && aligned16(a) &&
+      aligned16(b)) {
     cdist_small_kernel<<<dim3((unsigned)R, (unsigned)nb), 256, 0, st>>>(a, b, (int)R, (int)P, C, out);
     VADC_CHECK_LAUNCH("cdist_small_kernel");
     return VADC_OK;
@@ -476,7 +479,7 @@ extern "C" size_t vadc_cluster_bwd_workspace_bytes(int64_t N, int C, int K) {
   b += align_up((size_t)K * sizeof(float), 256);             // rcol
   b += align_up((size_t)ln_bwd_blocks(N) * 2 * C * sizeof(float), 256);
   // generic path on the tcgen05 GEMM: bf16 term copies of gR, feature, A, r and the centroids + split-K partials
-  b += 2 * tc_gemm_split_bytes((long long)n, C) + 2 * tc_gemm_split_bytes((long long)n, K) + tc_gemm_split_bytes(K, C);
+  b += 2 * tc_gemm_split_bytes((long long)n, C) + 2 * tc_gemm_split_bytes((long long)n, K) + tc_gemm_split_bytes(K, C) + 1024;
   b += 2 * align_up((size_t)bwd_tc_splits(N, C, K) * K * C * sizeof(float), 256);
   return std::max(std::max(b + 256, bwd_fused_workspace_bytes(N, C, K)), bwd_tc2_workspace_bytes(N, C, K));
 }
@@ -536,6 +539,38 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
     float* q1 = ws.take<float>((size_t)sk * KC);
     float* q2 = ws.take<float>((size_t)sk * KC);
     int rc;
+    if (!env_on("VADC_TC_BF16X3")) {
+      // two fp16 terms per operand, each scaled by the power of two of its measured bound (A: 2^13): 22 significant bits,
+      // 2/3 of the operand bytes and half the MMAs of the bf16 x3 split (VADC_TC_BF16X3 keeps that one)
+      unsigned* bits = ws.take<unsigned>(64);
+      float* sc = ws.take<float>(64);
+      VADC_CUDA(cudaMemsetAsync(bits, 0, 4 * sizeof(unsigned), st));
+      if (gR && (rc = tc_absmax_bits(gR, (long long)N * C, bits + 0, st))) return rc;
+      if ((rc = tc_absmax_bits(centers, (long long)K * C, bits + 1, st))) return rc;
+      if ((rc = tc_absmax_bits(feature, (long long)N * C, bits + 2, st))) return rc;
+      if ((rc = tc_cluster_bwd_scales(bits, 0, sc, st))) return rc;
+      if ((rc = tc_split2h(centers, K, C, sc + 1, cs, st))) return rc;
+      if (gR) {
+        if ((rc = tc_split2h(gR, N, C, sc + 0, gRs, st))) return rc;
+        if ((rc = launch_tc_gemm_h2<false>(gRs, cs, N, K, C, sc + 5, TcStoreEpi{gemm, K}, st))) return rc;
+      }
+      if ((rc = launch_bwd_rows(D, A, gR ? gemm : nullptr, gD, gA, g_loss_sq, N, K, alpha, r, rsum, st))) return rc;
+      if ((rc = tc_absmax_bits(r, (long long)N * K, bits + 3, st))) return rc;
+      if ((rc = tc_cluster_bwd_scales(bits, 1, sc, st))) return rc;
+      if ((rc = tc_split2h(r, N, K, sc + 4, rs, st))) return rc;
+      if ((rc = launch_tc_gemm_h2<true>(rs, cs, N, C, K, sc + 7, TcGzEpi{gz, feature, rsum, gF, C}, st))) return rc;
+      if (gR) {
+        if ((rc = tc_split2h(A, N, K, sc + 3, as, st))) return rc;
+        if ((rc = launch_tc_gemm_ex_h2<true, true>(as, gRs, K, C, N, sk, sc + 6, TcPartialEpi{q1, C, KC}, st))) return rc;
+      }
+      if ((rc = tc_split2h(feature, N, C, sc + 2, fs, st))) return rc;
+      if ((rc = launch_tc_gemm_ex_h2<true, true>(rs, fs, K, C, N, sk, sc + 8, TcPartialEpi{q2, C, KC}, st))) return rc;
+      cudaError_t e2 = launch_colsum(r, N, K, cpart, rcol, st);
+      if (e2 != cudaSuccess) return record_cuda_error(e2, "colsum r");
+      gcenters_finalize_kernel<<<(unsigned)((KC + 255) / 256), 256, 0, st>>>(gR ? q1 : nullptr, q2, sk, centers, rcol, K, C, gcenters);
+      VADC_CHECK_LAUNCH("gcenters_finalize_kernel");
+      return launch_ln_bwd(gz, x, mu, rstd, ln_w, N, C, gx, lnpart, g_ln_w, g_ln_b, st);
+    }
     if ((rc = tc_split3(centers, K, C, cs, st))) return rc;
     if (gR) {
       if ((rc = tc_split3(gR, N, C, gRs, st))) return rc;

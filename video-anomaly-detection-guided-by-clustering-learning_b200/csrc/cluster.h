@@ -10,7 +10,8 @@ int launch_ln_rows(const float* x, const float* w, const float* b, long long N, 
 int launch_row_sqnorm(const float* a, long long R, int C, float* out, cudaStream_t st);
 int softmin_blocks(long long R, int K);
 int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* A, long long* label,
-                        double* partial, float* loss_sq, cudaStream_t st, int k_valid = -1);
+                        double* partial, float* loss_sq, cudaStream_t st, int k_valid = -1,
+                        void* terms_h2 = nullptr, float sa = 0.f);     // optional: two fp16 terms of A * sa, [2][R*K]
 int launch_bwd_rows(const float* D, const float* A, const float* gemm, const float* gD,
                     const float* gA, const float* g_loss_sq, long long R, int K,
                     float alpha, float* r, float* rsum, cudaStream_t st);

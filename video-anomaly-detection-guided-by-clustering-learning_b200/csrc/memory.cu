@@ -136,7 +136,8 @@ memory_query_bwd_kernel(const float* __restrict__ query, const float* __restrict
 __global__ void __launch_bounds__(256)
 row_softmax_top2_kernel(const float* __restrict__ logits, long long N, int m,
                         float* __restrict__ out, long long* __restrict__ top1,
-                        long long* __restrict__ top2) {
+                        long long* __restrict__ top2,
+                        __half* __restrict__ terms /* optional: two fp16 terms of out * 2^13, [2][N*m] */) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -167,10 +168,50 @@ row_softmax_top2_kernel(const float* __restrict__ logits, long long N, int m,
     b1 = n1; i1 = j1; b2 = n2; i2 = j2;
   }
   float s = 0.f;
+  float* orow = out + row * m;
+  if ((m & 3) == 0 && ((reinterpret_cast<uintptr_t>(lr) | reinterpret_cast<uintptr_t>(orow)) & 15u) == 0) {
+    // 16-byte accesses (the row is L1-resident after the top-2 pass); terms as 8-byte stores
+    const float4* l4 = reinterpret_cast<const float4*>(lr);
+    const int n4 = m >> 2;
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = l4[i];
+      s += (expf(v.x - b1) + expf(v.y - b1)) + (expf(v.z - b1) + expf(v.w - b1));
+    }
+    s = warp_sum(s);
+    for (int i = lane; i < n4; i += 32) {
+      const float4 v = l4[i];
+      const float4 p = make_float4(expf(v.x - b1) / s, expf(v.y - b1) / s, expf(v.z - b1) / s, expf(v.w - b1) / s);
+      reinterpret_cast<float4*>(orow)[i] = p;
+      if (terms) {                             // the operand split of the read GEMM, written in the same pass
+        const float a[4] = {p.x * 8192.0f, p.y * 8192.0f, p.z * 8192.0f, p.w * 8192.0f};
+        __half h[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { h[0][j] = __float2half_rn(a[j]); h[1][j] = __float2half_rn(a[j] - __half2float(h[0][j])); }
+        reinterpret_cast<uint2*>(terms + row * m)[i] = *reinterpret_cast<uint2*>(h[0]);
+        reinterpret_cast<uint2*>(terms + N * m + row * m)[i] = *reinterpret_cast<uint2*>(h[1]);
+      }
+    }
+    if (lane == 0) {
+      if (top1) top1[row] = i1;
+      if (top2) top2[row] = (m > 1) ? i2 : 0;
+    }
+    return;
+  }
   for (int i = lane; i < m; i += 32) s += expf(lr[i] - b1);
   s = warp_sum(s);
-  float* orow = out + row * m;
-  for (int i = lane; i < m; i += 32) orow[i] = expf(lr[i] - b1) / s;
+  if (terms) {                                 // the operand split of the read GEMM, written in the same pass
+    __half* t0 = terms + row * m;
+    __half* t1 = t0 + N * m;
+    for (int i = lane; i < m; i += 32) {
+      const float p = expf(lr[i] - b1) / s;
+      orow[i] = p;
+      const float ps = p * 8192.0f;
+      const __half h = __float2half_rn(ps);
+      t0[i] = h; t1[i] = __float2half_rn(ps - __half2float(h));
+    }
+  } else {
+    for (int i = lane; i < m; i += 32) orow[i] = expf(lr[i] - b1) / s;
+  }
   if (lane == 0) {
     if (top1) top1[row] = i1;
     if (top2) top2[row] = (m > 1) ? i2 : 0;
@@ -178,45 +219,81 @@ row_softmax_top2_kernel(const float* __restrict__ logits, long long N, int m,
 }
 
 // ---- column softmax over tokens (Memory.py:140): online max/sum per chunk --
+__device__ __forceinline__ void online_add(float& mx, float& s, float v) {
+  if (v > mx) { s = s * expf(mx - v) + 1.0f; mx = v; } else { s += expf(v - mx); }
+}
+__device__ __forceinline__ void online_merge(float& mx, float& s, float omx, float os) {
+  if (omx == -INFINITY) return;
+  if (omx > mx) { s = s * expf(mx - omx) + os; mx = omx; } else { s += os * expf(omx - mx); }
+}
+
+// a thread owns a column of a row chunk; four independent (max, sum) chains over interleaved rows, merged in a fixed order
 __global__ void __launch_bounds__(256)
 col_stats_stage1_kernel(const float* __restrict__ logits, long long N, int m, long long rpb,
                         float* __restrict__ pmax, float* __restrict__ psum) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= m) return;
   long long r0 = (long long)blockIdx.y * rpb, r1 = min(N, r0 + rpb);
-  float mx = -INFINITY, s = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    float v = __ldg(logits + r * m + col);
-    if (v > mx) { s = s * expf(mx - v) + 1.0f; mx = v; } else { s += expf(v - mx); }
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sm[4] = {0.f, 0.f, 0.f, 0.f};
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(logits + (r + j) * m + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) online_add(mx[j], sm[j], v[j]);
   }
-  pmax[(long long)blockIdx.y * m + col] = mx;
-  psum[(long long)blockIdx.y * m + col] = s;
+  for (; r < r1; ++r) online_add(mx[0], sm[0], __ldg(logits + r * m + col));
+  online_merge(mx[0], sm[0], mx[1], sm[1]);
+  online_merge(mx[2], sm[2], mx[3], sm[3]);
+  online_merge(mx[0], sm[0], mx[2], sm[2]);
+  pmax[(long long)blockIdx.y * m + col] = mx[0];
+  psum[(long long)blockIdx.y * m + col] = sm[0];
 }
 
+// 32 columns per block, eight warps stride the chunks, merged through shared memory in warp order
 __global__ void __launch_bounds__(256)
 col_stats_stage2_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int chunks,
                         int m, float* __restrict__ colmax, float* __restrict__ colsum) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= m) return;
-  float mx = -INFINITY;
-  for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, pmax[(long long)c * m + col]);
-  float s = 0.f;
-  for (int c = 0; c < chunks; ++c) {
-    float pm = pmax[(long long)c * m + col];
-    if (pm > -INFINITY) s += psum[(long long)c * m + col] * expf(pm - mx);
+  __shared__ float smx[8][32], ssm[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  float mx = -INFINITY, s = 0.f;
+  if (col < m)
+    for (int c = wid; c < chunks; c += 8) online_merge(mx, s, pmax[(long long)c * m + col], psum[(long long)c * m + col]);
+  smx[wid][lane] = mx; ssm[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && col < m) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) online_merge(mx, s, smx[w][lane], ssm[w][lane]);
+    colmax[col] = mx;
+    colsum[col] = s;
   }
-  colmax[col] = mx;
-  colsum[col] = s;
 }
 
+// out[r, c] = exp(logits[r, c] - colmax[c]) / colsum[c]: a thread keeps the statistics of its column(s) in registers and
+// walks down a chunk of rows (VEC: four columns per thread, 16-byte accesses)
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 col_softmax_apply_kernel(const float* __restrict__ logits, const float* __restrict__ colmax,
-                         const float* __restrict__ colsum, long long total, int m,
+                         const float* __restrict__ colsum, long long N, int m, long long rpb,
                          float* __restrict__ out) {
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int col = (int)(i % m);
-    out[i] = expf(logits[i] - __ldg(colmax + col)) / __ldg(colsum + col);
+  const long long r0 = (long long)blockIdx.y * rpb, r1 = min(N, r0 + rpb);
+  if constexpr (VEC) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c4 >= m / 4) return;
+    const float4 cm = __ldg(reinterpret_cast<const float4*>(colmax) + c4), cs = __ldg(reinterpret_cast<const float4*>(colsum) + c4);
+    for (long long r = r0; r < r1; ++r) {
+      const float4 v = ld_stream(reinterpret_cast<const float4*>(logits + r * m) + c4);
+      float4 o;
+      o.x = expf(v.x - cm.x) / cs.x; o.y = expf(v.y - cm.y) / cs.y; o.z = expf(v.z - cm.z) / cs.z; o.w = expf(v.w - cm.w) / cs.w;
+      reinterpret_cast<float4*>(out + r * m)[c4] = o;
+    }
+  } else {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= m) return;
+    const float cm = __ldg(colmax + col), cs = __ldg(colsum + col);
+    for (long long r = r0; r < r1; ++r) out[r * m + col] = expf(logits[r * m + col] - cm) / cs;
   }
 }
 
@@ -532,8 +609,8 @@ extern "C" size_t vadc_memory_score_workspace_bytes(int64_t N, int m, int d) {
 
 extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, int m, int d,
                                  float* score_query, float* score_memory, float* colmax,
-                                 float* colsum, int64_t* top1, int64_t* top2, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+                                 float* colsum, int64_t* top1, int64_t* top2, void* score_memory_terms,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
   VADC_REQUIRE(N >= 0 && m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
   if (N == 0) return VADC_OK;
   VADC_REQUIRE(q && keys && score_memory && workspace, VADC_ERR_NULL_POINTER);
@@ -573,20 +650,25 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
     cudaError_t e = sgemm_auto((int)N, m, d, Aop, Bop, 0, 0, 1, 1, epi, st);
     if (e != cudaSuccess) return record_cuda_error(e, "memory score sgemm");
   }
-  row_softmax_top2_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(logits, N, m, score_memory, (long long*)top1, (long long*)top2);
+  // with a terms buffer (fp16 x2 mode): the read GEMM's operand split of score_memory is written in the same pass
+  __half* smt = (score_memory_terms && env_int("VADC_MEMORY_TERMS", 2) != 3) ? static_cast<__half*>(score_memory_terms) : nullptr;
+  row_softmax_top2_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(logits, N, m, score_memory, (long long*)top1, (long long*)top2, smt);
   VADC_CHECK_LAUNCH("row_softmax_top2_kernel");
   if (score_query) {
     long long rpb = (N + chunks - 1) / chunks;
     dim3 g1((m + 255) / 256, chunks);
     col_stats_stage1_kernel<<<g1, 256, 0, st>>>(logits, N, m, rpb, pmax, psum);
     VADC_CHECK_LAUNCH("col_stats_stage1_kernel");
-    col_stats_stage2_kernel<<<(m + 255) / 256, 256, 0, st>>>(pmax, psum, chunks, m, colmax, colsum);
+    col_stats_stage2_kernel<<<(m + 31) / 32, 256, 0, st>>>(pmax, psum, chunks, m, colmax, colsum);
     VADC_CHECK_LAUNCH("col_stats_stage2_kernel");
-    long long total = (long long)N * m;
-    long long nb = (total + 1023) / 1024;
-    long long cap = (long long)sm_count() * 16;
-    if (nb > cap) nb = cap;
-    col_softmax_apply_kernel<<<(unsigned)nb, 256, 0, st>>>(logits, colmax, colsum, total, m, score_query);
+    const bool vec = (m % 4) == 0 && aligned16(logits) && aligned16(score_query) && aligned16(colmax) && aligned16(colsum);
+    const int cols = vec ? m / 4 : m;
+    const unsigned gx = (unsigned)((cols + 255) / 256);
+    long long ach = std::max<long long>(1, std::min<long long>((N + 15) / 16, (8ll * sm_count() + gx - 1) / gx));   // >= 16 rows each
+    const long long arpb = (N + ach - 1) / ach;
+    ach = (N + arpb - 1) / arpb;
+    if (vec) col_softmax_apply_kernel<true><<<dim3(gx, (unsigned)ach), 256, 0, st>>>(logits, colmax, colsum, N, m, arpb, score_query);
+    else col_softmax_apply_kernel<false><<<dim3(gx, (unsigned)ach), 256, 0, st>>>(logits, colmax, colsum, N, m, arpb, score_query);
     VADC_CHECK_LAUNCH("col_softmax_apply_kernel");
   }
   return VADC_OK;
@@ -597,8 +679,8 @@ extern "C" size_t vadc_memory_read_workspace_bytes(int64_t N, int m, int d) {
   return tc_gemm_split_bytes((long long)n, m) + tc_gemm_split_bytes(m, d) + 1024;     // operand terms of score_memory and keys, scales
 }
 
-extern "C" int vadc_memory_read(const float* q, const float* score_memory, const float* keys,
-                                int64_t N, int m, int d, float* updated_query,
+extern "C" int vadc_memory_read(const float* q, const float* score_memory, const void* score_memory_terms,
+                                const float* keys, int64_t N, int m, int d, float* updated_query,
                                 void* workspace, size_t workspace_bytes, void* stream) {
   VADC_REQUIRE(N >= 0 && m > 0 && d > 0, VADC_ERR_BAD_SHAPE);
   if (N == 0) return VADC_OK;
@@ -622,9 +704,13 @@ extern "C" int vadc_memory_read(const float* q, const float* score_memory, const
     float* sc = ws.take<float>(64);
     if ((rc = tc_absmax_bits(keys, (long long)m * d, bits, st))) return rc;
     if ((rc = tc_pair_scales(nullptr, 8192.0f, bits, 0.f, sc, st))) return rc;
-    if ((rc = tc_split2h(score_memory, N, m, sc, ss, st))) return rc;
+    const void* sst = score_memory_terms;              // written by vadc_memory_score next to score_memory, or split here
+    if (!sst) {
+      if ((rc = tc_split2h(score_memory, N, m, sc, ss, st))) return rc;
+      sst = ss;
+    }
     if ((rc = tc_split2h(keys, m, d, sc + 1, ks, st))) return rc;
-    return launch_tc_gemm_h2<true>(ss, ks, N, d, m, sc + 2, TcReadEpi{updated_query, q, d}, st);
+    return launch_tc_gemm_h2<true>(sst, ks, N, d, m, sc + 2, TcReadEpi{updated_query, q, d}, st);
   }
   Operand Aop{score_memory, m, 1}, Bop{keys, d, 1};
   ReadEpilogue epi{updated_query, q, d};

@@ -152,7 +152,8 @@ template <int G>
 __global__ void __launch_bounds__(256)
 softmin_rows_kernel(const float* __restrict__ D, long long R, int K, int k_valid, float alpha,
                     float* __restrict__ A, long long* __restrict__ label,
-                    double* __restrict__ partial) {
+                    double* __restrict__ partial,
+                    __half* __restrict__ terms /* optional: two fp16 terms of A * sa, [2][R*K] */, float sa) {
   __shared__ double red[32];
   const int tid = threadIdx.x;
   const int g = tid / G, gl = tid % G;
@@ -195,6 +196,15 @@ softmin_rows_kernel(const float* __restrict__ D, long long R, int K, int k_valid
       a.z = expf(-alpha * (v.z - best)) / s;
       a.w = expf(-alpha * (v.w - best)) / s;
       ar[i] = a;
+      if (terms) {                          // the operand split of the x_rec GEMM, written in the same pass
+        const float b[4] = {a.x * sa, a.y * sa, a.z * sa, a.w * sa};
+        __half h[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { h[0][j] = __float2half_rn(b[j]); h[1][j] = __float2half_rn(b[j] - __half2float(h[0][j])); }
+        uint2* t = reinterpret_cast<uint2*>(terms + row * K) + i;
+        t[0] = *reinterpret_cast<uint2*>(h[0]);
+        reinterpret_cast<uint2*>(terms + R * K + row * K)[i] = *reinterpret_cast<uint2*>(h[1]);
+      }
       l += (da_sq(v.x, a.x) + da_sq(v.y, a.y)) + (da_sq(v.z, a.z) + da_sq(v.w, a.w));
     }
     lsum = (double)l;
@@ -317,7 +327,7 @@ colsum_stage2_kernel(const float* __restrict__ partial, int nchunks, int W, floa
 }
 
 inline int colsum_chunks(long long R) {
-  long long c = (R + 1023) / 1024;
+  long long c = (R + 255) / 256;          // 256 rows per block: enough blocks to fill the SMs at a few thousand rows
   if (c > 1024) c = 1024;
   if (c < 1) c = 1;
   return (int)c;

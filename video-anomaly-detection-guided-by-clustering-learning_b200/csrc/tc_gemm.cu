@@ -264,28 +264,43 @@ int tc_split3(const float* src, long long rows, long long cols, void* dst, cudaS
   return VADC_OK;
 }
 
-template <bool A_MN, bool B_MN, class Epi>
-int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
-                      Epi epi, cudaStream_t st) {
+template <int TERMS, bool A_MN, bool B_MN, class Epi>
+static int launch_tc_gemm_ex_t(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
+                               const float* acc_scale, Epi epi, cudaStream_t st) {
   constexpr int BN = 128;
+  if (TERMS == 2 && !acc_scale) return VADC_ERR_NULL_POINTER;
   CUtensorMap mA, mB;
   int rc;
-  if (A_MN) rc = tg::make_map3(&mA, a_split, Kd, M, 64);        // [Kd rows, M cols]: boxes of 64 k-rows x 64 m-cols
-  else rc = tg::make_map3(&mA, a_split, M, Kd, tg::BM);
+  if (A_MN) rc = tg::make_map3(&mA, a_split, Kd, M, 64, TERMS);   // [Kd rows, M cols]: boxes of 64 k-rows x 64 m-cols
+  else rc = tg::make_map3(&mA, a_split, M, Kd, tg::BM, TERMS);
   if (rc) return rc;
-  if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64);        // [Kd rows, N cols]: boxes of 64 k-rows x 64 n-cols
-  else rc = tg::make_map3(&mB, b_split, N, Kd, BN);             // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
+  if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64, TERMS);   // [Kd rows, N cols]: boxes of 64 k-rows x 64 n-cols
+  else rc = tg::make_map3(&mB, b_split, N, Kd, BN, TERMS);        // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
   if (rc) return rc;
-  const size_t smem = (size_t)(3 * tg::BM * 128 + 3 * BN * 128) + 1024;
-  auto kern = tg::tc_gemm_kernel<BN, 3, 1, A_MN, B_MN, Epi>;
+  constexpr int kSt = TERMS == 2 ? tg::kStagesH : 1;
+  const size_t smem = (size_t)kSt * TERMS * (tg::BM * 128 + BN * 128) + 1024;
+  auto kern = tg::tc_gemm_kernel<BN, TERMS, kSt, A_MN, B_MN, Epi>;
   VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
   if (splits < 1) splits = 1;
   const int per = (nkb + splits - 1) / splits;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)splits);
-  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0}, nullptr, epi);
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0}, acc_scale, epi);
   VADC_CHECK_LAUNCH("tc_gemm_kernel");
   return VADC_OK;
+}
+
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_ex(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
+                      Epi epi, cudaStream_t st) {
+  return launch_tc_gemm_ex_t<3, A_MN, B_MN, Epi>(a_split, b_split, M, N, Kd, splits, nullptr, epi, st);
+}
+
+// the same with fp16 x2 operands (tc_split2h) and the accumulators scaled by *acc_scale
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_ex_h2(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
+                         const float* acc_scale, Epi epi, cudaStream_t st) {
+  return launch_tc_gemm_ex_t<2, A_MN, B_MN, Epi>(a_split, b_split, M, N, Kd, splits, acc_scale, epi, st);
 }
 
 // nbatch independent [M,N,Kd] problems in ONE launch (blockIdx.z = batch): the operands of batch z start
@@ -487,6 +502,27 @@ int tc_fwd_scales_from_bits(const unsigned* cen_bits, const float* ln_w, const f
   return VADC_OK;
 }
 
+// generic cluster backward in fp16 x2: scales of gR, centers, feature (measured), A (2^13) and — once bwd_rows has run — r
+//   out[0] = s_g, [1] = s_c, [2] = s_f, [3] = s_a, [4] = s_r, [5] = 1/(s_g s_c), [6] = 1/(s_a s_g), [7] = 1/(s_r s_c), [8] = 1/(s_r s_f)
+// bits[0..3] = max |gR|, |centers|, |feature|, |r|; stage 0 fills everything that does not need r, stage 1 the rest
+namespace tg {
+__global__ void cluster_bwd_scales_kernel(const unsigned* bits, int stage, float* out) {
+  if (stage == 0) {
+    const float sg = pow2_scale(__uint_as_float(bits[0])), sc = pow2_scale(__uint_as_float(bits[1]));
+    const float sf = pow2_scale(__uint_as_float(bits[2])), sa = 8192.0f;
+    out[0] = sg; out[1] = sc; out[2] = sf; out[3] = sa; out[5] = 1.0f / (sg * sc); out[6] = 1.0f / (sa * sg);
+  } else {
+    const float sr = pow2_scale(__uint_as_float(bits[3]));
+    out[4] = sr; out[7] = 1.0f / (sr * out[1]); out[8] = 1.0f / (sr * out[2]);
+  }
+}
+}  // namespace tg
+int tc_cluster_bwd_scales(const unsigned* bits, int stage, float* out, cudaStream_t st) {
+  tg::cluster_bwd_scales_kernel<<<1, 1, 0, st>>>(bits, stage, out);
+  VADC_CHECK_LAUNCH("cluster_bwd_scales_kernel");
+  return VADC_OK;
+}
+
 int tc_absmax_bits(const float* src, long long n, unsigned* out, cudaStream_t st) {
   VADC_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned), st));
   const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 8));
@@ -504,26 +540,14 @@ int tc_pair_scales(const unsigned* a_bits, float a_given, const unsigned* b_bits
 template <bool B_MN, class Epi>
 int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, long long N, long long Kd,
                       const float* acc_scale, Epi epi, cudaStream_t st) {
-  constexpr int BN = 128;
-  CUtensorMap mA, mB;
-  int rc;
-  if ((rc = tg::make_map3(&mA, a_split, M, Kd, tg::BM, 2))) return rc;
-  if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64, 2);
-  else rc = tg::make_map3(&mB, b_split, N, Kd, BN, 2);
-  if (rc) return rc;
-  const size_t smem = (size_t)tg::kStagesH * 2 * (tg::BM * 128 + BN * 128) + 1024;
-  auto kern = tg::tc_gemm_kernel<BN, 2, tg::kStagesH, false, B_MN, Epi>;
-  VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), 1);
-  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, tg::ZOffsets{0, 0, 0, 0, 0}, acc_scale, epi);
-  VADC_CHECK_LAUNCH("tc_gemm_kernel(fp16 x2)");
-  return VADC_OK;
+  return launch_tc_gemm_ex_t<2, false, B_MN, Epi>(a_split, b_split, M, N, Kd, 1, acc_scale, epi, st);
 }
 template int launch_tc_gemm_h2<false, TcDistEpi>(const void*, const void*, long long, long long, long long, const float*, TcDistEpi, cudaStream_t);
 template int launch_tc_gemm_h2<true, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
 template int launch_tc_gemm_h2<false, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
 template int launch_tc_gemm_h2<true, TcReadEpi>(const void*, const void*, long long, long long, long long, const float*, TcReadEpi, cudaStream_t);
+template int launch_tc_gemm_h2<true, TcGzEpi>(const void*, const void*, long long, long long, long long, const float*, TcGzEpi, cudaStream_t);
+template int launch_tc_gemm_ex_h2<true, true, TcPartialEpi>(const void*, const void*, long long, long long, long long, int, const float*, TcPartialEpi, cudaStream_t);
 
 template <bool B_MN, class Epi>
 int launch_tc_gemm(const void* a_split, const void* b_split, long long M, long long N, long long Kd, Epi epi,

@@ -35,7 +35,12 @@ int launch_tc_gemm_h2(const void* a_split, const void* b_split, long long M, lon
 int tc_absmax_bits(const float* src, long long n, unsigned* out, cudaStream_t st);
 int tc_pair_scales(const unsigned* a_bits, float a_given, const unsigned* b_bits, float b_given, float* out3, cudaStream_t st);
 int tc_fwd_scales_from_bits(const unsigned* cen_bits, const float* ln_w, const float* ln_b, int C, float* out6, cudaStream_t st);
+int tc_cluster_bwd_scales(const unsigned* bits4, int stage, float* out9, cudaStream_t st);   // see tc_gemm.cu
 int tc_space_bwd_scales(const unsigned* r_bits, const float* fwd_sc, float* out3, cudaStream_t st);   // {s_r, 1/(s_c s_r), 1/(s_r s_z)}
+
+template <bool A_MN, bool B_MN, class Epi>
+int launch_tc_gemm_ex_h2(const void* a_split, const void* b_split, long long M, long long N, long long Kd, int splits,
+                         const float* acc_scale, Epi epi, cudaStream_t st);
 
 // batched form (blockIdx.z = batch): per-batch coordinate offsets along the operands' tensors — a_m / b_n along the
 // output-row / output-column dimension, a_k / b_k along the contraction dimension

@@ -37,10 +37,10 @@ def _dist_reduce(t, op):
 
 class _Scores:
     """everything ``get_score`` + the topk calls derive from one (query, keys) pair"""
-    __slots__ = ("q", "score_query", "score_memory", "colmax", "colsum", "top1", "top2")
+    __slots__ = ("q", "score_query", "score_memory", "colmax", "colsum", "top1", "top2", "score_memory_terms")
 
 
-def _compute_scores(q, keys, need_query_softmax=True):
+def _compute_scores(q, keys, need_query_softmax=True, want_read_terms=False):
     N, d = q.shape
     m = keys.shape[0]
     dev = q.device
@@ -52,10 +52,12 @@ def _compute_scores(q, keys, need_query_softmax=True):
     s.colsum = torch.empty((m,), device=dev, dtype=torch.float32)
     s.top1 = torch.empty((N,), device=dev, dtype=torch.int64)
     s.top2 = torch.empty((N,), device=dev, dtype=torch.int64)
+    # operand terms of score_memory for the read contraction, written in the softmax pass (opaque: 4 bytes per element)
+    s.score_memory_terms = torch.empty((N * m * 4 + 16,), device=dev, dtype=torch.uint8) if want_read_terms else None
     l = _lib.lib()
     ws = workspace(l.vadc_memory_score_workspace_bytes(N, m, d), dev)
     check(l.vadc_memory_score(ptr(q), ptr(keys), N, m, d, ptr(s.score_query), ptr(s.score_memory),
-                              ptr(s.colmax), ptr(s.colsum), ptr(s.top1), ptr(s.top2),
+                              ptr(s.colmax), ptr(s.colsum), ptr(s.top1), ptr(s.top2), ptr(s.score_memory_terms),
                               ptr(ws), ws.numel(), stream()), "vadc_memory_score")
     return s
 
@@ -74,7 +76,7 @@ class _MemoryForward(torch.autograd.Function):
         qc = f32c(query)
         q4 = mod.prepare_query(qc)
         q, shp = mod._flat(q4)
-        s = _compute_scores(q, keys_c)
+        s = _compute_scores(q, keys_c, want_read_terms=True)
         gathering_loss, spreading_loss = mod._losses(s, keys_c, train)
         gathering_loss = gathering_loss.clone()           # separate outputs, not two views of one buffer
         spreading_loss = None if spreading_loss is None else spreading_loss.clone()
@@ -215,7 +217,7 @@ class Memory(nn.Module):
         with torch.no_grad():
             q, shp = self._flat(query)
             keys_c = f32c(updated_memory)
-            s = _compute_scores(q, keys_c)
+            s = _compute_scores(q, keys_c, want_read_terms=True)
             return self._read(s, keys_c, shp), s.score_query, s.score_memory
 
     # -- kernels --------------------------------------------------------------
@@ -237,8 +239,8 @@ class Memory(nn.Module):
         uq = torch.empty((N, 2 * d), device=s.q.device, dtype=torch.float32)
         l = _lib.lib()
         ws = workspace(l.vadc_memory_read_workspace_bytes(N, m, d), uq.device)
-        check(l.vadc_memory_read(ptr(s.q), ptr(s.score_memory), ptr(keys), N, m, d, ptr(uq), ptr(ws), ws.numel(),
-                                 stream()), "vadc_memory_read")
+        check(l.vadc_memory_read(ptr(s.q), ptr(s.score_memory), ptr(s.score_memory_terms), ptr(keys),
+                                 N, m, d, ptr(uq), ptr(ws), ws.numel(), stream()), "vadc_memory_read")
         return uq.view(B, h, w, 2 * d).permute(0, 3, 1, 2)          # Memory.py:258-259
 
     def _segmented_update(self, q, keys, score_query, top1):
