@@ -315,9 +315,14 @@ static int cluster_fwd_impl(const float* x, const float* ln_w, const float* ln_b
     if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, feature, mu, rstd, zz, st, rowstats, fs, sc + 0))) return rc;
     if ((rc = launch_row_sqnorm(centers, K, C, cc, st))) return rc;
     if ((rc = tc_split2h(centers, K, C, sc + 1, cs, st))) return rc;
-    if ((rc = launch_tc_gemm_h2<false>(fs, cs, N, K, C, sc + 2, TcDistEpi{D, zz, cc, K}, st))) return rc;
+    // from K = 128 up the distance GEMM runs with the operands swapped (rows = centroids): coalesced stores of D
+    if (K >= 128 && !env_on("VADC_TC_ROW_EPILOGUE")) {
+      if ((rc = launch_tc_gemm_h2<false>(cs, fs, K, N, C, sc + 2, TcDistTEpi{D, cc, zz, K}, st))) return rc;
+    } else if ((rc = launch_tc_gemm_h2<false>(fs, cs, N, K, C, sc + 2, TcDistEpi{D, zz, cc, K}, st))) return rc;
     // softmin writes A and, in the same pass, its two fp16 terms scaled by s_a = 2^13 (the value fwd_scales_kernel puts in sc[3])
     if ((rc = launch_softmin_rows(D, N, K, alpha, A, (long long*)label, partial, loss_sq, st, k_valid, as, 8192.0f))) return rc;
+    if (C >= 128 && !env_on("VADC_TC_ROW_EPILOGUE"))       // rows = channels (centers [K,C] as the MN-major A operand): coalesced x_rec
+      return launch_tc_gemm_ex_h2<true, false>(cs, as, C, N, K, 1, sc + 4, TcStoreTEpi{x_rec, C}, st);
     return launch_tc_gemm_h2<true>(as, cs, N, C, K, sc + 4, TcStoreEpi{x_rec, C}, st);    // centers [K,C] read MN-major
   }
   if (use_tc) {
@@ -552,13 +557,17 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
       if ((rc = tc_split2h(centers, K, C, sc + 1, cs, st))) return rc;
       if (gR) {
         if ((rc = tc_split2h(gR, N, C, sc + 0, gRs, st))) return rc;
-        if ((rc = launch_tc_gemm_h2<false>(gRs, cs, N, K, C, sc + 5, TcStoreEpi{gemm, K}, st))) return rc;
+        if (K >= 128 && !env_on("VADC_TC_ROW_EPILOGUE")) {      // operands swapped: rows = centroids, coalesced stores
+          if ((rc = launch_tc_gemm_h2<false>(cs, gRs, K, N, C, sc + 5, TcStoreTEpi{gemm, K}, st))) return rc;
+        } else if ((rc = launch_tc_gemm_h2<false>(gRs, cs, N, K, C, sc + 5, TcStoreEpi{gemm, K}, st))) return rc;
       }
       if ((rc = launch_bwd_rows(D, A, gR ? gemm : nullptr, gD, gA, g_loss_sq, N, K, alpha, r, rsum, st))) return rc;
       if ((rc = tc_absmax_bits(r, (long long)N * K, bits + 3, st))) return rc;
       if ((rc = tc_cluster_bwd_scales(bits, 1, sc, st))) return rc;
       if ((rc = tc_split2h(r, N, K, sc + 4, rs, st))) return rc;
-      if ((rc = launch_tc_gemm_h2<true>(rs, cs, N, C, K, sc + 7, TcGzEpi{gz, feature, rsum, gF, C}, st))) return rc;
+      if (C >= 128 && !env_on("VADC_TC_ROW_EPILOGUE")) {     // rows = channels: coalesced loads of feature / gF and stores of gz
+        if ((rc = launch_tc_gemm_ex_h2<true, false>(cs, rs, C, N, K, 1, sc + 7, TcGzTEpi{gz, feature, rsum, gF, C}, st))) return rc;
+      } else if ((rc = launch_tc_gemm_h2<true>(rs, cs, N, C, K, sc + 7, TcGzEpi{gz, feature, rsum, gF, C}, st))) return rc;
       if (gR) {
         if ((rc = tc_split2h(A, N, K, sc + 3, as, st))) return rc;
         if ((rc = launch_tc_gemm_ex_h2<true, true>(as, gRs, K, C, N, sk, sc + 6, TcPartialEpi{q1, C, KC}, st))) return rc;

@@ -642,7 +642,10 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
       if ((rc = tc_pair_scales(bits, 0.f, bits + 1, 0.f, sc, st))) return rc;
       if ((rc = tc_split2h(q, N, d, sc, qs, st))) return rc;
       if ((rc = tc_split2h(keys, m, d, sc + 1, ks, st))) return rc;
-      if ((rc = launch_tc_gemm_h2<false>(qs, ks, N, m, d, sc + 2, TcStoreEpi{logits, m}, st))) return rc;
+      // operands swapped from m = 128 up (rows = memory slots): coalesced stores of the logits
+      if (m >= 128 && !env_on("VADC_TC_ROW_EPILOGUE")) {
+        if ((rc = launch_tc_gemm_h2<false>(ks, qs, m, N, d, sc + 2, TcStoreTEpi{logits, m}, st))) return rc;
+      } else if ((rc = launch_tc_gemm_h2<false>(qs, ks, N, m, d, sc + 2, TcStoreEpi{logits, m}, st))) return rc;
     }
   } else {
     Operand Aop{q, d, 1}, Bop{keys, 1, d};
@@ -710,6 +713,8 @@ extern "C" int vadc_memory_read(const float* q, const float* score_memory, const
       sst = ss;
     }
     if ((rc = tc_split2h(keys, m, d, sc + 1, ks, st))) return rc;
+    if (d >= 128 && !env_on("VADC_TC_ROW_EPILOGUE"))       // rows = channels (keys [m,d] as the MN-major A operand): coalesced output
+      return launch_tc_gemm_ex_h2<true, false>(ks, sst, d, N, m, 1, sc + 2, TcReadTEpi{updated_query, q, d}, st);
     return launch_tc_gemm_h2<true>(sst, ks, N, d, m, sc + 2, TcReadEpi{updated_query, q, d}, st);
   }
   Operand Aop{score_memory, m, 1}, Bop{keys, d, 1};

@@ -42,7 +42,10 @@ template <int TERMS, int STAGES> struct StageCfg { static constexpr int ctas = S
 
 // per-blockIdx.z coordinate offsets of a batched launch: output-row / contraction offsets of A, output-column /
 // contraction offsets of B (in elements of the respective tensor-map dimension)
-struct ZOffsets { int batched, a_m, a_k, b_n, b_k, pf; };   // pf: k-blocks prefetched into L2 together with every (pf+1)-th load
+// pf: k-blocks prefetched into L2 together with every (pf+1)-th load; m_fast: blockIdx.x walks the m-tiles (the launcher
+// lets the dimension with FEWER tiles vary fastest, so that the CTAs in flight share the small operand and stream the
+// big one from DRAM once: with 16 m-tiles x 512 n-tiles the other order re-read the n-side operand 16 times)
+struct ZOffsets { int batched, a_m, a_k, b_n, b_k, pf, m_fast; };
 
 __global__ void __launch_bounds__(256)
 split3_kernel(const float* __restrict__ src, long long n4, __nv_bfloat16* __restrict__ t0,
@@ -90,7 +93,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint64_t full[kStages], empty[kStages], accfull;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = (zo.m_fast ? blockIdx.x : blockIdx.y) * BM, n0 = (zo.m_fast ? blockIdx.y : blockIdx.x) * BN;
   // blockIdx.z is either a split-K slot (k-blocks [kb0, kb1), partial outputs) or, with zo.batched, the index
   // of an independent problem whose operands sit zo.* coordinates further along the same tensors; either way
   // the epilogue receives it
@@ -284,8 +287,10 @@ static int launch_tc_gemm_ex_t(const void* a_split, const void* b_split, long lo
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
   if (splits < 1) splits = 1;
   const int per = (nkb + splits - 1) / splits;
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)splits);
-  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0}, acc_scale, epi);
+  const unsigned nt = (unsigned)((N + BN - 1) / BN), mt = (unsigned)((M + tg::BM - 1) / tg::BM);
+  const int m_fast = (mt < nt && nt <= 65535u) ? 1 : 0;
+  dim3 grid(m_fast ? mt : nt, m_fast ? nt : mt, (unsigned)splits);
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0, 0, m_fast}, acc_scale, epi);
   VADC_CHECK_LAUNCH("tc_gemm_kernel");
   return VADC_OK;
 }
@@ -320,7 +325,7 @@ int launch_tc_gemm_batched_t(const void* a_split, long long a_rows, long long a_
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
   const size_t stage = (size_t)TERMS * (tg::BM * 128 + BN * 128);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)nbatch);
-  const tg::ZOffsets zo{1, off.a_m, off.a_k, off.b_n, off.b_k, nkb >= 4 ? env_int("VADC_TC_PREFETCH", 0) : 0};
+  const tg::ZOffsets zo{1, off.a_m, off.a_k, off.b_n, off.b_k, nkb >= 4 ? env_int("VADC_TC_PREFETCH", 0) : 0, 0};
   // two-stage ring, one CTA per SM: measured no better than two co-resident one-stage CTAs on the space head's long
   // contraction loops (distance GEMM, 16 k-blocks: 251 vs 210 us; gcenters, 8 k-blocks: 218 vs 212 us) — opt-in only
   if (TERMS == 3 && nkb >= 6 && env_on("VADC_TC_TWO_STAGE")) {
@@ -546,7 +551,12 @@ template int launch_tc_gemm_h2<false, TcDistEpi>(const void*, const void*, long 
 template int launch_tc_gemm_h2<true, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
 template int launch_tc_gemm_h2<false, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
 template int launch_tc_gemm_h2<true, TcReadEpi>(const void*, const void*, long long, long long, long long, const float*, TcReadEpi, cudaStream_t);
+template int launch_tc_gemm_h2<false, TcStoreTEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreTEpi, cudaStream_t);
+template int launch_tc_gemm_h2<false, TcDistTEpi>(const void*, const void*, long long, long long, long long, const float*, TcDistTEpi, cudaStream_t);
 template int launch_tc_gemm_h2<true, TcGzEpi>(const void*, const void*, long long, long long, long long, const float*, TcGzEpi, cudaStream_t);
+template int launch_tc_gemm_ex_h2<true, false, TcStoreTEpi>(const void*, const void*, long long, long long, long long, int, const float*, TcStoreTEpi, cudaStream_t);
+template int launch_tc_gemm_ex_h2<true, false, TcReadTEpi>(const void*, const void*, long long, long long, long long, int, const float*, TcReadTEpi, cudaStream_t);
+template int launch_tc_gemm_ex_h2<true, false, TcGzTEpi>(const void*, const void*, long long, long long, long long, int, const float*, TcGzTEpi, cudaStream_t);
 template int launch_tc_gemm_ex_h2<true, true, TcPartialEpi>(const void*, const void*, long long, long long, long long, int, const float*, TcPartialEpi, cudaStream_t);
 
 template <bool B_MN, class Epi>

@@ -88,6 +88,76 @@ struct TcStoreEpi {
   }
 };
 
+// ---- transposed forms: the GEMM is launched with its operands swapped, so its rows (TMEM lanes = epilogue threads)
+// run along the CONTIGUOUS dimension of the output and its 32 columns are 32 output rows: every store instruction of
+// a warp writes 128 contiguous bytes of one output row (row-per-lane epilogues write 16 bytes to each of 32 rows).
+// `c` = index along the output's contiguous dimension, `r0` = first of the 32 output rows.
+struct TcStoreTEpi {
+  float* out; long long ldo;
+  __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
+    float* o = out + (long long)r0 * ldo + c;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) o[(long long)j * ldo] = v[j];
+  }
+};
+
+// torch.cdist (mm form), transposed: out[r, c] = sqrt(max(0, |row r|^2 + |col c|^2 - 2 dot)); cn = norms along c, rn along r
+struct TcDistTEpi {
+  float* out; const float* cn; const float* rn; long long ldo;
+  __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
+    const float cc = cn[c];
+    float rr[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) rr[j] = __ldg(rn + r0 + min(j, nvalid - 1));
+    float* o = out + (long long)r0 * ldo + c;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = sqrtf(fmaxf(rr[j] + cc - 2.0f * v[j], 0.f));
+      if (j < nvalid) o[(long long)j * ldo] = d;
+    }
+  }
+};
+
+// Memory.read (Memory.py:249-261), transposed: c = channel, rows = tokens
+struct TcReadTEpi {
+  float* uq; const float* q; int d;
+  __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = __ldg(q + (long long)(r0 + min(j, nvalid - 1)) * d + c);
+    float* o = uq + (long long)r0 * 2 * d + c;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) { o[(long long)j * 2 * d] = t[j]; o[(long long)j * 2 * d + d] = v[j]; }
+  }
+};
+
+// gz = feature * rsum - r @ centers + gF (cluster backward, generic path), transposed: c = channel, rows = tokens
+struct TcGzTEpi {
+  float* out; const float* feature; const float* rsum; const float* gF; long long ld;
+  __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
+    float f[32], rs[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const long long r = r0 + min(j, nvalid - 1);
+      f[j] = __ldg(feature + r * ld + c); rs[j] = __ldg(rsum + r);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = f[j] * rs[j] - v[j];
+    if (gF) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __ldg(gF + (long long)(r0 + min(j, nvalid - 1)) * ld + c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += f[j];
+    }
+    float* o = out + (long long)r0 * ld + c;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) o[(long long)j * ld] = v[j];
+  }
+};
+
 // torch.cdist, mm form: sqrt(max(0, |a|^2 + |b|^2 - 2 a.b))
 struct TcDistEpi {
   float* out; const float* aa; const float* bb; long long ldo;
