@@ -795,6 +795,24 @@ def extra_benchmarks(V, dev, peak):
             "ms": ms, "tokens/s": 65536 / (ms * 1e-3), "alg_GB/s": byt / ms / 1e6, "frac_hbm": byt / ms / 1e6 / peak,
             "TFLOP/s": 3 * (4 * 1024 * 192) * 65536 / ms / 1e9}
     del mn, xn
+    # 8f-3: the encoder's downsample stage (Conv3d 96->192 (1,2,2)/(1,2,2) + GELU -> channel-last tokens, swin_transformer.py:575-585,
+    # :745) at the cfg2 batch, forward + backward, next to torch's conv3d + gelu + the rearrange copy on the same GPU
+    seq = torch.nn.Sequential(torch.nn.Conv3d(96, 192, (1, 2, 2), stride=(1, 2, 2)), torch.nn.GELU()).to(dev)
+    xe = torch.randn(64, 96, 8, 64, 64, device=dev, requires_grad=True)
+    ge = torch.randn(64, 8, 32, 32, 192, device=dev)
+
+    def tail_step(fused):
+        xe.grad = None
+        for p_ in seq.parameters():
+            p_.grad = None
+        y = V.downsample_gelu_tokens(xe, seq[0], seq[1]) if fused else seq(xe).permute(0, 2, 3, 4, 1).contiguous()
+        y.backward(ge)
+    ms_f, ms_t = time_op(lambda: tail_step(True), 5, flush), time_op(lambda: tail_step(False), 5, flush)
+    byt = 2 * xe.numel() * 4 + 2 * ge.numel() * 4 + xe.numel() * 4        # x, gx, out, gout + x again for the weight gradient
+    out["encoder_tail_fwd_bwd_524288tokens"] = {"ms": ms_f, "tokens/s": 524288 / (ms_f * 1e-3), "alg_GB/s": byt / ms_f / 1e6,
+                                                "frac_hbm": byt / ms_f / 1e6 / peak, "torch_same_gpu_ms": ms_t,
+                                                "speedup_vs_torch": ms_t / ms_f}
+    del xe, ge, seq
     # C3 at the full cfg2 batch (B=64: M=512) forward + backward from the space loss (backbone.py:94)
     xs = torch.randn(64, 8, 32, 32, 192, device=dev, requires_grad=True)
 

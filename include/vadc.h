@@ -346,6 +346,27 @@ int vadc_norm_timedebd_bwd(const float* x, const float* mu, const float* rstd, c
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * the encoder's downsample stage as a producer of channel-last tokens
+ *   nn.Sequential(Conv3d(Cin, Cout, kernel (1,2,2), stride (1,2,2)), GELU)   model/swin_transformer.py:575-585
+ *   followed by 'n c d h w -> n d h w c'                                      swin_transformer.py:745, model/backbone.py:82
+ * x [B,Cin,D,2H,2W] contiguous (channel-first); weight [Cout, Cin*4] = Conv3d.weight.reshape(Cout, -1); bias [Cout].
+ * out [B,D,H,W,Cout] channel-last = gelu(conv(x)) (exact erf GELU); pre (same shape, or NULL for inference) keeps the
+ * pre-activation the backward needs.  Backward: gout [B,D,H,W,Cout] -> gx [B,Cin,D,2H,2W], gweight [Cout,Cin*4], gbias.
+ * vadc_downsample_gelu_supported: 1 when the shape runs here (Cin even, Cout % 8 == 0, TMA row pitches); the entry
+ * points return VADC_ERR_UNSUPPORTED otherwise.
+ * ------------------------------------------------------------------------ */
+int vadc_downsample_gelu_supported(int B, int Cin, int D, int H, int W, int Cout);
+size_t vadc_downsample_gelu_workspace_bytes(int B, int Cin, int D, int H, int W, int Cout);
+int vadc_downsample_gelu_fwd(const float* x, const float* weight, const float* bias,
+                             int B, int Cin, int D, int H, int W, int Cout,
+                             float* out, float* pre,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int vadc_downsample_gelu_bwd(const float* x, const float* weight, const float* pre, const float* gout,
+                             int B, int Cin, int D, int H, int W, int Cout,
+                             float* gx, float* gweight, float* gbias,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * §8e: one-shot all-reduce(sum) of small fp32 messages over NVLink peer memory — replaces the two latency-bound
  * collectives per training step that utils/distritributed_model.py's gloo DDP (main_predict.py:171) implies for this
  * path: the scalar sum (D*A)^2 (backbone.py:98, full-batch norm) and [g cluster_center | g gamma | g beta].

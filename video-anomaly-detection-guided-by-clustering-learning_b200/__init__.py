@@ -21,6 +21,7 @@ from .distributed import (init_distributed_mode, fix_random_seeds, setup_for_dis
                           numa_local, pinned_like_local, gpu_local_cpus, enable_peer_allreduce,
                           disable_peer_allreduce, peer_allreduce_status)
 from .decoder_entry import norm_timedebd, fuse_decoder_entry
+from .encoder_tail import downsample_gelu_tokens, fuse_encoder_tail
 from .integration import patch_reference, load_pretrain_model, save_checkpoint, ClusterFeatureBank
 
 __all__ = [
@@ -29,6 +30,6 @@ __all__ = [
     "l1_mean", "mse_mean", "e4_norm", "e4_sum", "frame_mse", "clip_mse", "psnr", "anomly_score",
     "roc_auc_score", "regularity_auc", "minmax_score_device", "evaluate_videos", "eval_clip_starts", "eval_clip_starts_stride1", "gather_video_scores", "init_distributed_mode",
     "fix_random_seeds", "setup_for_distributed", "get_sha", "allreduce_sum_packed",
-    "global_frobenius", "shard_range", "numa_local", "pinned_like_local", "gpu_local_cpus", "enable_peer_allreduce", "disable_peer_allreduce", "peer_allreduce_status", "patch_reference", "load_pretrain_model", "save_checkpoint", "ClusterFeatureBank", "norm_timedebd", "fuse_decoder_entry", "launch_count",
+    "global_frobenius", "shard_range", "numa_local", "pinned_like_local", "gpu_local_cpus", "enable_peer_allreduce", "disable_peer_allreduce", "peer_allreduce_status", "patch_reference", "load_pretrain_model", "save_checkpoint", "ClusterFeatureBank", "norm_timedebd", "fuse_decoder_entry", "downsample_gelu_tokens", "fuse_encoder_tail", "launch_count",
     "IMPL_AUTO", "IMPL_SIMT", "IMPL_TCGEN05",
 ]

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvadc.so")
 STAMP = os.path.join(HERE, "build", "libvadc.stamp")
-SOURCES = ["abi.cu", "cluster.cu", "cluster_tc.cu", "cluster_fwd_ws.cu", "cluster_bwd_fused.cu", "cluster_bwd_tc2.cu", "tc_gemm.cu", "space_cluster.cu", "memory.cu", "reduce.cu", "collective.cu", "decoder_entry.cu", "umma_test.cu"]
+SOURCES = ["abi.cu", "cluster.cu", "cluster_tc.cu", "cluster_fwd_ws.cu", "cluster_bwd_fused.cu", "cluster_bwd_tc2.cu", "tc_gemm.cu", "space_cluster.cu", "memory.cu", "reduce.cu", "collective.cu", "decoder_entry.cu", "encoder_tail.cu", "umma_test.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

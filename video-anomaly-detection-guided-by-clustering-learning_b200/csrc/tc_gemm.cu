@@ -573,6 +573,8 @@ template int launch_tc_gemm<true, TcReadEpi>(const void*, const void*, long long
 template int launch_tc_gemm<true, TcGzEpi>(const void*, const void*, long long, long long, long long, TcGzEpi, cudaStream_t);
 template int launch_tc_gemm<false, TcTimeDebedEpi>(const void*, const void*, long long, long long, long long, TcTimeDebedEpi, cudaStream_t);
 template int launch_tc_gemm_ex<true, true, TcPartialEpi>(const void*, const void*, long long, long long, long long, int, TcPartialEpi, cudaStream_t);
+template int launch_tc_gemm_ex<true, false, TcStoreTEpi>(const void*, const void*, long long, long long, long long, int, TcStoreTEpi, cudaStream_t);
+template int launch_tc_gemm<false, TcBiasGeluTEpi>(const void*, const void*, long long, long long, long long, TcBiasGeluTEpi, cudaStream_t);
 #define VADC_TC_BATCHED(AMN, BMN, EPI)                                                                               \
   template int launch_tc_gemm_batched<AMN, BMN, EPI>(const void*, long long, long long, const void*, long long,       \
                                                      long long, long long, long long, long long, int, TcBatchOffsets, \

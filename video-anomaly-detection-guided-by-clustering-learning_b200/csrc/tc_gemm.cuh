@@ -119,6 +119,26 @@ struct TcDistTEpi {
   }
 };
 
+// encoder downsample stage (model/swin_transformer.py:575-585): bias + exact GELU, transposed (c = output channel, rows =
+// tokens, channel-last output); `pre` (optional) keeps the pre-activation for the backward
+struct TcBiasGeluTEpi {
+  float* out; float* pre; const float* bias; long long ld;
+  __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
+    const float b = bias[c];
+    float* o = out + (long long)r0 * ld + c;
+    float* p = pre ? pre + (long long)r0 * ld + c : nullptr;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = v[j] + b;
+      const float g = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));
+      if (j < nvalid) {
+        o[(long long)j * ld] = g;
+        if (p) p[(long long)j * ld] = a;
+      }
+    }
+  }
+};
+
 // Memory.read (Memory.py:249-261), transposed: c = channel, rows = tokens
 struct TcReadTEpi {
   float* uq; const float* q; int d;
