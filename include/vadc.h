@@ -345,6 +345,18 @@ int vadc_norm_timedebd_bwd(const float* x, const float* mu, const float* rstd, c
                            float* gx, float* g_ln_w, float* g_ln_b, float* gwk, float* gbias,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* predict mode (model/swin_decoder_predict.py:591-592): timedebd = Conv3d(C, C, kernel (2,1,1), stride (2,1,1)).
+ * x [N,C] channel-last tokens of an EVEN number of frames (HW tokens each); wk [C, 2C], wk[co, j*C + ci] =
+ * weight[co, ci, j]; out [N/2, C] channel-last (frame pairs merged).  Backward: gout [N/2, C] -> gx [N,C], g_ln_w/b [C],
+ * gwk [C, 2C] (same arrangement as wk), gbias [C].  Workspace: vadc_norm_timedebd_workspace_bytes(N, C). */
+int vadc_norm_timeconv_fwd(const float* x, const float* ln_w, const float* ln_b, const float* wk, const float* bias,
+                           int64_t N, int C, int64_t HW, float eps, float* out, float* mu, float* rstd,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int vadc_norm_timeconv_bwd(const float* x, const float* mu, const float* rstd, const float* ln_w, const float* ln_b,
+                           const float* wk, const float* gout, int64_t N, int C, int64_t HW, float eps,
+                           float* gx, float* g_ln_w, float* g_ln_b, float* gwk, float* gbias,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * the encoder's downsample stage as a producer of channel-last tokens
  *   nn.Sequential(Conv3d(Cin, Cout, kernel (1,2,2), stride (1,2,2)), GELU)   model/swin_transformer.py:575-585

@@ -97,6 +97,7 @@ extern "C" size_t vadc_norm_timedebd_workspace_bytes(int64_t N, int C) {
   b += align_up((size_t)timedebd_splits(N) * C * 2 * C * sizeof(float), 256);
   b += align_up((size_t)ln_bwd_blocks(N) * 2 * C * sizeof(float), 256);
   b += align_up(n * sizeof(float), 256) * 2;
+  b += align_up(n * C * sizeof(float), 256);              // z in fp32 (predict-mode entry: gathered pairwise afterwards)
   return b + 256;
 }
 
@@ -165,6 +166,98 @@ extern "C" int vadc_norm_timedebd_bwd(const float* x, const float* mu, const flo
   if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, nullptr, mu2, rstd2, nullptr, st, nullptr, zs))) return rc;
   // gWk [C, 2C] = Z^T gYm: both operands given as [tokens, .] (MN-major), split over the tokens
   if ((rc = launch_tc_gemm_ex<true, true>(zs, gys, C, 2 * C, N, sk, TcPartialEpi{q, 2 * C, (long long)C * 2 * C}, st))) return rc;
+  {
+    const long long n = (long long)C * 2 * C;
+    sum_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, sk, n, gwk);
+    VADC_CHECK_LAUNCH("sum_partials_kernel");
+  }
+  return launch_ln_bwd(gz, x, mu, rstd, ln_w, N, C, gx, lnpart, g_ln_w, g_ln_b, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// predict mode (model/swin_decoder_predict.py:591-592): timedebd = Conv3d(C, C, kernel (2,1,1), stride (2,1,1)) — two
+// consecutive frames of a token position, side by side, are ONE row of a [N/2, 2C] matrix Zp (the same pair gather the
+// non-predict backward applies to gY), and
+//   out [N/2, C] = Zp . Wk^T + bias,        Wk [co, j*C + ci] = weight[co, ci, j]
+// backward: gZp [N/2, 2C] = gY . Wk scattered back to the rows of the two frames (the ConvTranspose entry's forward
+// scatter without its bias), gWk = gY^T . Zp split over the tokens, gbias = column sums of gY, LayerNorm backward.
+// x [N, C] channel-last tokens of B * D frames (D even), HW tokens per frame; workspace: vadc_norm_timedebd_workspace_bytes.
+// ---------------------------------------------------------------------------------------------------------------------
+static int pair_terms(const float* x, const float* ln_w, const float* ln_b, int64_t N, int C, int64_t HW, float eps, float* z,
+                      float* mu, float* rstd, void* zp, cudaStream_t st) {
+  int rc;
+  if ((rc = launch_ln_rows(x, ln_w, ln_b, N, C, eps, z, mu, rstd, nullptr, st))) return rc;
+  const long long total4 = (long long)N * (C / 4);
+  const int grid = (int)std::min<long long>((total4 + 255) / 256, (long long)sm_count() * 8);
+  split3_frames_kernel<<<grid, 256, 0, st>>>(z, N / 2, C, HW, static_cast<__nv_bfloat16*>(zp));
+  VADC_CHECK_LAUNCH("split3_frames_kernel");
+  return VADC_OK;
+}
+
+extern "C" int vadc_norm_timeconv_fwd(const float* x, const float* ln_w, const float* ln_b, const float* wk,
+                                      const float* bias, int64_t N, int C, int64_t HW, float eps, float* out,
+                                      float* mu, float* rstd, void* workspace, size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(N >= 0 && C > 0 && HW > 0 && (C % 32) == 0 && C <= 1024, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(N % (2 * HW) == 0, VADC_ERR_BAD_SHAPE);                       // an even number of frames
+  if (N == 0) return VADC_OK;
+  VADC_REQUIRE(x && ln_w && ln_b && wk && bias && out && mu && rstd && workspace, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(aligned16(x) && aligned16(out) && aligned16(wk), VADC_ERR_MISALIGNED);
+  VADC_REQUIRE(workspace_bytes >= vadc_norm_timedebd_workspace_bytes(N, C), VADC_ERR_WORKSPACE);
+  VADC_REQUIRE(tc_gemm_shape_ok(N / 2, C, 2 * C, false), VADC_ERR_UNSUPPORTED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver ws(workspace, workspace_bytes);
+  void* zp = ws.take<uint8_t>(tc_gemm_split_bytes(N, C));
+  void* wsplit = ws.take<uint8_t>(tc_gemm_split_bytes(2 * C, C));
+  (void)ws.take<uint8_t>(tc_gemm_split_bytes(N, 2 * C));
+  float* z = ws.take<float>((size_t)N * C);                                  // the gZ slot of the backward
+  int rc;
+  if ((rc = pair_terms(x, ln_w, ln_b, N, C, HW, eps, z, mu, rstd, zp, st))) return rc;
+  if ((rc = tc_split3(wk, C, 2 * C, wsplit, st))) return rc;
+  // rows = output channels, columns = (frame pair, position): coalesced channel-last stores (a handful of rows: row form)
+  if (N / 2 >= 128) return launch_tc_gemm<false>(wsplit, zp, C, N / 2, 2 * C, TcBiasTEpi{out, bias, C}, st);
+  return launch_tc_gemm<false>(zp, wsplit, N / 2, C, 2 * C, TcBiasEpi{out, bias, C}, st);
+}
+
+extern "C" int vadc_norm_timeconv_bwd(const float* x, const float* mu, const float* rstd, const float* ln_w,
+                                      const float* ln_b, const float* wk, const float* gout, int64_t N, int C,
+                                      int64_t HW, float eps, float* gx, float* g_ln_w, float* g_ln_b, float* gwk,
+                                      float* gbias, void* workspace, size_t workspace_bytes, void* stream) {
+  VADC_REQUIRE(N >= 0 && C > 0 && HW > 0 && (C % 32) == 0 && C <= 1024, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(N % (2 * HW) == 0, VADC_ERR_BAD_SHAPE);
+  VADC_REQUIRE(g_ln_w && g_ln_b && gwk && gbias && workspace, VADC_ERR_NULL_POINTER);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 0) {
+    VADC_CUDA(cudaMemsetAsync(gwk, 0, sizeof(float) * C * 2 * C, st));
+    VADC_CUDA(cudaMemsetAsync(gbias, 0, sizeof(float) * C, st));
+    VADC_CUDA(cudaMemsetAsync(g_ln_w, 0, sizeof(float) * C, st));
+    VADC_CUDA(cudaMemsetAsync(g_ln_b, 0, sizeof(float) * C, st));
+    return VADC_OK;
+  }
+  VADC_REQUIRE(x && mu && rstd && ln_w && ln_b && wk && gout && gx, VADC_ERR_NULL_POINTER);
+  VADC_REQUIRE(aligned16(x) && aligned16(gout) && aligned16(wk) && aligned16(gx), VADC_ERR_MISALIGNED);
+  VADC_REQUIRE(workspace_bytes >= vadc_norm_timedebd_workspace_bytes(N, C), VADC_ERR_WORKSPACE);
+  Carver ws(workspace, workspace_bytes);
+  void* zp = ws.take<uint8_t>(tc_gemm_split_bytes(N, C));
+  void* wsplit = ws.take<uint8_t>(tc_gemm_split_bytes(2 * C, C));
+  void* gys = ws.take<uint8_t>(tc_gemm_split_bytes(N, 2 * C));
+  float* gz = ws.take<float>((size_t)N * C);
+  const int sk = timedebd_splits(N);
+  float* q = ws.take<float>((size_t)sk * C * 2 * C);
+  float* lnpart = ws.take<float>((size_t)ln_bwd_blocks(N) * 2 * C);
+  float* mu2 = ws.take<float>((size_t)N);
+  float* rstd2 = ws.take<float>((size_t)N);
+  float* z = ws.take<float>((size_t)N * C);
+  const long long Nh = N / 2;
+  int rc;
+  if ((rc = tc_split3(gout, Nh, C, gys, st))) return rc;
+  colsum32_kernel<<<(C + 31) / 32, 256, 0, st>>>(gout, Nh, C, gbias);
+  VADC_CHECK_LAUNCH("colsum32_kernel");
+  // gZp [N/2, 2C] = gY [N/2, C] . Wk (Wk [co rows, 2C cols] read MN-major), column half j -> the rows of frame 2f + j
+  if ((rc = tc_split3(wk, C, 2 * C, wsplit, st))) return rc;
+  if ((rc = launch_tc_gemm<true>(gys, wsplit, Nh, 2 * C, C, TcTimeDebedEpi{gz, nullptr, HW, C}, st))) return rc;
+  // Zp again: gWk [C, 2C] = gY^T Zp, both operands given as [pair rows, .] (MN-major), split over the rows
+  if ((rc = pair_terms(x, ln_w, ln_b, N, C, HW, eps, z, mu2, rstd2, zp, st))) return rc;
+  if ((rc = launch_tc_gemm_ex<true, true>(gys, zp, C, 2 * C, Nh, sk, TcPartialEpi{q, 2 * C, (long long)C * 2 * C}, st))) return rc;
   {
     const long long n = (long long)C * 2 * C;
     sum_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, sk, n, gwk);

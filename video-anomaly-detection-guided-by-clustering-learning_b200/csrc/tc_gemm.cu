@@ -574,6 +574,9 @@ template int launch_tc_gemm<true, TcGzEpi>(const void*, const void*, long long, 
 template int launch_tc_gemm<false, TcTimeDebedEpi>(const void*, const void*, long long, long long, long long, TcTimeDebedEpi, cudaStream_t);
 template int launch_tc_gemm_ex<true, true, TcPartialEpi>(const void*, const void*, long long, long long, long long, int, TcPartialEpi, cudaStream_t);
 template int launch_tc_gemm_ex<true, false, TcStoreTEpi>(const void*, const void*, long long, long long, long long, int, TcStoreTEpi, cudaStream_t);
+template int launch_tc_gemm<false, TcBiasEpi>(const void*, const void*, long long, long long, long long, TcBiasEpi, cudaStream_t);
+template int launch_tc_gemm<false, TcBiasTEpi>(const void*, const void*, long long, long long, long long, TcBiasTEpi, cudaStream_t);
+template int launch_tc_gemm<true, TcTimeDebedEpi>(const void*, const void*, long long, long long, long long, TcTimeDebedEpi, cudaStream_t);
 template int launch_tc_gemm<false, TcBiasGeluTEpi>(const void*, const void*, long long, long long, long long, TcBiasGeluTEpi, cudaStream_t);
 #define VADC_TC_BATCHED(AMN, BMN, EPI)                                                                               \
   template int launch_tc_gemm_batched<AMN, BMN, EPI>(const void*, long long, long long, const void*, long long,       \

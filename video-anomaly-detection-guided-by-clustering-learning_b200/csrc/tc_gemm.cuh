@@ -139,6 +139,28 @@ struct TcBiasGeluTEpi {
   }
 };
 
+// out[m, n] = acc + bias[n] (row per lane; for outputs with fewer than 8 rows the transposed form cannot take)
+struct TcBiasEpi {
+  float* out; const float* bias; long long ld;
+  __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += bias[n + min(j, nvalid - 1)];
+    tc_store_row32(out + m * ld + n, v, nvalid);
+  }
+};
+
+// out[r, c] = acc + bias[c], transposed (c = output channel, rows = tokens): the predict-mode decoder entry
+struct TcBiasTEpi {
+  float* out; const float* bias; long long ld;
+  __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
+    const float b = bias[c];
+    float* o = out + (long long)r0 * ld + c;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) o[(long long)j * ld] = v[j] + b;
+  }
+};
+
 // Memory.read (Memory.py:249-261), transposed: c = channel, rows = tokens
 struct TcReadTEpi {
   float* uq; const float* q; int d;
@@ -276,7 +298,8 @@ struct TcGzEpi {
   }
 };
 
-// decoder entry (model/swin_decoder_predict.py:590-602): ConvTranspose3d(C -> C, kernel (2,1,1), stride (2,1,1)) of the
+// decoder entry (model/swin_decoder_predict.py:590-602; bias may be null: the predict-mode entry's backward reuses the
+// scatter): ConvTranspose3d(C -> C, kernel (2,1,1), stride (2,1,1)) of the
 // channel-last tokens as ONE GEMM [N, C] x [C, 2C]: column j*C + co of token n = (frame f, pixel hw) is channel co of
 // output frame 2f + j, written channel-last: out[((f * 2 + j) * HW + hw) * C + co] + bias[co]
 struct TcTimeDebedEpi {
@@ -284,8 +307,10 @@ struct TcTimeDebedEpi {
   __device__ __forceinline__ void operator()(long long m, int n, float (&v)[32], int nvalid, int = 0) const {
     const int j = n / C, co = n - j * C;
     const long long f = m / HW, hw = m - f * HW;
+    if (bias) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) if (i < nvalid) v[i] += bias[co + i];
+      for (int i = 0; i < 32; ++i) v[i] += bias[co + min(i, nvalid - 1)];
+    }
     tc_store_row32(out + ((f * 2 + j) * HW + hw) * C + co, v, nvalid);
   }
 };
