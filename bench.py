@@ -808,10 +808,15 @@ def extra_benchmarks(V, dev, peak):
         y = V.downsample_gelu_tokens(xe, seq[0], seq[1]) if fused else seq(xe).permute(0, 2, 3, 4, 1).contiguous()
         y.backward(ge)
     ms_f, ms_t = time_op(lambda: tail_step(True), 5, flush), time_op(lambda: tail_step(False), 5, flush)
+    tf32_was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                               # ours is fp32-faithful: the like-for-like torch number
+    ms_t32 = time_op(lambda: tail_step(False), 5, flush)
+    torch.backends.cudnn.allow_tf32 = tf32_was
     byt = 2 * xe.numel() * 4 + 2 * ge.numel() * 4 + xe.numel() * 4        # x, gx, out, gout + x again for the weight gradient
     out["encoder_tail_fwd_bwd_524288tokens"] = {"ms": ms_f, "tokens/s": 524288 / (ms_f * 1e-3), "alg_GB/s": byt / ms_f / 1e6,
-                                                "frac_hbm": byt / ms_f / 1e6 / peak, "torch_same_gpu_ms": ms_t,
-                                                "speedup_vs_torch": ms_t / ms_f}
+                                                "frac_hbm": byt / ms_f / 1e6 / peak,
+                                                "torch_same_gpu_ms": {"cudnn_tf32_default": ms_t, "fp32": ms_t32},
+                                                "speedup_vs_torch": {"cudnn_tf32_default": ms_t / ms_f, "fp32": ms_t32 / ms_f}}
     del xe, ge, seq
     # C3 at the full cfg2 batch (B=64: M=512) forward + backward from the space loss (backbone.py:94)
     xs = torch.randn(64, 8, 32, 32, 192, device=dev, requires_grad=True)

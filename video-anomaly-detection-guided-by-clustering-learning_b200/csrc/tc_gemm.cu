@@ -207,6 +207,143 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, BN); }
 }
 
+// ---- persistent form ------------------------------------------------------------------------------------------------
+// One CTA per SM walks the output tiles (the dimension with fewer tiles fastest).  The operand ring (STAGES stages) runs
+// across tile boundaries, the accumulator is double-buffered in TMEM (2 x BN columns), and EIGHT epilogue warps (two per
+// TMEM lane quarter, splitting the columns) drain tile i while the MMA warp is already in tile i+1: the load -> MMA ->
+// epilogue chain of the one-tile-per-CTA kernel above — per-tile barrier set-up, TMEM allocation, a serial k-loop per CTA and
+// an epilogue that only overlaps a neighbour CTA's work — becomes three concurrent streams.  Short contraction loops with a
+// large output (distance / logits / x_rec GEMMs) gain the most: there the tile time is the epilogue's store time.
+constexpr int kThreadsP = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int TERMS, int STAGES, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(kThreadsP, 1)
+tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                       int M, int N, int Kd, int mt, int nt, int m_fast, const float* __restrict__ acc_scale, Epi epi) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t kATerm = BM * 128u, kBTerm = BN * 128u;
+  constexpr uint32_t kStage = (uint32_t)TERMS * (kATerm + kBTerm);
+  __shared__ uint64_t full[STAGES], empty[STAGES], accfull[2], accempty[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (Kd + BK - 1) / BK;
+  const long long ntiles = (long long)mt * nt;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&accfull[b], 1); mbar_init(&accempty[b], 8); }
+    fence_mbar_init();
+    prefetch_tmap(&mapA); prefetch_tmap(&mapB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t s0 = smem_u32(smem);
+  auto tile_mn = [&](long long t, int& m0, int& n0) {
+    const int a = (int)(t % (m_fast ? mt : nt)), b = (int)(t / (m_fast ? mt : nt));
+    m0 = (m_fast ? a : b) * BM; n0 = (m_fast ? b : a) * BN;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int m0, n0;
+      tile_mn(t, m0, n0);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % STAGES;
+        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[s], kStage);
+        const uint32_t a = s0 + s * kStage, b = a + (uint32_t)TERMS * kATerm;
+        const int k0 = kb * BK;
+#pragma unroll
+        for (int tt = 0; tt < TERMS; ++tt) {
+          if constexpr (!A_MN) {
+            tma_load_3d(&mapA, a + tt * kATerm, &full[s], k0, m0, tt);
+          } else {
+#pragma unroll
+            for (int mb = 0; mb < BM / 64; ++mb) tma_load_3d(&mapA, a + tt * kATerm + mb * 8192u, &full[s], m0 + mb * 64, k0, tt);
+          }
+          if constexpr (!B_MN) {
+            tma_load_3d(&mapB, b + tt * kBTerm, &full[s], k0, n0, tt);
+          } else {
+#pragma unroll
+            for (int nb = 0; nb < BN / 64; ++nb) tma_load_3d(&mapB, b + tt * kBTerm + nb * 8192u, &full[s], n0 + nb * 64, k0, tt);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = instr_desc(TERMS == 2 ? 0u /* fp16 */ : kFmtBF16, BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr int kProducts = TERMS == 2 ? 3 : 6;
+    constexpr int ta[6] = {TERMS == 2 ? 1 : 2, TERMS == 2 ? 0 : 1, 0, 1, 0, 0};   // small products first
+    constexpr int tb[6] = {0, 1, TERMS == 2 ? 0 : 2, 0, 1, 0};
+    uint32_t it = 0, lt = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1;
+      mbar_wait(&accempty[buf], ((lt >> 1) & 1) ^ 1);           // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t acc = tmem + buf * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a = s0 + s * kStage, b = a + (uint32_t)TERMS * kATerm;
+#pragma unroll
+        for (int pr = 0; pr < kProducts; ++pr) {
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t ad = A_MN ? smem_desc_sw128(a + ta[pr] * kATerm + kk * 2048u, 8192, 1024)
+                                     : smem_desc_sw128(a + ta[pr] * kATerm + kk * 32u, 0, 1024);
+            const uint64_t bd = B_MN ? smem_desc_sw128(b + tb[pr] * kBTerm + kk * 2048u, 8192, 1024)
+                                     : smem_desc_sw128(b + tb[pr] * kBTerm + kk * 32u, 0, 1024);
+            mma_f16(acc, ad, bd, idesc, (kb > 0 || pr > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(&accfull[buf]);
+    }
+  } else if (warp >= 2) {
+    // ---------------------------------------------------------------- epilogue: thread = row = TMEM lane, two warps per quarter
+    const int q = warp & 3, hh = (warp - 2) >> 2;
+    const float sc = acc_scale ? __ldg(acc_scale) : 1.0f;
+    uint32_t lt = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      int m0, n0;
+      tile_mn(t, m0, n0);
+      const uint32_t buf = lt & 1;
+      mbar_wait(&accfull[buf], (lt >> 1) & 1);
+      tc_fence_after();
+      const long long m = (long long)m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        float v[32];
+        const int col = hh * (BN / 2) + c * 32;
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)col, v);
+        if (TERMS == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= sc;
+        }
+        const int n = n0 + col;
+        if (m < M && n < N) epi(m, n, v, min(32, N - n), 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive1(&accempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 2 * BN); }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -280,6 +417,18 @@ static int launch_tc_gemm_ex_t(const void* a_split, const void* b_split, long lo
   if (B_MN) rc = tg::make_map3(&mB, b_split, Kd, N, 64, TERMS);   // [Kd rows, N cols]: boxes of 64 k-rows x 64 n-cols
   else rc = tg::make_map3(&mB, b_split, N, Kd, BN, TERMS);        // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
   if (rc) return rc;
+  const unsigned ntl = (unsigned)((N + BN - 1) / BN), mtl = (unsigned)((M + tg::BM - 1) / tg::BM);
+  if (splits <= 1 && (long long)ntl * mtl > sm_count() && !env_on("VADC_TC_NO_PERSIST")) {
+    // persistent CTAs: three 64 KB (fp16 x2) or two 96 KB (bf16 x3) stages, double-buffered accumulator
+    constexpr int kStP = TERMS == 2 ? 3 : 2;
+    const size_t smemp = (size_t)kStP * TERMS * (tg::BM * 128 + BN * 128) + 1024;
+    auto kp = tg::tc_gemm_persist_kernel<BN, TERMS, kStP, A_MN, B_MN, Epi>;
+    VADC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
+    const int m_fast = mtl < ntl ? 1 : 0;
+    kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)mtl, (int)ntl, m_fast, acc_scale, epi);
+    VADC_CHECK_LAUNCH("tc_gemm_persist_kernel");
+    return VADC_OK;
+  }
   constexpr int kSt = TERMS == 2 ? tg::kStagesH : 1;
   const size_t smem = (size_t)kSt * TERMS * (tg::BM * 128 + BN * 128) + 1024;
   auto kern = tg::tc_gemm_kernel<BN, TERMS, kSt, A_MN, B_MN, Epi>;
