@@ -92,15 +92,30 @@ struct TcStoreEpi {
 // run along the CONTIGUOUS dimension of the output and its 32 columns are 32 output rows: every store instruction of
 // a warp writes 128 contiguous bytes of one output row (row-per-lane epilogues write 16 bytes to each of 32 rows).
 // `c` = index along the output's contiguous dimension, `r0` = first of the 32 output rows.
+// (full 32-row groups take a branch-free path: one pointer bump and one store per row)
+__device__ __forceinline__ void tc_store_col32(float* o, long long ld, const float (&v)[32], int nvalid) {
+  if (nvalid == 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { *o = v[j]; o += ld; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { if (j < nvalid) *o = v[j]; o += ld; }
+  }
+}
+
 struct TcStoreTEpi {
   float* out; long long ldo;
   __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
-    float* o = out + (long long)r0 * ldo + c;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) o[(long long)j * ldo] = v[j];
+    tc_store_col32(out + (long long)r0 * ldo + c, ldo, v, nvalid);
   }
 };
+
+// sqrt for the two-term fp16 paths (22 significant bits already): MUFU.SQRT, <= 1 ulp, no slow-path branch per element
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // torch.cdist (mm form), transposed: out[r, c] = sqrt(max(0, |row r|^2 + |col c|^2 - 2 dot)); cn = norms along c, rn along r
 struct TcDistTEpi {
@@ -108,14 +123,19 @@ struct TcDistTEpi {
   __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
     const float cc = cn[c];
     float rr[32];
+    if (nvalid == 32 && ((r0 & 3) == 0)) {               // rn + r0 is 16-byte aligned (rn comes from the workspace carver)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) rr[j] = __ldg(rn + r0 + min(j, nvalid - 1));
-    float* o = out + (long long)r0 * ldo + c;
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(rn + r0) + j);
+        rr[4 * j] = t.x; rr[4 * j + 1] = t.y; rr[4 * j + 2] = t.z; rr[4 * j + 3] = t.w;
+      }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float d = sqrtf(fmaxf(rr[j] + cc - 2.0f * v[j], 0.f));
-      if (j < nvalid) o[(long long)j * ldo] = d;
+      for (int j = 0; j < 32; ++j) rr[j] = __ldg(rn + r0 + min(j, nvalid - 1));
     }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = sqrt_approx(fmaxf(fmaf(-2.0f, v[j], rr[j] + cc), 0.f));
+    tc_store_col32(out + (long long)r0 * ldo + c, ldo, v, nvalid);
   }
 };
 
@@ -154,10 +174,9 @@ struct TcBiasTEpi {
   float* out; const float* bias; long long ld;
   __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
     const float b = bias[c];
-    float* o = out + (long long)r0 * ld + c;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) o[(long long)j * ld] = v[j] + b;
+    for (int j = 0; j < 32; ++j) v[j] += b;
+    tc_store_col32(out + (long long)r0 * ld + c, ld, v, nvalid);
   }
 };
 
@@ -168,10 +187,8 @@ struct TcReadTEpi {
     float t[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) t[j] = __ldg(q + (long long)(r0 + min(j, nvalid - 1)) * d + c);
-    float* o = uq + (long long)r0 * 2 * d + c;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) { o[(long long)j * 2 * d] = t[j]; o[(long long)j * 2 * d + d] = v[j]; }
+    tc_store_col32(uq + (long long)r0 * 2 * d + c, 2ll * d, t, nvalid);
+    tc_store_col32(uq + (long long)r0 * 2 * d + d + c, 2ll * d, v, nvalid);
   }
 };
 
@@ -193,10 +210,7 @@ struct TcGzTEpi {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += f[j];
     }
-    float* o = out + (long long)r0 * ld + c;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) o[(long long)j * ld] = v[j];
+    tc_store_col32(out + (long long)r0 * ld + c, ld, v, nvalid);
   }
 };
 
@@ -237,10 +251,7 @@ struct TcBatchDistEpi {
 struct TcSpaceGzEpi {
   float* out; long long MP; int P;
   __device__ __forceinline__ void operator()(long long p, int n, float (&v)[32], int nvalid, int z) const {
-    float* o = out + (long long)z * MP + (long long)n * P + p;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) o[(long long)j * P] = v[j];
+    tc_store_col32(out + (long long)z * MP + (long long)n * P + p, P, v, nvalid);
   }
 };
 
