@@ -222,7 +222,8 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
 template <int BN, int TERMS, int STAGES, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kThreadsP, 1)
 tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                       int M, int N, int Kd, int mt, int nt, int m_fast, const float* __restrict__ acc_scale, Epi epi) {
+                       int M, int N, int Kd, int mt, int nt, int nz, int m_fast, const ZOffsets zo,
+                       const float* __restrict__ acc_scale, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t kATerm = BM * 128u, kBTerm = BN * 128u;
@@ -231,7 +232,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (Kd + BK - 1) / BK;
-  const long long ntiles = (long long)mt * nt;
+  const long long per_z = (long long)mt * nt, ntiles = per_z * nz;    // nz independent problems (batched launches), z slowest
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&accfull[b], 1); mbar_init(&accempty[b], 8); }
@@ -244,8 +245,10 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t s0 = smem_u32(smem);
-  auto tile_mn = [&](long long t, int& m0, int& n0) {
-    const int a = (int)(t % (m_fast ? mt : nt)), b = (int)(t / (m_fast ? mt : nt));
+  auto tile_mn = [&](long long t, int& m0, int& n0, int& z) {
+    z = (int)(t / per_z);
+    const long long r = t - (long long)z * per_z;
+    const int a = (int)(r % (m_fast ? mt : nt)), b = (int)(r / (m_fast ? mt : nt));
     m0 = (m_fast ? a : b) * BM; n0 = (m_fast ? b : a) * BN;
   };
 
@@ -253,8 +256,9 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     // ---------------------------------------------------------------- TMA producer
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      int m0, n0;
-      tile_mn(t, m0, n0);
+      int m0, n0, z;
+      tile_mn(t, m0, n0, z);
+      const int am = m0 + z * zo.a_m, ak = z * zo.a_k, bn = n0 + z * zo.b_n, bk = z * zo.b_k;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % STAGES;
         mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -264,16 +268,16 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 #pragma unroll
         for (int tt = 0; tt < TERMS; ++tt) {
           if constexpr (!A_MN) {
-            tma_load_3d(&mapA, a + tt * kATerm, &full[s], k0, m0, tt);
+            tma_load_3d(&mapA, a + tt * kATerm, &full[s], k0 + ak, am, tt);
           } else {
 #pragma unroll
-            for (int mb = 0; mb < BM / 64; ++mb) tma_load_3d(&mapA, a + tt * kATerm + mb * 8192u, &full[s], m0 + mb * 64, k0, tt);
+            for (int mb = 0; mb < BM / 64; ++mb) tma_load_3d(&mapA, a + tt * kATerm + mb * 8192u, &full[s], am + mb * 64, k0 + ak, tt);
           }
           if constexpr (!B_MN) {
-            tma_load_3d(&mapB, b + tt * kBTerm, &full[s], k0, n0, tt);
+            tma_load_3d(&mapB, b + tt * kBTerm, &full[s], k0 + bk, bn, tt);
           } else {
 #pragma unroll
-            for (int nb = 0; nb < BN / 64; ++nb) tma_load_3d(&mapB, b + tt * kBTerm + nb * 8192u, &full[s], n0 + nb * 64, k0, tt);
+            for (int nb = 0; nb < BN / 64; ++nb) tma_load_3d(&mapB, b + tt * kBTerm + nb * 8192u, &full[s], bn + nb * 64, k0 + bk, tt);
           }
         }
       }
@@ -316,8 +320,8 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
     const float sc = acc_scale ? __ldg(acc_scale) : 1.0f;
     uint32_t lt = 0;
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
-      int m0, n0;
-      tile_mn(t, m0, n0);
+      int m0, n0, z;
+      tile_mn(t, m0, n0, z);
       const uint32_t buf = lt & 1;
       mbar_wait(&accfull[buf], (lt >> 1) & 1);
       tc_fence_after();
@@ -332,7 +336,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           for (int j = 0; j < 32; ++j) v[j] *= sc;
         }
         const int n = n0 + col;
-        if (m < M && n < N) epi(m, n, v, min(32, N - n), 0);
+        if (m < M && n < N) epi(m, n, v, min(32, N - n), z);
       }
       tc_fence_before();
       __syncwarp();
@@ -425,7 +429,8 @@ static int launch_tc_gemm_ex_t(const void* a_split, const void* b_split, long lo
     auto kp = tg::tc_gemm_persist_kernel<BN, TERMS, kStP, A_MN, B_MN, Epi>;
     VADC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
     const int m_fast = mtl < ntl ? 1 : 0;
-    kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)mtl, (int)ntl, m_fast, acc_scale, epi);
+    kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)mtl, (int)ntl, 1, m_fast,
+                                                  tg::ZOffsets{0, 0, 0, 0, 0, 0, 0}, acc_scale, epi);
     VADC_CHECK_LAUNCH("tc_gemm_persist_kernel");
     return VADC_OK;
   }
@@ -475,6 +480,17 @@ int launch_tc_gemm_batched_t(const void* a_split, long long a_rows, long long a_
   const size_t stage = (size_t)TERMS * (tg::BM * 128 + BN * 128);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)nbatch);
   const tg::ZOffsets zo{1, off.a_m, off.a_k, off.b_n, off.b_k, nkb >= 4 ? env_int("VADC_TC_PREFETCH", 0) : 0, 0};
+  if ((long long)grid.x * grid.y * grid.z > sm_count() && !env_on("VADC_TC_NO_PERSIST") && !env_on("VADC_TC_NO_PERSIST_BATCHED")) {
+    constexpr int kStP = TERMS == 2 ? 3 : 2;
+    const size_t smemp = kStP * stage + 1024;
+    auto kp = tg::tc_gemm_persist_kernel<BN, TERMS, kStP, A_MN, B_MN, Epi>;
+    VADC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
+    const int m_fast = grid.y < grid.x ? 1 : 0;
+    kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)grid.y, (int)grid.x, nbatch, m_fast, zo,
+                                                  acc_scale, epi);
+    VADC_CHECK_LAUNCH("tc_gemm_persist_kernel(batched)");
+    return VADC_OK;
+  }
   // two-stage ring, one CTA per SM: measured no better than two co-resident one-stage CTAs on the space head's long
   // contraction loops (distance GEMM, 16 k-blocks: 251 vs 210 us; gcenters, 8 k-blocks: 218 vs 212 us) — opt-in only
   if (TERMS == 3 && nkb >= 6 && env_on("VADC_TC_TWO_STAGE")) {
