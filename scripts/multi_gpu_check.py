@@ -27,7 +27,14 @@ def say(*a):
 
 def _excepthook(tp, val, tb):
     import traceback
-    print(f"[rank {rank}] FAILED: " + "".join(traceback.format_exception_only(tp, val)).strip()[:500], flush=True)
+    msg = f"[rank {rank}] FAILED: " + "".join(traceback.format_exception(tp, val, tb)).strip()[-1500:]
+    print(msg, flush=True)
+    try:                                              # torchrun's summary drops the message: keep it where gpurun merges files back
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(f"gpurun_out/multi_gpu_check_rank{rank}.err", "w") as fh:
+            fh.write(msg + "\n")
+    except OSError:
+        pass
     sys.__excepthook__(tp, val, tb)
 
 
@@ -50,7 +57,10 @@ for it in range(50):
         dist.all_reduce(w)
     V.allreduce_sum_packed(ts)
     for a, b in zip(ts, want):
-        assert rel(a, b) < 1e-5, (it, rel(a, b))             # NCCL adds in its own order; ours in rank order
+        # NCCL adds in its own order, ours in rank order: compare against the size of the summands, not of the sum (a sum of
+        # `world` standard normals that nearly cancels — the one-element message — has no relative accuracy to speak of)
+        err = float((a.double() - b.double()).abs().max()) / max(float(b.double().abs().max()), float(world) ** 0.5)
+        assert err < 1e-5, (it, tuple(a.shape), err)
     chk = torch.stack([t.double().sum() for t in ts])
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -79,7 +89,8 @@ with torch.cuda.stream(s):
         for w in want:
             dist.all_reduce(w)
         for a, b in zip(buf, want):
-            assert rel(a, b) < 1e-5, ("graph", it, rel(a, b))
+            err = float((a.double() - b.double()).abs().max()) / max(float(b.double().abs().max()), float(world) ** 0.5)
+            assert err < 1e-5, ("graph", it, tuple(a.shape), err)
     del gr
 torch.cuda.synchronize()
 say("1b. ... and replayed 20x from a CUDA graph with new inputs")

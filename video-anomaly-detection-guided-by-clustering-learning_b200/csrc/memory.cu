@@ -23,25 +23,33 @@ query_norm_kernel(const float* __restrict__ query, int d, long long HW, float* _
   inv[(long long)b * HW + hw] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
 }
 
-// 32x32 tiled transpose with the per-position scale: q[(b*HW+hw), c] = query[b,c,hw]*inv
+// tiled transpose with the per-position scale: q[(b*HW+hw), c] = query[b,c,hw]*inv; a block moves 32 positions x 128
+// channels (128-byte reads per channel row, 512 contiguous bytes per written token row)
 __global__ void __launch_bounds__(256)
 query_transpose_kernel(const float* __restrict__ query, const float* __restrict__ inv, int d,
                        long long HW, float* __restrict__ q) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[128][33];
   const int b = blockIdx.z;
   const long long hw0 = (long long)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
+  const int c0 = blockIdx.y * 128;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  for (int j = ty; j < 32; j += 8) {
-    int c = c0 + j;
-    long long hw = hw0 + tx;
+#pragma unroll 4
+  for (int j = ty; j < 128; j += 8) {
+    const int c = c0 + j;
+    const long long hw = hw0 + tx;
     tile[j][tx] = (c < d && hw < HW) ? __ldg(query + ((long long)b * d + c) * HW + hw) : 0.f;
   }
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
-    long long hw = hw0 + j;
-    int c = c0 + tx;
-    if (hw < HW && c < d) q[((long long)b * HW + hw) * d + c] = tile[tx][j] * __ldg(inv + (long long)b * HW + hw);
+    const long long hw = hw0 + j;
+    if (hw >= HW) continue;
+    const float sc = __ldg(inv + (long long)b * HW + hw);
+    float* dst = q + ((long long)b * HW + hw) * d + c0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tx + 32 * i;
+      if (c0 + c < d) dst[c] = tile[c][j] * sc;
+    }
   }
 }
 
@@ -132,7 +140,8 @@ memory_query_bwd_kernel(const float* __restrict__ query, const float* __restrict
 }
 
 // ---- row softmax over m + top-1 / top-2 (Memory.py:141,185,223,241) -------
-// one warp per token row of logits [N, m]
+// one warp per token row of logits [N, m] (parking the row in shared memory for the second and third pass was measured
+// slower — 519 vs 383 us at N = 65536, m = 2000: 64 KB per block leaves three blocks per SM)
 __global__ void __launch_bounds__(256)
 row_softmax_top2_kernel(const float* __restrict__ logits, long long N, int m,
                         float* __restrict__ out, long long* __restrict__ top1,
@@ -576,7 +585,7 @@ extern "C" int vadc_memory_prepare_query(const float* query, int B, int d, int64
   dim3 g1((unsigned)((HW + 255) / 256), B);
   query_norm_kernel<<<g1, 256, 0, st>>>(query, d, HW, inv);
   VADC_CHECK_LAUNCH("query_norm_kernel");
-  dim3 g2((unsigned)((HW + 31) / 32), (d + 31) / 32, B);
+  dim3 g2((unsigned)((HW + 31) / 32), (d + 127) / 128, B);
   query_transpose_kernel<<<g2, 256, 0, st>>>(query, inv, d, HW, q);
   VADC_CHECK_LAUNCH("query_transpose_kernel");
   return VADC_OK;
