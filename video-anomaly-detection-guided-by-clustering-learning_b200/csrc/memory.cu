@@ -139,6 +139,87 @@ memory_query_bwd_kernel(const float* __restrict__ query, const float* __restrict
   }
 }
 
+// (value desc, index asc) top-2 pairs of two lanes merged; used by both row-softmax kernels
+__device__ __forceinline__ void top2_merge_warp(float& b1, int& i1, float& b2, int& i2) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o);
+    int oi1 = __shfl_xor_sync(0xffffffffu, i1, o), oi2 = __shfl_xor_sync(0xffffffffu, i2, o);
+    bool other_first = (ob1 > b1) || (ob1 == b1 && oi1 < i1);
+    float n1, n2; int j1, j2;
+    if (other_first) {
+      n1 = ob1; j1 = oi1;
+      bool s = (b1 > ob2) || (b1 == ob2 && i1 < oi2);
+      n2 = s ? b1 : ob2; j2 = s ? i1 : oi2;
+    } else {
+      n1 = b1; j1 = i1;
+      bool s = (ob1 > b2) || (ob1 == b2 && oi1 < i2);
+      n2 = s ? ob1 : b2; j2 = s ? oi1 : i2;
+    }
+    b1 = n1; i1 = j1; b2 = n2; i2 = j2;
+  }
+}
+
+// register-resident row: m % 4 == 0, m <= 128 V4, 16-byte aligned rows — the logits row is read ONCE (V4 float4 per lane,
+// all in flight together), top-2, sum and output come from registers
+template <int V4>
+__global__ void __launch_bounds__(256)
+row_softmax_top2_reg_kernel(const float* __restrict__ logits, long long N, int m, float* __restrict__ out,
+                            long long* __restrict__ top1, long long* __restrict__ top2, __half* __restrict__ terms) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float4* l4 = reinterpret_cast<const float4*>(logits + row * m);
+  const int n4 = m >> 2;
+  float4 v[V4];
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < n4 ? ld_stream(l4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  }
+  float b1 = -INFINITY, b2 = -INFINITY;
+  int i1 = 0x7fffffff, i2 = 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    const int base = 4 * (lane + 32 * k);
+    const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (e[j] > b1) { b2 = b1; i2 = i1; b1 = e[j]; i1 = base + j; }
+      else if (e[j] > b2) { b2 = e[j]; i2 = base + j; }
+    }
+  }
+  top2_merge_warp(b1, i1, b2, i2);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    v[k] = make_float4(expf(v[k].x - b1), expf(v[k].y - b1), expf(v[k].z - b1), expf(v[k].w - b1));
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  s = warp_sum(s);
+  float* orow = out + row * m;
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    const int i = lane + 32 * k;
+    if (i < n4) {
+      const float4 p = make_float4(v[k].x / s, v[k].y / s, v[k].z / s, v[k].w / s);
+      reinterpret_cast<float4*>(orow)[i] = p;
+      if (terms) {                             // the operand split of the read GEMM, written in the same pass
+        const float a[4] = {p.x * 8192.0f, p.y * 8192.0f, p.z * 8192.0f, p.w * 8192.0f};
+        __half h[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { h[0][j] = __float2half_rn(a[j]); h[1][j] = __float2half_rn(a[j] - __half2float(h[0][j])); }
+        reinterpret_cast<uint2*>(terms + row * m)[i] = *reinterpret_cast<uint2*>(h[0]);
+        reinterpret_cast<uint2*>(terms + N * m + row * m)[i] = *reinterpret_cast<uint2*>(h[1]);
+      }
+    }
+  }
+  if (lane == 0) {
+    if (top1) top1[row] = i1;
+    if (top2) top2[row] = (m > 1) ? i2 : 0;
+  }
+}
+
 // ---- row softmax over m + top-1 / top-2 (Memory.py:141,185,223,241) -------
 // one warp per token row of logits [N, m] (parking the row in shared memory for the second and third pass was measured
 // slower — 519 vs 383 us at N = 65536, m = 2000: 64 KB per block leaves three blocks per SM)
@@ -158,24 +239,7 @@ row_softmax_top2_kernel(const float* __restrict__ logits, long long N, int m,
     if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = i; }
     else if (v > b2) { b2 = v; i2 = i; }
   }
-  // merge (value desc, index asc) pairs across the warp
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o);
-    int oi1 = __shfl_xor_sync(0xffffffffu, i1, o), oi2 = __shfl_xor_sync(0xffffffffu, i2, o);
-    bool other_first = (ob1 > b1) || (ob1 == b1 && oi1 < i1);
-    float n1, n2; int j1, j2;
-    if (other_first) {
-      n1 = ob1; j1 = oi1;
-      bool s = (b1 > ob2) || (b1 == ob2 && i1 < oi2);
-      n2 = s ? b1 : ob2; j2 = s ? i1 : oi2;
-    } else {
-      n1 = b1; j1 = i1;
-      bool s = (ob1 > b2) || (ob1 == b2 && oi1 < i2);
-      n2 = s ? ob1 : b2; j2 = s ? oi1 : i2;
-    }
-    b1 = n1; i1 = j1; b2 = n2; i2 = j2;
-  }
+  top2_merge_warp(b1, i1, b2, i2);
   float s = 0.f;
   float* orow = out + row * m;
   if ((m & 3) == 0 && ((reinterpret_cast<uintptr_t>(lr) | reinterpret_cast<uintptr_t>(orow)) & 15u) == 0) {
@@ -664,7 +728,16 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
   }
   // with a terms buffer (fp16 x2 mode): the read GEMM's operand split of score_memory is written in the same pass
   __half* smt = (score_memory_terms && env_int("VADC_MEMORY_TERMS", 2) != 3) ? static_cast<__half*>(score_memory_terms) : nullptr;
-  row_softmax_top2_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(logits, N, m, score_memory, (long long*)top1, (long long*)top2, smt);
+  {
+    const unsigned rg = (unsigned)((N + 7) / 8);
+    long long* t1 = (long long*)top1;
+    long long* t2 = (long long*)top2;
+    const bool regs = (m % 4) == 0 && m <= 2048 && aligned16(logits) && aligned16(score_memory) && (!smt || aligned16(smt));
+    if (regs && m <= 512) row_softmax_top2_reg_kernel<4><<<rg, 256, 0, st>>>(logits, N, m, score_memory, t1, t2, smt);
+    else if (regs && m <= 1024) row_softmax_top2_reg_kernel<8><<<rg, 256, 0, st>>>(logits, N, m, score_memory, t1, t2, smt);
+    else if (regs) row_softmax_top2_reg_kernel<16><<<rg, 256, 0, st>>>(logits, N, m, score_memory, t1, t2, smt);
+    else row_softmax_top2_kernel<<<rg, 256, 0, st>>>(logits, N, m, score_memory, t1, t2, smt);
+  }
   VADC_CHECK_LAUNCH("row_softmax_top2_kernel");
   if (score_query) {
     long long rpb = (N + chunks - 1) / chunks;
