@@ -202,3 +202,40 @@ def test_cluster_feature_bank_matches_the_reference_visualisation_loop():
     d2, l2 = bank.tsne_selection()
     np.testing.assert_array_equal(d2, data)
     np.testing.assert_array_equal(l2, label)
+
+
+def test_fuse_functions_leave_parameters_alone_and_pass_cpu_inputs_through():
+    """``fuse_encoder_tail`` / ``fuse_decoder_entry`` bind new forwards on the reference's module instances: the state_dict
+    is untouched, and inputs the CUDA kernels do not take (here: CPU tensors) run through the original modules — or, for
+    the decoder entry whose LayerNorm was folded in, fail loudly instead of silently skipping the normalisation"""
+    import torch
+    import torch.nn as nn
+    import videoad_b200 as V
+
+    class Enc(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.downsample = nn.ModuleList([nn.Sequential(nn.Conv3d(4, 8, (1, 2, 2), stride=(1, 2, 2)), nn.GELU()), nn.Identity()])
+
+    class Dec(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.timedebd = nn.Conv3d(8, 8, (2, 1, 1), stride=(2, 1, 1))
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder, self.decoder, self.norm = Enc(), Dec(), nn.LayerNorm(8)
+
+    torch.manual_seed(0)
+    m = M()
+    keys = list(m.state_dict().keys())
+    x = torch.randn(1, 4, 2, 6, 6)
+    want = m.encoder.downsample[0](x)
+    assert V.fuse_encoder_tail(m) == 1                     # the Identity stage is left alone
+    assert list(m.state_dict().keys()) == keys
+    assert torch.equal(m.encoder.downsample[0](x), want)   # CPU input: the original conv + GELU
+    V.fuse_decoder_entry(m)
+    assert list(m.state_dict().keys()) == keys
+    with pytest.raises(RuntimeError):                      # no CPU path behind the fused entry
+        m.decoder.timedebd(torch.randn(1, 8, 2, 3, 3))
