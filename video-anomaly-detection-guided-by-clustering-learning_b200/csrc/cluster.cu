@@ -65,14 +65,24 @@ gcenters_finalize_kernel(const float* __restrict__ p1, const float* __restrict__
   out[i] = s + centers[i] * rcol[i / C];
 }
 
+// partial [nblocks, 2C] -> gw, gb: a block owns 32 columns, eight row groups stride the blocks (fixed order: deterministic)
 __global__ void __launch_bounds__(256)
 ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
                        float* __restrict__ gw, float* __restrict__ gb) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * C) return;
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 2 * C + c];
-  if (c < C) gw[c] = s; else gb[c - C] = s;
+  if (c < 2 * C)
+    for (int b = wid; b < nblocks; b += 8) s += partial[(size_t)b * 2 * C + c];
+  red[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && c < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += red[ww][lane];
+    if (c < C) gw[c] = t; else gb[c - C] = t;
+  }
 }
 
 __global__ void zero_kernel(float* p, long long n) {
@@ -193,7 +203,7 @@ int launch_ln_bwd(const float* gz, const float* x, const float* mu, const float*
   else return VADC_ERR_UNSUPPORTED;
 #undef LB_CASE
   VADC_CHECK_LAUNCH("ln_bwd_rows_kernel");
-  ln_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, nb, C, gw, gb);
+  ln_bwd_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nb, C, gw, gb);
   VADC_CHECK_LAUNCH("ln_bwd_finalize_kernel");
   return VADC_OK;
 }
