@@ -15,17 +15,22 @@ def run(A, B, b_mn):
     M, Kd = A.shape
     Nn = B.shape[1] if b_mn else B.shape[0]
     l = _lib.lib()
-    out = torch.empty((M, Nn), device=dev(), dtype=torch.float32)
+    # guard rows before and after the output: a tile epilogue that ignores the ragged edge would overwrite them
+    big = torch.full((M + 16, Nn), float("nan"), device=dev(), dtype=torch.float32)
+    out = big[8:8 + M]
     ws = torch.empty(l.vadc_debug_tc_gemm_workspace_bytes(M, Nn, Kd), device=dev(), dtype=torch.uint8)
     At, Bt = T(A), T(B)
     _lib.check(l.vadc_debug_tc_gemm(_lib.ptr(At), _lib.ptr(Bt), M, Nn, Kd, int(b_mn), _lib.ptr(out), _lib.ptr(ws),
                                     ws.numel(), _lib.stream()), "vadc_debug_tc_gemm")
     torch.cuda.synchronize()
+    assert bool(torch.isnan(big[:8]).all()) and bool(torch.isnan(big[8 + M:]).all()), "write outside the output rows"
     return to_np(out)
 
 
 @pytest.mark.parametrize("M,Nn,Kd", [(128, 128, 64), (300, 32, 192), (1000, 256, 768), (515, 1024, 192),
-                                     (2048, 2000, 768), (77, 16, 768), (129, 136, 200), (4096, 64, 768)])
+                                     (2048, 2000, 768), (77, 16, 768), (129, 136, 200), (4096, 64, 768),
+                                     (3001, 1096, 200),        # more tiles than SMs: the persistent kernel, ragged M / N / Kd
+                                     (20000, 136, 64)])        # persistent, one k-block per tile, 157 x 2 tiles
 @pytest.mark.parametrize("b_mn", [0, 1])
 def test_tc_gemm_vs_float64(M, Nn, Kd, b_mn):
     rng = np.random.default_rng(M + Nn + Kd + b_mn)
