@@ -38,6 +38,13 @@ def test_workspace_queries_are_pure_host_functions():
     assert l.vadc_space_cluster_fwd_workspace_bytes(8, 784, 192, 128) > 0
     assert l.vadc_memory_score_workspace_bytes(2048, 2000, 768) >= 2048 * 2000 * 4
     assert l.vadc_pixel_loss_workspace_bytes(1 << 20) > 0
+    # round 2: opaque saved state of the space head (operand terms on the tensor-core path; without a device the query
+    # answers for the fp32 fallback), decoder entry, encoder tail
+    assert l.vadc_space_cluster_saved_bytes(8, 784, 192, 128) >= 192 * 8 * 784 * 4
+    assert l.vadc_space_cluster_bwd_workspace_bytes(8, 784, 192, 128) > 0
+    assert l.vadc_norm_timedebd_workspace_bytes(6272, 192) > 6272 * 192 * 4
+    assert l.vadc_downsample_gelu_workspace_bytes(2, 96, 4, 28, 28, 192) > 2 * 4 * 28 * 28 * 96 * 4 * 6
+    assert l.vadc_downsample_gelu_fwd(None, None, None, 2, 96, 4, 28, 28, 192, None, None, None, 0, None) == -2     # NULL pointers
 
 
 def test_argument_validation_happens_before_any_cuda_call():
