@@ -162,6 +162,8 @@ __device__ __forceinline__ void top2_merge_warp(float& b1, int& i1, float& b2, i
 
 // register-resident row: m % 4 == 0, m <= 128 V4, 16-byte aligned rows — the logits row is read ONCE (V4 float4 per lane,
 // all in flight together), top-2, sum and output come from registers
+// (writing score_query = exp(logit - colmax) / colsum from the same registers was tried: 190 registers, one block per SM,
+// 823 us against 328 + 187 for this kernel and the separate column pass; capped at 128 registers it spills — not kept)
 template <int V4>
 __global__ void __launch_bounds__(256)
 row_softmax_top2_reg_kernel(const float* __restrict__ logits, long long N, int m, float* __restrict__ out,
@@ -341,6 +343,27 @@ col_stats_stage2_kernel(const float* __restrict__ pmax, const float* __restrict_
     for (int w = 1; w < 8; ++w) online_merge(mx, s, smx[w][lane], ssm[w][lane]);
     colmax[col] = mx;
     colsum[col] = s;
+  }
+}
+
+// one level of the partial-statistics tree: [chunks_in, m] -> [gridDim.y, m], block y merges `per` consecutive chunks
+__global__ void __launch_bounds__(256)
+col_stats_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int chunks_in, int per, int m,
+                       float* __restrict__ omax, float* __restrict__ osum) {
+  __shared__ float smx[8][32], ssm[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int c0 = blockIdx.y * per, c1 = min(chunks_in, c0 + per);
+  float mx = -INFINITY, s = 0.f;
+  if (col < m)
+    for (int c = c0 + wid; c < c1; c += 8) online_merge(mx, s, pmax[(long long)c * m + col], psum[(long long)c * m + col]);
+  smx[wid][lane] = mx; ssm[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && col < m) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) online_merge(mx, s, smx[w][lane], ssm[w][lane]);
+    omax[(long long)blockIdx.y * m + col] = mx;
+    osum[(long long)blockIdx.y * m + col] = s;
   }
 }
 
@@ -676,7 +699,9 @@ extern "C" int vadc_memory_query_bwd(const float* query, const float* keys, cons
 extern "C" size_t vadc_memory_score_workspace_bytes(int64_t N, int m, int d) {
   (void)d;
   size_t n = (size_t)(N > 0 ? N : 1);
-  return align_up(n * m * sizeof(float), 256) + 2 * align_up((size_t)col_chunks(N) * m * sizeof(float), 256) +
+  const size_t groups = std::max<size_t>((n + 31) / 32, (size_t)col_chunks(N));      // 32-token groups of the GEMM epilogue
+  return align_up(n * m * sizeof(float), 256) + 2 * align_up(groups * m * sizeof(float), 256) +
+         2 * align_up(((groups + 63) / 64) * m * sizeof(float), 256) +               // second level of the statistics tree
          tc_gemm_split_bytes((long long)n, d) + tc_gemm_split_bytes(m, d) + 1024;     // operand terms of q and keys, scales
 }
 
@@ -694,8 +719,12 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
   Carver ws(workspace, workspace_bytes);
   float* logits = ws.take<float>((size_t)N * m);
   int chunks = col_chunks(N);
-  float* pmax = ws.take<float>((size_t)chunks * m);
-  float* psum = ws.take<float>((size_t)chunks * m);
+  const size_t groups = std::max<size_t>(((size_t)N + 31) / 32, (size_t)chunks);
+  float* pmax = ws.take<float>(groups * m);
+  float* psum = ws.take<float>(groups * m);
+  float* pmax2 = ws.take<float>(((groups + 63) / 64) * m);
+  float* psum2 = ws.take<float>(((groups + 63) / 64) * m);
+  bool have_groups = false;                    // the GEMM epilogue left per-32-token column statistics in pmax / psum
   if (tc_gemm_shape_ok(N, m, d, false) && !env_on("VADC_NO_TC_GEMM")) {
     // q . keys^T on tcgen05 (m = 2000, d = 768 is tensor-bound: 244 flop/B)
     void* qs = ws.take<uint8_t>(tc_gemm_split_bytes(N, d));
@@ -717,7 +746,10 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
       if ((rc = tc_split2h(keys, m, d, sc + 1, ks, st))) return rc;
       // operands swapped from m = 128 up (rows = memory slots): coalesced stores of the logits
       if (m >= 128 && !env_on("VADC_TC_ROW_EPILOGUE")) {
-        if ((rc = launch_tc_gemm_h2<false>(ks, qs, m, N, d, sc + 2, TcStoreTEpi{logits, m}, st))) return rc;
+        if (score_query && !env_on("VADC_MEMORY_NO_FUSED_STATS")) {
+          if ((rc = launch_tc_gemm_h2<false>(ks, qs, m, N, d, sc + 2, TcLogitsColStatsTEpi{logits, m, pmax, psum}, st))) return rc;
+          have_groups = true;
+        } else if ((rc = launch_tc_gemm_h2<false>(ks, qs, m, N, d, sc + 2, TcStoreTEpi{logits, m}, st))) return rc;
       } else if ((rc = launch_tc_gemm_h2<false>(qs, ks, N, m, d, sc + 2, TcStoreEpi{logits, m}, st))) return rc;
     }
   } else {
@@ -725,6 +757,27 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
     StoreLogits epi{logits, m};
     cudaError_t e = sgemm_auto((int)N, m, d, Aop, Bop, 0, 0, 1, 1, epi, st);
     if (e != cudaSuccess) return record_cuda_error(e, "memory score sgemm");
+  }
+  // column statistics first (score_query's softmax over the tokens): from the epilogue's 32-token groups through a
+  // two-level tree, or from a pass over the logits
+  if (score_query) {
+    const float* lm = pmax;
+    const float* ls = psum;
+    int nch = chunks;
+    if (have_groups) {
+      const int ng = (int)(((size_t)N + 31) / 32);
+      nch = (ng + 63) / 64;
+      col_stats_merge_kernel<<<dim3((m + 31) / 32, nch), 256, 0, st>>>(pmax, psum, ng, 64, m, pmax2, psum2);
+      VADC_CHECK_LAUNCH("col_stats_merge_kernel");
+      lm = pmax2; ls = psum2;
+    } else {
+      long long rpb = (N + chunks - 1) / chunks;
+      dim3 g1((m + 255) / 256, chunks);
+      col_stats_stage1_kernel<<<g1, 256, 0, st>>>(logits, N, m, rpb, pmax, psum);
+      VADC_CHECK_LAUNCH("col_stats_stage1_kernel");
+    }
+    col_stats_stage2_kernel<<<(m + 31) / 32, 256, 0, st>>>(lm, ls, nch, m, colmax, colsum);
+    VADC_CHECK_LAUNCH("col_stats_stage2_kernel");
   }
   // with a terms buffer (fp16 x2 mode): the read GEMM's operand split of score_memory is written in the same pass
   __half* smt = (score_memory_terms && env_int("VADC_MEMORY_TERMS", 2) != 3) ? static_cast<__half*>(score_memory_terms) : nullptr;
@@ -740,12 +793,6 @@ extern "C" int vadc_memory_score(const float* q, const float* keys, int64_t N, i
   }
   VADC_CHECK_LAUNCH("row_softmax_top2_kernel");
   if (score_query) {
-    long long rpb = (N + chunks - 1) / chunks;
-    dim3 g1((m + 255) / 256, chunks);
-    col_stats_stage1_kernel<<<g1, 256, 0, st>>>(logits, N, m, rpb, pmax, psum);
-    VADC_CHECK_LAUNCH("col_stats_stage1_kernel");
-    col_stats_stage2_kernel<<<(m + 31) / 32, 256, 0, st>>>(pmax, psum, chunks, m, colmax, colsum);
-    VADC_CHECK_LAUNCH("col_stats_stage2_kernel");
     const bool vec = (m % 4) == 0 && aligned16(logits) && aligned16(score_query) && aligned16(colmax) && aligned16(colsum);
     const int cols = vec ? m / 4 : m;
     const unsigned gx = (unsigned)((cols + 255) / 256);

@@ -716,6 +716,7 @@ template int launch_tc_gemm_h2<false, TcDistEpi>(const void*, const void*, long 
 template int launch_tc_gemm_h2<true, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
 template int launch_tc_gemm_h2<false, TcStoreEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreEpi, cudaStream_t);
 template int launch_tc_gemm_h2<true, TcReadEpi>(const void*, const void*, long long, long long, long long, const float*, TcReadEpi, cudaStream_t);
+template int launch_tc_gemm_h2<false, TcLogitsColStatsTEpi>(const void*, const void*, long long, long long, long long, const float*, TcLogitsColStatsTEpi, cudaStream_t);
 template int launch_tc_gemm_h2<false, TcStoreTEpi>(const void*, const void*, long long, long long, long long, const float*, TcStoreTEpi, cudaStream_t);
 template int launch_tc_gemm_h2<false, TcDistTEpi>(const void*, const void*, long long, long long, long long, const float*, TcDistTEpi, cudaStream_t);
 template int launch_tc_gemm_h2<true, TcGzEpi>(const void*, const void*, long long, long long, long long, const float*, TcGzEpi, cudaStream_t);

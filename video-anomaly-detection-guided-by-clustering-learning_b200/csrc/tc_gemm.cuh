@@ -110,6 +110,24 @@ struct TcStoreTEpi {
   }
 };
 
+// memory logits (Memory.py:133-143), transposed (c = memory slot, rows = tokens): stores the logits and, from the same
+// registers, the slot's online (max, sum exp) over this group of 32 tokens — the column-softmax statistics of
+// `score_query` without another pass over [N, m]; pmax / psum [ceil(N / 32), m]
+struct TcLogitsColStatsTEpi {
+  float* out; long long ldo; float* pmax; float* psum;
+  __device__ __forceinline__ void operator()(long long c, int r0, float (&v)[32], int nvalid, int = 0) const {
+    tc_store_col32(out + (long long)r0 * ldo + c, ldo, v, nvalid);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < nvalid ? v[j] : -INFINITY);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += j < nvalid ? expf(v[j] - mx) : 0.f;
+    const long long g = (long long)(r0 >> 5) * ldo + c;
+    pmax[g] = mx; psum[g] = s;
+  }
+};
+
 // sqrt for the two-term fp16 paths (22 significant bits already): MUFU.SQRT, <= 1 ulp, no slow-path branch per element
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
