@@ -14,13 +14,30 @@ namespace vadc {
 // query [B, d, HW]: norms over d for every (b, hw); threads run along hw.
 __global__ void __launch_bounds__(256)
 query_norm_kernel(const float* __restrict__ query, int d, long long HW, float* __restrict__ inv) {
-  const long long hw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // 32 positions per block (lanes), the eight warps split the channels: 128-byte reads, four independent chains per thread
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long hw = (long long)blockIdx.x * 32 + lane;
   const int b = blockIdx.y;
-  if (hw >= HW) return;
-  const float* p = query + (long long)b * d * HW + hw;
-  float s = 0.f;
-  for (int c = 0; c < d; ++c) { float v = __ldg(p + (long long)c * HW); s += v * v; }
-  inv[(long long)b * HW + hw] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (hw < HW) {
+    const float* p = query + (long long)b * d * HW + hw;
+    int c = wid;
+    for (; c + 24 < d; c += 32) {
+      const float v0 = __ldg(p + (long long)c * HW), v1 = __ldg(p + (long long)(c + 8) * HW);
+      const float v2 = __ldg(p + (long long)(c + 16) * HW), v3 = __ldg(p + (long long)(c + 24) * HW);
+      s0 += v0 * v0; s1 += v1 * v1; s2 += v2 * v2; s3 += v3 * v3;
+    }
+    for (; c < d; c += 8) { const float v = __ldg(p + (long long)c * HW); s0 += v * v; }
+  }
+  red[wid][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (wid == 0 && hw < HW) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][lane];
+    inv[(long long)b * HW + hw] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  }
 }
 
 // tiled transpose with the per-position scale: q[(b*HW+hw), c] = query[b,c,hw]*inv; a block moves 32 positions x 128
@@ -669,7 +686,7 @@ extern "C" int vadc_memory_prepare_query(const float* query, int B, int d, int64
   VADC_REQUIRE(workspace_bytes >= vadc_memory_prepare_query_workspace_bytes(B, HW), VADC_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* inv = static_cast<float*>(workspace);
-  dim3 g1((unsigned)((HW + 255) / 256), B);
+  dim3 g1((unsigned)((HW + 31) / 32), B);
   query_norm_kernel<<<g1, 256, 0, st>>>(query, d, HW, inv);
   VADC_CHECK_LAUNCH("query_norm_kernel");
   dim3 g2((unsigned)((HW + 31) / 32), (d + 127) / 128, B);

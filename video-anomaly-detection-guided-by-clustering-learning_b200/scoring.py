@@ -251,6 +251,8 @@ def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size, mod
                 ws = workspace(l.vadc_frame_mse_workspace_bytes(batch_size, frame_num, Hv * Wv, Cv), v.device)
                 ws_ptr, ws_bytes = ctypes.c_void_p(ws.data_ptr()), ws.numel()
                 fast = l.vadc_frame_mse_strided.raw
+                sptr = ctypes.c_void_p(torch.cuda.current_stream(v.device).cuda_stream)      # once per video, not per batch
+                HWv = Hv * Wv
             labs = []
             for starts in batches:
                 nb = len(starts)
@@ -264,13 +266,13 @@ def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size, mod
                         r = recon if (recon.stride(-1) == 1 and recon.stride(-2) == Wv and recon.data_ptr() % 4 == 0) else recon.contiguous()
                         rc = fast(ctypes.c_void_p(r.data_ptr()), r.stride(0), r.stride(1), r.stride(2),
                                   ctypes.c_void_p(vptr + 4 * (voff + starts[0] * st_t)), step * st_t, st_c, st_t,
-                                  nb, Cv, frame_num, Hv * Wv, ctypes.c_void_p(mse_ptr + 4 * off), ctypes.c_void_p(ps_ptr + 8 * off),
-                                  ws_ptr, ws_bytes, ctypes.c_void_p(torch.cuda.current_stream(v.device).cuda_stream))
+                                  nb, Cv, frame_num, HWv, ctypes.c_void_p(mse_ptr + 4 * off), ctypes.c_void_p(ps_ptr + 8 * off),
+                                  ws_ptr, ws_bytes, sptr)
                         if rc != 0:
                             check(rc, "vadc_frame_mse_strided")
                     else:
                         frame_mse(recon, clip, want_psnr=True, out_mse=mse_all[off:off + k], out_psnr=ps_all[off:off + k])
-                    labs.extend(lab[s0:s0 + frame_num] for s0 in starts)
+                    labs.append(starts)                                                  # frame labels gathered once per video below
                 else:
                     k = nb
                     if mode == "first_frame":
@@ -286,7 +288,12 @@ def evaluate_videos(model_fn, videos, labels, scenes, frame_num, batch_size, mod
                     labs.append(lab[np.asarray(starts) + (frame_num if (mode == "first_frame" or ispredict) else 0)])
                 off += k
             seg.append(seg[-1] + n)
-            order.append((i, np.concatenate(labs) if labs else np.zeros(0, lab.dtype)))
+            if mode == "contrast":
+                st_all = np.fromiter((s0 for b_ in labs for s0 in b_), dtype=np.int64)
+                lv = np.asarray(lab)[(st_all[:, None] + np.arange(frame_num)[None, :]).ravel()] if len(st_all) else np.zeros(0, np.asarray(lab).dtype)
+            else:
+                lv = np.concatenate(labs) if labs else np.zeros(0, lab.dtype)
+            order.append((i, lv))
         score = minmax_score_device(ps_all, torch.tensor(seg, device=ps_all.device, dtype=torch.int64)).cpu().numpy()
         for (i, lv), a, b in zip(order, seg[:-1], seg[1:]):
             if b > a and not np.isfinite(score[a:b]).all():
