@@ -158,11 +158,12 @@ int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* 
 
 int launch_bwd_rows(const float* D, const float* A, const float* gemm, const float* gD,
                     const float* gA, const float* g_loss_sq, long long R, int K,
-                    float alpha, float* r, float* rsum, cudaStream_t st) {
+                    float alpha, float* r, float* rsum, cudaStream_t st, unsigned* absmax_bits) {
   if (R == 0) return VADC_OK;
   int G = group_for(K);
   int nb = (int)((R + (256 / G) - 1) / (256 / G));
-#define BR_CASE(GG) bwd_rows_kernel<GG><<<nb, 256, 0, st>>>(D, A, gemm, gD, gA, g_loss_sq, R, K, alpha, r, rsum)
+  if (absmax_bits) VADC_CUDA(cudaMemsetAsync(absmax_bits, 0, sizeof(unsigned), st));
+#define BR_CASE(GG) bwd_rows_kernel<GG><<<nb, 256, 0, st>>>(D, A, gemm, gD, gA, g_loss_sq, R, K, alpha, r, rsum, absmax_bits)
   switch (G) {
     case 4: BR_CASE(4); break;
     case 8: BR_CASE(8); break;
@@ -571,8 +572,8 @@ extern "C" int vadc_cluster_bwd(const float* x, const float* mu, const float* rs
           if ((rc = launch_tc_gemm_h2<false>(cs, gRs, K, N, C, sc + 5, TcStoreTEpi{gemm, K}, st))) return rc;
         } else if ((rc = launch_tc_gemm_h2<false>(gRs, cs, N, K, C, sc + 5, TcStoreEpi{gemm, K}, st))) return rc;
       }
-      if ((rc = launch_bwd_rows(D, A, gR ? gemm : nullptr, gD, gA, g_loss_sq, N, K, alpha, r, rsum, st))) return rc;
-      if ((rc = tc_absmax_bits(r, (long long)N * K, bits + 3, st))) return rc;
+      // (max |r| for the fp16 scale of r comes out of the row pass itself)
+      if ((rc = launch_bwd_rows(D, A, gR ? gemm : nullptr, gD, gA, g_loss_sq, N, K, alpha, r, rsum, st, bits + 3))) return rc;
       if ((rc = tc_cluster_bwd_scales(bits, 1, sc, st))) return rc;
       if ((rc = tc_split2h(r, N, K, sc + 4, rs, st))) return rc;
       if (C >= 128 && !env_on("VADC_TC_ROW_EPILOGUE")) {     // rows = channels: coalesced loads of feature / gF and stores of gz

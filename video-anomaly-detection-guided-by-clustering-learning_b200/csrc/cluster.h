@@ -14,7 +14,8 @@ int launch_softmin_rows(const float* D, long long R, int K, float alpha, float* 
                         void* terms_h2 = nullptr, float sa = 0.f);     // optional: two fp16 terms of A * sa, [2][R*K]
 int launch_bwd_rows(const float* D, const float* A, const float* gemm, const float* gD,
                     const float* gA, const float* g_loss_sq, long long R, int K,
-                    float alpha, float* r, float* rsum, cudaStream_t st);
+                    float alpha, float* r, float* rsum, cudaStream_t st,
+                    unsigned* absmax_bits = nullptr);     // optional: max |r| as float bits (zeroed here, atomicMax per block)
 int ln_bwd_blocks(long long N);
 int launch_ln_bwd(const float* gz, const float* x, const float* mu, const float* rstd,
                   const float* w, long long N, int C, float* gx, float* partial, float* gw,

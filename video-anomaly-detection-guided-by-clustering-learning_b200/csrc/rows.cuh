@@ -244,12 +244,15 @@ bwd_rows_kernel(const float* __restrict__ D, const float* __restrict__ A,
                 const float* __restrict__ gemm, const float* __restrict__ gD,
                 const float* __restrict__ gA, const float* __restrict__ g_loss_sq,
                 long long R, int K, float alpha,
-                float* __restrict__ r, float* __restrict__ rsum) {
+                float* __restrict__ r, float* __restrict__ rsum,
+                unsigned* __restrict__ absmax_bits /* optional: max |r| as float bits (atomicMax; zeroed by the caller) */) {
+  __shared__ float bmax[8];
   const int tid = threadIdx.x;
   const int g = tid / G, gl = tid % G;
   const long long row = (long long)blockIdx.x * (blockDim.x / G) + g;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) / G * G));
-  if (row >= R) return;
+  float amax = 0.f;
+  if (row < R) {
   const float sc = g_loss_sq ? 2.0f * __ldg(g_loss_sq) : 0.f;
   const int nv = K >> 2;
   const long long base = row * K;
@@ -288,10 +291,23 @@ bwd_rows_kernel(const float* __restrict__ D, const float* __restrict__ A,
     o.w = (d.w == 0.f) ? 0.f : gd.w / d.w;
     reinterpret_cast<float4*>(r + base)[i] = o;
     rs += (o.x + o.y) + (o.z + o.w);
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
   }
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) rs += __shfl_xor_sync(gmask, rs, o, G);
   if (gl == 0) rsum[row] = rs;
+  }
+  if (absmax_bits) {                         // block maximum -> one atomic per block (max is order-independent: deterministic)
+    amax = warp_max(amax);
+    if ((tid & 31) == 0) bmax[tid >> 5] = amax;
+    __syncthreads();
+    if (tid == 0) {
+      float m = bmax[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, bmax[w]);
+      if (m > 0.f && isfinite(m)) atomicMax(absmax_bits, __float_as_uint(m));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -653,7 +653,7 @@ extern "C" size_t vadc_space_cluster_bwd_workspace_bytes(int64_t M, int P, int C
   b += align_up((size_t)C * K * sizeof(float), 256);                   // rcol
   b += align_up((size_t)std::max(space_ln_bwd_blocks(M * (int64_t)P, C, true), space_ln_bwd_blocks(M * (int64_t)P, C, false)) * 2 * C * sizeof(float), 256);
   if ((P % 8) == 0 && (K % 64) == 0) b += tc_gemm_split_bytes((long long)m, (long long)C * K) + 512;     // r terms, scales
-  return b + 256;
+  return b + 512;
 }
 
 extern "C" int vadc_space_cluster_bwd(const float* x, const float* mu, const float* rstd,
@@ -682,9 +682,11 @@ extern "C" int vadc_space_cluster_bwd(const float* x, const float* mu, const flo
   const bool tiled = ln_bwd_tile_ok(C, P, tc);
   int nb = space_ln_bwd_blocks(T, C, tiled);
   float* lnpart = ws.take<float>((size_t)nb * 2 * C);
+  unsigned* rbits = ws.take<unsigned>(64);       // max |r| (float bits) for the fp16 scale of r: comes out of the row pass
   int rc;
   cudaError_t e;
-  if ((rc = launch_bwd_rows(Ds, As, nullptr, gD, gA, g_loss_sq, M * (long long)C, K, alpha, r, rsum, st))) return rc;
+  if ((rc = launch_bwd_rows(Ds, As, nullptr, gD, gA, g_loss_sq, M * (long long)C, K, alpha, r, rsum, st,
+                            (tc && space_nt(C) == 2) ? rbits : nullptr))) return rc;
   if (tc) {
     // r as [M, C K] (batch c = its K-column window), centers as [C K, P] and zt as [C M, P] (terms the forward kept):
     //   acc[c]^T = centers[c]^T r[:,c,:]^T   (gzt = zt rsum - acc is formed by the LayerNorm backward)   rows = positions p:
@@ -702,10 +704,8 @@ extern "C" int vadc_space_cluster_bwd(const float* x, const float* mu, const flo
     if (e != cudaSuccess) return record_cuda_error(e, "space colsum r");
     if (nt == 2) {
       // r has no a-priori bound: scale from its measured max (device-side, no host sync)
-      unsigned* bits = ws.take<unsigned>(64);
       float* bsc = ws.take<float>(64);
-      if ((rc = tc_absmax_bits(r, (long long)M * C * K, bits, st))) return rc;
-      if ((rc = tc_space_bwd_scales(bits, fsc, bsc, st))) return rc;
+      if ((rc = tc_space_bwd_scales(rbits, fsc, bsc, st))) return rc;
       if ((rc = tc_split2h(r, M, (long long)C * K, bsc, rs, st))) return rc;
       if ((rc = launch_tc_gemm_batched_h2<true, false>(cs, (long long)C * K, P, rs, M, (long long)C * K, P, M, K, C, oz, bsc + 1,
                                                        egz, st))) return rc;
