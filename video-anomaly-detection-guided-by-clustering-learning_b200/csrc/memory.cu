@@ -441,13 +441,22 @@ memory_losses_kernel(const float* __restrict__ q, const float* __restrict__ keys
     const float* pos = keys + top1[row] * d;
     const float* neg = top2 ? keys + top2[row] * d : nullptr;
     float s1 = 0.f, sap = 0.f, san = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      float qv = qr[c], pv = __ldg(pos + c);
-      float e = qv - pv;
+    auto term = [&](float qv, float pv, float nv) {
+      const float e = qv - pv;
       s1 += e * e;
-      float ep = e + 1e-6f;                       // pairwise_distance eps (TripletMarginLoss)
+      const float ep = e + 1e-6f;                 // pairwise_distance eps (TripletMarginLoss)
       sap += ep * ep;
-      if (neg) { float en = qv - __ldg(neg + c) + 1e-6f; san += en * en; }
+      if (neg) { const float en = qv - nv + 1e-6f; san += en * en; }
+    };
+    if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(keys)) & 15u) == 0) {
+      for (int c = lane; c < (d >> 2); c += 32) {            // 16-byte loads: a quarter of the load instructions in flight longer
+        const float4 qv = ld_stream(reinterpret_cast<const float4*>(qr) + c);
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(pos) + c);
+        const float4 nv = neg ? __ldg(reinterpret_cast<const float4*>(neg) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        term(qv.x, pv.x, nv.x); term(qv.y, pv.y, nv.y); term(qv.z, pv.z, nv.z); term(qv.w, pv.w, nv.w);
+      }
+    } else {
+      for (int c = lane; c < d; c += 32) term(qr[c], __ldg(pos + c), neg ? __ldg(neg + c) : 0.f);
     }
     s1 = warp_sum(s1); sap = warp_sum(sap); san = warp_sum(san);
     if (lane == 0) {
@@ -460,7 +469,7 @@ memory_losses_kernel(const float* __restrict__ q, const float* __restrict__ keys
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = gt; partial[2 * blockIdx.x + 1] = st; }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 memory_losses_finalize_kernel(const double* __restrict__ partial, int nb, double nd, double n,
                               float* __restrict__ out) {
   __shared__ double red[32];
@@ -886,7 +895,7 @@ extern "C" int vadc_memory_losses(const float* q, const float* keys, const int64
   int nb = (int)((N + 7) / 8);
   memory_losses_kernel<<<nb, 256, 0, st>>>(q, keys, (const long long*)top1, (const long long*)top2, N, d, partial);
   VADC_CHECK_LAUNCH("memory_losses_kernel");
-  memory_losses_finalize_kernel<<<1, 256, 0, st>>>(partial, nb, (double)N * d, (double)N, out);
+  memory_losses_finalize_kernel<<<1, 1024, 0, st>>>(partial, nb, (double)N * d, (double)N, out);
   VADC_CHECK_LAUNCH("memory_losses_finalize_kernel");
   return VADC_OK;
 }
