@@ -37,15 +37,15 @@ constexpr int BM = 128, BK = 64, kThreads = 192;
 #endif
 constexpr int kStagesH = VADC_TC_STAGES_H;
 // co-resident CTAs per SM for a ring of STAGES stages: one-stage CTAs share an SM (two at 96 KB, three at 64 KB), a deeper
-// ring owns it (bf16 x3 two-stage ring = 192 KB: opt-in, see launch_tc_gemm_batched).
+// ring owns it.
 template <int TERMS, int STAGES> struct StageCfg { static constexpr int ctas = STAGES > 1 ? 1 : (TERMS == 2 ? 3 : 2); };
 
 // per-blockIdx.z coordinate offsets of a batched launch: output-row / contraction offsets of A, output-column /
 // contraction offsets of B (in elements of the respective tensor-map dimension)
-// pf: k-blocks prefetched into L2 together with every (pf+1)-th load; m_fast: blockIdx.x walks the m-tiles (the launcher
+// m_fast: blockIdx.x walks the m-tiles (the launcher
 // lets the dimension with FEWER tiles vary fastest, so that the CTAs in flight share the small operand and stream the
 // big one from DRAM once: with 16 m-tiles x 512 n-tiles the other order re-read the n-side operand 16 times)
-struct ZOffsets { int batched, a_m, a_k, b_n, b_k, pf, m_fast; };
+struct ZOffsets { int batched, a_m, a_k, b_n, b_k, m_fast; };
 
 __global__ void __launch_bounds__(256)
 split3_kernel(const float* __restrict__ src, long long n4, __nv_bfloat16* __restrict__ t0,
@@ -65,10 +65,6 @@ split3_kernel(const float* __restrict__ src, long long n4, __nv_bfloat16* __rest
     reinterpret_cast<uint2*>(t1)[i] = *reinterpret_cast<uint2*>(h[1]);
     reinterpret_cast<uint2*>(t2)[i] = *reinterpret_cast<uint2*>(h[2]);
   }
-}
-
-__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 __device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t smem_dst, uint64_t* bar, int c0, int c1, int c2) {
@@ -138,19 +134,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
           for (int nb = 0; nb < BN / 64; ++nb)                // [64 k-rows x 64 n-cols] boxes, 8 KB apart
             tma_load_3d(&mapB, b + t * kBTerm + nb * 8192u, &full[s], bn + nb * 64, k0 + bk, t);
-        }
-      }
-      // K-major operands arrive as 128-byte pieces of rows a whole row pitch apart: a DRAM page is opened for 128 bytes
-      // and closed again long before the next k-block asks for its neighbour.  Ask L2 for the next zo.pf k-blocks of the
-      // same rows NOW, so that DRAM sees (pf + 1) x 128 contiguous bytes per row at once.
-      if (zo.pf > 0 && kb % (zo.pf + 1) == 0) {
-        for (int d = 1; d <= zo.pf && kb + d < nkb; ++d) {
-          const int kp = k0 + d * BK;
-#pragma unroll
-          for (int t = 0; t < TERMS; ++t) {
-            if constexpr (!A_MN) tma_prefetch_3d(&mapA, kp + ak, am, t);
-            if constexpr (!B_MN) tma_prefetch_3d(&mapB, kp + bk, bn, t);
-          }
         }
       }
     }
@@ -430,7 +413,7 @@ static int launch_tc_gemm_ex_t(const void* a_split, const void* b_split, long lo
     VADC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
     const int m_fast = mtl < ntl ? 1 : 0;
     kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)mtl, (int)ntl, 1, m_fast,
-                                                  tg::ZOffsets{0, 0, 0, 0, 0, 0, 0}, acc_scale, epi);
+                                                  tg::ZOffsets{0, 0, 0, 0, 0, 0}, acc_scale, epi);
     VADC_CHECK_LAUNCH("tc_gemm_persist_kernel");
     return VADC_OK;
   }
@@ -444,7 +427,7 @@ static int launch_tc_gemm_ex_t(const void* a_split, const void* b_split, long lo
   const unsigned nt = (unsigned)((N + BN - 1) / BN), mt = (unsigned)((M + tg::BM - 1) / tg::BM);
   const int m_fast = (mt < nt && nt <= 65535u) ? 1 : 0;
   dim3 grid(m_fast ? mt : nt, m_fast ? nt : mt, (unsigned)splits);
-  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0, 0, m_fast}, acc_scale, epi);
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, per, tg::ZOffsets{0, 0, 0, 0, 0, m_fast}, acc_scale, epi);
   VADC_CHECK_LAUNCH("tc_gemm_kernel");
   return VADC_OK;
 }
@@ -479,7 +462,7 @@ int launch_tc_gemm_batched_t(const void* a_split, long long a_rows, long long a_
   const int nkb = (int)((Kd + tg::BK - 1) / tg::BK);
   const size_t stage = (size_t)TERMS * (tg::BM * 128 + BN * 128);
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + tg::BM - 1) / tg::BM), (unsigned)nbatch);
-  const tg::ZOffsets zo{1, off.a_m, off.a_k, off.b_n, off.b_k, nkb >= 4 ? env_int("VADC_TC_PREFETCH", 0) : 0, 0};
+  const tg::ZOffsets zo{1, off.a_m, off.a_k, off.b_n, off.b_k, 0};
   if ((long long)grid.x * grid.y * grid.z > sm_count() && !env_on("VADC_TC_NO_PERSIST") && !env_on("VADC_TC_NO_PERSIST_BATCHED")) {
     constexpr int kStP = TERMS == 2 ? 3 : 2;
     const size_t smemp = kStP * stage + 1024;
@@ -491,19 +474,12 @@ int launch_tc_gemm_batched_t(const void* a_split, long long a_rows, long long a_
     VADC_CHECK_LAUNCH("tc_gemm_persist_kernel(batched)");
     return VADC_OK;
   }
-  // two-stage ring, one CTA per SM: measured no better than two co-resident one-stage CTAs on the space head's long
-  // contraction loops (distance GEMM, 16 k-blocks: 251 vs 210 us; gcenters, 8 k-blocks: 218 vs 212 us) — opt-in only
-  if (TERMS == 3 && nkb >= 6 && env_on("VADC_TC_TWO_STAGE")) {
-    auto kern = tg::tc_gemm_kernel<BN, TERMS, 2, A_MN, B_MN, Epi>;
-    const size_t smem = 2 * stage + 1024;
-    VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, acc_scale, epi);
-  } else {
-    auto kern = tg::tc_gemm_kernel<BN, TERMS, 1, A_MN, B_MN, Epi>;
-    const size_t smem = stage + 1024;
-    VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, acc_scale, epi);
-  }
+  // (a two-stage ring with one CTA per SM and an L2 prefetch of the following k-blocks were both measured on the space
+  // head's long contraction loops and were no better than two co-resident one-stage CTAs: 251 vs 210 us, no change)
+  auto kern = tg::tc_gemm_kernel<BN, TERMS, 1, A_MN, B_MN, Epi>;
+  const size_t smem = stage + 1024;
+  VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, tg::kThreads, smem, st>>>(mA, mB, (int)M, (int)N, (int)Kd, nkb, zo, acc_scale, epi);
   VADC_CHECK_LAUNCH("tc_gemm_kernel(batched)");
   return VADC_OK;
 }
