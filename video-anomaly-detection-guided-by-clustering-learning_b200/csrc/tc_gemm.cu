@@ -205,7 +205,7 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
 template <int BN, int TERMS, int STAGES, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kThreadsP, 1)
 tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                       int M, int N, int Kd, int mt, int nt, int nz, int m_fast, const ZOffsets zo,
+                       int M, int N, int Kd, int mt, int nt, int nz, int m_fast, int kb_per_split, const ZOffsets zo,
                        const float* __restrict__ acc_scale, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -215,7 +215,13 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (Kd + BK - 1) / BK;
-  const long long per_z = (long long)mt * nt, ntiles = per_z * nz;    // nz independent problems (batched launches), z slowest
+  // nz (z slowest) = independent problems of a batched launch, or — kb_per_split > 0 — split-K slots of one problem: slot z
+  // contracts k-blocks [z kb_per_split, ...) and hands z to the epilogue (partial outputs; an empty slot writes zeros)
+  const long long per_z = (long long)mt * nt, ntiles = per_z * nz;
+  auto k_range = [&](int z, int& kb0, int& kcnt) {
+    kb0 = kb_per_split > 0 ? z * kb_per_split : 0;
+    kcnt = kb_per_split > 0 ? max(0, min(nkb - kb0, kb_per_split)) : nkb;
+  };
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&accfull[b], 1); mbar_init(&accempty[b], 8); }
@@ -242,12 +248,14 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       int m0, n0, z;
       tile_mn(t, m0, n0, z);
       const int am = m0 + z * zo.a_m, ak = z * zo.a_k, bn = n0 + z * zo.b_n, bk = z * zo.b_k;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
+      int kb0, kcnt;
+      k_range(z, kb0, kcnt);
+      for (int kb = 0; kb < kcnt; ++kb, ++it) {
         const uint32_t s = it % STAGES;
         mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
         mbar_expect_tx(&full[s], kStage);
         const uint32_t a = s0 + s * kStage, b = a + (uint32_t)TERMS * kATerm;
-        const int k0 = kb * BK;
+        const int k0 = (kb0 + kb) * BK;
 #pragma unroll
         for (int tt = 0; tt < TERMS; ++tt) {
           if constexpr (!A_MN) {
@@ -277,7 +285,10 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       mbar_wait(&accempty[buf], ((lt >> 1) & 1) ^ 1);           // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t acc = tmem + buf * BN;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
+      int kb0, kcnt;
+      k_range((int)(t / per_z), kb0, kcnt);
+      if (kcnt == 0) { mbar_arrive1(&accfull[buf]); continue; }  // empty split-K slot: nothing to contract
+      for (int kb = 0; kb < kcnt; ++kb, ++it) {
         const uint32_t s = it % STAGES;
         mbar_wait(&full[s], (it / STAGES) & 1);
         tc_fence_after();
@@ -309,14 +320,21 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       mbar_wait(&accfull[buf], (lt >> 1) & 1);
       tc_fence_after();
       const long long m = (long long)m0 + q * 32 + lane;
+      int kb0, kcnt;
+      k_range(z, kb0, kcnt);
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         float v[32];
         const int col = hh * (BN / 2) + c * 32;
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)col, v);
-        if (TERMS == 2) {
+        if (kcnt > 0) {
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)col, v);
+          if (TERMS == 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= sc;
+            for (int j = 0; j < 32; ++j) v[j] *= sc;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
         const int n = n0 + col;
         if (m < M && n < N) epi(m, n, v, min(32, N - n), z);
@@ -405,14 +423,17 @@ static int launch_tc_gemm_ex_t(const void* a_split, const void* b_split, long lo
   else rc = tg::make_map3(&mB, b_split, N, Kd, BN, TERMS);        // [N rows, Kd cols]: boxes of BN rows x 64 k-cols
   if (rc) return rc;
   const unsigned ntl = (unsigned)((N + BN - 1) / BN), mtl = (unsigned)((M + tg::BM - 1) / tg::BM);
-  if (splits <= 1 && (long long)ntl * mtl > sm_count() && !env_on("VADC_TC_NO_PERSIST")) {
+  if (splits < 1) splits = 1;
+  if ((long long)ntl * mtl * splits > sm_count() && !env_on("VADC_TC_NO_PERSIST")) {
     // persistent CTAs: three 64 KB (fp16 x2) or two 96 KB (bf16 x3) stages, double-buffered accumulator
     constexpr int kStP = TERMS == 2 ? 3 : 2;
     const size_t smemp = (size_t)kStP * TERMS * (tg::BM * 128 + BN * 128) + 1024;
     auto kp = tg::tc_gemm_persist_kernel<BN, TERMS, kStP, A_MN, B_MN, Epi>;
     VADC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
     const int m_fast = mtl < ntl ? 1 : 0;
-    kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)mtl, (int)ntl, 1, m_fast,
+    const int nkbp = (int)((Kd + tg::BK - 1) / tg::BK);
+    const int perp = splits > 1 ? (nkbp + splits - 1) / splits : 0;          // split-K: k-blocks per slot
+    kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)mtl, (int)ntl, splits, m_fast, perp,
                                                   tg::ZOffsets{0, 0, 0, 0, 0, 0}, acc_scale, epi);
     VADC_CHECK_LAUNCH("tc_gemm_persist_kernel");
     return VADC_OK;
@@ -469,7 +490,7 @@ int launch_tc_gemm_batched_t(const void* a_split, long long a_rows, long long a_
     auto kp = tg::tc_gemm_persist_kernel<BN, TERMS, kStP, A_MN, B_MN, Epi>;
     VADC_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
     const int m_fast = grid.y < grid.x ? 1 : 0;
-    kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)grid.y, (int)grid.x, nbatch, m_fast, zo,
+    kp<<<sm_count(), tg::kThreadsP, smemp, st>>>(mA, mB, (int)M, (int)N, (int)Kd, (int)grid.y, (int)grid.x, nbatch, m_fast, 0, zo,
                                                   acc_scale, epi);
     VADC_CHECK_LAUNCH("tc_gemm_persist_kernel(batched)");
     return VADC_OK;
