@@ -145,7 +145,8 @@ constexpr int kTileTok = 64, kTileLd = kTileTok + 1, kMaxCpl = 8, kTokPerWarp = 
 // the chunk's share of |zt[c,m,:]|^2 (sqpart [C*M, chunks]; fp32 zt is then never materialised).
 // CPL = channels per lane (C <= 32 CPL).
 // NT = 0: fp32 zt; 3: three bf16 terms; 2: two fp16 terms of zt * *scale (a power of two from the LayerNorm bound).
-template <int NT, int CPL>
+// FULL: C == 32 CPL, no per-channel predicates.
+template <int NT, int CPL, bool FULL>
 __global__ void __launch_bounds__(256)
 ln_transpose_tile_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                          int M, int P, int C, float eps, float* __restrict__ zt, float* __restrict__ mu,
@@ -162,31 +163,32 @@ ln_transpose_tile_kernel(const float* __restrict__ x, const float* __restrict__ 
   for (int i = 0; i < kTokPerWarp; ++i) {
     const float* xr = x + (t0 + min(wid + 8 * i, np - 1)) * C;       // rows past the chunk: a valid row, result unused
 #pragma unroll
-    for (int q = 0; q < CPL; ++q) v[i][q] = lane + 32 * q < C ? __ldg(xr + lane + 32 * q) : 0.f;
+    for (int q = 0; q < CPL; ++q) v[i][q] = (FULL || lane + 32 * q < C) ? __ldg(xr + lane + 32 * q) : 0.f;
   }
   float wv[CPL], bv[CPL];
 #pragma unroll
   for (int q = 0; q < CPL; ++q) {
     const int c = lane + 32 * q;
-    wv[q] = c < C ? __ldg(w + c) : 0.f; bv[q] = c < C ? __ldg(b + c) : 0.f;
+    wv[q] = (FULL || c < C) ? __ldg(w + c) : 0.f; bv[q] = (FULL || c < C) ? __ldg(b + c) : 0.f;
   }
+  const float invC = 1.0f / (float)C;        // one division per thread instead of two per token (each a branchy subroutine)
 #pragma unroll
   for (int i = 0; i < kTokPerWarp; ++i) {
     const int rr = wid + 8 * i;
     float s = 0.f;
 #pragma unroll
     for (int q = 0; q < CPL; ++q) s += v[i][q];
-    const float mean = warp_sum(s) / (float)C;
+    const float mean = warp_sum(s) * invC;
     float qq = 0.f;
 #pragma unroll
     for (int q = 0; q < CPL; ++q)
-      if (lane + 32 * q < C) { const float d = v[i][q] - mean; qq += d * d; }
-    const float rs = 1.0f / sqrtf(warp_sum(qq) / (float)C + eps);
+      if (FULL || lane + 32 * q < C) { const float d = v[i][q] - mean; qq += d * d; }
+    const float rs = rsqrtf(warp_sum(qq) * invC + eps);       // as torch's CUDA LayerNorm (rsqrt)
     if (rr < np) {
 #pragma unroll
       for (int q = 0; q < CPL; ++q) {
         const int c = lane + 32 * q;
-        if (c < C) tile[c * kTileLd + rr] = (v[i][q] - mean) * rs * wv[q] + bv[q];
+        if (FULL || c < C) tile[c * kTileLd + rr] = (v[i][q] - mean) * rs * wv[q] + bv[q];
       }
       if (lane == 0) { mu[t0 + rr] = mean; rstd[t0 + rr] = rs; }
     }
@@ -293,6 +295,7 @@ ln_bwd_transposed_tile_kernel(const float* __restrict__ gzt, const float* __rest
   }
   if (!FULL) for (int i = C * kTileLd + threadIdx.x; i < CP * kTileLd + 2 * CP; i += 256) tile[i] = 0.f;
   const long long ntiles = (T + kTileTok - 1) / kTileTok;
+  const float invC = 1.0f / (float)C;        // one division per thread, not two branchy ones per token
   for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
     const long long t0 = tl * kTileTok;
     const int np = (int)min((long long)kTileTok, T - t0);
@@ -345,7 +348,7 @@ ln_bwd_transposed_tile_kernel(const float* __restrict__ gzt, const float* __rest
         s1 += g[q]; s2 += g[q] * xh[i][q];
         aw[q] += gv * xh[i][q]; ab[q] += gv;
       }
-      s1 = warp_sum(s1) / (float)C; s2 = warp_sum(s2) / (float)C;
+      s1 = warp_sum(s1) * invC; s2 = warp_sum(s2) * invC;
       if (on) {
         float* go = gx + (t0 + rr) * C + lane;
 #pragma unroll
@@ -456,7 +459,7 @@ static int launch_ln_transpose_tile_cpl(const float* x, const float* w, const fl
                                         float* zt, float* mu, float* rstd, void* terms, const float* scale, float* sqpart,
                                         cudaStream_t st) {
   const size_t smem = (size_t)C * kTileLd * sizeof(float);
-  auto kern = ln_transpose_tile_kernel<NT, CPL>;
+  auto kern = C == 32 * CPL ? ln_transpose_tile_kernel<NT, CPL, true> : ln_transpose_tile_kernel<NT, CPL, false>;
   if (smem > 48 * 1024) VADC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)((long long)M * space_chunks(P)), 256, smem, st>>>(x, w, b, M, P, C, eps, zt, mu, rstd, terms, scale, sqpart);
   VADC_CHECK_LAUNCH("ln_transpose_tile_kernel");
