@@ -201,16 +201,17 @@ ln_transpose_tile_kernel(const float* __restrict__ x, const float* __restrict__ 
     const bool tok = 4 * l16 < np;
     uint16_t* const tbase = static_cast<uint16_t*>(terms_) + t0 + 4 * l16;
     const float sc = NT == 2 ? __ldg(scale) : 1.0f;
+    // pointers advance by 16 channels per iteration (no per-iteration 64-bit multiplies)
+    uint16_t* d = tbase + (long long)(2 * wid + half) * T;
+    float* sp = sqpart + ((long long)(2 * wid + half) * M + m) * chunks + j;
+    const float* tp = tile + (2 * wid + half) * kTileLd + 4 * l16;
+    const long long dstep = 16 * T, sstep = 16ll * M * chunks;
 #pragma unroll 2
-    for (int cc = 2 * wid; cc < C; cc += 16) {
+    for (int cc = 2 * wid; cc < C; cc += 16, d += dstep, sp += sstep, tp += 16 * kTileLd) {
       const int c = cc + half;
-      const bool ok = tok && c < C;
+      const bool ok = tok && (FULL || c < C);
       float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (ok) {
-        const float* tp = tile + c * kTileLd + 4 * l16;
-        v[0] = tp[0]; v[1] = tp[1]; v[2] = tp[2]; v[3] = tp[3];
-      }
-      uint16_t* d = tbase + (long long)c * T;
+      if (ok) { v[0] = tp[0]; v[1] = tp[1]; v[2] = tp[2]; v[3] = tp[3]; }
       if constexpr (NT == 3) {
         __nv_bfloat162 h[3][2];
 #pragma unroll
@@ -241,7 +242,7 @@ ln_transpose_tile_kernel(const float* __restrict__ x, const float* __restrict__ 
       float sq = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      if (l16 == 0 && c < C) sqpart[((long long)c * M + m) * chunks + j] = sq;
+      if (l16 == 0 && (FULL || c < C)) *sp = sq;
     }
   } else {
     for (int c = wid; c < C; c += 8) {
