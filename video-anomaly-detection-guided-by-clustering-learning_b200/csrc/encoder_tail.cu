@@ -139,6 +139,25 @@ tail_colsum_stage1_kernel(const float* __restrict__ a, long long R, int C, long 
   part[(long long)blockIdx.y * C + c] = (s0 + s1) + (s2 + s3);
 }
 
+// partial [chunks, C] -> out [C]: a block owns 32 columns, eight warps stride the chunks (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+tail_colsum_stage2_kernel(const float* __restrict__ part, int chunks, int C, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < C)
+    for (int b = wid; b < chunks; b += 8) s += part[(size_t)b * C + c];
+  red[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    out[c] = t;
+  }
+}
+
 static int tail_splits(long long NT, int Cout, int K4) {
   const long long tiles = (long long)((Cout + 127) / 128) * ((K4 + 127) / 128);
   const long long nkb = (NT + 63) / 64;
@@ -238,8 +257,8 @@ extern "C" int vadc_downsample_gelu_bwd(const float* x, const float* weight, con
     const long long rpb = (NT + cch - 1) / cch;
     tail_colsum_stage1_kernel<<<dim3((Cout + 255) / 256, cch), 256, 0, st>>>(gpre, NT, Cout, rpb, cpart);
     VADC_CHECK_LAUNCH("tail_colsum_stage1_kernel");
-    tail_sum_partials_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(cpart, cch, Cout, gbias);
-    VADC_CHECK_LAUNCH("tail_sum_partials_kernel");
+    tail_colsum_stage2_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(cpart, cch, Cout, gbias);
+    VADC_CHECK_LAUNCH("tail_colsum_stage2_kernel");
   }
   // g_A[token, k] = sum_co g_pre[token, co] W[co, k]: rows = k (W [Cout, K4] is the MN-major A operand), columns = tokens
   if ((rc = tc_split3(weight, Cout, K4, wsp, st))) return rc;
